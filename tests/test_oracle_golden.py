@@ -1,0 +1,115 @@
+"""CPU: pin the C oracle to the reference (golden transitions made by the unchanged reference)."""
+import numpy as np
+import pytest
+
+import fa_oracle
+import golden_util
+
+
+@pytest.mark.parametrize("name", ["env_3v3.npz", "env_5v5.npz", "env_2v1.npz"])
+def test_oracle_matches_reference_transitions(name):
+    g = golden_util.load(name)
+    N, A = g["act"].shape
+    env = fa_oracle.OracleEnv(N, g["n_guards"], g["n_attackers"], max_steps=golden_util.CAP)
+    env.st_f[:] = g["pre_f"]
+    env.st_i[:] = g["pre_i"]
+    env.time_step[:] = g["t_shift"]
+    obs, rew, done, result, margin = env.step(g["act"], want_margin=True)
+    # float64 restatement in the reference's evaluation order: tight tolerance
+    assert np.abs(obs - g["obs"]).max() <= 1e-12
+    assert np.abs(rew - g["rew"]).max() <= 1e-12
+    np.testing.assert_array_equal(done, g["done"])
+    np.testing.assert_array_equal(result, g["result"])
+    np.testing.assert_array_equal(env.st_i, g["post_i"])          # alive/justDied/hit/wasHit/counters
+    pd, gpd = env.st_f[:, :, 5], g["post_pd"]
+    assert np.array_equal(np.isnan(pd), np.isnan(gpd))
+    assert np.nanmax(np.abs(pd - gpd)) <= 1e-12
+    np.testing.assert_array_equal(env.time_step, g["t_shift"] + 1)
+    fin = np.isfinite(g["margin"])
+    assert np.array_equal(np.isfinite(margin), fin)
+    assert np.abs(margin[fin] - g["margin"][fin]).max() <= 1e-9   # SVD pinv vs closed form
+    # the fixtures really exercise the path
+    assert (g["pre_i"][:, :, 0] != g["post_i"][:, :, 0]).sum() > 0
+    assert done.sum() > 0
+
+
+def test_golden_covers_all_results():
+    g = golden_util.load("env_3v3.npz")
+    assert set(np.unique(g["result"])) == {0, 1, 2, 3}
+
+
+def test_reference_recorded_trajectory_kat():
+    """out_files/1.npy (test_fortattack.py:129-133): actions were not stored, so for every alive
+    agent-step SOME action in 0..7 must reproduce the next row; dead rows are frozen."""
+    traj = np.load(golden_util.GOLDEN + "/ref_traj_5v5.npy")      # [36,10,6] alive,x,y,ang,vx,vy
+    T, A, _ = traj.shape
+    n_checked = 0
+    for t in range(T - 1):
+        cur, nxt = traj[t], traj[t + 1]
+        # candidate next states for all 8^1 actions of each agent need the OTHER agents' positions
+        # only through contact forces, which do not depend on actions -> per-agent search is exact.
+        best = np.full(A, np.inf)
+        for a in range(8):
+            env = fa_oracle.OracleEnv(1, 5, 5, max_steps=1000)
+            env.st_f[0, :, 0:2] = cur[:, 1:3]
+            env.st_f[0, :, 2:4] = cur[:, 4:6]
+            env.st_f[0, :, 4] = cur[:, 3]
+            # agents that die in this transition must already be excluded from the force pass
+            env.st_i[0, :, 0] = (nxt[:, 0] > 0).astype(np.uint8)
+            act = np.full((1, A), a if a != 7 else 0, np.int32)    # shooting is tested elsewhere
+            obs, _, _, _ = env.step(act)
+            err = np.abs(obs[0][:, 1:] - nxt[:, 1:]).max(axis=1)
+            best = np.minimum(best, err)
+        alive_next = nxt[:, 0] > 0
+        assert best[alive_next].max() < 1e-9, (t, best)
+        n_checked += int(alive_next.sum())
+        dead = cur[:, 0] == 0
+        assert np.array_equal(cur[dead, 1:], nxt[dead, 1:])       # frozen once dead
+        just_died = (cur[:, 0] > 0) & ~alive_next
+        assert np.array_equal(cur[just_died, 1:], nxt[just_died, 1:])   # killed before the move
+    assert n_checked > 150
+
+
+def test_philox_known_answer():
+    # Random123 kat_vectors: philox4x32-10, counter 0, key 0
+    out = fa_oracle.philox(0, 0, [0, 0, 0, 0])
+    assert [hex(int(v)) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    out = fa_oracle.philox(0xffffffff, 0xffffffff, [0xffffffff] * 4)
+    assert [hex(int(v)) for v in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+def test_reset_distribution_and_determinism():
+    env = fa_oracle.OracleEnv(20000, 3, 3, seed=7)
+    o = env.reset()
+    g, a = o[:, :3], o[:, 3:]
+    assert np.all(o[:, :, 0] == 1) and np.all(o[:, :, 4:] == 0)
+    assert np.allclose(g[:, :, 3], 3 * np.pi / 2) and np.allclose(a[:, :, 3], np.pi / 2)
+    assert g[:, :, 1].min() > -0.06 and g[:, :, 1].max() < 0.06
+    assert g[:, :, 2].min() > 0.64 and g[:, :, 2].max() < 0.8
+    assert a[:, :, 1].min() > -1 and a[:, :, 1].max() < 1
+    assert a[:, :, 2].min() > -0.8 and a[:, :, 2].max() < -0.64
+    assert abs(a[:, :, 1].mean()) < 0.02 and abs(a[:, :, 1].std() - 2 / np.sqrt(12)) < 0.02
+    # the reference's reset draws (golden) live in the same boxes
+    gold = golden_util.load("env_3v3.npz")["reset_obs"]
+    assert np.abs(gold[:, :3, 1]).max() < 0.06 and gold[:, 3:, 2].max() < -0.64
+    # keyed by (seed, global env id, episode): shard-invariant
+    env2 = fa_oracle.OracleEnv(100, 3, 3, seed=7, env_id0=500)
+    assert np.array_equal(env2.reset(), o[500:600])
+    o2 = env.reset()
+    assert not np.array_equal(o2, o) and np.all(env.episode == 2)
+
+
+def test_step_many_equals_repeated_step_and_threads():
+    rng = np.random.RandomState(0)
+    T, E = 130, 64
+    acts = rng.randint(0, 8, size=(T, E, 6)).astype(np.int32)
+    e1 = fa_oracle.OracleEnv(E, 3, 3, max_steps=40, seed=3)
+    e2 = fa_oracle.OracleEnv(E, 3, 3, max_steps=40, seed=3, n_threads=4)
+    e1.reset(); e2.reset()
+    obs, rew, done, res = e2.step_many(acts)
+    for t in range(T):
+        o, r, d, rs = e1.step(acts[t], auto_reset=True)
+        assert np.array_equal(o, obs[t]) and np.array_equal(r, rew[t])
+        assert np.array_equal(d, done[t]) and np.array_equal(rs, res[t])
+    assert done.sum() >= 3 * E      # cap 40 -> at least 3 resets per env
+    assert np.array_equal(e1.st_f, e2.st_f, equal_nan=True)
