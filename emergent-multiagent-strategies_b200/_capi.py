@@ -1,0 +1,85 @@
+"""ctypes binding of libfortattack_b200.so (include/fortattack.h).
+
+The library is the product: if it is missing or was not built, importing this module raises --
+there is no CPU or PyTorch fallback for the step path.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfortattack_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+FA_ABI_VERSION = 1
+FA_F32, FA_F64 = 0, 1
+FA_MAX_TEAM = 5
+
+# every symbol include/fortattack.h declares
+SYMBOLS = ("fa_abi_version", "fa_last_error", "fa_workspace_bytes", "fa_create", "fa_destroy", "fa_reset",
+           "fa_step", "fa_step_many", "fa_step_host", "fa_get_state", "fa_set_state", "fa_alive_counts",
+           "fa_set_max_steps", "fa_launch_count", "fa_kernel_info")
+
+
+class FaConfig(ctypes.Structure):
+    _fields_ = [("n_envs", ctypes.c_int32), ("n_guards", ctypes.c_int32), ("n_attackers", ctypes.c_int32),
+                ("max_steps", ctypes.c_int32), ("scalar", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("seed", ctypes.c_uint64), ("env_id0", ctypes.c_uint64)]
+
+
+class FaState(ctypes.Structure):
+    _fields_ = [("d_st_f", ctypes.c_void_p), ("d_st_i", ctypes.c_void_p), ("d_time_step", ctypes.c_void_p),
+                ("d_episode", ctypes.c_void_p)]
+
+
+class FaError(RuntimeError):
+    pass
+
+
+def build(force=False, jobs=6):
+    """Compile csrc/ with nvcc for sm_100a (make -C csrc).  Works without a GPU."""
+    import subprocess
+    if force:
+        subprocess.check_call(["make", "-C", CSRC, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", CSRC, "-j%d" % jobs], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FaError("%s is missing: build it with `make -C %s -j6` (or __graft_entry__.build()); "
+                      "the FortAttack step path has no fallback implementation" % (LIB_PATH, CSRC))
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u64p = ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    L.fa_abi_version.restype = ctypes.c_int
+    L.fa_last_error.restype = ctypes.c_char_p
+    L.fa_workspace_bytes.argtypes = [ctypes.POINTER(FaConfig), ctypes.POINTER(ctypes.c_size_t)]
+    L.fa_create.argtypes = [ctypes.POINTER(FaConfig), vp, ctypes.POINTER(vp)]
+    L.fa_destroy.argtypes = [vp]
+    L.fa_reset.argtypes = [vp, vp, vp, vp]
+    L.fa_step.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+    L.fa_step_many.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    L.fa_step_host.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+    L.fa_get_state.argtypes = [vp, ctypes.POINTER(FaState), vp]
+    L.fa_set_state.argtypes = [vp, ctypes.POINTER(FaState), vp]
+    L.fa_alive_counts.argtypes = [vp, vp, vp]
+    L.fa_set_max_steps.argtypes = [vp, i32]
+    L.fa_launch_count.argtypes = [vp, u64p]
+    L.fa_kernel_info.argtypes = [vp, i32p, i32p, i32p, i32p]
+    for name in SYMBOLS:
+        getattr(L, name)   # AttributeError here = the library does not match the header
+    if L.fa_abi_version() != FA_ABI_VERSION:
+        raise FaError("libfortattack_b200.so has ABI %d, binding expects %d" % (L.fa_abi_version(), FA_ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise FaError("libfortattack_b200: %s (code %d)" % (lib().fa_last_error().decode(), rc))

@@ -1,0 +1,160 @@
+"""Device-resident batch of E independent FortAttack environments.
+
+Host-side mirror of the reference's env seam for the batched configurations:
+`reset()` / `step(actions)` have the meaning of FortAttackGlobalEnv.reset / .step
+(gym_fortattack/fortattack.py:127-186) applied to every env at once, with agent-major tensors
+(`obs[i]`, `reward[i]` index an agent, exactly what Learner.update_rollout / RolloutStorage.insert
+take: learner.py:239-243, rlcore/storage.py:33-43).  All arithmetic happens in the CUDA library
+(csrc/, through include/fortattack.h); PyTorch only owns the memory and the stream.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+
+
+class FortAttackBatch(object):
+    def __init__(self, n_envs, n_guards=3, n_attackers=3, max_steps=100, seed=0, env_id0=0, device="cuda:0",
+                 dtype=torch.float32):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _capi.FaError("FortAttackBatch needs a CUDA device (got %r); there is no CPU path" % (device,))
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        self.device, self.dtype = dev, dtype
+        self.E, self.n_guards, self.n_attackers = int(n_envs), int(n_guards), int(n_attackers)
+        self.A = self.n_guards + self.n_attackers
+        self._lib = _capi.lib()
+        self.cfg = _capi.FaConfig(self.E, self.n_guards, self.n_attackers, int(max_steps),
+                                  _capi.FA_F64 if dtype == torch.float64 else _capi.FA_F32,
+                                  dev.index if dev.index is not None else torch.cuda.current_device(),
+                                  int(seed), int(env_id0))
+        nbytes = ctypes.c_size_t()
+        _capi.check(self._lib.fa_workspace_bytes(ctypes.byref(self.cfg), ctypes.byref(nbytes)))
+        with torch.cuda.device(dev):
+            # torch's caching allocator hands out 512-byte aligned blocks
+            self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            h = ctypes.c_void_p()
+            torch.cuda.synchronize(dev)
+            _capi.check(self._lib.fa_create(ctypes.byref(self.cfg), self.workspace.data_ptr(), ctypes.byref(h)))
+        self._h = h
+        self.max_steps = int(max_steps)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _new(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.dtype, device=self.device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the env seam -----------------------------------------------------------------------------
+    def reset(self, mask=None, out=None):
+        """Reset every env (or those with mask != 0); returns obs [A, E, 6] of all envs."""
+        obs = out if out is not None else self._new(self.A, self.E, 6)
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _capi.check(self._lib.fa_reset(self._h, m.data_ptr() if m is not None else None, obs.data_ptr(),
+                                       self._stream()))
+        return obs
+
+    def step(self, actions, auto_reset=True, out=None):
+        """actions int32 [A, E] -> (obs [A,E,6], reward [A,E], done u8 [E], result u8 [E])."""
+        a = self._actions(actions, (self.A, self.E))
+        if out is None:
+            out = (self._new(self.A, self.E, 6), self._new(self.A, self.E),
+                   self._new(self.E, dtype=torch.uint8), self._new(self.E, dtype=torch.uint8))
+        obs, rew, done, result = out
+        _capi.check(self._lib.fa_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                      result.data_ptr(), int(bool(auto_reset)), self._stream()))
+        return obs, rew, done, result
+
+    def step_many(self, actions, out=None, store_obs=True):
+        """actions int32 [T, A, E]: T steps in one persistent launch (auto-reset on)."""
+        T = int(actions.shape[0])
+        a = self._actions(actions, (T, self.A, self.E))
+        if out is None:
+            out = (self._new(T, self.A, self.E, 6) if store_obs else None, self._new(T, self.A, self.E),
+                   self._new(T, self.E, dtype=torch.uint8), self._new(T, self.E, dtype=torch.uint8))
+        obs, rew, done, result = out
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _capi.check(self._lib.fa_step_many(self._h, T, a.data_ptr(), ptr(obs), ptr(rew), ptr(done), ptr(result),
+                                           self._stream()))
+        return obs, rew, done, result
+
+    def _actions(self, actions, shape):
+        a = actions
+        if a.device != self.device or a.dtype != torch.int32 or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=torch.int32).contiguous()
+        if tuple(a.shape) != shape:
+            raise ValueError("actions must have shape %r, got %r" % (shape, tuple(a.shape)))
+        return a
+
+    # -- host-buffer step (numpy-facing env.step) --------------------------------------------------
+    def make_host_buffers(self):
+        """Page-locked host buffers for step_host: actions, obs, reward, done, result."""
+        pin = dict(pin_memory=True)
+        return (torch.zeros(self.A, self.E, dtype=torch.int32, **pin),
+                torch.empty(self.A, self.E, 6, dtype=self.dtype, **pin), torch.empty(self.A, self.E, dtype=self.dtype, **pin),
+                torch.empty(self.E, dtype=torch.uint8, **pin), torch.empty(self.E, dtype=torch.uint8, **pin))
+
+    def step_host(self, h_actions, h_obs, h_rew, h_done, h_result, auto_reset=True):
+        """One env.step() with HOST tensors: H2D actions, fused step, D2H results, synchronous."""
+        _capi.check(self._lib.fa_step_host(self._h, h_actions.data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
+                                           h_done.data_ptr(), h_result.data_ptr(), int(bool(auto_reset)),
+                                           self._stream()))
+        return h_obs, h_rew, h_done, h_result
+
+    # -- state exchange (canonical float64 layout, include/fortattack.h FaState) -------------------
+    def get_state(self):
+        st_f = self._new(self.E, self.A, 6, dtype=torch.float64)
+        st_i = self._new(self.E, self.A, 6, dtype=torch.uint8)
+        t = self._new(self.E, dtype=torch.int32)
+        ep = self._new(self.E, dtype=torch.int32)       # bit pattern of uint32
+        s = _capi.FaState(st_f.data_ptr(), st_i.data_ptr(), t.data_ptr(), ep.data_ptr())
+        _capi.check(self._lib.fa_get_state(self._h, ctypes.byref(s), self._stream()))
+        return st_f, st_i, t, ep
+
+    def set_state(self, st_f, st_i, time_step, episode):
+        dev = self.device
+        st_f = torch.as_tensor(st_f).to(device=dev, dtype=torch.float64).contiguous()
+        st_i = torch.as_tensor(st_i).to(device=dev, dtype=torch.uint8).contiguous()
+        t = torch.as_tensor(time_step).to(device=dev, dtype=torch.int32).contiguous()
+        ep = torch.as_tensor(episode).to(device=dev).to(torch.int32).contiguous()
+        assert tuple(st_f.shape) == (self.E, self.A, 6) and tuple(st_i.shape) == (self.E, self.A, 6)
+        assert tuple(t.shape) == (self.E,) and tuple(ep.shape) == (self.E,)
+        s = _capi.FaState(st_f.data_ptr(), st_i.data_ptr(), t.data_ptr(), ep.data_ptr())
+        _capi.check(self._lib.fa_set_state(self._h, ctypes.byref(s), self._stream()))
+        torch.cuda.current_stream(dev).synchronize()    # the temporaries above may be freed on return
+
+    def alive_counts(self):
+        """(numAliveGuards [E], numAliveAttackers [E]) int32 (core.py:113-114)."""
+        c = self._new(2, self.E, dtype=torch.int32)
+        _capi.check(self._lib.fa_alive_counts(self._h, c.data_ptr(), self._stream()))
+        return c[0], c[1]
+
+    def set_max_steps(self, max_steps):
+        _capi.check(self._lib.fa_set_max_steps(self._h, int(max_steps)))
+        self.max_steps = int(max_steps)
+
+    def launch_count(self):
+        n = ctypes.c_uint64()
+        _capi.check(self._lib.fa_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def kernel_info(self):
+        v = [ctypes.c_int32() for _ in range(4)]
+        _capi.check(self._lib.fa_kernel_info(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("regs", "block", "grid", "smem"), [x.value for x in v]))

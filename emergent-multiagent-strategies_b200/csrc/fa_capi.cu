@@ -1,0 +1,396 @@
+// fa_capi.cu -- the C ABI of include/fortattack.h: argument checking, workspace carving, kernel
+// dispatch by (n_guards, n_attackers, scalar).  No device allocation happens here; every device byte
+// belongs to the caller (a PyTorch tensor).
+#include "../../include/fortattack.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "fa_launch.h"
+
+namespace fa {
+
+__global__ void fa_alive_counts_kernel(const uint32_t *fl, int32_t *counts, int nE, int n_guards, int A) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nE) return;
+    int g = 0, a = 0;
+    for (int i = 0; i < A; ++i) {
+        const int al = fl[(size_t)i * nE + e] & F_ALIVE;
+        if (i < n_guards) g += al; else a += al;
+    }
+    counts[e] = g;
+    counts[nE + e] = a;
+}
+
+#define FA_EXTERN(NG)                                                                                                  \
+    extern template cudaError_t launch_step_g<NG, float>(int, bool, const StepParams<float> &, int, int, cudaStream_t);  \
+    extern template cudaError_t launch_step_g<NG, double>(int, bool, const StepParams<double> &, int, int, cudaStream_t); \
+    extern template cudaError_t launch_reset_g<NG, float>(int, const StateView<float> &, const uint8_t *, float *, int,  \
+                                                          uint64_t, uint64_t, int, int, cudaStream_t);                   \
+    extern template cudaError_t launch_reset_g<NG, double>(int, const StateView<double> &, const uint8_t *, double *,    \
+                                                           int, uint64_t, uint64_t, int, int, cudaStream_t);             \
+    extern template cudaError_t step_attr_g<NG, float>(int, bool, cudaFuncAttributes *);                                 \
+    extern template cudaError_t step_attr_g<NG, double>(int, bool, cudaFuncAttributes *);
+FA_EXTERN(1) FA_EXTERN(2) FA_EXTERN(3) FA_EXTERN(4) FA_EXTERN(5)
+
+#define FA_DISPATCH_NG(ng, CALL)          \
+    switch (ng) {                         \
+    case 1: return CALL(1);               \
+    case 2: return CALL(2);               \
+    case 3: return CALL(3);               \
+    case 4: return CALL(4);               \
+    case 5: return CALL(5);               \
+    default: return cudaErrorInvalidValue; \
+    }
+
+template <typename R>
+static cudaError_t launch_step(int ng, int na, bool many, const StepParams<R> &p, int grid, int block, cudaStream_t s) {
+#define CALL(NG) launch_step_g<NG, R>(na, many, p, grid, block, s)
+    FA_DISPATCH_NG(ng, CALL)
+#undef CALL
+}
+template <typename R>
+static cudaError_t launch_reset(int ng, int na, const StateView<R> &st, const uint8_t *mask, R *obs, int E, uint64_t seed,
+                                uint64_t id0, int grid, int block, cudaStream_t s) {
+#define CALL(NG) launch_reset_g<NG, R>(na, st, mask, obs, E, seed, id0, grid, block, s)
+    FA_DISPATCH_NG(ng, CALL)
+#undef CALL
+}
+template <typename R> static cudaError_t step_attr(int ng, int na, bool many, cudaFuncAttributes *out) {
+#define CALL(NG) step_attr_g<NG, R>(na, many, out)
+    FA_DISPATCH_NG(ng, CALL)
+#undef CALL
+}
+
+}  // namespace fa
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                           \
+        if (e_ != cudaSuccess) return fail(FA_ECUDA, "%s: %s (%s)", #expr, cudaGetErrorString(e_), __func__); \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct FaHandle {
+    FaConfig cfg;
+    int A;
+    size_t rs;          // sizeof(Real)
+    char *ws;           // workspace base
+    // state planes
+    void *pv, *ap;
+    uint32_t *fl;
+    int32_t *tstep;
+    uint32_t *episode;
+    // device staging for fa_step_host
+    int32_t *s_act;
+    void *s_obs, *s_rew;
+    uint8_t *s_done, *s_result;
+    int block, grid;
+    int sm_count;
+    uint64_t launches;
+};
+
+struct Carve {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+struct Layout {
+    size_t pv, ap, fl, tstep, episode, s_act, s_obs, s_rew, s_done, s_result, total;
+};
+
+static Layout make_layout(const FaConfig &c) {
+    const size_t E = (size_t)c.n_envs, A = (size_t)(c.n_guards + c.n_attackers);
+    const size_t rs = c.scalar == FA_F64 ? 8 : 4;
+    Carve k;
+    Layout L;
+    L.pv = k.take(A * E * 4 * rs);
+    L.ap = k.take(A * E * 2 * rs);
+    L.fl = k.take(A * E * 4);
+    L.tstep = k.take(E * 4);
+    L.episode = k.take(E * 4);
+    L.s_act = k.take(A * E * 4);
+    L.s_obs = k.take(A * E * 6 * rs);
+    L.s_rew = k.take(A * E * rs);
+    L.s_done = k.take(E);
+    L.s_result = k.take(E);
+    L.total = k.off;
+    return L;
+}
+
+static int check_cfg(const FaConfig *c) {
+    if (!c) return fail(FA_EINVAL, "config is NULL");
+    if (c->n_envs < 1) return fail(FA_EINVAL, "n_envs must be >= 1 (got %d)", c->n_envs);
+    if (c->n_guards < 1 || c->n_guards > FA_MAX_TEAM || c->n_attackers < 1 || c->n_attackers > FA_MAX_TEAM)
+        return fail(FA_EINVAL, "unsupported team sizes %dv%d: kernels exist for 1..%d guards x 1..%d attackers",
+                    c->n_guards, c->n_attackers, FA_MAX_TEAM, FA_MAX_TEAM);
+    if (c->max_steps < 1) return fail(FA_EINVAL, "max_steps must be >= 1 (got %d)", c->max_steps);
+    if (c->scalar != FA_F32 && c->scalar != FA_F64) return fail(FA_EINVAL, "scalar must be FA_F32 or FA_F64");
+    if ((uint64_t)c->n_envs * (uint64_t)(c->n_guards + c->n_attackers) * 6ull >= (1ull << 40))
+        return fail(FA_EINVAL, "n_envs too large");
+    return FA_OK;
+}
+
+template <typename R> static fa::StateView<R> view(const FaHandle *h) {
+    fa::StateView<R> v;
+    v.pv = reinterpret_cast<typename fa::VecT<R>::T4 *>(h->pv);
+    v.ap = reinterpret_cast<typename fa::VecT<R>::T2 *>(h->ap);
+    v.fl = h->fl;
+    v.tstep = h->tstep;
+    v.episode = h->episode;
+    return v;
+}
+
+// Few envs: one warp per block so the launch spreads over as many SMs as possible (E=4096 -> 128
+// SMs busy); many envs: 128-thread blocks (4 warps share one 6/12 KB obs stage).
+static void pick_launch(FaHandle *h) {
+    const int E = h->cfg.n_envs;
+    int block = 128;
+    while (block > 32 && (E + block - 1) / block < 2 * h->sm_count) block >>= 1;
+    h->block = block;
+    h->grid = (E + block - 1) / block;
+}
+
+#define NEED_HANDLE(h) \
+    if (!(h)) return fail(FA_EINVAL, "handle is NULL")
+
+template <typename R>
+static cudaError_t do_step(FaHandle *h, bool many, int T, const int32_t *act, void *obs, void *rew, uint8_t *done,
+                           uint8_t *result, int auto_reset, cudaStream_t s) {
+    const FaConfig &c = h->cfg;
+    fa::StepParams<R> p;
+    p.st = view<R>(h);
+    p.act = act;
+    p.obs = static_cast<R *>(obs);
+    p.rew = static_cast<R *>(rew);
+    p.done = done;
+    p.result = result;
+    p.E = c.n_envs;
+    p.T = T;
+    p.max_steps = c.max_steps;
+    p.auto_reset = auto_reset;
+    // 16-byte vector stores of obs need every plane (stride E*6*sizeof(R)) to keep 16-byte alignment
+    p.obs_vec_ok = ((size_t)c.n_envs * 6 * sizeof(R)) % 16 == 0 && ((uintptr_t)obs % 16) == 0;
+    p.seed = c.seed;
+    p.env_id0 = c.env_id0;
+    return fa::launch_step<R>(c.n_guards, c.n_attackers, many, p, h->grid, h->block, s);
+}
+
+static int step_common(FaHandle *h, bool many, int T, const int32_t *d_actions, void *d_obs, void *d_reward,
+                       uint8_t *d_done, uint8_t *d_result, int auto_reset, void *stream) {
+    NEED_HANDLE(h);
+    if (!d_actions) return fail(FA_EINVAL, "actions is NULL");
+    if (T < 1) return fail(FA_EINVAL, "T must be >= 1 (got %d)", T);
+    if (d_obs && (uintptr_t)d_obs % (2 * h->rs)) return fail(FA_EALIGN, "obs must be aligned to %zu bytes", 2 * h->rs);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = h->cfg.scalar == FA_F64
+                        ? do_step<double>(h, many, T, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, s)
+                        : do_step<float>(h, many, T, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, s);
+    CUDA_TRY(e);
+    h->launches += 1;
+    return FA_OK;
+}
+
+extern "C" {
+
+int fa_abi_version(void) { return FA_ABI_VERSION; }
+
+const char *fa_last_error(void) { return g_err; }
+
+int fa_workspace_bytes(const FaConfig *cfg, size_t *out_bytes) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!out_bytes) return fail(FA_EINVAL, "out_bytes is NULL");
+    *out_bytes = make_layout(*cfg).total;
+    return FA_OK;
+}
+
+int fa_create(const FaConfig *cfg, void *d_workspace, FaHandle **out) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if (!d_workspace || !out) return fail(FA_EINVAL, "workspace / out is NULL");
+    if ((uintptr_t)d_workspace % 256) return fail(FA_EALIGN, "workspace must be 256-byte aligned");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(FA_ENODEVICE, "no CUDA device is visible; this library has no CPU path");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FA_EINVAL, "device %d out of range (0..%d)", cfg->device, ndev - 1);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(FA_ENODEVICE, "device %d is sm_%d%d; this library only carries sm_100a (B200) code", cfg->device,
+                    prop.major, prop.minor);
+    FaHandle *h = new (std::nothrow) FaHandle();
+    if (!h) return fail(FA_EINVAL, "out of host memory");
+    h->cfg = *cfg;
+    h->A = cfg->n_guards + cfg->n_attackers;
+    h->rs = cfg->scalar == FA_F64 ? 8 : 4;
+    h->ws = static_cast<char *>(d_workspace);
+    const Layout L = make_layout(*cfg);
+    h->pv = h->ws + L.pv;
+    h->ap = h->ws + L.ap;
+    h->fl = reinterpret_cast<uint32_t *>(h->ws + L.fl);
+    h->tstep = reinterpret_cast<int32_t *>(h->ws + L.tstep);
+    h->episode = reinterpret_cast<uint32_t *>(h->ws + L.episode);
+    h->s_act = reinterpret_cast<int32_t *>(h->ws + L.s_act);
+    h->s_obs = h->ws + L.s_obs;
+    h->s_rew = h->ws + L.s_rew;
+    h->s_done = reinterpret_cast<uint8_t *>(h->ws + L.s_done);
+    h->s_result = reinterpret_cast<uint8_t *>(h->ws + L.s_result);
+    h->sm_count = prop.multiProcessorCount;
+    h->launches = 0;
+    pick_launch(h);
+    const int E = cfg->n_envs, ib = 256, ig = (E + ib - 1) / ib;
+    if (cfg->scalar == FA_F64) fa::fa_init_kernel<double><<<ig, ib>>>(view<double>(h), E, h->A);
+    else fa::fa_init_kernel<float><<<ig, ib>>>(view<float>(h), E, h->A);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(FA_ECUDA, "state initialisation failed: %s", cudaGetErrorString(e));
+    }
+    h->launches += 1;
+    *out = h;
+    return FA_OK;
+}
+
+int fa_destroy(FaHandle *h) {
+    delete h;
+    return FA_OK;
+}
+
+int fa_reset(FaHandle *h, const uint8_t *d_env_mask, void *d_obs, void *stream) {
+    NEED_HANDLE(h);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const FaConfig &c = h->cfg;
+    cudaError_t e;
+    if (c.scalar == FA_F64)
+        e = fa::launch_reset<double>(c.n_guards, c.n_attackers, view<double>(h), d_env_mask, static_cast<double *>(d_obs),
+                                     c.n_envs, c.seed, c.env_id0, h->grid, h->block, s);
+    else
+        e = fa::launch_reset<float>(c.n_guards, c.n_attackers, view<float>(h), d_env_mask, static_cast<float *>(d_obs),
+                                    c.n_envs, c.seed, c.env_id0, h->grid, h->block, s);
+    CUDA_TRY(e);
+    h->launches += 1;
+    return FA_OK;
+}
+
+int fa_step(FaHandle *h, const int32_t *d_actions, void *d_obs, void *d_reward, uint8_t *d_done, uint8_t *d_result,
+            int auto_reset, void *stream) {
+    return step_common(h, false, 1, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, stream);
+}
+
+int fa_step_many(FaHandle *h, int T, const int32_t *d_actions, void *d_obs, void *d_reward, uint8_t *d_done,
+                 uint8_t *d_result, void *stream) {
+    return step_common(h, true, T, d_actions, d_obs, d_reward, d_done, d_result, 1, stream);
+}
+
+int fa_step_host(FaHandle *h, const int32_t *h_actions, void *h_obs, void *h_reward, uint8_t *h_done,
+                 uint8_t *h_result, int auto_reset, void *stream) {
+    NEED_HANDLE(h);
+    if (!h_actions) return fail(FA_EINVAL, "actions is NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t E = (size_t)h->cfg.n_envs, A = (size_t)h->A;
+    CUDA_TRY(cudaMemcpyAsync(h->s_act, h_actions, A * E * 4, cudaMemcpyHostToDevice, s));
+    int rc = step_common(h, false, 1, h->s_act, h_obs ? h->s_obs : nullptr, h_reward ? h->s_rew : nullptr,
+                         h_done ? h->s_done : nullptr, h_result ? h->s_result : nullptr, auto_reset, stream);
+    if (rc) return rc;
+    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->s_obs, A * E * 6 * h->rs, cudaMemcpyDeviceToHost, s));
+    if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->s_rew, A * E * h->rs, cudaMemcpyDeviceToHost, s));
+    if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->s_done, E, cudaMemcpyDeviceToHost, s));
+    if (h_result) CUDA_TRY(cudaMemcpyAsync(h_result, h->s_result, E, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return FA_OK;
+}
+
+int fa_get_state(FaHandle *h, const FaState *out, void *stream) {
+    NEED_HANDLE(h);
+    if (!out || !out->d_st_f || !out->d_st_i || !out->d_time_step || !out->d_episode)
+        return fail(FA_EINVAL, "FaState has a NULL member");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int E = h->cfg.n_envs, b = 128, g = (E + b - 1) / b;
+    if (h->cfg.scalar == FA_F64)
+        fa::fa_get_state_kernel<double><<<g, b, 0, s>>>(view<double>(h), out->d_st_f, out->d_st_i, out->d_time_step,
+                                                        out->d_episode, E, h->A);
+    else
+        fa::fa_get_state_kernel<float><<<g, b, 0, s>>>(view<float>(h), out->d_st_f, out->d_st_i, out->d_time_step,
+                                                       out->d_episode, E, h->A);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return FA_OK;
+}
+
+int fa_set_state(FaHandle *h, const FaState *in, void *stream) {
+    NEED_HANDLE(h);
+    if (!in || !in->d_st_f || !in->d_st_i || !in->d_time_step || !in->d_episode)
+        return fail(FA_EINVAL, "FaState has a NULL member");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int E = h->cfg.n_envs, b = 128, g = (E + b - 1) / b;
+    if (h->cfg.scalar == FA_F64)
+        fa::fa_set_state_kernel<double><<<g, b, 0, s>>>(view<double>(h), in->d_st_f, in->d_st_i, in->d_time_step,
+                                                        in->d_episode, E, h->A);
+    else
+        fa::fa_set_state_kernel<float><<<g, b, 0, s>>>(view<float>(h), in->d_st_f, in->d_st_i, in->d_time_step,
+                                                       in->d_episode, E, h->A);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return FA_OK;
+}
+
+int fa_alive_counts(FaHandle *h, int32_t *d_counts, void *stream) {
+    NEED_HANDLE(h);
+    if (!d_counts) return fail(FA_EINVAL, "counts is NULL");
+    const int E = h->cfg.n_envs, b = 128, g = (E + b - 1) / b;
+    fa::fa_alive_counts_kernel<<<g, b, 0, static_cast<cudaStream_t>(stream)>>>(h->fl, d_counts, E, h->cfg.n_guards, h->A);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return FA_OK;
+}
+
+int fa_set_max_steps(FaHandle *h, int32_t max_steps) {
+    NEED_HANDLE(h);
+    if (max_steps < 1) return fail(FA_EINVAL, "max_steps must be >= 1 (got %d)", max_steps);
+    h->cfg.max_steps = max_steps;
+    return FA_OK;
+}
+
+int fa_launch_count(const FaHandle *h, uint64_t *out) {
+    NEED_HANDLE(h);
+    if (!out) return fail(FA_EINVAL, "out is NULL");
+    *out = h->launches;
+    return FA_OK;
+}
+
+int fa_kernel_info(const FaHandle *h, int32_t *regs, int32_t *block, int32_t *grid, int32_t *smem) {
+    NEED_HANDLE(h);
+    cudaFuncAttributes a;
+    cudaError_t e = h->cfg.scalar == FA_F64 ? fa::step_attr<double>(h->cfg.n_guards, h->cfg.n_attackers, false, &a)
+                                            : fa::step_attr<float>(h->cfg.n_guards, h->cfg.n_attackers, false, &a);
+    CUDA_TRY(e);
+    if (regs) *regs = a.numRegs;
+    if (block) *block = h->block;
+    if (grid) *grid = h->grid;
+    if (smem) *smem = (int32_t)a.sharedSizeBytes;
+    return FA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,4 @@
+#include "fa_inst.cuh"
+namespace fa {
+FA_INSTANTIATE(5)
+}

@@ -1,0 +1,46 @@
+"""Shared helpers of the GPU parity tests: CUDA engine <-> oracle state plumbing and tolerances."""
+import numpy as np
+import torch
+
+import fortattack_b200 as fab
+
+# north_star: observations / rewards within 1e-5 in fp32 (relative for the unbounded heading channel);
+# double mode runs the same kernels in fp64 and must agree to rounding.
+TOL = {torch.float32: (1e-5, 1e-5), torch.float64: (1e-11, 1e-11)}
+# fp32 hit predicates are compared exactly where the oracle's barycentric margin exceeds this
+MARGIN_F32 = 1e-5
+
+
+def make(E, ng, na, dtype, max_steps=100, seed=0, env_id0=0):
+    return fab.FortAttackBatch(E, ng, na, max_steps=max_steps, seed=seed, env_id0=env_id0, device="cuda:0",
+                               dtype=dtype)
+
+
+def push(env, st_f, st_i, t, ep):
+    env.set_state(torch.from_numpy(np.ascontiguousarray(st_f)), torch.from_numpy(np.ascontiguousarray(st_i)),
+                  torch.from_numpy(np.ascontiguousarray(t, dtype=np.int32)),
+                  torch.from_numpy(np.ascontiguousarray(ep).astype(np.int64)))
+
+
+def pull(env):
+    st_f, st_i, t, ep = env.get_state()
+    return (st_f.cpu().numpy(), st_i.cpu().numpy(), t.cpu().numpy(), ep.cpu().numpy().astype(np.uint32))
+
+
+def acts_dev(act_env_major):
+    """[E, A] (oracle layout) -> int32 cuda tensor [A, E]."""
+    return torch.from_numpy(np.ascontiguousarray(act_env_major.T.astype(np.int32))).cuda()
+
+
+def to_env_major(t):
+    """[A, E, ...] cuda tensor -> numpy [E, A, ...] float64."""
+    a = t.detach().cpu().numpy()
+    return np.swapaxes(a, 0, 1).astype(np.float64) if a.dtype.kind == "f" else np.swapaxes(a, 0, 1)
+
+
+def close(got, ref, dtype, what):
+    atol, rtol = TOL[dtype]
+    err = np.abs(got - ref) - (atol + rtol * np.abs(ref))
+    bad = np.argwhere(~(err <= 0))          # NaN-safe
+    assert bad.size == 0, "%s: %d mismatches, first at %s got %r ref %r (max |d| %.3g)" % (
+        what, len(bad), bad[0], got[tuple(bad[0])], ref[tuple(bad[0])], np.nanmax(np.abs(got - ref)))

@@ -1,0 +1,211 @@
+"""GPU parity of the fused CUDA step (through the C ABI) against the oracle and the golden transitions
+produced by the unchanged reference.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import fa_oracle
+import golden_util
+from gpu_util import MARGIN_F32, acts_dev, close, make, pull, push, to_env_major
+
+pytestmark = pytest.mark.gpu
+DTYPES = [torch.float64, torch.float32]
+
+
+def _compare_transition(env, dtype, pre_f, pre_i, t, ep, act, ref, margin, auto_reset=False, what=""):
+    """Teacher-forced: inject the pre-state, take ONE CUDA step, compare everything with `ref`
+    (dict obs,rew,done,result,post_i,post_pd,t_post).  Returns #envs excluded from the exact mask
+    comparison (fp32 only: oracle hit predicate closer than MARGIN_F32 to its boundary)."""
+    push(env, pre_f, pre_i, t, ep)
+    obs, rew, done, result = env.step(acts_dev(act), auto_reset=auto_reset)
+    st_f, st_i, t_post, _ = pull(env)
+    obs, rew = to_env_major(obs), to_env_major(rew)
+    done, result = done.cpu().numpy(), result.cpu().numpy()
+    keep = np.ones(len(act), bool)
+    if dtype == torch.float32:
+        keep = ~(margin < MARGIN_F32)
+    k = keep
+    assert np.array_equal(st_i[k], ref["post_i"][k]), what + " alive/justDied/hit/wasHit/counters"
+    assert np.array_equal(done[k], ref["done"][k]) and np.array_equal(result[k], ref["result"][k]), what + " done"
+    close(obs[k], ref["obs"][k], dtype, what + " obs")
+    close(rew[k], ref["rew"][k], dtype, what + " reward")
+    pd, rpd = st_f[k][:, :, 5], ref["post_pd"][k]
+    assert np.array_equal(np.isnan(pd), np.isnan(rpd)), what + " prevDist None-ness"
+    close(np.nan_to_num(pd), np.nan_to_num(rpd), dtype, what + " prevDist")
+    if "t_post" in ref:
+        assert np.array_equal(t_post[k], ref["t_post"][k]), what + " time_step"
+    return int((~keep).sum())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", ["env_3v3.npz", "env_5v5.npz", "env_2v1.npz"])
+def test_golden_reference_transitions(name, dtype):
+    """Every transition recorded from the unchanged reference (tests/golden/make_env_golden.py)."""
+    g = golden_util.load(name)
+    N = g["act"].shape[0]
+    env = make(N, g["n_guards"], g["n_attackers"], dtype, max_steps=golden_util.CAP)
+    ref = dict(obs=g["obs"], rew=g["rew"], done=g["done"], result=g["result"], post_i=g["post_i"],
+               post_pd=g["post_pd"], t_post=g["t_shift"] + 1)
+    excluded = _compare_transition(env, dtype, g["pre_f"], g["pre_i"], g["t_shift"], np.zeros(N, np.uint32),
+                                   g["act"], ref, g["margin"], what=name)
+    assert excluded <= 2
+    assert ref["done"].sum() > 0 and (g["pre_i"][:, :, 0] != g["post_i"][:, :, 0]).sum() > 0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ng,na,E,steps", [(3, 3, 4096, 130), (5, 5, 1024, 110), (1, 1, 257, 60), (4, 2, 100, 60)])
+def test_teacher_forced_vs_oracle(ng, na, E, steps, dtype):
+    """SURVEY 8d parity gate: oracle state -> fa_set_state -> fa_step -> compare, every step, with the
+    shoot-heavy action stream and in-kernel auto-reset (Philox streams must match the oracle's)."""
+    rng = np.random.RandomState(5)
+    ora = fa_oracle.OracleEnv(E, ng, na, max_steps=40, seed=11, env_id0=1000, n_threads=8)
+    env = make(E, ng, na, dtype, max_steps=40, seed=11, env_id0=1000)
+    o0 = ora.reset()
+    close(to_env_major(env.reset()), o0, dtype, "reset obs")
+    excluded = kills = dones = 0
+    for s in range(steps):
+        act = rng.choice(8, size=(E, ng + na), p=[.1] * 7 + [.3]).astype(np.int32)
+        pre = (ora.st_f.copy(), ora.st_i.copy(), ora.time_step.copy(), ora.episode.copy())
+        obs, rew, done, result, margin = ora.step(act, auto_reset=True, want_margin=True)
+        ref = dict(obs=obs, rew=rew, done=done, result=result, post_i=ora.st_i, post_pd=ora.st_f[:, :, 5],
+                   t_post=ora.time_step)
+        excluded += _compare_transition(env, dtype, *pre, act, ref, margin, auto_reset=True, what="step %d" % s)
+        kills += int((pre[1][:, :, 0] > ora.st_i[:, :, 0]).sum())
+        dones += int(done.sum())
+        _, _, _, ep = pull(env)
+        assert np.array_equal(ep[~(margin < MARGIN_F32)], ora.episode[~(margin < MARGIN_F32)])
+    assert dones >= E and kills > 0
+    assert excluded <= max(2, int(2e-5 * E * steps * (ng + na)))   # ~1e-5 * 0.23 per laser test
+
+
+@pytest.mark.parametrize("ng,na", [(3, 3), (5, 5)])
+def test_free_run_double_tracks_oracle(ng, na):
+    """Double mode, no re-sync for 300 steps (several episodes with resets): same trajectories."""
+    E, T = 512, 300
+    rng = np.random.RandomState(9)
+    ora = fa_oracle.OracleEnv(E, ng, na, max_steps=50, seed=3, n_threads=8)
+    env = make(E, ng, na, torch.float64, max_steps=50, seed=3)
+    ora.reset(); env.reset()
+    acts = rng.randint(0, 8, size=(T, E, ng + na)).astype(np.int32)
+    o_obs, o_rew, o_done, o_res = ora.step_many(acts)
+    a = torch.from_numpy(np.ascontiguousarray(np.swapaxes(acts, 1, 2))).cuda()
+    obs, rew, done, res = env.step_many(a)
+    obs = np.swapaxes(obs.cpu().numpy(), 1, 2); rew = np.swapaxes(rew.cpu().numpy(), 1, 2)
+    assert np.array_equal(done.cpu().numpy(), o_done) and np.array_equal(res.cpu().numpy(), o_res)
+    assert np.abs(obs - o_obs).max() < 1e-7 and np.abs(rew - o_rew).max() < 1e-7
+    assert o_done.sum() >= 5 * E
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("ng,na,E", [(3, 3, 4096), (5, 5, 333), (2, 1, 31), (3, 3, 1)])
+def test_step_many_equals_repeated_step(ng, na, E, dtype):
+    """The persistent T-step launch and T single-step launches are the same arithmetic: bit-equal."""
+    T = 70
+    g = torch.Generator(device="cuda").manual_seed(1)
+    acts = torch.randint(0, 8, (T, ng + na, E), generator=g, device="cuda", dtype=torch.int32)
+    e1 = make(E, ng, na, dtype, max_steps=30, seed=2)
+    e2 = make(E, ng, na, dtype, max_steps=30, seed=2)
+    assert torch.equal(e1.reset(), e2.reset())
+    obs, rew, done, res = e2.step_many(acts)
+    for t in range(T):
+        o, r, d, rs = e1.step(acts[t], auto_reset=True)
+        assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]), "step %d" % t
+        assert torch.equal(d, done[t]) and torch.equal(rs, res[t])
+    for x, y in zip(e1.get_state(), e2.get_state()):
+        assert torch.equal(torch.nan_to_num(x.double()), torch.nan_to_num(y.double()))
+    assert int(done.sum()) >= 2 * E
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_state_roundtrip_and_alive_counts(dtype):
+    g = golden_util.load("env_5v5.npz")
+    N = g["act"].shape[0]
+    env = make(N, 5, 5, dtype)
+    ep = np.arange(N).astype(np.uint32)
+    push(env, g["pre_f"], g["pre_i"], g["t_pre"], ep)
+    st_f, st_i, t, ep2 = pull(env)
+    assert np.array_equal(st_i, g["pre_i"]) and np.array_equal(t, g["t_pre"]) and np.array_equal(ep2, ep)
+    tol = 0 if dtype == torch.float64 else 1e-5
+    assert np.nanmax(np.abs(st_f - g["pre_f"]) / (1 + np.abs(g["pre_f"]))) <= tol
+    assert np.array_equal(np.isnan(st_f), np.isnan(g["pre_f"]))
+    ng_alive, na_alive = env.alive_counts()
+    assert np.array_equal(ng_alive.cpu().numpy(), g["pre_i"][:, :5, 0].sum(1))
+    assert np.array_equal(na_alive.cpu().numpy(), g["pre_i"][:, 5:, 0].sum(1))
+
+
+def test_shard_invariance_and_seed():
+    """Envs are keyed by global id: a shard [1000,1100) reproduces rows of the full batch."""
+    T = 120
+    g = torch.Generator(device="cuda").manual_seed(4)
+    acts = torch.randint(0, 8, (T, 6, 2048), generator=g, device="cuda", dtype=torch.int32)
+    full = make(2048, 3, 3, torch.float32, max_steps=25, seed=77)
+    part = make(100, 3, 3, torch.float32, max_steps=25, seed=77, env_id0=1000)
+    other = make(100, 3, 3, torch.float32, max_steps=25, seed=78, env_id0=1000)
+    o_full, o_part, o_other = full.reset(), part.reset(), other.reset()
+    assert torch.equal(o_full[:, 1000:1100], o_part) and not torch.equal(o_part, o_other)
+    of, rf, df, _ = full.step_many(acts)
+    op, rp, dp, _ = part.step_many(acts[:, :, 1000:1100].contiguous())
+    assert torch.equal(of[:, :, 1000:1100], op) and torch.equal(rf[:, :, 1000:1100], rp)
+    assert torch.equal(df[:, 1000:1100], dp)
+
+
+def test_step_host_matches_device_step():
+    E = 1000
+    e1, e2 = make(E, 3, 3, torch.float32, seed=5), make(E, 3, 3, torch.float32, seed=5)
+    e1.reset(); e2.reset()
+    bufs = e2.make_host_buffers()
+    rng = np.random.RandomState(0)
+    for _ in range(20):
+        a = torch.from_numpy(rng.randint(0, 8, size=(6, E)).astype(np.int32))
+        o, r, d, rs = e1.step(a.cuda())
+        bufs[0].copy_(a)
+        ho, hr, hd, hrs = e2.step_host(*bufs)
+        assert torch.equal(o.cpu(), ho) and torch.equal(r.cpu(), hr) and torch.equal(d.cpu(), hd) and torch.equal(rs.cpu(), hrs)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (3v3 x 4096 envs x 1000 steps, cap 100) and a >L2 batch: size-independent
+    properties of the reference semantics."""
+    for E, T in ((4096, 1000), (1 << 20, 12)):
+        env = make(E, 3, 3, torch.float32, max_steps=100, seed=0)
+        prev = env.reset()
+        g = torch.Generator(device="cuda").manual_seed(0)
+        n_done = 0
+        chunk = 50 if E == 4096 else T
+        for c in range(T // chunk):
+            acts = torch.randint(0, 8, (chunk, 6, E), generator=g, device="cuda", dtype=torch.int32)
+            obs, rew, done, res = env.step_many(acts)
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            allobs = torch.cat([prev[None], obs], 0)
+            cont = (done[:, None, :] == 0)                                   # [chunk,1,E]: no reset at t
+            was_dead = (allobs[:-1, :, :, 0] == 0) & cont
+            # dead agents are frozen and stay dead within an episode (core.py:324 loops over alive only)
+            assert torch.equal(allobs[1:][was_dead], allobs[:-1][was_dead])
+            # positions stay inside the walls' soft band, |v| <= max_speed
+            assert (obs[..., 1].abs() < 1.2).all() and (obs[..., 2].abs() < 1.0).all()
+            assert ((obs[..., 4] ** 2 + obs[..., 5] ** 2) <= 9.0001).all()
+            # done <=> result != 0 ; after a reset everyone is alive with zero velocity
+            assert torch.equal(done != 0, res != 0)
+            fresh = obs.permute(0, 2, 1, 3)[done != 0]                       # [n,A,6]
+            assert (fresh[:, :, 0] == 1).all() and (fresh[:, :, 4:] == 0).all()
+            # rewards are bounded by the scenario's terms
+            assert rew.abs().max() <= 10 + 10 + 3 * 3 + 3 + 2
+            n_done += int(done.sum())
+            prev = obs[-1]
+        if E == 4096:
+            assert n_done >= 10 * E          # cap 100 over 1000 steps
+            counts = torch.bincount(res.flatten().long(), minlength=4)
+            assert counts[2] > 0
+
+
+def test_errors_are_loud():
+    import fortattack_b200 as fab
+    with pytest.raises(fab.FaError):
+        fab.FortAttackBatch(16, 6, 3)                      # unsupported team size
+    with pytest.raises(fab.FaError):
+        fab.FortAttackBatch(0, 3, 3)
+    env = make(8, 3, 3, torch.float32)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(6, 9, dtype=torch.int32, device="cuda"))
+    info = env.kernel_info()
+    assert info["regs"] > 0 and info["block"] in (32, 64, 128) and env.launch_count() >= 1
