@@ -83,6 +83,22 @@ __device__ __forceinline__ double max_t(double a, double b) { return fmax(a, b);
 __device__ __forceinline__ float min_t(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double min_t(double a, double b) { return fmin(a, b); }
 
+// Penetration depth for overlap t (= dist_min - dist, or -wall_distance): the reference's softplus
+// k*log(1+exp(t/k)) with k = contact_margin = 1e-10 (core.py:452,468).  It differs from max(0,t) by at
+// most k*ln2 = 6.9e-11 -- invisible in float, but agents resting exactly on a wall (t == 0) do see it
+// in float64, so double mode evaluates the softplus itself (np.logaddexp(0, t/k) * k).
+__device__ __forceinline__ float penetration(float t) { return fmaxf(0.0f, t); }
+__device__ __forceinline__ double penetration(double t) {
+    const double k = 1e-10, x = t / k;
+    if (x > 40.0) return (x + log1p(exp(-x))) * k;
+    if (x < -745.0) return 0.0;
+    return (x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x))) * k;
+}
+// squared centre distance below which a pair can exchange a contact force that is not < 1e-16
+template <typename R> struct ContactGate;
+template <> struct ContactGate<float> { static constexpr float R2 = 0.1f * 0.1f; };
+template <> struct ContactGate<double> { static constexpr double R2 = (0.1 + 1e-7) * (0.1 + 1e-7); };
+
 // ------------------------------------------------------------------------------------------------
 // scenario constants: core.py:32,100-101,115-128 ; fortattack_env_v1.py:16-17,33-35
 template <typename R> struct K {
@@ -277,11 +293,10 @@ __device__ __forceinline__ bool step_env(Env<NG + NA, R> &s, const int (&act)[NG
         for (int b = a + 1; b < A; ++b) {
             const R dx = s.x[a] - s.x[b], dy = s.y[a] - s.y[b];
             const R r2 = dx * dx + dy * dy;
-            // softplus with k=1e-10 is max(0, dist_min - dist) to 7e-11; outside contact it is < 1e-10
-            if (r2 < C::DIST_MIN2 && (alive >> a & 1u) && (alive >> b & 1u)) {
+            if (r2 < ContactGate<R>::R2 && (alive >> a & 1u) && (alive >> b & 1u)) {
                 const R rinv = rsqrt_t(r2);
                 const R dist = r2 * rinv;
-                const R g = C::CONTACT_FORCE * (C::DIST_MIN - dist) * rinv;   // r2 == 0 -> NaN like the reference
+                const R g = C::CONTACT_FORCE * penetration(C::DIST_MIN - dist) * rinv;   // r2 == 0 -> NaN like the reference
                 fx[a] += g * dx; fy[a] += g * dy;
                 fx[b] -= g * dx; fy[b] -= g * dy;
             }
@@ -293,8 +308,8 @@ __device__ __forceinline__ bool step_env(Env<NG + NA, R> &s, const int (&act)[NG
     for (int i = 0; i < A; ++i) {
         if (alive >> i & 1u) {
             const R x = s.x[i], y = s.y[i];
-            const R wx = C::CONTACT_FORCE * (max_t(R(0), -C::WALL_X - x) - max_t(R(0), x - C::WALL_X));
-            const R wy = C::CONTACT_FORCE * (max_t(R(0), -C::WALL_Y - y) - max_t(R(0), y - C::WALL_Y));
+            const R wx = C::CONTACT_FORCE * (penetration(-C::WALL_X - x) - penetration(x - C::WALL_X));
+            const R wy = C::CONTACT_FORCE * (penetration(-C::WALL_Y - y) - penetration(y - C::WALL_Y));
             R vx = s.vx[i] * C::DAMP + (fx[i] + wx) * C::DT;
             R vy = s.vy[i] * C::DAMP + (fy[i] + wy) * C::DT;
             const R sp2 = vx * vx + vy * vy;

@@ -38,9 +38,30 @@ def to_env_major(t):
     return np.swapaxes(a, 0, 1).astype(np.float64) if a.dtype.kind == "f" else np.swapaxes(a, 0, 1)
 
 
-def close(got, ref, dtype, what):
+def contact_slack(pre_f, alive, dtype):
+    """Extra absolute tolerance [E, A] for agents in contact, float mode only.
+
+    The contact force 100*(0.1-dist)*delta/dist (core.py:440-456) amplifies the rounding of the fp64
+    oracle state to the engine's fp32 state (<= 6e-8 per coordinate) by 1/dist: guards spawn inside a
+    0.12 x 0.16 box (fortattack_env_v1.py:70) and often overlap almost exactly.  Bound on the velocity
+    error: dt * 10 * 2 * 1.2e-7 / dist = 2.4e-7 / dist (SURVEY 7.1 measured the same effect: errors
+    > 3e-6 only with a teammate closer than 0.013).  Zero for pairs farther apart than the contact range."""
+    E, A, _ = pre_f.shape
+    slack = np.zeros((E, A))
+    if dtype == torch.float64:
+        return slack
+    p = pre_f[:, :, 0:2]
+    d = np.sqrt(((p[:, :, None, :] - p[:, None, :, :]) ** 2).sum(-1))
+    pair = (alive[:, :, None] > 0) & (alive[:, None, :] > 0) & ~np.eye(A, dtype=bool)[None]
+    d = np.where(pair & (d < 0.1), d, np.inf)
+    return (2.5e-7 / np.maximum(d, 1e-12)).sum(-1)
+
+
+def close(got, ref, dtype, what, slack=None):
     atol, rtol = TOL[dtype]
     err = np.abs(got - ref) - (atol + rtol * np.abs(ref))
+    if slack is not None:
+        err = err - slack
     bad = np.argwhere(~(err <= 0))          # NaN-safe
     assert bad.size == 0, "%s: %d mismatches, first at %s got %r ref %r (max |d| %.3g)" % (
         what, len(bad), bad[0], got[tuple(bad[0])], ref[tuple(bad[0])], np.nanmax(np.abs(got - ref)))
