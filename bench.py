@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- FortAttack step-only throughput (BASELINE.json config 2) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE env.step() of every environment of the batch: 3 guards v 3 attackers, 4096 envs per
+GPU (weak scaling: envs are independent, each rank owns its own shard, no collective on the data
+path), uniform random actions, episode cap 100 with in-kernel auto-reset.
+
+One JSON line (rank 0):
+  value        agent-steps/s, whole job, device-resident: K launches of the fused single-step kernel
+               (fa_step) replayed from one CUDA graph, actions pre-generated in HBM, CUDA-event timed,
+               max over ranks
+  e2e          the same metric through the host-buffer API (FortAttackBatch.step_host -> fa_step_host):
+               every step copies that step's actions from pinned host memory, runs the kernel and reads
+               obs/reward/done/result back to pinned host memory, synchronously
+  roofline     fa_step_kernel: algorithmic bytes per launch (88 B/agent-step + 12 B/env-step)
+               / average launch duration over the timed region, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the CPU oracle port (oracle/fa_oracle.c, float64, pthreads on all host cores) on a
+               bounded sample of the same workload (rank 0, N=1 only)
+--impl reference times that CPU implementation as the whole arm (the reference itself is Python and
+does not exist on the GPU box; oracle/ is its C restatement, pinned to it by tests/golden).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NG, NA, E_PER_GPU, CAP = 3, 3, 4096, 100
+A = NG + NA
+BYTES_AGENT_STEP, BYTES_ENV_STEP = 88, 12           # SURVEY.md 8(d), single-step API, fp32
+METRIC = "agent-steps/sec, FortAttack 3v3 x 4096 envs per GPU, step-only"
+UNIT = "agent-steps/s"
+WORKLOAD = ("FortAttack 3v3 (BASELINE.json configs[1]), %d envs per GPU, step-only, uniform random actions, "
+            "episode cap %d, in-kernel auto-reset" % (E_PER_GPU, CAP))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(n_steps, warm, threads, rank_seed=0):
+    """agent-steps/s of the CPU oracle port on the bench workload (E_PER_GPU envs), all outputs stored."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import fa_oracle
+    env = fa_oracle.OracleEnv(E_PER_GPU, NG, NA, max_steps=CAP, seed=0, n_threads=threads)
+    env.reset()
+    rng = np.random.RandomState(rank_seed)
+    chunk = 50
+    acts = rng.randint(0, 8, size=(chunk, E_PER_GPU, A)).astype(np.int32)
+    out = env.alloc_out(chunk)
+    done_steps = 0
+    while done_steps < warm:
+        env.step_many(acts[:min(chunk, warm - done_steps)], out=tuple(o[:min(chunk, warm - done_steps)] for o in out))
+        done_steps += chunk
+    t0 = time.perf_counter()
+    left = n_steps
+    while left > 0:
+        n = min(chunk, left)
+        env.step_many(acts[:n], out=tuple(o[:n] for o in out))
+        left -= n
+    dt = time.perf_counter() - t0
+    return E_PER_GPU * A * n_steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    # bounded: at most ~60 s of CPU work whatever K is
+    probe, _ = cpu_oracle_rate(20, 5, cores)
+    k = max(1, min(args.steps, int(60.0 * probe / (E_PER_GPU * A))))
+    rate, dt = cpu_oracle_rate(k, args.warmup, cores)
+    sample = "%d env.step() calls of %d envs (oracle/fa_oracle.c float64, %d pthreads), %.1f s" % (k, E_PER_GPU, cores, dt)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU arm runs one shard of %d envs on the host cores whatever N is" % E_PER_GPU},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fortattack_b200 as fab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the step path has no CPU implementation (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W, E = args.steps, max(3, args.warmup), args.envs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, env_id0=rank * E, device=dev)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts = torch.randint(0, 8, (K, A, E), generator=g, device=dev, dtype=torch.int32)     # K*98 KB
+    R = min(K, 256)                                                                        # output ring
+    obs = torch.empty(R, A, E, 6, device=dev); rew = torch.empty(R, A, E, device=dev)
+    done = torch.empty(R, E, dtype=torch.uint8, device=dev); res = torch.empty(R, E, dtype=torch.uint8, device=dev)
+
+    def step(t):
+        r = t % R
+        env.step(acts[t], auto_reset=True, out=(obs[r], rew[r], done[r], res[r]))
+
+    # ---- warm-up (eager), then capture the K-step rollout into one CUDA graph -------------------
+    for t in range(W):
+        step(t)
+    torch.cuda.synchronize(dev)
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for t in range(K):
+                    step(t)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph.replay()                                   # upload + one more untimed pass
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = env.launch_count()
+    reps = max(1, args.reps)
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for t in range(K):
+                step(t)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        best = ms if best is None else min(best, ms)
+    gpu_launches = K if graph is not None else (env.launch_count() - launches0) // reps
+    ms_total = best
+    value = world * E * A * K / (ms_total * 1e-3)
+
+    # ---- end to end: host actions -> device -> host results, every step -------------------------
+    Ke = min(K, args.e2e_steps)
+    hb = env.make_host_buffers()
+    h_acts = torch.empty(Ke, A, E, dtype=torch.int32).pin_memory()
+    h_acts.copy_(acts[:Ke].cpu())
+    ptr0, stride = h_acts.data_ptr(), A * E * 4
+    lib, h, stream = fab._capi.lib(), env._h, torch.cuda.current_stream(dev).cuda_stream
+    for t in range(W):
+        env.step_host(h_acts[t], *hb[1:])
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(Ke):
+        rc = lib.fa_step_host(h, ptr0 + t * stride, hb[1].data_ptr(), hb[2].data_ptr(), hb[3].data_ptr(),
+                              hb[4].data_ptr(), 1, stream)
+        if rc:
+            fab._capi.check(rc)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * E * A * Ke / e2e_s
+    h2d = A * E * 4
+    d2h = A * E * 6 * 4 + A * E * 4 + E + E
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel + larger batches + the persistent T-step kernel ---------
+    peak, peak_src = peaks()
+    bytes_launch = E * (A * BYTES_AGENT_STEP + BYTES_ENV_STEP)
+    achieved = bytes_launch / (ms_total * 1e-3 / K) / 1e9
+    info = env.kernel_info()
+    roofline = {"kernel": "fa::fa_step_kernel<3,3,float,false>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": bytes_launch, "launch_us": 1e3 * ms_total / K,
+                "regs": info["regs"], "block": info["block"], "grid": info["grid"]}
+    extra = {}
+    if rank == 0 and world == 1 and not args.quick:
+        extra["roofline_sweep"] = sweep(fab, torch, dev, peak)
+        extra["persistent"] = persistent(fab, torch, dev, peak, E, min(K, 1000))
+    del env
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "n_guards": NG, "n_attackers": NA,
+                       "launch": "CUDA graph of K fa_step launches" if graph is not None else "eager fa_step launches",
+                       "l2": ("not flushed: the action stream (%.0f MB) and the obs/reward output ring (%.0f MB) are "
+                              "sized against the 126 MB L2; the %.1f MB env state is re-read every step by construction"
+                              % (acts.numel() * 4 / 1e6, (obs.numel() + rew.numel()) * 4 / 1e6, E * A * 28 / 1e6)),
+                       "sharding": "independent env shards per rank, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "api": "FortAttackBatch.step_host / fa_step_host"},
+            "gpu_launches": int(gpu_launches), "roofline": roofline}
+    line.update(extra)
+    if rank == 0 and world == 1 and not args.quick:
+        cores = len(os.sched_getaffinity(0))
+        probe, _ = cpu_oracle_rate(20, 5, cores)
+        n = max(20, int(12.0 * probe / (E_PER_GPU * A)))
+        rate, dt = cpu_oracle_rate(n, 5, cores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d env.step() calls of %d envs, oracle/fa_oracle.c (float64, %d pthreads), %.1f s"
+                                          % (n, E_PER_GPU, cores, dt)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep(fab, torch, dev, peak):
+    """Single-step kernel at batch sizes whose working set leaves the L2 (eager launches, CUDA events)."""
+    out = []
+    for E in (4096, 65536, 1 << 20, 1 << 22):
+        env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, device=dev)
+        env.reset()
+        n = 12 if E >= (1 << 20) else 50
+        acts = torch.randint(0, 8, (n, A, E), device=dev, dtype=torch.int32)
+        o = (torch.empty(A, E, 6, device=dev), torch.empty(A, E, device=dev),
+             torch.empty(E, dtype=torch.uint8, device=dev), torch.empty(E, dtype=torch.uint8, device=dev))
+        for t in range(3):
+            env.step(acts[t], out=o)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for t in range(n):
+            env.step(acts[t], out=o)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = 1e3 * e0.elapsed_time(e1) / n
+        gbs = E * (A * BYTES_AGENT_STEP + BYTES_ENV_STEP) / (us * 1e-6) / 1e9
+        out.append({"envs": E, "launch_us": us, "agent_steps_per_s": E * A / (us * 1e-6), "achieved_gbs": gbs,
+                    "frac": gbs / peak, "working_set_mb": E * (A * BYTES_AGENT_STEP + BYTES_ENV_STEP) / 1e6})
+        del env, acts, o
+    return out
+
+
+def persistent(fab, torch, dev, peak, E, T):
+    """fa_step_many: T steps in one launch, state in registers (32 B/agent-step + 2 B/env-step + state/T)."""
+    env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, device=dev)
+    env.reset()
+    acts = torch.randint(0, 8, (T, A, E), device=dev, dtype=torch.int32)
+    out = (torch.empty(T, A, E, 6, device=dev), torch.empty(T, A, E, device=dev),
+           torch.empty(T, E, dtype=torch.uint8, device=dev), torch.empty(T, E, dtype=torch.uint8, device=dev))
+    env.step_many(acts, out=out)
+    best = None
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        env.step_many(acts, out=out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    b = E * (A * 32 + 2 + (A * 56 + 12) / T)
+    gbs = b / (best * 1e-3 / T) / 1e9
+    return {"api": "fa_step_many", "steps_per_launch": T, "envs": E, "us_per_step": 1e3 * best / T,
+            "agent_steps_per_s": E * A * T / (best * 1e-3), "achieved_gbs": gbs, "frac": gbs / peak}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=E_PER_GPU, help="envs per GPU (default: the BASELINE config)")
+    ap.add_argument("--reps", type=int, default=3, help="timed repetitions of the K-step region (best is reported)")
+    ap.add_argument("--e2e-steps", type=int, default=500)
+    ap.add_argument("--no-graph", action="store_true", help="launch the K steps eagerly instead of from a CUDA graph")
+    ap.add_argument("--quick", action="store_true", help="skip the batch-size sweep, persistent kernel and CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

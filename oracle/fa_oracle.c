@@ -366,10 +366,10 @@ static void *thread_main(void *p) {
 }
 
 static void dispatch(Job base, int n_threads) {
-    if (n_threads > 64) n_threads = 64;
+    if (n_threads > 256) n_threads = 256;
     if (n_threads <= 1 || base.E < 2 * n_threads) { base.e0 = 0; base.e1 = base.E; thread_main(&base); return; }
-    pthread_t th[64];
-    Job jobs[64];
+    pthread_t th[256];
+    Job jobs[256];
     for (int k = 0; k < n_threads; ++k) {
         jobs[k] = base;
         jobs[k].e0 = (int)((long long)base.E * k / n_threads);
