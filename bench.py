@@ -253,6 +253,23 @@ def run_ours(args):
     h2d = A * E * 4
     d2h = A * E * 6 * 4 + A * E * 4 + E + E
     clocks = sampler.stop() if rank == 0 else None
+    e2e_staged = None
+    if rank == 0 and world == 1 and not args.quick:       # the copy-based variant of the same call, for comparison
+        os.environ["FA_HOST_PATH"] = "staged"
+        env2 = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, device=dev)
+        os.environ.pop("FA_HOST_PATH")
+        env2.reset()
+        hb2 = env2.make_host_buffers()
+        for t in range(W):
+            env2.step_host(h_acts[t], *hb2[1:])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for t in range(Ke):
+            lib.fa_step_host(env2._h, ptr0 + t * stride, hb2[1].data_ptr(), hb2[2].data_ptr(), hb2[3].data_ptr(),
+                             hb2[4].data_ptr(), 1, stream)
+        torch.cuda.synchronize(dev)
+        e2e_staged = E * A * Ke / (time.perf_counter() - t0)
+        del env2
 
     # ---- roofline of the dominant kernel + larger batches + the persistent T-step kernel ---------
     peak, peak_src = peaks()
@@ -279,7 +296,9 @@ def run_ours(args):
                        "sharding": "independent env shards per rank, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "api": "FortAttackBatch.step_host / fa_step_host"},
+                    "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "api": "FortAttackBatch.step_host / fa_step_host",
+                    "path": "kernel reads actions / writes results through mapped pinned host memory (no DMA calls)",
+                    "staged_copy_path_value": e2e_staged},
             "gpu_launches": int(gpu_launches), "roofline": roofline}
     line.update(extra)
     if rank == 0 and world == 1 and not args.quick:

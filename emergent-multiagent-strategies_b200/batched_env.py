@@ -104,11 +104,20 @@ class FortAttackBatch(object):
 
     # -- host-buffer step (numpy-facing env.step) --------------------------------------------------
     def make_host_buffers(self):
-        """Page-locked host buffers for step_host: actions, obs, reward, done, result."""
-        pin = dict(pin_memory=True)
-        return (torch.zeros(self.A, self.E, dtype=torch.int32, **pin),
-                torch.empty(self.A, self.E, 6, dtype=self.dtype, **pin), torch.empty(self.A, self.E, dtype=self.dtype, **pin),
-                torch.empty(self.E, dtype=torch.uint8, **pin), torch.empty(self.E, dtype=torch.uint8, **pin))
+        """Page-locked host buffers for step_host: actions, obs, reward, done, result.  The four result
+        buffers are views of ONE pinned block laid out as fa_host_layout() says, so the staged path
+        returns them in a single copy and the mapped path writes them in place."""
+        off = [ctypes.c_size_t() for _ in range(4)]
+        _capi.check(self._lib.fa_host_layout(self._h, *[ctypes.byref(o) for o in off]))
+        o_rew, o_done, o_res, total = [o.value for o in off]
+        block = torch.zeros(total, dtype=torch.uint8).pin_memory()
+        rs = 8 if self.dtype == torch.float64 else 4
+        n = self.A * self.E
+        obs = block[:n * 6 * rs].view(self.dtype).view(self.A, self.E, 6)
+        rew = block[o_rew:o_rew + n * rs].view(self.dtype).view(self.A, self.E)
+        done, res = block[o_done:o_done + self.E], block[o_res:o_res + self.E]
+        self._host_block = block
+        return (torch.zeros(self.A, self.E, dtype=torch.int32).pin_memory(), obs, rew, done, res)
 
     def step_host(self, h_actions, h_obs, h_rew, h_done, h_result, auto_reset=True):
         """One env.step() with HOST tensors: H2D actions, fused step, D2H results, synchronous."""

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -101,6 +102,7 @@ struct FaHandle {
     int block, grid;
     int sm_count;
     uint64_t launches;
+    int host_path;      // fa_step_host: 0 auto, 1 staged only, 2 mapped only (env FA_HOST_PATH)
 };
 
 struct Carve {
@@ -258,6 +260,8 @@ int fa_create(const FaConfig *cfg, void *d_workspace, FaHandle **out) {
     h->s_result = reinterpret_cast<uint8_t *>(h->ws + L.s_result);
     h->sm_count = prop.multiProcessorCount;
     h->launches = 0;
+    h->host_path = 0;
+    if (const char *hp = getenv("FA_HOST_PATH")) h->host_path = !strcmp(hp, "staged") ? 1 : (!strcmp(hp, "mapped") ? 2 : 0);
     pick_launch(h);
     const int E = cfg->n_envs, ib = 256, ig = (E + ib - 1) / ib;
     if (cfg->scalar == FA_F64) fa::fa_init_kernel<double><<<ig, ib>>>(view<double>(h), E, h->A);
@@ -304,21 +308,72 @@ int fa_step_many(FaHandle *h, int T, const int32_t *d_actions, void *d_obs, void
     return step_common(h, true, T, d_actions, d_obs, d_reward, d_done, d_result, 1, stream);
 }
 
+// Device-visible alias of a host pointer if it is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a
+// pinned PyTorch tensor), else NULL.
+static void *mapped_alias(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int fa_step_host(FaHandle *h, const int32_t *h_actions, void *h_obs, void *h_reward, uint8_t *h_done,
                  uint8_t *h_result, int auto_reset, void *stream) {
     NEED_HANDLE(h);
     if (!h_actions) return fail(FA_EINVAL, "actions is NULL");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t E = (size_t)h->cfg.n_envs, A = (size_t)h->A;
+    const size_t nb_obs = A * E * 6 * h->rs, nb_rew = A * E * h->rs;
+
+    // Path 1 (zero-copy): every buffer is page-locked -> the kernel reads the actions and writes its
+    // results straight through the mapped host addresses; one launch + one stream sync, no DMA calls.
+    if (h->host_path != 1) {
+        void *m_act = mapped_alias(h_actions);
+        void *m_obs = mapped_alias(h_obs), *m_rew = mapped_alias(h_reward);
+        void *m_done = mapped_alias(h_done), *m_res = mapped_alias(h_result);
+        const bool all = m_act && (!h_obs || m_obs) && (!h_reward || m_rew) && (!h_done || m_done) && (!h_result || m_res);
+        if (all) {
+            int rc = step_common(h, false, 1, static_cast<const int32_t *>(m_act), m_obs, m_rew,
+                                 static_cast<uint8_t *>(m_done), static_cast<uint8_t *>(m_res), auto_reset, stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(s));
+            return FA_OK;
+        }
+        if (h->host_path == 2) return fail(FA_EINVAL, "FA_HOST_PATH=mapped but a host buffer is not page-locked");
+    }
+
+    // Path 2 (staged): async copies through the workspace staging area; obs|reward|done|result are
+    // contiguous there, so host buffers laid out the same way come back in ONE device->host copy.
     CUDA_TRY(cudaMemcpyAsync(h->s_act, h_actions, A * E * 4, cudaMemcpyHostToDevice, s));
     int rc = step_common(h, false, 1, h->s_act, h_obs ? h->s_obs : nullptr, h_reward ? h->s_rew : nullptr,
                          h_done ? h->s_done : nullptr, h_result ? h->s_result : nullptr, auto_reset, stream);
     if (rc) return rc;
-    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->s_obs, A * E * 6 * h->rs, cudaMemcpyDeviceToHost, s));
-    if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->s_rew, A * E * h->rs, cudaMemcpyDeviceToHost, s));
-    if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->s_done, E, cudaMemcpyDeviceToHost, s));
-    if (h_result) CUDA_TRY(cudaMemcpyAsync(h_result, h->s_result, E, cudaMemcpyDeviceToHost, s));
+    const bool packed = h_obs && h_reward && h_done && h_result &&
+                        (char *)h_reward == (char *)h_obs + ((char *)h->s_rew - (char *)h->s_obs) &&
+                        (char *)h_done == (char *)h_obs + ((char *)h->s_done - (char *)h->s_obs) &&
+                        (char *)h_result == (char *)h_obs + ((char *)h->s_result - (char *)h->s_obs);
+    if (packed) {
+        const size_t total = (size_t)((char *)h->s_result - (char *)h->s_obs) + E;
+        CUDA_TRY(cudaMemcpyAsync(h_obs, h->s_obs, total, cudaMemcpyDeviceToHost, s));
+    } else {
+        if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->s_obs, nb_obs, cudaMemcpyDeviceToHost, s));
+        if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->s_rew, nb_rew, cudaMemcpyDeviceToHost, s));
+        if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->s_done, E, cudaMemcpyDeviceToHost, s));
+        if (h_result) CUDA_TRY(cudaMemcpyAsync(h_result, h->s_result, E, cudaMemcpyDeviceToHost, s));
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
+    return FA_OK;
+}
+
+int fa_host_layout(const FaHandle *h, size_t *off_reward, size_t *off_done, size_t *off_result, size_t *total) {
+    NEED_HANDLE(h);
+    if (off_reward) *off_reward = (size_t)((char *)h->s_rew - (char *)h->s_obs);
+    if (off_done) *off_done = (size_t)((char *)h->s_done - (char *)h->s_obs);
+    if (off_result) *off_result = (size_t)((char *)h->s_result - (char *)h->s_obs);
+    if (total) *total = (size_t)((char *)h->s_result - (char *)h->s_obs) + (size_t)h->cfg.n_envs;
     return FA_OK;
 }
 

@@ -98,9 +98,9 @@ int fa_workspace_bytes(const FaConfig *cfg, size_t *out_bytes);
 
 /* Replaces: make_fortattack_env(num_steps) + FortAttackEnvV1.__init__ + World.__init__
  * (fortattack.py:17-27, fortattack_env_v1.py:10-45, core.py:109-128) for E envs at once.
- * d_workspace: fa_workspace_bytes() bytes, 256-byte aligned, owned by the caller.  The state is
- * initialised like the reference's constructor (which already resets once): every env is reset
- * with episode 0 and prevDist = None. */
+ * d_workspace: fa_workspace_bytes() bytes, 256-byte aligned, owned by the caller.  Every env starts
+ * un-reset (agents at the origin, alive, prevDist = None as in core.py:104, episode 0): call fa_reset before
+ * the first step, as the reference's callers do (train_fortattack.py:29). */
 int fa_create(const FaConfig *cfg, void *d_workspace, FaHandle **out);
 int fa_destroy(FaHandle *h);
 
@@ -125,11 +125,19 @@ int fa_step(FaHandle *h, const int32_t *d_actions, void *d_obs, void *d_reward, 
 int fa_step_many(FaHandle *h, int T, const int32_t *d_actions, void *d_obs, void *d_reward,
                  uint8_t *d_done, uint8_t *d_result, void *stream);
 
-/* Same as fa_step with HOST buffers: copies actions host->device, steps, copies obs / reward /
- * done / result device->host on `stream` and waits for them.  This is the call the numpy-facing
- * env.step() of the Python facade makes.  Staging buffers live in the workspace. */
+/* Same as fa_step with HOST buffers; returns when the results are in host memory.  This is the call the
+ * numpy-facing env.step() of the Python facade makes.
+ *  - all buffers page-locked (cudaHostAlloc / cudaHostRegister / pinned torch tensors): the kernel reads the
+ *    actions and writes its results directly through the mapped host addresses (one launch, no copies);
+ *  - otherwise: actions are copied host->device, results device->host, through staging buffers in the
+ *    workspace; buffers laid out as fa_host_layout() describes come back in a single copy.
+ * Environment FA_HOST_PATH=staged|mapped forces one path (read at fa_create). */
 int fa_step_host(FaHandle *h, const int32_t *h_actions, void *h_obs, void *h_reward, uint8_t *h_done,
                  uint8_t *h_result, int auto_reset, void *stream);
+
+/* Byte offsets of reward / done / result relative to obs, and the total size, of the packed host result
+ * block that fa_step_host's staged path returns in one copy. */
+int fa_host_layout(const FaHandle *h, size_t *off_reward, size_t *off_done, size_t *off_result, size_t *total);
 
 /* Full state exchange in the canonical layout (device pointers).  fa_set_state accepts any state
  * the reference can be in; FA_F32 handles store ang as (ang mod 2pi, turn count < 65536). */

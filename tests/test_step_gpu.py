@@ -182,11 +182,16 @@ def test_shard_invariance_and_seed():
     assert torch.equal(df[:, 1000:1100], dp)
 
 
-def test_step_host_matches_device_step():
+@pytest.mark.parametrize("path,pinned", [("auto", True), ("staged", True), ("auto", False)])
+def test_step_host_matches_device_step(path, pinned, monkeypatch):
+    """fa_step_host: mapped (zero-copy) path, packed staged path, and pageable buffers."""
     E = 1000
+    monkeypatch.setenv("FA_HOST_PATH", path)
     e1, e2 = make(E, 3, 3, torch.float32, seed=5), make(E, 3, 3, torch.float32, seed=5)
     e1.reset(); e2.reset()
     bufs = e2.make_host_buffers()
+    if not pinned:
+        bufs = tuple(torch.empty_like(b, pin_memory=False) for b in bufs)
     rng = np.random.RandomState(0)
     for _ in range(20):
         a = torch.from_numpy(rng.randint(0, 8, size=(6, E)).astype(np.int32))
