@@ -1,0 +1,183 @@
+"""Team policy / value network of the reference (mpnn.py:17-443), written for batched rollouts.
+
+Same parameters, names and shapes as the reference's MPNN so that its checkpoints load unchanged
+(`state_dict` keys: encoder.0, oppEncoder.0, oppAttn.W_{query,key,val,out}, oppUpdate.0 (present, never
+used: mpnn.py:44-45), messages.W_{query,key,val,out}, update.0, value_head.{0,2}, policy_head.0,
+dist.linear), same call surface (`act`, `evaluate_actions`, `get_value`, `attn_mat`, `opp_attn_mat`,
+`is_recurrent`), same arithmetic:
+
+    h    = ReLU(encoder(own))            own rows are agent-major [n*B, d]       mpnn.py:127,132
+    hOpp = ReLU(oppEncoder(opp))                                                 mpnn.py:128,133
+    eOpp = softmax(K(h) Q(hOpp)^T / sqrt(dk)) V(hOpp) W_out   over opponents     mpnn.py:376-443
+    h    = [h, eOpp]; 3 x { m = selfattn(h) without the diagonal ; h = ReLU(update([h, m])) }  :142-159
+    value = value_head(h) ; logits = dist.linear(policy_head(h))                 mpnn.py:174-205
+
+Differences in form, not in results: one fused QKV product per attention instead of three, the
+diagonal mask is a constant tensor instead of a Python loop (mpnn.py:297-298), and the attention
+matrices are kept on the device and only copied to the host when `attn_mat` / `opp_attn_mat` is read
+(the reference synchronises the device twice per forward, mpnn.py:140,166).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+try:
+    from .rlcore.distributions import Categorical
+except ImportError:          # imported top-level (drop-in mode: this directory is on sys.path)
+    from rlcore.distributions import Categorical
+
+
+def weights_init(m):
+    # orthogonal Linear weights, zero bias (mpnn.py:9-14) -- also overrides Categorical's gain
+    if isinstance(m, nn.Linear):
+        nn.init.orthogonal_(m.weight.data)
+        if m.bias is not None:
+            m.bias.data.fill_(0)
+
+
+class _Attention(nn.Module):
+    """Parameter container shared by both attention blocks (mpnn.py:208-247, 334-374)."""
+
+    def __init__(self, n_heads, input_dim, embed_dim):
+        super().__init__()
+        if n_heads != 1:
+            raise NotImplementedError("the reference only ever builds single-head attention (mpnn.py:42,47)")
+        self.n_heads, self.input_dim, self.embed_dim = n_heads, input_dim, embed_dim
+        self.key_dim = self.val_dim = embed_dim // n_heads
+        self.norm_factor = 1.0 / math.sqrt(self.key_dim)
+        self.W_query = nn.Parameter(torch.empty(n_heads, input_dim, self.key_dim))
+        self.W_key = nn.Parameter(torch.empty(n_heads, input_dim, self.key_dim))
+        self.W_val = nn.Parameter(torch.empty(n_heads, input_dim, self.val_dim))
+        self.W_out = nn.Parameter(torch.empty(n_heads, self.key_dim, embed_dim))
+        for p in self.parameters():                       # U(-1/sqrt(d), 1/sqrt(d)) (mpnn.py:243-247)
+            p.data.uniform_(-1.0 / math.sqrt(p.size(-1)), 1.0 / math.sqrt(p.size(-1)))
+
+
+class MultiHeadAttention(_Attention):
+    """Intra-team attention without self-messages (mpnn.py:249-331). q: [B, n, d] -> ([B, n, e], [1,B,n,n])."""
+
+    def forward(self, q, h=None, mask=None, return_attn=False):
+        if h is not None or mask is not None:
+            raise NotImplementedError("the FortAttack path calls messages(h, mask=None) only (mpnn.py:157)")
+        B, n, d = q.shape
+        if n == 1:                                        # a lone agent receives a zero message (mpnn.py:262-270)
+            out, attn = q.new_zeros(B, 1, self.embed_dim), q.new_zeros(1, B, 1, 1)
+            return (out, attn) if return_attn else out
+        w = torch.cat((self.W_query[0], self.W_key[0], self.W_val[0]), dim=1)       # [d, 3k]
+        qkv = q.reshape(B * n, d) @ w
+        Q, K, V = qkv.view(B, n, 3, -1).unbind(2)
+        comp = self.norm_factor * torch.matmul(Q, K.transpose(1, 2))                # [B, n, n]
+        comp = comp.masked_fill(torch.eye(n, dtype=torch.bool, device=q.device), -math.inf)
+        attn = F.softmax(comp, dim=-1)
+        out = (torch.matmul(attn, V).reshape(B * n, -1) @ self.W_out[0]).view(B, n, self.embed_dim)
+        return (out, attn.unsqueeze(0)) if return_attn else out
+
+
+class MultiHeadOppAttention(_Attention):
+    """Attention of each team member over the opponents; note the reference's naming: keys come from the
+    own team, queries and values from the opponents (mpnn.py:409-417)."""
+
+    def __init__(self, n_heads, input_dim, opp_input_dim, embed_dim):
+        super().__init__(n_heads, input_dim, embed_dim)
+        self.opp_input_dim = opp_input_dim
+
+    def forward(self, h, hOpp, mask=None, return_attn=False):
+        B, n, d = h.shape
+        m = hOpp.shape[1]
+        qv = hOpp.reshape(B * m, -1) @ torch.cat((self.W_query[0], self.W_val[0]), dim=1)
+        Q, V = qv.view(B, m, 2, -1).unbind(2)
+        K = (h.reshape(B * n, d) @ self.W_key[0]).view(B, n, -1)
+        attn = F.softmax(self.norm_factor * torch.matmul(K, Q.transpose(1, 2)), dim=-1)   # [B, n, m]
+        out = (torch.matmul(attn, V).reshape(B * n, -1) @ self.W_out[0]).view(B, n, self.embed_dim)
+        return (out, attn) if return_attn else out
+
+
+class MPNN(nn.Module):
+    def __init__(self, action_space, num_agents, num_opp_agents, num_entities=0, input_size=16, hidden_dim=128,
+                 embed_dim=None, pos_index=2, norm_in=False, nonlin=nn.ReLU, n_heads=1, mask_dist=None,
+                 entity_mp=False, policy_layers=1):
+        super().__init__()
+        if entity_mp or norm_in:
+            raise NotImplementedError("entity message passing / input batch-norm are not on the FortAttack path "
+                                      "(learner.py:36-41 passes entity_mp=False; norm_in defaults to False)")
+        self.h_dim, self.nonlin = hidden_dim, nonlin
+        self.num_agents, self.num_opp_agents, self.num_entities = num_agents, num_opp_agents, num_entities
+        self.K = 3                                                                 # message passing rounds
+        self.embed_dim = hidden_dim if embed_dim is None else embed_dim
+        self.n_heads, self.mask_dist, self.input_size = n_heads, mask_dist, input_size
+        self.entity_mp, self.policy_layers, self.pos_index = entity_mp, policy_layers, pos_index
+        half = hidden_dim // 2
+        self.encoder = nn.Sequential(nn.Linear(input_size, half), nonlin(inplace=True))
+        self.oppEncoder = nn.Sequential(nn.Linear(input_size, half), nonlin(inplace=True))
+        self.oppAttn = MultiHeadOppAttention(n_heads, half, half, self.embed_dim // 2)
+        self.oppUpdate = nn.Sequential(nn.Linear(half + self.embed_dim // 2, half), nonlin(inplace=True))
+        self.messages = MultiHeadAttention(n_heads, hidden_dim, self.embed_dim)
+        self.update = nn.Sequential(nn.Linear(hidden_dim + self.embed_dim, hidden_dim), nonlin(inplace=True))
+        self.value_head = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nonlin(inplace=True),
+                                        nn.Linear(hidden_dim, 1))
+        if policy_layers == 1:
+            self.policy_head = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nonlin(inplace=True))
+        elif policy_layers == 2:
+            self.policy_head = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nonlin(inplace=True),
+                                             nn.Linear(hidden_dim, hidden_dim))
+        else:
+            raise ValueError("policy_layers must be 1 or 2")
+        self.dist = Categorical(hidden_dim, action_space.shape[0])                 # mpnn.py:73-74
+        self.is_recurrent = False
+        self.in_fn = lambda x: x
+        self.apply(weights_init)
+        self._attn = self._opp_attn = None
+        self.dropout_mask = self.dead_mask = None
+
+    # attention matrices of the last forward, as the reference exposes them (numpy, first env only
+    # when batched: `.squeeze(0).squeeze(0)` of [1,B,n,n], mpnn.py:140,166); copied lazily
+    @property
+    def attn_mat(self):
+        if self._attn is None:
+            import numpy as np
+            return np.ones((self.num_agents, self.num_agents))                     # mpnn.py:86
+        return self._attn.squeeze(0).squeeze(0).detach().cpu().numpy()
+
+    @property
+    def opp_attn_mat(self):
+        return None if self._opp_attn is None else self._opp_attn.squeeze(0).squeeze(0).detach().cpu().numpy()
+
+    def _fwd(self, inp, oppInp, masks=None):
+        n, m, half = self.num_agents, self.num_opp_agents, self.h_dim // 2
+        h = self.encoder(inp).view(n, -1, half).transpose(0, 1)                    # [B, n, 64]
+        hOpp = self.oppEncoder(oppInp).view(m, -1, half).transpose(0, 1)           # [B, m, 64]
+        eOpp, self._opp_attn = self.oppAttn(h, hOpp, masks, return_attn=True)
+        h = torch.cat((h, eOpp), dim=2)                                            # [B, n, 128]
+        attn = None
+        for _ in range(self.K):
+            msg, attn = self.messages(h, return_attn=True)
+            h = self.update(torch.cat((h, msg), dim=2))
+        self._attn = attn
+        return h.transpose(0, 1).reshape(-1, self.h_dim)                           # agent-major rows again
+
+    def forward(self, inp, state, mask=None):
+        raise NotImplementedError
+
+    def _value(self, x):
+        return self.value_head(x)
+
+    def _policy(self, x):
+        return self.policy_head(x)
+
+    def act(self, inp, state, oppInp, mask=None, deterministic=False):
+        x = self._fwd(inp, oppInp, mask)
+        value = self._value(x)
+        dist = self.dist(self._policy(x))
+        action = dist.mode() if deterministic else dist.sample()
+        return value, action, dist.log_probs(action).view(-1, 1), state
+
+    def evaluate_actions(self, inp, state, oppInp, mask, action):
+        x = self._fwd(inp, oppInp, mask)
+        value = self._value(x)
+        dist = self.dist(self._policy(x))
+        return value, dist.log_probs(action), dist.entropy(), state
+
+    def get_value(self, inp, state, oppInp, mask):
+        return self._value(self._fwd(inp, oppInp, mask))

@@ -1,0 +1,155 @@
+"""Team-shared clipped PPO of the reference (rlcore/algo/ppo.py:89-246).
+
+`JointPPO(actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef, lr, eps,
+max_grad_norm, use_clipped_value_loss).update(rollouts_list, opp_rollouts_list) -> (value_loss,
+action_loss, dist_entropy)` with the same arithmetic: per-agent advantage normalisation, one shared
+random permutation of the T*P sample indices per epoch so the teammates' rows stay time-aligned,
+agent-major minibatches, alive-mask weighting of every loss term divided by mask.mean(), Adam,
+gradient-norm clipping.  Random draws (torch.randperm per epoch, as SubsetRandomSampler does) match the
+reference, so equal seeds give equal updates.
+
+Multi-GPU (new): pass `process_group=`; each rank holds its own env shard, gradients are
+summed with ONE all-reduce over a flat buffer per optimizer step and the loss normalisers
+(mask.mean(), advantage mean/std) are made global, so N ranks x P/N envs reproduce 1 rank x P envs.
+The three `.item()` syncs per minibatch of the reference (ppo.py:194-196) are replaced by on-device
+accumulation with a single sync per update.
+"""
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+
+def magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_list, num_mini_batch, perm=None):
+    """Time-aligned multi-agent minibatches (ppo.py:207-246): for every chunk of one random permutation of
+    the T*P indices, the rows of all teammates for those indices, concatenated agent-major."""
+    num_steps, num_processes = rollouts_list[0].rewards.size()[0:2]
+    batch_size = num_processes * num_steps
+    mini_batch_size = int(batch_size / num_mini_batch)
+    if perm is None:
+        perm = torch.randperm(batch_size)                     # == SubsetRandomSampler(range(batch_size))
+    flat = lambda t: t.view(-1, t.size(-1))
+    own_obs = [flat(r.obs[:-1]) for r in rollouts_list]
+    opp_obs = [flat(r.obs[:-1]) for r in opp_rollouts_list]
+    hid = [flat(r.recurrent_hidden_states[:-1]) for r in rollouts_list]
+    act = [flat(r.actions) for r in rollouts_list]
+    val = [flat(r.value_preds[:-1]) for r in rollouts_list]
+    ret = [flat(r.returns[:-1]) for r in rollouts_list]
+    msk = [flat(r.masks[:-1]) for r in rollouts_list]
+    olp = [flat(r.action_log_probs) for r in rollouts_list]
+    adv = [a.reshape(-1, 1) for a in advantages_list]
+    for i in range(0, batch_size, mini_batch_size):           # BatchSampler(..., drop_last=False)
+        idx = perm[i:i + mini_batch_size].to(own_obs[0].device)
+        take = lambda lst: torch.cat([t[idx] for t in lst], 0)
+        obs_batch = take(own_obs)
+        mask = obs_batch[:, 0].clone().view(-1, 1)            # alive flag = observation feature 0 (ppo.py:224)
+        yield (obs_batch, mask, take(opp_obs), take(hid), take(act), take(val), take(ret), take(msk),
+               take(olp), take(adv))
+
+
+class JointPPO(object):
+    def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
+                 lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=False, process_group=None):
+        self.actor_critic = actor_critic
+        self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
+        self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
+        self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
+        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr)     # eps is ignored by the reference too (:114)
+        self.process_group = process_group
+
+    # -- distributed helpers (identity on one rank) ------------------------------------------------
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.process_group) if self.process_group is not None else 1
+
+    def _allreduce(self, t):
+        import torch.distributed as dist
+        if self.process_group is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
+        return t
+
+    def _advantages(self, rollout):
+        adv = rollout.returns[:-1] - rollout.value_preds[:-1]
+        if self.process_group is None:
+            return (adv - adv.mean()) / (adv.std() + 1e-5)               # ppo.py:121-123 (unbiased std)
+        s = self._allreduce(torch.stack([adv.sum(), (adv * adv).sum(), adv.new_tensor(float(adv.numel()))]).double())
+        n, mean = s[2], s[0] / s[2]
+        var = (s[1] - n * mean * mean) / (n - 1)
+        return ((adv - mean.to(adv.dtype)) / (var.clamp_min(0).sqrt().to(adv.dtype) + 1e-5))
+
+    def update(self, rollouts_list, opp_rollouts_list):
+        advantages_list = [self._advantages(r) for r in rollouts_list]
+        dev = rollouts_list[0].rewards.device
+        totals = torch.zeros(3, device=dev)
+        params = [p for p in self.actor_critic.parameters()]
+        world = self._world()
+        n_updates = 0
+        for _ in range(self.ppo_epoch):
+            if self.actor_critic.is_recurrent:
+                raise NotImplementedError("sampler not implemented for recurrent policies")
+            for sample in magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_list,
+                                                        self.num_mini_batch):
+                (obs_batch, mask, obs_opp_batch, hid_batch, actions_batch, value_preds_batch, return_batch,
+                 masks_batch, old_log_probs_batch, adv_targ) = sample
+                values, action_log_probs, dist_entropy, _ = self.actor_critic.evaluate_actions(
+                    obs_batch, hid_batch, obs_opp_batch, masks_batch, actions_batch)
+
+                # Every loss term is `(x * mask).mean()`, divided by mask.mean() unless that is 0
+                # (ppo.py:150-187).  One rank: literally that.  G ranks: the same quotient with GLOBAL sums,
+                # sum_r(local sum) / sum_r(mask sum); each rank scales its local sum by G / global mask sum so
+                # that the average of the ranks' gradients is the gradient of the global loss.
+                mmean = mask.mean()
+                if world == 1:
+                    denom = torch.where(mmean != 0, mmean, torch.ones_like(mmean))
+                    mmean_of = lambda x: x.mean() / denom
+                else:
+                    g = self._allreduce(torch.stack([mask.sum(), mask.new_tensor(float(mask.numel()))]))
+                    denom = torch.where(g[0] != 0, g[0], g[1]) / world
+                    mmean_of = lambda x: x.sum() / denom
+                    mmean = g[0] / g[1]
+
+                entropy = mmean_of(dist_entropy * mask[:, 0])
+                ratio = mask * torch.exp(action_log_probs - old_log_probs_batch)
+                surr1 = ratio * adv_targ
+                surr2 = torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param) * adv_targ
+                action_loss = mmean_of(mask * -torch.min(surr1, surr2))
+                if self.use_clipped_value_loss:
+                    clipped = value_preds_batch + (values - value_preds_batch).clamp(-self.clip_param, self.clip_param)
+                    v = 0.5 * torch.max((values - return_batch).pow(2), (clipped - return_batch).pow(2))
+                    value_loss = mmean_of(v * mask)
+                elif world == 1:
+                    # scalar mse times the mask, averaged, over mask.mean(): the mask cancels (ppo.py:182-187)
+                    value_loss = mmean_of(0.5 * (return_batch - values).pow(2).mean() * mask)
+                else:
+                    value_loss = 0.5 * (return_batch - values).pow(2).mean() * (mmean != 0)
+
+                self.optimizer.zero_grad()
+                (value_loss * self.value_loss_coef + action_loss - entropy * self.entropy_coef).backward()
+                if world > 1:
+                    grads = [p.grad for p in params if p.grad is not None]
+                    flat = torch.cat([g_.reshape(-1) for g_ in grads])          # one 158 153-float buffer
+                    self._allreduce(flat).div_(world)
+                    off = 0
+                    for g_ in grads:
+                        g_.copy_(flat[off:off + g_.numel()].view_as(g_))
+                        off += g_.numel()
+                nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
+                self.optimizer.step()
+                totals += torch.stack([value_loss.detach(), action_loss.detach(), entropy.detach()])
+                n_updates += 1
+        if world > 1:
+            totals = self._allreduce(totals) / world
+        v, a, e = (totals / max(n_updates, 1)).tolist()          # the only host sync of the update
+        return v, a, e
+
+
+class PPO(JointPPO):
+    """rlagent.Neo builds one of these per agent and never uses it (rlagent.py:16-17, ppo.py:8): kept so
+    that the reference's rlagent.py imports and constructs unchanged."""
+
+    def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
+                 lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=True):
+        super().__init__(actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
+                         lr=lr, eps=eps, max_grad_norm=max_grad_norm, use_clipped_value_loss=use_clipped_value_loss)
+
+    def update(self, rollouts):
+        raise NotImplementedError("single-agent PPO is unused by the FortAttack scripts (rlcore/algo/ppo.py:8)")
