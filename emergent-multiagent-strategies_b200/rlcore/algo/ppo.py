@@ -19,27 +19,33 @@ import torch.nn as nn
 import torch.optim as optim
 
 
-def magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_list, num_mini_batch, perm=None):
+def magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_list, num_mini_batch, perm=None,
+                                  index_batches=None):
     """Time-aligned multi-agent minibatches (ppo.py:207-246): for every chunk of one random permutation of
     the T*P indices, the rows of all teammates for those indices, concatenated agent-major."""
     num_steps, num_processes = rollouts_list[0].rewards.size()[0:2]
     batch_size = num_processes * num_steps
     mini_batch_size = int(batch_size / num_mini_batch)
-    if perm is None:
+    if perm is None and index_batches is None:
         perm = torch.randperm(batch_size)                     # == SubsetRandomSampler(range(batch_size))
-    flat = lambda t: t.view(-1, t.size(-1))
-    own_obs = [flat(r.obs[:-1]) for r in rollouts_list]
-    opp_obs = [flat(r.obs[:-1]) for r in opp_rollouts_list]
-    hid = [flat(r.recurrent_hidden_states[:-1]) for r in rollouts_list]
-    act = [flat(r.actions) for r in rollouts_list]
-    val = [flat(r.value_preds[:-1]) for r in rollouts_list]
-    ret = [flat(r.returns[:-1]) for r in rollouts_list]
-    msk = [flat(r.masks[:-1]) for r in rollouts_list]
-    olp = [flat(r.action_log_probs) for r in rollouts_list]
-    adv = [a.reshape(-1, 1) for a in advantages_list]
-    for i in range(0, batch_size, mini_batch_size):           # BatchSampler(..., drop_last=False)
-        idx = perm[i:i + mini_batch_size].to(own_obs[0].device)
-        take = lambda lst: torch.cat([t[idx] for t in lst], 0)
+    # rows are addressed as (t, env) = divmod(index, P): no flattening, so the buffers may be strided
+    # views of shared [T, A, E, ...] blocks (rollout.SharedRollouts) as well as the reference's own layout
+    own_obs = [r.obs[:-1] for r in rollouts_list]
+    opp_obs = [r.obs[:-1] for r in opp_rollouts_list]
+    hid = [r.recurrent_hidden_states[:-1] for r in rollouts_list]
+    act = [r.actions for r in rollouts_list]
+    val = [r.value_preds[:-1] for r in rollouts_list]
+    ret = [r.returns[:-1] for r in rollouts_list]
+    msk = [r.masks[:-1] for r in rollouts_list]
+    olp = [r.action_log_probs for r in rollouts_list]
+    adv = list(advantages_list)
+    dev = own_obs[0].device
+    if index_batches is None:                                  # BatchSampler(..., drop_last=False)
+        index_batches = [perm[i:i + mini_batch_size] for i in range(0, batch_size, mini_batch_size)]
+    for idx in index_batches:
+        idx = idx.to(dev)
+        ti, ei = torch.div(idx, num_processes, rounding_mode="floor"), idx % num_processes
+        take = lambda lst: torch.cat([t[ti, ei] for t in lst], 0)
         obs_batch = take(own_obs)
         mask = obs_batch[:, 0].clone().view(-1, 1)            # alive flag = observation feature 0 (ppo.py:224)
         yield (obs_batch, mask, take(opp_obs), take(hid), take(act), take(val), take(ret), take(msk),
@@ -67,6 +73,16 @@ class JointPPO(object):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
         return t
 
+    def _perm(self, rollout):
+        """One permutation of the T*P sample indices per epoch; rank 0's draw is used by every rank."""
+        T, P = rollout.rewards.size()[0:2]
+        perm = torch.randperm(T * P)
+        if self.process_group is not None:
+            import torch.distributed as dist
+            perm = perm.to(rollout.rewards.device)
+            dist.broadcast(perm, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
+        return perm
+
     def _advantages(self, rollout):
         adv = rollout.returns[:-1] - rollout.value_preds[:-1]
         if self.process_group is None:
@@ -76,18 +92,25 @@ class JointPPO(object):
         var = (s[1] - n * mean * mean) / (n - 1)
         return ((adv - mean.to(adv.dtype)) / (var.clamp_min(0).sqrt().to(adv.dtype) + 1e-5))
 
-    def update(self, rollouts_list, opp_rollouts_list):
+    def update(self, rollouts_list, opp_rollouts_list, index_batches=None):
+        """index_batches (optional, testing): per epoch, a list of index tensors to use as the minibatches
+        instead of chunks of a fresh random permutation."""
         advantages_list = [self._advantages(r) for r in rollouts_list]
         dev = rollouts_list[0].rewards.device
         totals = torch.zeros(3, device=dev)
         params = [p for p in self.actor_critic.parameters()]
         world = self._world()
         n_updates = 0
-        for _ in range(self.ppo_epoch):
+        for epoch in range(self.ppo_epoch):
             if self.actor_critic.is_recurrent:
                 raise NotImplementedError("sampler not implemented for recurrent policies")
-            for sample in magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_list,
-                                                        self.num_mini_batch):
+            if index_batches is not None:
+                gen = magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_list,
+                                                    self.num_mini_batch, index_batches=index_batches[epoch])
+            else:
+                gen = magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_list,
+                                                    self.num_mini_batch, perm=self._perm(rollouts_list[0]))
+            for sample in gen:
                 (obs_batch, mask, obs_opp_batch, hid_batch, actions_batch, value_preds_batch, return_batch,
                  masks_batch, old_log_probs_batch, adv_targ) = sample
                 values, action_log_probs, dist_entropy, _ = self.actor_critic.evaluate_actions(

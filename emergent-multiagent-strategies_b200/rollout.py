@@ -1,0 +1,175 @@
+"""Batched rollout / training driver: train_fortattack.train + Learner for E environments at once.
+
+The reference steps ONE env per process (train_fortattack.py:24-25,51-104) and keeps one RolloutStorage
+per agent (rlagent.py:13).  This driver keeps the same protocol and the same objects -- one
+RolloutStorage per agent with num_processes = E, one MPNN + JointPPO per team -- but
+  * all buffers live in shared device blocks [T+1, A, E, ...]; each agent's RolloutStorage is a view,
+    so the step kernel writes observations and rewards of step t straight into slot t+1 / t of every
+    agent's storage (no per-agent copies: learner.py:239-243 does A host->device copies per step);
+  * episode ends are per env: the kernel auto-resets finished envs, the returned row is the new episode's
+    first observation (what initialize_new_episode stores, rlagent.py:28-31) and `ends[t+1, e]` records
+    the end point (train_fortattack.py:98);
+  * GAE runs once over all envs with those per-env end points (RolloutStorage.compute_returns_batched ==
+    Learner.wrap_horizon per env, learner.py:191-211);
+  * multi-GPU: every rank owns the env shard [rank*E, (rank+1)*E); rollouts need no communication, the
+    PPO step all-reduces one flat gradient buffer per optimizer step (JointPPO(process_group=...)).
+Checkpoints use the reference's file format ({'models': [state_dict per agent], 'ob_rms': (None, None)},
+train_fortattack.py:121-128) and its loading rule (models[0] -> guards, models[-1] -> attackers,
+learner.py:245-249).
+"""
+import torch
+
+from .batched_env import FortAttackBatch
+from .mpnn import MPNN
+from .rlcore.algo import JointPPO
+from .rlcore.storage import RolloutStorage
+
+
+class _Shape(object):
+    def __init__(self, *shape):
+        self.shape = shape
+
+
+class SharedRollouts(object):
+    """A RolloutStorage per agent, all views of shared [T(+1), A, E, ...] blocks."""
+
+    def __init__(self, num_steps, n_agents, n_envs, device):
+        T, A, E = num_steps, n_agents, n_envs
+        z = lambda *s, **k: torch.zeros(*s, device=device, **k)
+        self.obs = z(T + 1, A, E, 6)
+        self.rewards = z(T, A, E)
+        self.value_preds = z(T + 1, A, E, 1)
+        self.returns = z(T + 1, A, E, 1)
+        self.action_log_probs = z(T, A, E, 1)
+        self.actions = z(T, A, E, 1, dtype=torch.long)
+        self.actions_i32 = z(T, A, E, dtype=torch.int32)            # what the step kernel reads
+        self.masks = torch.ones(T + 1, A, E, 1, device=device)
+        self.hidden = z(T + 1, A, E, 1)
+        self.ends = z(T + 1, E, dtype=torch.bool)                   # per-env end points (train_fortattack.py:98)
+        self.done = z(T, E, dtype=torch.uint8)
+        self.result = z(T, E, dtype=torch.uint8)
+        self.agents = []
+        for i in range(A):
+            r = RolloutStorage.__new__(RolloutStorage)
+            r.obs, r.rewards = self.obs[:, i], self.rewards[:, i].unsqueeze(-1)
+            r.value_preds, r.returns = self.value_preds[:, i], self.returns[:, i]
+            r.action_log_probs, r.actions = self.action_log_probs[:, i], self.actions[:, i]
+            r.masks, r.recurrent_hidden_states = self.masks[:, i], self.hidden[:, i]
+            r.num_steps, r.step = T, 0
+            self.agents.append(r)
+
+    def after_update(self):
+        # RolloutStorage.after_update for every agent at once (storage.py:51-56)
+        self.obs[0].copy_(self.obs[-1])
+        self.obs[1:] = 0
+        self.masks[0].copy_(self.masks[-1])
+        self.ends.zero_()
+
+
+class BatchedTrainer(object):
+    def __init__(self, n_envs, n_guards=3, n_attackers=3, num_steps=128, max_episode_steps=100, device="cuda:0",
+                 seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
+                 num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
+                 use_clipped_value_loss=True, process_group=None):
+        self.device = torch.device(device)
+        self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
+        self.A = n_guards + n_attackers
+        self.gamma, self.tau = gamma, tau
+        self.env = FortAttackBatch(n_envs, n_guards, n_attackers, max_steps=max_episode_steps, seed=seed,
+                                   env_id0=env_id0, device=self.device)
+        mk = lambda n, m: MPNN(action_space=_Shape(8), num_agents=n, num_opp_agents=m, num_entities=0,
+                               input_size=6, hidden_dim=hidden_dim, pos_index=2).to(self.device)
+        self.policies = [mk(n_guards, n_attackers), mk(n_attackers, n_guards)]     # guards first (learner.py:57-69)
+        self.trainers = [JointPPO(p, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef, lr=lr,
+                                  max_grad_norm=max_grad_norm, use_clipped_value_loss=use_clipped_value_loss,
+                                  process_group=process_group) for p in self.policies]
+        self.process_group = process_group
+        if process_group is not None:                    # replicas start from rank 0's weights
+            import torch.distributed as dist
+            for p in self.policies:
+                for t in p.parameters():
+                    dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0), group=process_group)
+        self.roll = SharedRollouts(num_steps, self.A, n_envs, self.device)
+        self.teams = [list(range(0, n_guards)), list(range(n_guards, self.A))]
+        self.roll.obs[0].copy_(self.env.reset())
+        self.episode_rewards = torch.zeros(self.A, n_envs, device=self.device)
+
+    # -- Learner.act (learner.py:143-172): one forward per team over agent-major rows ----------------
+    @torch.no_grad()
+    def act(self, step):
+        R = self.roll
+        for team, opp, policy in ((self.teams[0], self.teams[1], self.policies[0]),
+                                  (self.teams[1], self.teams[0], self.policies[1])):
+            own = R.obs[step, team[0]:team[-1] + 1].reshape(-1, 6)
+            oth = R.obs[step, opp[0]:opp[-1] + 1].reshape(-1, 6)
+            value, action, logp, _ = policy.act(own, None, oth, None, deterministic=False)
+            n = len(team)
+            R.value_preds[step, team[0]:team[-1] + 1] = value.view(n, self.E, 1)
+            R.actions[step, team[0]:team[-1] + 1] = action.view(n, self.E, 1)
+            R.action_log_probs[step, team[0]:team[-1] + 1] = logp.view(n, self.E, 1)
+        R.actions_i32[step].copy_(R.actions[step, :, :, 0])
+        return R.actions_i32[step]
+
+    # -- the data-collection loop of train_fortattack.train (:51-104) for E envs ---------------------
+    @torch.no_grad()
+    def collect(self):
+        R = self.roll
+        self.episode_rewards.zero_()
+        for step in range(self.T):
+            masks = R.obs[step, :, :, 0]                                   # alive flags before the step (:53)
+            actions = self.act(step)
+            # obs of step+1, rewards of step, done/result are written in place by the kernel
+            self.env.step(actions, auto_reset=True, out=(R.obs[step + 1], R.rewards[step], R.done[step], R.result[step]))
+            R.masks[step + 1, :, :, 0] = masks                             # RolloutStorage.insert (storage.py:41)
+            finished = R.done[step] != 0
+            R.ends[step + 1] = finished                                    # end_pts.append(step) after step += 1
+            # initialize_new_episode(step, obs, masks): the reset obs is already in place; masks become
+            # the new episode's alive flags (= 1)                         (train_fortattack.py:100-104)
+            R.masks[step + 1, :, :, 0] = torch.where(finished[None, :], R.obs[step + 1, :, :, 0], R.masks[step + 1, :, :, 0])
+            self.episode_rewards += R.rewards[step] * masks
+        R.ends[self.T] = True                                              # (:108-109)
+        return self.episode_rewards
+
+    # -- Learner.wrap_horizon (learner.py:191-211) ---------------------------------------------------
+    @torch.no_grad()
+    def wrap_horizon(self):
+        R, T = self.roll, self.T
+        for team, opp, policy in ((self.teams[0], self.teams[1], self.policies[0]),
+                                  (self.teams[1], self.teams[0], self.policies[1])):
+            own = R.obs[T, team[0]:team[-1] + 1].reshape(-1, 6)
+            oth = R.obs[T, opp[0]:opp[-1] + 1].reshape(-1, 6)
+            nv = policy.get_value(own, None, oth, None).view(len(team), self.E, 1)
+            for k, i in enumerate(team):
+                R.agents[i].compute_returns_batched(nv[k], R.ends, self.gamma, self.tau)
+
+    # -- Learner.update (learner.py:175-188) ---------------------------------------------------------
+    def update(self, train_guards_only=False):
+        vals = []
+        trainers = self.trainers[:1] if train_guards_only else self.trainers
+        for t, trainer in enumerate(trainers):
+            own = [self.roll.agents[i] for i in self.teams[t]]
+            opp = [self.roll.agents[i] for i in self.teams[1 - t]]
+            vals.append(trainer.update(own, opp))
+        return vals
+
+    def after_update(self):
+        self.roll.after_update()
+
+    def train_once(self, train_guards_only=False):
+        rewards = self.collect()
+        self.wrap_horizon()
+        vals = self.update(train_guards_only)
+        self.after_update()
+        return rewards, vals
+
+    # -- checkpoints in the reference's format --------------------------------------------------------
+    def state(self):
+        sd = [self.policies[0].state_dict()] * self.ng + [self.policies[1].state_dict()] * self.na
+        return {"models": sd, "ob_rms": (None, None)}
+
+    def save(self, path):
+        torch.save(self.state(), path)
+
+    def load_models(self, models):
+        self.policies[0].load_state_dict(models[0])        # learner.py:245-249
+        self.policies[1].load_state_dict(models[-1])

@@ -1,0 +1,114 @@
+"""GPU: the gym facade and the batched rollout driver (collect -> GAE -> PPO) on top of the CUDA engine."""
+import os
+import subprocess
+import sys
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+
+import fa_oracle
+import fortattack_b200 as fab
+
+pytestmark = pytest.mark.gpu
+PKG = "emergent-multiagent-strategies_b200"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_gym_facade_surface_and_semantics():
+    gf = import_module(PKG + ".gym_fortattack.fortattack")
+    env = gf.make_fortattack_env(30, n_guards=5, n_attackers=5, seed=3)
+    # what learner.setup_master / Learner / the scripts touch
+    assert env.n == 10 and env.action_space[9].n == 8 and env.observation_space[0].shape == (6,)
+    assert env.action_spaces[0].shape == (8,) and env.ob_rms is None and env.world.numGuards == 5
+    assert [a.attacker for a in env.world.policy_agents] == [False] * 5 + [True] * 5
+    assert env.world.max_time_steps == 30 and env.world.time_step == 0
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (10, 6) and obs.dtype == np.float64
+    # the same trajectory as the oracle, free-running in lockstep with teacher-forced oracle state
+    ora = fa_oracle.OracleEnv(1, 5, 5, max_steps=30, seed=3)
+    ora.reset(); ora.reset()                       # constructor reset + env.reset() (fortattack_env_v1.py:45)
+    assert np.abs(obs - ora.observe()[0]).max() < 1e-6
+    rng = np.random.RandomState(0)
+    n_done = 0
+    for s in range(200):
+        act = rng.choice(8, size=10, p=[.1] * 7 + [.3])
+        o, r, d, info = env.step(act)
+        st = env._batch.get_state()
+        assert isinstance(r, list) and len(r) == 10 and isinstance(d, bool) and list(info) == ["n"] and len(info["n"]) == 10
+        assert env.world.numAliveAttackers == int(o[5:, 0].sum()) and env.world.numAliveGuards == int(o[:5, 0].sum())
+        if d:
+            n_done += 1
+            assert env.world.gameResult.sum() == 1
+            o = env.reset()
+            assert env.world.gameResult.sum() == 0 and env.world.time_step == 0 and (o[:, 0] == 1).all()
+    assert n_done >= 6
+    env.world.max_time_steps = 5
+    for s in range(5):
+        o, r, d, _ = env.step(np.zeros(10, int))
+    assert d and env.world.gameResult[1] == 1
+
+
+def test_drop_in_import_paths():
+    """With the package directory first on sys.path the reference's own import statements resolve here:
+    `from gym_fortattack.fortattack import make_fortattack_env` (utils.py:5), `from rlcore.algo import JointPPO`
+    (learner.py:3), `from rlcore.storage import RolloutStorage` (rlagent.py:2), `from mpnn import MPNN` (learner.py:5)."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from gym_fortattack.fortattack import make_fortattack_env\n"
+            "from rlcore.algo import JointPPO, PPO\nfrom rlcore.storage import RolloutStorage\nfrom mpnn import MPNN\n"
+            "env = make_fortattack_env(20, n_guards=2, n_attackers=2)\n"
+            "o = env.reset(); o, r, d, i = env.step([0, 1, 2, 7])\nprint('ok', o.shape)\n") % os.path.join(ROOT, PKG)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok (4, 6)" in out.stdout, out.stderr[-2000:]
+
+
+def test_batched_collect_matches_per_env_protocol():
+    """collect() + wrap_horizon() for E envs == the reference protocol applied to each env separately."""
+    ro = import_module(PKG + ".rollout")
+    storage = import_module(PKG + ".rlcore.storage")
+    torch.manual_seed(0)
+    tr = ro.BatchedTrainer(64, 3, 3, num_steps=48, max_episode_steps=15, hidden_dim=32, seed=9)
+    tr.collect()
+    tr.wrap_horizon()
+    R = tr.roll
+    assert int(R.done.sum()) >= 3 * 64
+    # stored obs of step t+1 is the reset obs where the env finished at step t: everyone alive, at rest
+    fin = R.done != 0
+    nxt = R.obs[1:].permute(0, 2, 1, 3)[fin]
+    assert (nxt[:, :, 0] == 1).all() and (nxt[:, :, 4:] == 0).all()
+    assert torch.equal(R.ends[1:-1], fin[:-1]) and bool(R.ends[-1].all())
+    # masks[t+1] = alive flags of obs[t], except after a reset (all alive)
+    exp = torch.where(fin[:, None, :], torch.ones_like(R.obs[:-1, :, :, 0]), R.obs[:-1, :, :, 0])
+    assert torch.equal(R.masks[1:, :, :, 0], exp)
+    for i in (0, 4):
+        for e in (0, 17, 63):
+            one = storage.RolloutStorage(48, 1, (6,), None, 1)
+            one.rewards.copy_(R.agents[i].rewards[:, e:e + 1].cpu())
+            one.value_preds.copy_(R.agents[i].value_preds[:, e:e + 1].cpu())
+            one.masks.copy_(R.agents[i].masks[:, e:e + 1].cpu())
+            start = 0
+            for end_pt in torch.nonzero(R.ends[:, e]).flatten().tolist():
+                one.compute_returns(one.value_preds[end_pt].clone(), True, tr.gamma, tr.tau, start, end_pt)
+                start = end_pt + 1
+            assert torch.allclose(one.returns[:, 0], R.agents[i].returns[:, e].cpu(), atol=1e-5)
+
+
+def test_training_runs_and_checkpoint_format(tmp_path):
+    ro = import_module(PKG + ".rollout")
+    torch.manual_seed(1)
+    tr = ro.BatchedTrainer(256, 3, 3, num_steps=32, max_episode_steps=25, hidden_dim=128, ppo_epoch=2, num_mini_batch=4)
+    before = [p.detach().clone() for p in tr.policies[0].parameters()]
+    for _ in range(2):
+        rewards, vals = tr.train_once()
+        assert torch.isfinite(rewards).all() and all(np.isfinite(v).all() for v in vals) and len(vals) == 2
+    assert any(not torch.equal(a, b) for a, b in zip(before, tr.policies[0].parameters()))
+    path = str(tmp_path / "ep0.pt")
+    tr.save(path)
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"models", "ob_rms"} and ck["ob_rms"] == (None, None) and len(ck["models"]) == 6
+    assert len(ck["models"][0]) == 24 and sum(v.numel() for v in ck["models"][0].values()) == 158153
+    tr2 = ro.BatchedTrainer(8, 3, 3, num_steps=4, hidden_dim=128)
+    tr2.load_models(ck["models"])
+    for a, b in zip(tr.policies[1].parameters(), tr2.policies[1].parameters()):
+        assert torch.equal(a, b)
