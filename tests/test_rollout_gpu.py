@@ -44,6 +44,7 @@ def test_gym_facade_surface_and_semantics():
             o = env.reset()
             assert env.world.gameResult.sum() == 0 and env.world.time_step == 0 and (o[:, 0] == 1).all()
     assert n_done >= 6
+    env.reset()
     env.world.max_time_steps = 5
     for s in range(5):
         o, r, d, _ = env.step(np.zeros(10, int))
