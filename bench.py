@@ -276,14 +276,15 @@ def run_ours(args):
     bytes_launch = E * (A * BYTES_AGENT_STEP + BYTES_ENV_STEP)
     achieved = bytes_launch / (ms_total * 1e-3 / K) / 1e9
     info = env.kernel_info()
-    roofline = {"kernel": "fa::fa_step_kernel<3,3,float,false>", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "fa::fa_step_wide_kernel<3,3,float,false>" if info["mapping"] == "agent" else "fa::fa_step_kernel<3,3,float,false>", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": bytes_launch, "launch_us": 1e3 * ms_total / K,
-                "regs": info["regs"], "block": info["block"], "grid": info["grid"]}
+                "regs": info["regs"], "block": info["block"], "grid": info["grid"], "mapping": info["mapping"]}
     extra = {}
     if rank == 0 and world == 1 and not args.quick:
         extra["roofline_sweep"] = sweep(fab, torch, dev, peak)
         extra["persistent"] = persistent(fab, torch, dev, peak, E, min(K, 1000))
+        extra["persistent_thread_per_env"] = persistent(fab, torch, dev, peak, E, min(K, 1000), "env")
     del env
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -318,8 +319,9 @@ def run_ours(args):
 def sweep(fab, torch, dev, peak):
     """Single-step kernel at batch sizes whose working set leaves the L2 (eager launches, CUDA events)."""
     out = []
-    for E in (4096, 65536, 1 << 20, 1 << 22):
-        env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, device=dev)
+    for E, mapping in ((4096, "agent"), (4096, "env"), (16384, "agent"), (16384, "env"), (65536, "agent"), (65536, "env"),
+                       (1 << 20, "env"), (1 << 22, "env")):
+        env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, device=dev, mapping=mapping)
         env.reset()
         n = 12 if E >= (1 << 20) else 50
         acts = torch.randint(0, 8, (n, A, E), device=dev, dtype=torch.int32)
@@ -336,15 +338,15 @@ def sweep(fab, torch, dev, peak):
         torch.cuda.synchronize(dev)
         us = 1e3 * e0.elapsed_time(e1) / n
         gbs = E * (A * BYTES_AGENT_STEP + BYTES_ENV_STEP) / (us * 1e-6) / 1e9
-        out.append({"envs": E, "launch_us": us, "agent_steps_per_s": E * A / (us * 1e-6), "achieved_gbs": gbs,
+        out.append({"envs": E, "mapping": mapping, "launch_us": us, "agent_steps_per_s": E * A / (us * 1e-6), "achieved_gbs": gbs,
                     "frac": gbs / peak, "working_set_mb": E * (A * BYTES_AGENT_STEP + BYTES_ENV_STEP) / 1e6})
         del env, acts, o
     return out
 
 
-def persistent(fab, torch, dev, peak, E, T):
+def persistent(fab, torch, dev, peak, E, T, mapping="auto"):
     """fa_step_many: T steps in one launch, state in registers (32 B/agent-step + 2 B/env-step + state/T)."""
-    env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, device=dev)
+    env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=0, device=dev, mapping=mapping)
     env.reset()
     acts = torch.randint(0, 8, (T, A, E), device=dev, dtype=torch.int32)
     out = (torch.empty(T, A, E, 6, device=dev), torch.empty(T, A, E, device=dev),
@@ -362,7 +364,7 @@ def persistent(fab, torch, dev, peak, E, T):
         best = ms if best is None else min(best, ms)
     b = E * (A * 32 + 2 + (A * 56 + 12) / T)
     gbs = b / (best * 1e-3 / T) / 1e9
-    return {"api": "fa_step_many", "steps_per_launch": T, "envs": E, "us_per_step": 1e3 * best / T,
+    return {"api": "fa_step_many", "mapping": env.kernel_info()["mapping"], "steps_per_launch": T, "envs": E, "us_per_step": 1e3 * best / T,
             "agent_steps_per_s": E * A * T / (best * 1e-3), "achieved_gbs": gbs, "frac": gbs / peak}
 
 

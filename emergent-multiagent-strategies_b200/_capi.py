@@ -13,6 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 FA_ABI_VERSION = 1
 FA_F32, FA_F64 = 0, 1
 FA_MAX_TEAM = 5
+FA_MAP_AUTO, FA_MAP_ENV, FA_MAP_AGENT = 0, 1, 2
 
 # every symbol include/fortattack.h declares
 SYMBOLS = ("fa_abi_version", "fa_last_error", "fa_workspace_bytes", "fa_create", "fa_destroy", "fa_reset",
@@ -23,7 +24,7 @@ SYMBOLS = ("fa_abi_version", "fa_last_error", "fa_workspace_bytes", "fa_create",
 class FaConfig(ctypes.Structure):
     _fields_ = [("n_envs", ctypes.c_int32), ("n_guards", ctypes.c_int32), ("n_attackers", ctypes.c_int32),
                 ("max_steps", ctypes.c_int32), ("scalar", ctypes.c_int32), ("device", ctypes.c_int32),
-                ("seed", ctypes.c_uint64), ("env_id0", ctypes.c_uint64)]
+                ("mapping", ctypes.c_int32), ("reserved", ctypes.c_int32), ("seed", ctypes.c_uint64), ("env_id0", ctypes.c_uint64)]
 
 
 class FaState(ctypes.Structure):
@@ -73,7 +74,7 @@ def lib():
     L.fa_alive_counts.argtypes = [vp, vp, vp]
     L.fa_set_max_steps.argtypes = [vp, i32]
     L.fa_launch_count.argtypes = [vp, u64p]
-    L.fa_kernel_info.argtypes = [vp, i32p, i32p, i32p, i32p]
+    L.fa_kernel_info.argtypes = [vp, i32p, i32p, i32p, i32p, i32p]
     for name in SYMBOLS:
         getattr(L, name)   # AttributeError here = the library does not match the header
     if L.fa_abi_version() != FA_ABI_VERSION:

@@ -16,7 +16,7 @@ from . import _capi
 
 class FortAttackBatch(object):
     def __init__(self, n_envs, n_guards=3, n_attackers=3, max_steps=100, seed=0, env_id0=0, device="cuda:0",
-                 dtype=torch.float32):
+                 dtype=torch.float32, mapping="auto"):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _capi.FaError("FortAttackBatch needs a CUDA device (got %r); there is no CPU path" % (device,))
@@ -29,7 +29,8 @@ class FortAttackBatch(object):
         self.cfg = _capi.FaConfig(self.E, self.n_guards, self.n_attackers, int(max_steps),
                                   _capi.FA_F64 if dtype == torch.float64 else _capi.FA_F32,
                                   dev.index if dev.index is not None else torch.cuda.current_device(),
-                                  int(seed), int(env_id0))
+                                  {"auto": _capi.FA_MAP_AUTO, "env": _capi.FA_MAP_ENV, "agent": _capi.FA_MAP_AGENT}[mapping],
+                                  0, int(seed), int(env_id0))
         nbytes = ctypes.c_size_t()
         _capi.check(self._lib.fa_workspace_bytes(ctypes.byref(self.cfg), ctypes.byref(nbytes)))
         with torch.cuda.device(dev):
@@ -164,6 +165,8 @@ class FortAttackBatch(object):
         return n.value
 
     def kernel_info(self):
-        v = [ctypes.c_int32() for _ in range(4)]
+        v = [ctypes.c_int32() for _ in range(5)]
         _capi.check(self._lib.fa_kernel_info(self._h, *[ctypes.byref(x) for x in v]))
-        return dict(zip(("regs", "block", "grid", "smem"), [x.value for x in v]))
+        d = dict(zip(("regs", "block", "grid", "smem", "mapping"), [x.value for x in v]))
+        d["mapping"] = {_capi.FA_MAP_ENV: "env", _capi.FA_MAP_AGENT: "agent"}[d["mapping"]]
+        return d

@@ -26,14 +26,14 @@ __global__ void fa_alive_counts_kernel(const uint32_t *fl, int32_t *counts, int 
 }
 
 #define FA_EXTERN(NG)                                                                                                  \
-    extern template cudaError_t launch_step_g<NG, float>(int, bool, const StepParams<float> &, int, int, cudaStream_t);  \
-    extern template cudaError_t launch_step_g<NG, double>(int, bool, const StepParams<double> &, int, int, cudaStream_t); \
+    extern template cudaError_t launch_step_g<NG, float>(int, bool, bool, const StepParams<float> &, int, int, cudaStream_t);  \
+    extern template cudaError_t launch_step_g<NG, double>(int, bool, bool, const StepParams<double> &, int, int, cudaStream_t); \
     extern template cudaError_t launch_reset_g<NG, float>(int, const StateView<float> &, const uint8_t *, float *, int,  \
                                                           uint64_t, uint64_t, int, int, cudaStream_t);                   \
     extern template cudaError_t launch_reset_g<NG, double>(int, const StateView<double> &, const uint8_t *, double *,    \
                                                            int, uint64_t, uint64_t, int, int, cudaStream_t);             \
-    extern template cudaError_t step_attr_g<NG, float>(int, bool, cudaFuncAttributes *);                                 \
-    extern template cudaError_t step_attr_g<NG, double>(int, bool, cudaFuncAttributes *);
+    extern template cudaError_t step_attr_g<NG, float>(int, bool, bool, cudaFuncAttributes *);                                 \
+    extern template cudaError_t step_attr_g<NG, double>(int, bool, bool, cudaFuncAttributes *);
 FA_EXTERN(1) FA_EXTERN(2) FA_EXTERN(3) FA_EXTERN(4) FA_EXTERN(5)
 
 #define FA_DISPATCH_NG(ng, CALL)          \
@@ -47,8 +47,9 @@ FA_EXTERN(1) FA_EXTERN(2) FA_EXTERN(3) FA_EXTERN(4) FA_EXTERN(5)
     }
 
 template <typename R>
-static cudaError_t launch_step(int ng, int na, bool many, const StepParams<R> &p, int grid, int block, cudaStream_t s) {
-#define CALL(NG) launch_step_g<NG, R>(na, many, p, grid, block, s)
+static cudaError_t launch_step(int ng, int na, bool many, bool wide, const StepParams<R> &p, int grid, int block,
+                               cudaStream_t s) {
+#define CALL(NG) launch_step_g<NG, R>(na, many, wide, p, grid, block, s)
     FA_DISPATCH_NG(ng, CALL)
 #undef CALL
 }
@@ -59,8 +60,8 @@ static cudaError_t launch_reset(int ng, int na, const StateView<R> &st, const ui
     FA_DISPATCH_NG(ng, CALL)
 #undef CALL
 }
-template <typename R> static cudaError_t step_attr(int ng, int na, bool many, cudaFuncAttributes *out) {
-#define CALL(NG) step_attr_g<NG, R>(na, many, out)
+template <typename R> static cudaError_t step_attr(int ng, int na, bool many, bool wide, cudaFuncAttributes *out) {
+#define CALL(NG) step_attr_g<NG, R>(na, many, wide, out)
     FA_DISPATCH_NG(ng, CALL)
 #undef CALL
 }
@@ -100,6 +101,7 @@ struct FaHandle {
     void *s_obs, *s_rew;
     uint8_t *s_done, *s_result;
     int block, grid;
+    bool wide;          // one thread per agent (small batches) instead of one thread per env
     int sm_count;
     uint64_t launches;
     int host_path;      // fa_step_host: 0 auto, 1 staged only, 2 mapped only (env FA_HOST_PATH)
@@ -145,6 +147,7 @@ static int check_cfg(const FaConfig *c) {
                     c->n_guards, c->n_attackers, FA_MAX_TEAM, FA_MAX_TEAM);
     if (c->max_steps < 1) return fail(FA_EINVAL, "max_steps must be >= 1 (got %d)", c->max_steps);
     if (c->scalar != FA_F32 && c->scalar != FA_F64) return fail(FA_EINVAL, "scalar must be FA_F32 or FA_F64");
+    if (c->mapping < FA_MAP_AUTO || c->mapping > FA_MAP_AGENT) return fail(FA_EINVAL, "mapping must be FA_MAP_AUTO/ENV/AGENT");
     if ((uint64_t)c->n_envs * (uint64_t)(c->n_guards + c->n_attackers) * 6ull >= (1ull << 40))
         return fail(FA_EINVAL, "n_envs too large");
     return FA_OK;
@@ -164,6 +167,14 @@ template <typename R> static fa::StateView<R> view(const FaHandle *h) {
 // SMs busy); many envs: 128-thread blocks (4 warps share one 6/12 KB obs stage).
 static void pick_launch(FaHandle *h) {
     const int E = h->cfg.n_envs;
+    // FA_MAP_AUTO: thread-per-agent while thread-per-env could not even put two warps on every SM
+    // sub-partition (E < 2 * 4 * 32 * #SM = 37 888 on a B200); measured crossover in DESIGN.md
+    h->wide = h->cfg.mapping == FA_MAP_AGENT || (h->cfg.mapping == FA_MAP_AUTO && E < 2 * 4 * 32 * h->sm_count);
+    if (h->wide) {
+        h->block = 32 * h->A;
+        h->grid = (E + 31) / 32;
+        return;
+    }
     int block = 128;
     while (block > 32 && (E + block - 1) / block < 2 * h->sm_count) block >>= 1;
     h->block = block;
@@ -192,7 +203,7 @@ static cudaError_t do_step(FaHandle *h, bool many, int T, const int32_t *act, vo
     p.obs_vec_ok = ((size_t)c.n_envs * 6 * sizeof(R)) % 16 == 0 && ((uintptr_t)obs % 16) == 0;
     p.seed = c.seed;
     p.env_id0 = c.env_id0;
-    return fa::launch_step<R>(c.n_guards, c.n_attackers, many, p, h->grid, h->block, s);
+    return fa::launch_step<R>(c.n_guards, c.n_attackers, many, h->wide, p, h->grid, h->block, s);
 }
 
 static int step_common(FaHandle *h, bool many, int T, const int32_t *d_actions, void *d_obs, void *d_reward,
@@ -435,16 +446,18 @@ int fa_launch_count(const FaHandle *h, uint64_t *out) {
     return FA_OK;
 }
 
-int fa_kernel_info(const FaHandle *h, int32_t *regs, int32_t *block, int32_t *grid, int32_t *smem) {
+int fa_kernel_info(const FaHandle *h, int32_t *regs, int32_t *block, int32_t *grid, int32_t *smem, int32_t *mapping) {
     NEED_HANDLE(h);
     cudaFuncAttributes a;
-    cudaError_t e = h->cfg.scalar == FA_F64 ? fa::step_attr<double>(h->cfg.n_guards, h->cfg.n_attackers, false, &a)
-                                            : fa::step_attr<float>(h->cfg.n_guards, h->cfg.n_attackers, false, &a);
+    cudaError_t e = h->cfg.scalar == FA_F64
+                        ? fa::step_attr<double>(h->cfg.n_guards, h->cfg.n_attackers, false, h->wide, &a)
+                        : fa::step_attr<float>(h->cfg.n_guards, h->cfg.n_attackers, false, h->wide, &a);
     CUDA_TRY(e);
     if (regs) *regs = a.numRegs;
     if (block) *block = h->block;
     if (grid) *grid = h->grid;
     if (smem) *smem = (int32_t)a.sharedSizeBytes;
+    if (mapping) *mapping = h->wide ? FA_MAP_AGENT : FA_MAP_ENV;
     return FA_OK;
 }
 

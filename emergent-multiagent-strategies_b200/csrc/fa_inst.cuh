@@ -7,12 +7,17 @@ namespace fa {
 #define FA_FOR_NA(X) X(1) X(2) X(3) X(4) X(5)
 
 template <int NG, typename R>
-cudaError_t launch_step_g(int na, bool many, const StepParams<R> &p, int grid, int block, cudaStream_t stream) {
+cudaError_t launch_step_g(int na, bool many, bool wide, const StepParams<R> &p, int grid, int block, cudaStream_t stream) {
     switch (na) {
-#define FA_CASE(NA)                                                                   \
-    case NA:                                                                          \
-        if (many) fa_step_kernel<NG, NA, R, true><<<grid, block, 0, stream>>>(p);     \
-        else fa_step_kernel<NG, NA, R, false><<<grid, block, 0, stream>>>(p);         \
+#define FA_CASE(NA)                                                                          \
+    case NA:                                                                                 \
+        if (wide) {                                                                          \
+            if (many) fa_step_wide_kernel<NG, NA, R, true><<<grid, block, 0, stream>>>(p);   \
+            else fa_step_wide_kernel<NG, NA, R, false><<<grid, block, 0, stream>>>(p);       \
+        } else {                                                                             \
+            if (many) fa_step_kernel<NG, NA, R, true><<<grid, block, 0, stream>>>(p);        \
+            else fa_step_kernel<NG, NA, R, false><<<grid, block, 0, stream>>>(p);            \
+        }                                                                                    \
         break;
         FA_FOR_NA(FA_CASE)
 #undef FA_CASE
@@ -34,11 +39,14 @@ cudaError_t launch_reset_g(int na, const StateView<R> &st, const uint8_t *mask, 
     return cudaGetLastError();
 }
 
-template <int NG, typename R> cudaError_t step_attr_g(int na, bool many, cudaFuncAttributes *out) {
+template <int NG, typename R> cudaError_t step_attr_g(int na, bool many, bool wide, cudaFuncAttributes *out) {
     switch (na) {
-#define FA_CASE(NA)                                                                                  \
-    case NA:                                                                                         \
-        return many ? cudaFuncGetAttributes(out, (const void *)fa_step_kernel<NG, NA, R, true>)      \
+#define FA_CASE(NA)                                                                                            \
+    case NA:                                                                                                   \
+        if (wide)                                                                                              \
+            return many ? cudaFuncGetAttributes(out, (const void *)fa_step_wide_kernel<NG, NA, R, true>)       \
+                        : cudaFuncGetAttributes(out, (const void *)fa_step_wide_kernel<NG, NA, R, false>);     \
+        return many ? cudaFuncGetAttributes(out, (const void *)fa_step_kernel<NG, NA, R, true>)                \
                     : cudaFuncGetAttributes(out, (const void *)fa_step_kernel<NG, NA, R, false>);
         FA_FOR_NA(FA_CASE)
 #undef FA_CASE
@@ -47,13 +55,13 @@ template <int NG, typename R> cudaError_t step_attr_g(int na, bool many, cudaFun
 }
 
 #define FA_INSTANTIATE(NG)                                                                                        \
-    template cudaError_t launch_step_g<NG, float>(int, bool, const StepParams<float> &, int, int, cudaStream_t);  \
-    template cudaError_t launch_step_g<NG, double>(int, bool, const StepParams<double> &, int, int, cudaStream_t); \
+    template cudaError_t launch_step_g<NG, float>(int, bool, bool, const StepParams<float> &, int, int, cudaStream_t);  \
+    template cudaError_t launch_step_g<NG, double>(int, bool, bool, const StepParams<double> &, int, int, cudaStream_t); \
     template cudaError_t launch_reset_g<NG, float>(int, const StateView<float> &, const uint8_t *, float *, int,  \
                                                    uint64_t, uint64_t, int, int, cudaStream_t);                   \
     template cudaError_t launch_reset_g<NG, double>(int, const StateView<double> &, const uint8_t *, double *,    \
                                                     int, uint64_t, uint64_t, int, int, cudaStream_t);             \
-    template cudaError_t step_attr_g<NG, float>(int, bool, cudaFuncAttributes *);                                 \
-    template cudaError_t step_attr_g<NG, double>(int, bool, cudaFuncAttributes *);
+    template cudaError_t step_attr_g<NG, float>(int, bool, bool, cudaFuncAttributes *);                                 \
+    template cudaError_t step_attr_g<NG, double>(int, bool, bool, cudaFuncAttributes *);
 
 }  // namespace fa

@@ -502,6 +502,233 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) fa_step_kernel(const StepParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same step with ONE THREAD PER AGENT, for batches too small to fill the GPU with one thread per
+// env (E=4096 is 128 warps on 592 warp schedulers; the per-env instruction chain, not bandwidth, is
+// the limit there).  Block = A warps x 32 envs: warp i holds agent i of 32 consecutive envs, so global
+// accesses stay exactly as coalesced as in the thread-per-env kernel; the per-env agent block needed by
+// the O(A^2) laser and contact tests is staged in shared memory ([A][32] planes, conflict-free) across
+// three block barriers per step:  positions/flags -> laser + kill -> forces/integrate -> reward/done.
+template <int A, typename R> struct WideShared {
+    R x0[A][32], y0[A][32];        // pre-move positions
+    R cs[A][32], sn[A][32];        // heading of agents that shoot this step
+    R d1[A][32];                   // post-move distance to the door
+    uint32_t f0[A][32];            // bit 0 alive before the step, bit 1 shoots
+    uint32_t a1[A][32];            // alive after the kill
+};
+
+template <int NG, int NA, typename R, bool MANY>
+__global__ void __launch_bounds__(32 * (NG + NA)) fa_step_wide_kernel(const StepParams<R> p) {
+    constexpr int A = NG + NA;
+    constexpr int NOPP_MAX = NG > NA ? NG : NA;
+    typedef K<R> C;
+    __shared__ WideShared<A, R> sh;
+    __shared__ __align__(16) R stage[A][2][32 * OBS_DIM];
+    const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;          // agent index = warp index
+    const int e = blockIdx.x * 32 + lane;
+    const bool valid = e < p.E;
+    const int ec = valid ? e : p.E - 1;
+    const size_t E = (size_t)p.E;
+    const bool vec = p.obs_vec_ok && (blockIdx.x * 32 + 32 <= p.E);
+    const bool attacker = i >= NG;                                     // warp-uniform
+    const int j0 = attacker ? 0 : NG, nopp = attacker ? NG : NA;      // the other team
+
+    Env<1, R> s;                                                       // this thread's agent
+    {
+        const typename VecT<R>::T4 v = p.st.pv[i * E + ec];
+        const typename VecT<R>::T2 w = p.st.ap[i * E + ec];
+        s.x[0] = v.x; s.y[0] = v.y; s.vx[0] = v.z; s.vy[0] = v.w; s.ang[0] = w.x; s.pd[0] = w.y;
+        s.fl[0] = p.st.fl[i * E + ec];
+        s.t = p.st.tstep[ec];
+    }
+    uint32_t ep = p.st.episode[ec];
+    int act = p.act[i * E + ec];
+    const int T = MANY ? p.T : 1;
+    for (int t = 0; t < T; ++t) {
+        int nxt = 0;
+        if (MANY && t + 1 < T) nxt = p.act[((size_t)(t + 1) * A + i) * E + ec];
+        R x = s.x[0], y = s.y[0];
+        uint32_t fl = s.fl[0];
+        // ---- stage the agent block --------------------------------------------------------------
+        const bool alive0 = fl & F_ALIVE, shoot = act == 7;
+        if (alive0) fl &= ~(F_HIT | F_WASHIT);
+        R sn = R(0), cs = R(0);
+        if (shoot && alive0) AngOps<R>::sincos_heading(s.ang[0], sn, cs);
+        sh.x0[i][lane] = x; sh.y0[i][lane] = y; sh.cs[i][lane] = cs; sh.sn[i][lane] = sn;
+        sh.f0[i][lane] = (alive0 ? 1u : 0u) | (shoot ? 2u : 0u);
+        __syncthreads();
+        // ---- apply_laser_effect: as shooter and as victim (core.py:254-302) ----------------------
+        if (alive0) {
+            const R p1x = x + C::SIZE * cs, p1y = y + C::SIZE * sn;
+#pragma unroll
+            for (int jj = 0; jj < NOPP_MAX; ++jj) {
+                if (jj < nopp) {
+                    const int j = j0 + jj;
+                    const uint32_t fj = sh.f0[j][lane];
+                    if (fj & 1u) {
+                        const R xj = sh.x0[j][lane], yj = sh.y0[j][lane];
+                        if (shoot) {
+                            const R dx = xj - p1x, dy = yj - p1y;
+                            const R a = (dx * cs + dy * sn) * C::INV_LC8, b = (dy * cs - dx * sn) * C::INV_LS8;
+                            if (a <= R(1) && a + b >= R(0) && a - b >= R(0)) {
+                                fl |= F_HIT;
+                                if (((fl >> F_NHIT_SHIFT) & F_CNT_MASK) < F_CNT_MASK) fl += 1u << F_NHIT_SHIFT;
+                            }
+                        }
+                        if (fj & 2u) {
+                            const R cj = sh.cs[j][lane], sj = sh.sn[j][lane];
+                            const R dx = x - (xj + C::SIZE * cj), dy = y - (yj + C::SIZE * sj);
+                            const R a = (dx * cj + dy * sj) * C::INV_LC8, b = (dy * cj - dx * sj) * C::INV_LS8;
+                            if (a <= R(1) && a + b >= R(0) && a - b >= R(0)) {
+                                fl |= F_WASHIT;
+                                if (((fl >> F_NWAS_SHIFT) & F_CNT_MASK) < F_CNT_MASK) fl += 1u << F_NWAS_SHIFT;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!alive0) fl &= ~F_JD;
+        else if (fl & F_WASHIT) fl = (fl & ~F_ALIVE) | F_JD;
+        const bool alive1 = fl & F_ALIVE;
+        sh.a1[i][lane] = alive1 ? 1u : 0u;
+        __syncthreads();
+        // ---- forces on this agent + integrate (core.py:204-213) ---------------------------------
+        if (alive1) {
+            R fx = act == 1 ? C::ACCEL : (act == 2 ? -C::ACCEL : R(0));
+            R fy = act == 3 ? C::ACCEL : (act == 4 ? -C::ACCEL : R(0));
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                if (j != i && sh.a1[j][lane]) {
+                    const R dx = x - sh.x0[j][lane], dy = y - sh.y0[j][lane];
+                    const R r2 = dx * dx + dy * dy;
+                    if (r2 < ContactGate<R>::R2) {
+                        const R rinv = rsqrt_t(r2);
+                        const R g = C::CONTACT_FORCE * penetration(C::DIST_MIN - r2 * rinv) * rinv;
+                        fx += g * dx; fy += g * dy;
+                    }
+                }
+            }
+            fx += C::CONTACT_FORCE * (penetration(-C::WALL_X - x) - penetration(x - C::WALL_X));
+            fy += C::CONTACT_FORCE * (penetration(-C::WALL_Y - y) - penetration(y - C::WALL_Y));
+            R vx = s.vx[0] * C::DAMP + fx * C::DT, vy = s.vy[0] * C::DAMP + fy * C::DT;
+            const R sp2 = vx * vx + vy * vy;
+            if (sp2 > C::MAX_SPEED * C::MAX_SPEED) {
+                const R k = C::MAX_SPEED * rsqrt_t(sp2);
+                vx *= k; vy *= k;
+            }
+            AngOps<R>::advance(s.ang[0], fl, act);
+            s.vx[0] = vx; s.vy[0] = vy;
+            x += vx * C::DT; y += vy * C::DT;
+        }
+        const R ddy = y - C::DOOR_Y;
+        const R d = sqrt_t(x * x + ddy * ddy);
+        sh.d1[i][lane] = d;
+        __syncthreads();
+        // ---- reward, done (fortattack_env_v1.py:87-188, fortattack.py:202-225) -------------------
+        int n_alive_att = 0;
+        R min_att = R(1e30);
+#pragma unroll
+        for (int j = NG; j < A; ++j) {
+            if (sh.a1[j][lane]) { n_alive_att += 1; min_att = min_t(min_att, sh.d1[j][lane]); }
+        }
+        const bool reached = min_att < C::FORT_DIM;
+        R r = R(0);
+        if (fl & (F_ALIVE | F_JD)) {
+            const R pd = s.pd[0];
+            const bool has_prev = pd == pd;
+            if (attacker) {
+                if (has_prev) r += R(2) * (pd - d);
+                if (d < C::FORT_DIM) r += R(10);
+                if (shoot) r -= R(1);
+                if (fl & F_HIT) r += R(3);
+                if (fl & F_WASHIT) r -= R(3);
+                if (n_alive_att == 0) r -= R(10);
+            } else {
+                if (has_prev) {
+                    if (d > C::GUARD_RING && pd <= C::GUARD_RING) r = R(-1);
+                    else if (d <= C::GUARD_RING && pd > C::GUARD_RING) r = R(1);
+                }
+                if (reached) r -= R(10);
+                if (shoot) r -= R(0.1);
+                if (fl & F_HIT) r += R(3);
+                if (fl & F_WASHIT) r -= R(3);
+                if (n_alive_att == 0) r += R(10);
+            }
+            s.pd[0] = d;
+        }
+        int result;
+        bool dn = true;
+        if (reached) result = 3;
+        else if (n_alive_att == 0) result = 1;
+        else if (s.t == p.max_steps - 1) result = 2;
+        else { result = 0; dn = false; }
+        s.t += 1;
+        s.x[0] = x; s.y[0] = y; s.fl[0] = fl;
+        if (dn && (MANY || p.auto_reset)) {
+            // reset_world for this thread's agent: Philox block of its pair, lanes (2h, 2h+1)
+            uint32_t c[4] = {(uint32_t)(p.env_id0 + (uint64_t)ec), (uint32_t)((p.env_id0 + (uint64_t)ec) >> 32), ep,
+                             (uint32_t)(i >> 1)};
+            philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), c);
+            const int h = i & 1;
+            const double ux = u01(h ? c[2] : c[0]), uy = u01(h ? c[3] : c[1]);
+            double px, py;
+            if (attacker) {
+                px = __dadd_rn(-1.0, __dmul_rn(1.0 - (-1.0), ux));
+                py = __dadd_rn(-0.8, __dmul_rn(0.8 * -0.8 - (-0.8), uy));
+            } else {
+                const double lo = -0.8 * 0.15 / 2, hi = 0.8 * 0.15 / 2;
+                px = __dadd_rn(lo, __dmul_rn(hi - lo, ux));
+                py = __dadd_rn(0.8 * 0.8, __dmul_rn(0.8 - 0.8 * 0.8, uy));
+            }
+            s.x[0] = (R)px; s.y[0] = (R)py; s.vx[0] = R(0); s.vy[0] = R(0);
+            uint32_t f = (s.fl[0] & (F_JD | (~0u << F_WRAP_SHIFT))) | F_ALIVE;
+            AngOps<R>::set_reset(s.ang[0], f, attacker);
+            s.fl[0] = f;
+            s.t = 0;
+            ep += 1;
+        }
+        // ---- outputs ----------------------------------------------------------------------------
+        const size_t plane = (size_t)t * A;
+        if (p.rew != nullptr && valid) p.rew[(plane + i) * E + e] = r;
+        if (i == 0 && valid) {
+            if (p.done != nullptr) p.done[(size_t)t * E + e] = dn ? 1 : 0;
+            if (p.result != nullptr) p.result[(size_t)t * E + e] = (uint8_t)result;
+        }
+        if (p.obs != nullptr) {
+            typedef typename VecT<R>::T2 T2;
+            T2 o0, o1, o2;
+            o0.x = (s.fl[0] & F_ALIVE) ? R(1) : R(0); o0.y = s.x[0];
+            o1.x = s.y[0]; o1.y = AngOps<R>::full(s.ang[0], s.fl[0]);
+            o2.x = s.vx[0]; o2.y = s.vy[0];
+            R *obs_t = p.obs + plane * E * OBS_DIM;
+            if (vec) {
+                R *sb = stage[i][t & 1];
+                T2 *w = reinterpret_cast<T2 *>(sb + lane * OBS_DIM);
+                w[0] = o0; w[1] = o1; w[2] = o2;
+                __syncwarp();
+                const uint4 *src = reinterpret_cast<const uint4 *>(sb);
+                uint4 *dst = reinterpret_cast<uint4 *>(obs_t + (i * E + (size_t)(e - lane)) * OBS_DIM);
+                constexpr int NV = 32 * OBS_DIM * (int)sizeof(R) / 16;
+#pragma unroll
+                for (int q = lane; q < NV; q += 32) dst[q] = src[q];
+            } else if (valid) {
+                T2 *g = reinterpret_cast<T2 *>(obs_t + (i * E + (size_t)e) * OBS_DIM);
+                g[0] = o0; g[1] = o1; g[2] = o2;
+            }
+        }
+        if (MANY) act = nxt;
+    }
+    if (valid) {
+        typename VecT<R>::T4 v; v.x = s.x[0]; v.y = s.y[0]; v.z = s.vx[0]; v.w = s.vy[0];
+        typename VecT<R>::T2 w; w.x = s.ang[0]; w.y = s.pd[0];
+        p.st.pv[i * E + e] = v;
+        p.st.ap[i * E + e] = w;
+        p.st.fl[i * E + e] = s.fl[0];
+        if (i == 0) { p.st.tstep[e] = s.t; p.st.episode[e] = ep; }
+    }
+}
+
 // fa_reset: reset the masked envs (all if mask == nullptr) and report every env's observation.
 template <int NG, int NA, typename R>
 __global__ void __launch_bounds__(32 * MAX_WARPS)

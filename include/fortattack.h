@@ -56,6 +56,10 @@ enum {
 
 enum { FA_F32 = 0, FA_F64 = 1 };
 
+/* Thread mapping of the step kernel: one thread per env (large batches, register-resident agent block) or one
+ * thread per agent (small batches, shared-memory agent block); AUTO picks by batch size. */
+enum { FA_MAP_AUTO = 0, FA_MAP_ENV = 1, FA_MAP_AGENT = 2 };
+
 #define FA_MAX_TEAM 5    /* kernels are instantiated for 1..5 guards x 1..5 attackers */
 
 typedef struct FaHandle FaHandle;
@@ -69,6 +73,8 @@ typedef struct FaConfig {
     int32_t max_steps;     /* world.max_time_steps, episode cap (fortattack.py:21) */
     int32_t scalar;        /* FA_F32 (production) or FA_F64 (parity mode, same kernels in double) */
     int32_t device;        /* CUDA device ordinal */
+    int32_t mapping;       /* FA_MAP_AUTO / FA_MAP_ENV / FA_MAP_AGENT */
+    int32_t reserved;      /* 0 */
     uint64_t seed;         /* Philox key of the reset streams */
     uint64_t env_id0;      /* global id of env 0 of this shard: resets are keyed by (seed, env_id0+e, episode) */
 } FaConfig;
@@ -154,8 +160,9 @@ int fa_set_max_steps(FaHandle *h, int32_t max_steps);
 int fa_launch_count(const FaHandle *h, uint64_t *out);
 
 /* Static facts about the step kernel chosen for this handle (for DESIGN.md / bench.py):
- * registers per thread, threads per block, blocks per launch, static shared memory bytes. */
-int fa_kernel_info(const FaHandle *h, int32_t *regs, int32_t *block, int32_t *grid, int32_t *smem);
+ * registers per thread, threads per block, blocks per launch, static shared memory bytes, and the mapping in
+ * use (FA_MAP_ENV or FA_MAP_AGENT). */
+int fa_kernel_info(const FaHandle *h, int32_t *regs, int32_t *block, int32_t *grid, int32_t *smem, int32_t *mapping);
 
 #ifdef __cplusplus
 }

@@ -11,9 +11,12 @@ TOL = {torch.float32: (1e-5, 1e-5), torch.float64: (1e-11, 1e-11)}
 MARGIN_F32 = 1e-5
 
 
-def make(E, ng, na, dtype, max_steps=100, seed=0, env_id0=0):
+MAPPINGS = ["env", "agent"]      # thread-per-env and thread-per-agent kernels: both must pass every parity gate
+
+
+def make(E, ng, na, dtype, max_steps=100, seed=0, env_id0=0, mapping="auto"):
     return fab.FortAttackBatch(E, ng, na, max_steps=max_steps, seed=seed, env_id0=env_id0, device="cuda:0",
-                               dtype=dtype)
+                               dtype=dtype, mapping=mapping)
 
 
 def push(env, st_f, st_i, t, ep):

@@ -6,7 +6,7 @@ import torch
 
 import fa_oracle
 import golden_util
-from gpu_util import MARGIN_F32, acts_dev, close, contact_slack, make, pull, push, to_env_major
+from gpu_util import MAPPINGS, MARGIN_F32, acts_dev, close, contact_slack, make, pull, push, to_env_major
 
 pytestmark = pytest.mark.gpu
 DTYPES = [torch.float64, torch.float32]
@@ -41,13 +41,15 @@ def _compare_transition(env, dtype, pre_f, pre_i, t, ep, act, ref, margin, auto_
     return int((~keep).sum())
 
 
+@pytest.mark.parametrize("mapping", MAPPINGS)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("name", ["env_3v3.npz", "env_5v5.npz", "env_2v1.npz"])
-def test_golden_reference_transitions(name, dtype):
+def test_golden_reference_transitions(name, dtype, mapping):
     """Every transition recorded from the unchanged reference (tests/golden/make_env_golden.py)."""
     g = golden_util.load(name)
     N = g["act"].shape[0]
-    env = make(N, g["n_guards"], g["n_attackers"], dtype, max_steps=golden_util.CAP)
+    env = make(N, g["n_guards"], g["n_attackers"], dtype, max_steps=golden_util.CAP, mapping=mapping)
+    assert env.kernel_info()["mapping"] == mapping
     ref = dict(obs=g["obs"], rew=g["rew"], done=g["done"], result=g["result"], post_i=g["post_i"],
                post_pd=g["post_pd"], t_post=g["t_shift"] + 1)
     excluded = _compare_transition(env, dtype, g["pre_f"], g["pre_i"], g["t_shift"], np.zeros(N, np.uint32),
@@ -56,14 +58,15 @@ def test_golden_reference_transitions(name, dtype):
     assert ref["done"].sum() > 0 and (g["pre_i"][:, :, 0] != g["post_i"][:, :, 0]).sum() > 0
 
 
+@pytest.mark.parametrize("mapping", MAPPINGS)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("ng,na,E,steps", [(3, 3, 4096, 130), (5, 5, 1024, 110), (1, 1, 257, 60), (4, 2, 100, 60)])
-def test_teacher_forced_vs_oracle(ng, na, E, steps, dtype):
+def test_teacher_forced_vs_oracle(ng, na, E, steps, dtype, mapping):
     """SURVEY 8d parity gate: oracle state -> fa_set_state -> fa_step -> compare, every step, with the
     shoot-heavy action stream and in-kernel auto-reset (Philox streams must match the oracle's)."""
     rng = np.random.RandomState(5)
     ora = fa_oracle.OracleEnv(E, ng, na, max_steps=40, seed=11, env_id0=1000, n_threads=8)
-    env = make(E, ng, na, dtype, max_steps=40, seed=11, env_id0=1000)
+    env = make(E, ng, na, dtype, max_steps=40, seed=11, env_id0=1000, mapping=mapping)
     o0 = ora.reset()
     close(to_env_major(env.reset()), o0, dtype, "reset obs")
     excluded = kills = dones = 0
@@ -80,7 +83,7 @@ def test_teacher_forced_vs_oracle(ng, na, E, steps, dtype):
         assert np.array_equal(ep[~(margin < MARGIN_F32)], ora.episode[~(margin < MARGIN_F32)])
     assert dones >= E and kills > 0
     if dtype == torch.float32:
-        _quantised_teacher_forcing(ng, na, min(E, 1024), 60)
+        _quantised_teacher_forcing(ng, na, min(E, 1024), 60, mapping)
     assert excluded <= max(2, int(2e-5 * E * steps * (ng + na)))   # ~1e-5 * 0.23 per laser test
 
 
@@ -92,12 +95,12 @@ def _quantise(st_f):
     return q
 
 
-def _quantised_teacher_forcing(ng, na, E, steps):
+def _quantised_teacher_forcing(ng, na, E, steps, mapping):
     """Same gate with the oracle started from the fp32-representable state each step: isolates the
     kernel's arithmetic from state rounding, so the plain 1e-5 bound must hold with NO contact slack."""
     rng = np.random.RandomState(6)
     ora = fa_oracle.OracleEnv(E, ng, na, max_steps=40, seed=12, n_threads=8)
-    env = make(E, ng, na, torch.float32, max_steps=40, seed=12)
+    env = make(E, ng, na, torch.float32, max_steps=40, seed=12, mapping=mapping)
     ora.reset(); env.reset()
     for s in range(steps):
         ora.st_f[:] = _quantise(ora.st_f)
@@ -111,13 +114,14 @@ def _quantised_teacher_forcing(ng, na, E, steps):
         assert np.array_equal(d.cpu().numpy()[k], done[k]) and np.array_equal(rs.cpu().numpy()[k], result[k])
 
 
+@pytest.mark.parametrize("mapping", MAPPINGS)
 @pytest.mark.parametrize("ng,na", [(3, 3), (5, 5)])
-def test_free_run_double_tracks_oracle(ng, na):
+def test_free_run_double_tracks_oracle(ng, na, mapping):
     """Double mode, no re-sync for 300 steps (several episodes with resets): same trajectories."""
     E, T = 512, 300
     rng = np.random.RandomState(9)
     ora = fa_oracle.OracleEnv(E, ng, na, max_steps=50, seed=3, n_threads=8)
-    env = make(E, ng, na, torch.float64, max_steps=50, seed=3)
+    env = make(E, ng, na, torch.float64, max_steps=50, seed=3, mapping=mapping)
     ora.reset(); env.reset()
     acts = rng.randint(0, 8, size=(T, E, ng + na)).astype(np.int32)
     o_obs, o_rew, o_done, o_res = ora.step_many(acts)
@@ -129,15 +133,16 @@ def test_free_run_double_tracks_oracle(ng, na):
     assert o_done.sum() >= 5 * E
 
 
+@pytest.mark.parametrize("mapping", MAPPINGS)
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("ng,na,E", [(3, 3, 4096), (5, 5, 333), (2, 1, 31), (3, 3, 1)])
-def test_step_many_equals_repeated_step(ng, na, E, dtype):
+def test_step_many_equals_repeated_step(ng, na, E, dtype, mapping):
     """The persistent T-step launch and T single-step launches are the same arithmetic: bit-equal."""
     T = 70
     g = torch.Generator(device="cuda").manual_seed(1)
     acts = torch.randint(0, 8, (T, ng + na, E), generator=g, device="cuda", dtype=torch.int32)
-    e1 = make(E, ng, na, dtype, max_steps=30, seed=2)
-    e2 = make(E, ng, na, dtype, max_steps=30, seed=2)
+    e1 = make(E, ng, na, dtype, max_steps=30, seed=2, mapping=mapping)
+    e2 = make(E, ng, na, dtype, max_steps=30, seed=2, mapping=mapping)
     assert torch.equal(e1.reset(), e2.reset())
     obs, rew, done, res = e2.step_many(acts)
     for t in range(T):
@@ -236,6 +241,22 @@ def test_full_size_properties():
             assert counts[2] > 0
 
 
+def test_both_mappings_agree_and_auto_picks_by_batch_size():
+    """Thread-per-env and thread-per-agent run the same physics: 200 free-running steps stay within float
+    rounding of each other (contact forces are summed in a different order), masks identical."""
+    T, E = 60, 2048
+    g = torch.Generator(device="cuda").manual_seed(8)
+    acts = torch.randint(0, 8, (T, 6, E), generator=g, device="cuda", dtype=torch.int32)
+    ea, eb = make(E, 3, 3, torch.float64, max_steps=20, seed=1, mapping="env"), make(E, 3, 3, torch.float64, max_steps=20, seed=1, mapping="agent")
+    assert torch.equal(ea.reset(), eb.reset())
+    oa, ra, da, sa = ea.step_many(acts)
+    ob, rb, db, sb = eb.step_many(acts)
+    assert torch.equal(da, db) and torch.equal(sa, sb) and torch.equal(oa[..., 0], ob[..., 0])
+    assert (oa - ob).abs().max() < 1e-9 and (ra - rb).abs().max() < 1e-9
+    assert make(4096, 3, 3, torch.float32).kernel_info()["mapping"] == "agent"
+    assert make(1 << 17, 3, 3, torch.float32).kernel_info()["mapping"] == "env"
+
+
 def test_errors_are_loud():
     import fortattack_b200 as fab
     with pytest.raises(fab.FaError):
@@ -246,4 +267,4 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         env.step(torch.zeros(6, 9, dtype=torch.int32, device="cuda"))
     info = env.kernel_info()
-    assert info["regs"] > 0 and info["block"] in (32, 64, 128) and env.launch_count() >= 1
+    assert info["regs"] > 0 and info["block"] in (32, 64, 128, 192) and env.launch_count() >= 1
