@@ -297,13 +297,17 @@ int fa_reset(FaHandle *h, const uint8_t *d_env_mask, void *d_obs, void *stream) 
     NEED_HANDLE(h);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const FaConfig &c = h->cfg;
+    // fa_reset_kernel is always one thread per env
+    int rblock = 128;
+    while (rblock > 32 && (c.n_envs + rblock - 1) / rblock < 2 * h->sm_count) rblock >>= 1;
+    const int rgrid = (c.n_envs + rblock - 1) / rblock;
     cudaError_t e;
     if (c.scalar == FA_F64)
         e = fa::launch_reset<double>(c.n_guards, c.n_attackers, view<double>(h), d_env_mask, static_cast<double *>(d_obs),
-                                     c.n_envs, c.seed, c.env_id0, h->grid, h->block, s);
+                                     c.n_envs, c.seed, c.env_id0, rgrid, rblock, s);
     else
         e = fa::launch_reset<float>(c.n_guards, c.n_attackers, view<float>(h), d_env_mask, static_cast<float *>(d_obs),
-                                    c.n_envs, c.seed, c.env_id0, h->grid, h->block, s);
+                                    c.n_envs, c.seed, c.env_id0, rgrid, rblock, s);
     CUDA_TRY(e);
     h->launches += 1;
     return FA_OK;
