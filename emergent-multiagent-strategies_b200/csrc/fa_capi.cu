@@ -71,13 +71,16 @@ template <typename R> static cudaError_t step_attr(int ng, int na, bool many, bo
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char *fmt, ...) {
+// shared with the other translation units of the library (mp_policy.cu, rl_kernels.cu): records the calling
+// thread's message for fa_last_error() and returns `code`
+int fa_internal_fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
     return code;
 }
+#define fail fa_internal_fail
 #define CUDA_TRY(expr)                                                                                     \
     do {                                                                                                   \
         cudaError_t e_ = (expr);                                                                           \

@@ -1,0 +1,619 @@
+// mp_policy.cu -- the reference's team policy forward (MPNN._fwd + act, mpnn.py:117-205) as ONE
+// persistent sm_100a kernel: dense layers on tcgen05 tensor cores (fp16 operands, fp32 accumulators in
+// tensor memory), everything else (input encoders, both attentions, heads, sampling) in fp32 on the
+// CUDA cores of the same CTA.  C ABI: include/fortattack_policy.h.
+//
+// Tile = 128 rows = EPT environments x up to 5 agents, row r = a * EPT + e (EPT = 128 / max(n_own, n_opp)),
+// so the rows an agent attends to (same e, other a) are in the same tile.  Thread r of the four
+// "row" warps owns row r for the whole network: it is tensor-memory lane r (tcgen05.ld 32x32b gives a
+// thread its own accumulator row), it writes row r of the next layer's fp16 A operand into shared
+// memory, and it reads other rows only for the two attentions.
+//
+// Warp roles (192 threads, two CTAs resident per SM so that one CTA's tensor-core phases overlap the
+// other's CUDA-core phases):
+//   warps 0-3  row threads (epilogues, encoders, attention, heads)
+//   warp 4     weight producer: streams the packed weight chunks global -> shared with cp.async.bulk
+//              into a ring of NS stages (full/empty mbarriers)
+//   warp 5     MMA issuer: one thread issues every tcgen05.mma of the static schedule c_tab[]
+// Synchronisation: a_ready (128 arrivals: "operand written / accumulator columns drained") row -> MMA,
+// acc_ready (tcgen05.commit) MMA -> row, named barrier 1 among the row threads.
+//
+// Shared memory: bufH [128 x 128 fp16] current h (A operand), bufX [128 x 128 fp16] K -> V -> message
+// (exchange between rows, then A operand), NS x 16 KB weight ring, 10 KB fp32 constants.
+// Tensor memory: 256 columns.
+//
+// blob layout (fp16 part, byte offsets; every chunk is an N=64 slice in canonical K-major order):
+//        0 oppAttn.W_key^T   [64 x 64]      8192 oppAttn.W_query^T      16384 oppAttn.W_val^T
+//    24576 oppAttn.W_out^T
+//    32768 messages.W_query^T lo/hi [64 x 128] x2     65536 messages.W_key^T lo/hi     98304 messages.W_val^T lo/hi
+//   131072 U1 lo   147456 W' lo   163840 U1 hi   180224 W' hi      (update.0.weight = [U1 | U2],
+//          W' = U2 . messages.W_out^T : the attention's output projection folded into the update layer)
+//   196608 value_head.0.weight lo/hi     229376 policy_head.0.weight lo/hi          (total 262144)
+// fp32 part (float index): 0 encoder [64][8]={w0..w5,bias,0}  512 oppEncoder  1024 update.0.bias
+//   1152 value_head.0.bias  1280 value_head.2.weight  1408 policy_head.0.bias  1536 dist.linear.weight^T [128][8]
+//   2560 dist.linear.bias[8]  2568 value_head.2.bias
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../include/fortattack_policy.h"
+#include "mp_umma.cuh"
+
+int fa_internal_fail(int code, const char *fmt, ...);
+
+namespace mp {
+
+constexpr int STAGE_BYTES = 16384;             // one weight chunk (N = 64 slice, K <= 128)
+constexpr uint32_t A_LBO = 128, A_SBO = 2048; // activation operands: 128 rows x K = 128
+constexpr int OFF_H = 0, OFF_X = 32768, OFF_CONST = 65536, OFF_RING = OFF_CONST + 10368;   // ring last: NS stages
+constexpr int smem_bytes(int ns) { return OFF_RING + ns * STAGE_BYTES; }
+constexpr int N_CHUNKS = 38;
+constexpr int ROW_THREADS = 128, THREADS = 192;
+constexpr int TMEM_COLS = 256;
+
+// fp32 constant offsets
+constexpr int C_ENC = 0, C_OENC = 512, C_UB = 1024, C_VB = 1152, C_VW = 1280, C_PB = 1408, C_DW = 1536, C_DB = 2560,
+              C_VB2 = 2568;
+
+struct Chunk {
+    uint32_t off, bytes;   // in the blob
+    uint32_t a_off;        // shared-memory byte offset of the A operand
+    uint32_t b_sbo;        // SBO of the weight chunk (K * 16)
+    uint16_t ksteps, tmem_col;
+    uint8_t acc, wait_a, commit_acc, pad;
+};
+#define CK64(off, abuf, tcol, wa, cm) {off, 8192u, abuf, 1024u, 4, tcol, 0, wa, cm, 0}
+#define CK128(off, abuf, tcol, acc, wa, cm) {off, 16384u, abuf, 2048u, 8, tcol, acc, wa, cm, 0}
+#define ROUND_CHUNKS                                                                                              \
+    CK128(32768u, OFF_H, 0, 0, 1, 0), CK128(49152u, OFF_H, 64, 0, 0, 0), CK128(65536u, OFF_H, 128, 0, 0, 0),       \
+        CK128(81920u, OFF_H, 192, 0, 0, 1), /* Q | K */                                                             \
+        CK128(98304u, OFF_H, 128, 0, 1, 0), CK128(114688u, OFF_H, 192, 0, 0, 1), /* V */                            \
+        CK128(131072u, OFF_H, 0, 0, 1, 0), CK128(147456u, OFF_X, 0, 1, 0, 0), CK128(163840u, OFF_H, 64, 0, 0, 0),  \
+        CK128(180224u, OFF_X, 64, 1, 0, 1) /* update: h.U1 + m.W' */
+__constant__ Chunk c_tab[N_CHUNKS] = {
+    CK64(0u, OFF_H, 0, 1, 0), CK64(8192u, OFF_X, 64, 0, 0), CK64(16384u, OFF_X, 128, 0, 1),   // K_own | Q_opp | V_opp
+    CK64(24576u, OFF_X, 0, 1, 1),                                                             // oppAttn out projection
+    ROUND_CHUNKS, ROUND_CHUNKS, ROUND_CHUNKS,
+    CK128(196608u, OFF_H, 0, 0, 1, 0), CK128(212992u, OFF_H, 64, 0, 0, 0), CK128(229376u, OFF_H, 128, 0, 0, 0),
+    CK128(245760u, OFF_H, 192, 0, 0, 1)};                                                     // value | policy hidden
+
+struct Params {
+    const uint8_t *blob;
+    const float *obs_own, *obs_opp;     // [n][E][6]
+    const int64_t *action_in;
+    float *value, *logp, *entropy, *logits;
+    int64_t *action;
+    int32_t *action_i32;
+    uint32_t *status;
+    uint64_t seed, offset, env_id0;
+    int n_own, n_opp, E, ept, n_tiles, mode;
+    unsigned long long *trace;   // optional: clock64() of row thread 0 of CTA 0 at every phase boundary of its first tile
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = h1 ^ c[1] ^ k0, n2 = h0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+}
+
+// tensor-memory columns [col, col+ncols) of this thread's row -> fp16 row segment k0.. of a canonical operand;
+// ncols is a multiple of 64: two 32-column loads are in flight per tcgen05.wait
+template <bool BIAS_RELU>
+__device__ __forceinline__ void drain(uint32_t taddr, int ncols, uint8_t *buf, int r, int k0, const float *bias) {
+    for (int c = 0; c < ncols; c += 64) {
+        uint32_t v[2][32];
+        tmem_ld32(taddr + (uint32_t)c, v[0]);
+        tmem_ld32(taddr + (uint32_t)c + 32u, v[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {          // 8 columns -> one 16-byte chunk
+                uint32_t h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float x = __uint_as_float(v[half][g * 8 + 2 * j]), y = __uint_as_float(v[half][g * 8 + 2 * j + 1]);
+                    if (BIAS_RELU) {
+                        const float2 b = *reinterpret_cast<const float2 *>(bias + c + half * 32 + g * 8 + 2 * j);
+                        x = fmaxf(x + b.x, 0.0f);
+                        y = fmaxf(y + b.y, 0.0f);
+                    }
+                    h[j] = pack_h2(x, y);
+                }
+                *reinterpret_cast<uint4 *>(buf + canon_off(r, k0 + c + half * 32 + g * 8, A_LBO, A_SBO)) =
+                    make_uint4(h[0], h[1], h[2], h[3]);
+            }
+        }
+    }
+}
+
+// ReLU(W x + b) for the 6-float observation, 64 outputs -> fp16 row segment [0, 64) of buf (mpnn.py:127-128)
+__device__ __forceinline__ void encode(const float *W8, const float (&o)[6], uint8_t *buf, int r) {
+#pragma unroll 2
+    for (int j0 = 0; j0 < 64; j0 += 8) {
+        uint32_t h[4];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj += 2) {
+            float y[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(W8 + (j0 + jj + q) * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(W8 + (j0 + jj + q) * 8 + 4);
+                float acc = w1.z;   // bias
+                acc = fmaf(w0.x, o[0], acc); acc = fmaf(w0.y, o[1], acc); acc = fmaf(w0.z, o[2], acc);
+                acc = fmaf(w0.w, o[3], acc); acc = fmaf(w1.x, o[4], acc); acc = fmaf(w1.y, o[5], acc);
+                y[q] = fmaxf(acc, 0.0f);
+            }
+            h[jj >> 1] = pack_h2(y[0], y[1]);
+        }
+        *reinterpret_cast<uint4 *>(buf + canon_off(r, j0, A_LBO, A_SBO)) = make_uint4(h[0], h[1], h[2], h[3]);
+    }
+}
+
+__device__ __forceinline__ void load_obs(const float *obs, int n, int a, int E, int eg, float (&o)[6]) {
+    if (a < n && eg < E) {
+        const float2 *p = reinterpret_cast<const float2 *>(obs + ((size_t)a * E + eg) * MP_OBS_DIM);
+        const float2 v0 = p[0], v1 = p[1], v2 = p[2];
+        o[0] = v0.x; o[1] = v0.y; o[2] = v1.x; o[3] = v1.y; o[4] = v2.x; o[5] = v2.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) o[i] = 0.0f;
+    }
+}
+
+// dot products of 32 fp32 values (this row's accumulator columns) with the fp16 segments (four 16-byte
+// chunks starting at byte offset koff) of up to `cnt` other rows
+__device__ __forceinline__ void dot32(const uint32_t (&v)[32], const uint8_t *buf, const uint32_t (&rowoff)[MP_MAX_TEAM], int cnt,
+                                      uint32_t koff, float (&s)[MP_MAX_TEAM]) {
+#pragma unroll
+    for (int b = 0; b < MP_MAX_TEAM; ++b) {
+        if (b < cnt) {
+            float acc0 = s[b], acc1 = 0.0f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint4 u = *reinterpret_cast<const uint4 *>(buf + rowoff[b] + koff + (uint32_t)g * A_LBO);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_h2(w[j]);
+                    acc0 = fmaf(__uint_as_float(v[g * 8 + 2 * j]), f.x, acc0);
+                    acc1 = fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), f.y, acc1);
+                }
+            }
+            s[b] = acc0 + acc1;
+        }
+    }
+}
+
+// softmax over the first cnt entries (cnt = 0: a lone agent receives a zero message, mpnn.py:262-270)
+__device__ __forceinline__ void softmax_small(float (&s)[MP_MAX_TEAM], int cnt, float scale) {
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int b = 0; b < MP_MAX_TEAM; ++b) {
+        s[b] = b < cnt ? s[b] * scale : -CUDART_INF_F;
+        mx = fmaxf(mx, s[b]);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int b = 0; b < MP_MAX_TEAM; ++b) {
+        s[b] = b < cnt ? __expf(s[b] - mx) : 0.0f;
+        sum += s[b];
+    }
+    const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+#pragma unroll
+    for (int b = 0; b < MP_MAX_TEAM; ++b) s[b] *= inv;
+}
+
+// 8 columns (one 16-byte chunk at byte offset koff) of sum_b p[b] * row_b, packed to fp16
+__device__ __forceinline__ uint4 mix8(const uint8_t *buf, const uint32_t (&rowoff)[MP_MAX_TEAM], int n, uint32_t koff,
+                                      const float (&p)[MP_MAX_TEAM]) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int b = 0; b < MP_MAX_TEAM; ++b) {
+        if (b < n) {
+            const uint4 u = *reinterpret_cast<const uint4 *>(buf + rowoff[b] + koff);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_h2(w[j]);
+                acc[2 * j] = fmaf(p[b], f.x, acc[2 * j]);
+                acc[2 * j + 1] = fmaf(p[b], f.y, acc[2 * j + 1]);
+            }
+        }
+    }
+    return make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
+}
+
+// NS = weight ring stages.  NS = 2 leaves room for two resident CTAs per SM, NS = 6/7 is one CTA per SM with a
+// deep prefetch queue (the weight stream is L2-latency-bound with a shallow ring).
+template <int NS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_a_ready, bar_acc;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *bufH = smem + OFF_H, *bufX = smem + OFF_X;
+    float *C = reinterpret_cast<float *>(smem + OFF_CONST);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_a_ready, ROW_THREADS);
+        mbar_init(&bar_acc, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc<TMEM_COLS>(&tmem_base_s);
+    {   // fp32 constants: plain loads, once per CTA
+        const float4 *src = reinterpret_cast<const float4 *>(p.blob + MP_BLOB_F16_BYTES);
+        float4 *dst = reinterpret_cast<float4 *>(C);
+        for (int i = tid; i < MP_BLOB_CONST_FLOATS / 4; i += THREADS) dst[i] = src[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 4) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < N_CHUNKS; ++c, ++g) {
+                    const uint32_t s = g % NS, ph = (g / NS) & 1u;
+                    mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 3);
+                    mbar_expect_tx(&bar_full[s], c_tab[c].bytes);
+                    bulk_g2s(smem + OFF_RING + s * STAGE_BYTES, p.blob + c_tab[c].off, c_tab[c].bytes, &bar_full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16(128, 64);
+            const uint32_t sbase = smem_u32(smem);
+            uint32_t g = 0, pa = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < N_CHUNKS; ++c, ++g) {
+                    const Chunk ch = c_tab[c];
+                    const uint32_t s = g % NS, ph = (g / NS) & 1u;
+                    if (ch.wait_a) { mbar_wait(&bar_a_ready, pa, p.status, 4); pa ^= 1u; }
+                    mbar_wait(&bar_full[s], ph, p.status, 5);
+                    tc_fence_after();
+                    const uint32_t a0 = sbase + ch.a_off, b0 = sbase + OFF_RING + s * STAGE_BYTES;
+                    for (uint32_t k = 0; k < ch.ksteps; ++k)
+                        umma_f16(tmem + ch.tmem_col, smem_desc(a0 + k * 2u * A_LBO, A_LBO, A_SBO),
+                                 smem_desc(b0 + k * 2u * A_LBO, A_LBO, ch.b_sbo), idesc, k > 0 || ch.acc);
+                    umma_commit(&bar_empty[s]);
+                    if (ch.commit_acc) umma_commit(&bar_acc);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= row threads =================
+        const int r = tid;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const int ept = p.ept, n_own = p.n_own, n_opp = p.n_opp;
+        const int a = r / ept, e = r - a * ept;
+        // byte offsets of the rows this row attends to: opponents (b, e) for every b; team mates (b, e), b != a
+        uint32_t rowoff[MP_MAX_TEAM], rowoth[MP_MAX_TEAM];
+#pragma unroll
+        for (int b = 0; b < MP_MAX_TEAM; ++b) {
+            const int rb = min(b * ept + e, 127);
+            rowoff[b] = (uint32_t)(rb >> 3) * A_SBO + (uint32_t)(rb & 7) * 16u;
+            const int ro = min((b + (b >= a ? 1 : 0)) * ept + e, 127);
+            rowoth[b] = (uint32_t)(ro >> 3) * A_SBO + (uint32_t)(ro & 7) * 16u;
+        }
+        const int n_oth = n_own - 1;
+        uint32_t pc = 0;
+        int ti = 0;
+#define ARRIVE_A() do { tc_fence_before(); fence_async_smem(); mbar_arrive(&bar_a_ready); } while (0)
+#define TS() do { if (p.trace != nullptr && r == 0 && blockIdx.x == 0 && tile == 0 && ti < 96) p.trace[ti++] = clock64(); } while (0)
+#define WAIT_ACC(code) do { mbar_wait(&bar_acc, pc, p.status, code); pc ^= 1u; tc_fence_after(); } while (0)
+
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int eg = tile * ept + e;
+            TS();
+            // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64) ----------
+            {
+                float o[6];
+                load_obs(p.obs_own, n_own, a, p.E, eg, o);
+                encode(C + C_ENC, o, bufH, r);
+                load_obs(p.obs_opp, n_opp, a, p.E, eg, o);
+                encode(C + C_OENC, o, bufX, r);
+            }
+            ARRIVE_A();
+            TS();
+            // ---- attention over the opponents (mpnn.py:409-437): K from the own team, Q and V from the opponents
+            WAIT_ACC(6);
+            TS();
+            drain<false>(trow + 64, 64, bufX, r, 64, nullptr);    // Q_opp -> bufX[:, 64:128)
+            TS();
+            drain<false>(trow + 128, 64, bufX, r, 0, nullptr);    // V_opp -> bufX[:, 0:64)   (hOpp is dead)
+            TS();
+            bar_rows();
+            TS();
+            uint32_t m[64];
+            {
+                float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                uint32_t v[2][32];
+                tmem_ld32(trow, v[0]);
+                tmem_ld32(trow + 32u, v[1]);
+                tmem_ld_wait();
+                dot32(v[0], bufX, rowoff, n_opp, 8u * A_LBO, s);     // Q_opp lives at k = 64..127
+                dot32(v[1], bufX, rowoff, n_opp, 12u * A_LBO, s);
+                softmax_small(s, n_opp, 0.125f);                     // 1/sqrt(64)
+                TS();
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {
+                    const uint4 u = mix8(bufX, rowoff, n_opp, (uint32_t)kc * A_LBO, s);
+                    m[kc * 4] = u.x; m[kc * 4 + 1] = u.y; m[kc * 4 + 2] = u.z; m[kc * 4 + 3] = u.w;
+                }
+            }
+            bar_rows();
+            TS();
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc)
+                *reinterpret_cast<uint4 *>(bufX + canon_off(r, kc * 8, A_LBO, A_SBO)) =
+                    make_uint4(m[kc * 4], m[kc * 4 + 1], m[kc * 4 + 2], m[kc * 4 + 3]);
+            ARRIVE_A();
+            TS();
+            WAIT_ACC(7);
+            TS();
+            drain<false>(trow + 0, 64, bufH, r, 64, nullptr);     // eOpp -> bufH[:, 64:128): h = [h0 | eOpp] (mpnn.py:142)
+            TS();
+            ARRIVE_A();
+            TS();
+
+            // ---- three message-passing rounds (mpnn.py:156-158) ------------------------------------------
+            for (int round = 0; round < 3; ++round) {
+                WAIT_ACC(8);                                       // Q in columns [0,128), K in [128,256)
+                TS();
+                drain<false>(trow + 128, 128, bufX, r, 0, nullptr);
+                TS();
+                ARRIVE_A();                                        // K columns are free: the V product may start
+                TS();
+                bar_rows();
+                TS();
+                float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[2][32];
+                    tmem_ld32(trow + (uint32_t)(c * 64), v[0]);
+                    tmem_ld32(trow + (uint32_t)(c * 64 + 32), v[1]);
+                    tmem_ld_wait();
+                    dot32(v[0], bufX, rowoth, n_oth, (uint32_t)(c * 8) * A_LBO, s);
+                    dot32(v[1], bufX, rowoth, n_oth, (uint32_t)(c * 8 + 4) * A_LBO, s);
+                }
+                softmax_small(s, n_oth, 0.08838834764831845f);     // 1/sqrt(128); no self message (mpnn.py:297-298)
+                TS();
+                bar_rows();                                        // every row has read K
+                TS();
+                WAIT_ACC(9);
+                TS();
+                drain<false>(trow + 128, 128, bufX, r, 0, nullptr);   // V
+                TS();
+                bar_rows();
+                TS();
+#pragma unroll
+                for (int kc = 0; kc < 16; ++kc) {
+                    const uint4 u = mix8(bufX, rowoth, n_oth, (uint32_t)kc * A_LBO, s);
+                    m[kc * 4] = u.x; m[kc * 4 + 1] = u.y; m[kc * 4 + 2] = u.z; m[kc * 4 + 3] = u.w;
+                }
+                bar_rows();                                        // every row has read V
+                TS();
+#pragma unroll
+                for (int kc = 0; kc < 16; ++kc)
+                    *reinterpret_cast<uint4 *>(bufX + canon_off(r, kc * 8, A_LBO, A_SBO)) =
+                        make_uint4(m[kc * 4], m[kc * 4 + 1], m[kc * 4 + 2], m[kc * 4 + 3]);
+                ARRIVE_A();
+                TS();
+                WAIT_ACC(10);
+                TS();
+                drain<true>(trow + 0, 128, bufH, r, 0, C + C_UB);  // h = ReLU(update([h, msg]))
+                TS();
+                ARRIVE_A();
+                TS();
+            }
+
+            // ---- heads (mpnn.py:174-205): value_head, policy_head, dist.linear, Categorical --------------
+            WAIT_ACC(11);
+            TS();
+            float value = C[C_VB2];
+            float lg[MP_ACTIONS];
+#pragma unroll
+            for (int k = 0; k < MP_ACTIONS; ++k) lg[k] = C[C_DB + k];
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32], w[32];
+                tmem_ld32(trow + (uint32_t)(c * 32), v);
+                tmem_ld32(trow + (uint32_t)(128 + c * 32), w);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int k = c * 32 + j;
+                    value = fmaf(fmaxf(__uint_as_float(v[j]) + C[C_VB + k], 0.0f), C[C_VW + k], value);
+                    const float x = fmaxf(__uint_as_float(w[j]) + C[C_PB + k], 0.0f);
+                    const float4 d0 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8);
+                    const float4 d1 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8 + 4);
+                    lg[0] = fmaf(x, d0.x, lg[0]); lg[1] = fmaf(x, d0.y, lg[1]); lg[2] = fmaf(x, d0.z, lg[2]);
+                    lg[3] = fmaf(x, d0.w, lg[3]); lg[4] = fmaf(x, d1.x, lg[4]); lg[5] = fmaf(x, d1.y, lg[5]);
+                    lg[6] = fmaf(x, d1.z, lg[6]); lg[7] = fmaf(x, d1.w, lg[7]);
+                }
+            }
+            TS();
+            if (a < n_own && eg < p.E) {
+                float mx = lg[0];
+#pragma unroll
+                for (int k = 1; k < MP_ACTIONS; ++k) mx = fmaxf(mx, lg[k]);
+                float pr[MP_ACTIONS], sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < MP_ACTIONS; ++k) { pr[k] = expf(lg[k] - mx); sum += pr[k]; }
+                const float lse = mx + logf(sum), inv = 1.0f / sum;
+                const size_t row = (size_t)a * p.E + eg;
+                int act = 0;
+                if (p.mode == MP_MODE_SAMPLE) {
+                    const uint64_t env = p.env_id0 + (uint64_t)eg;
+                    uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)p.offset,
+                                       (uint32_t)(p.offset >> 32) ^ ((uint32_t)a << 24)};
+                    philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), ctr);
+                    const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                    // inverse CDF over softmax(logits): the distribution of dist.sample() (distributions.py:11-13)
+                    float cum = 0.0f;
+                    bool found = false;
+                    act = MP_ACTIONS - 1;
+#pragma unroll
+                    for (int k = 0; k < MP_ACTIONS - 1; ++k) {
+                        cum += pr[k] * inv;
+                        if (!found && u < cum) { act = k; found = true; }
+                    }
+                } else if (p.mode == MP_MODE_ARGMAX) {
+#pragma unroll
+                    for (int k = 1; k < MP_ACTIONS; ++k) if (lg[k] > lg[act]) act = k;
+                } else {
+                    act = (int)p.action_in[row];
+                    act = act < 0 ? 0 : (act > MP_ACTIONS - 1 ? MP_ACTIONS - 1 : act);
+                }
+                float lp = 0.0f, ent = 0.0f;
+#pragma unroll
+                for (int k = 0; k < MP_ACTIONS; ++k) {
+                    const float l = lg[k] - lse;
+                    if (k == act) lp = l;
+                    ent -= pr[k] * inv * l;
+                }
+                if (p.value) p.value[row] = value;
+                if (p.action) p.action[row] = act;
+                if (p.action_i32) p.action_i32[row] = act;
+                if (p.logp) p.logp[row] = lp;
+                if (p.entropy) p.entropy[row] = ent;
+                if (p.logits) {
+                    float4 *o = reinterpret_cast<float4 *>(p.logits + row * MP_ACTIONS);
+                    o[0] = make_float4(lg[0], lg[1], lg[2], lg[3]);
+                    o[1] = make_float4(lg[4], lg[5], lg[6], lg[7]);
+                }
+            }
+        }
+#undef TS
+#undef ARRIVE_A
+#undef WAIT_ACC
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+}  // namespace mp
+
+// ---- host side ------------------------------------------------------------------------------------
+namespace {
+struct Variant {
+    const void *fn;
+    int ns, minb;
+    void (*launch)(const mp::Params &, int grid, cudaStream_t);
+    bool attr_done;
+};
+template <int NS, int MINB> void launch_v(const mp::Params &p, int grid, cudaStream_t st) {
+    mp::mp_policy_kernel<NS, MINB><<<grid, mp::THREADS, mp::smem_bytes(NS), st>>>(p);
+}
+#define MP_VARIANT(NS, MINB) {(const void *)mp::mp_policy_kernel<NS, MINB>, NS, MINB, launch_v<NS, MINB>, false}
+Variant g_variants[] = {MP_VARIANT(2, 2), MP_VARIANT(6, 1), MP_VARIANT(9, 1)};
+constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
+int g_default_variant = 0;
+unsigned long long *g_trace = nullptr;
+
+// MP_VARIANT=<index> (read once) overrides the default; used by the benchmarks to compare configurations
+Variant *pick_variant() {
+    static int chosen = -1;
+    if (chosen < 0) {
+        chosen = g_default_variant;
+        const char *ev = getenv("MP_VARIANT");
+        if (ev && ev[0] >= '0' && ev[0] < '0' + N_VARIANTS && ev[1] == 0) chosen = ev[0] - '0';
+    }
+    return &g_variants[chosen];
+}
+int prepare(Variant *v) {
+    if (v->attr_done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, mp::smem_bytes(v->ns));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(v->fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fa_internal_fail(-2, "mp_policy_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    v->attr_done = true;
+    return 0;
+}
+}  // namespace
+
+extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const float *d_obs_opp, int n_own, int n_opp,
+                          int n_envs, int mode, uint64_t seed, uint64_t offset, uint64_t env_id0, const int64_t *d_action_in,
+                          float *d_value, int64_t *d_action, int32_t *d_action_i32, float *d_logp, float *d_entropy,
+                          float *d_logits, uint32_t *d_status, void *stream) {
+    if (!d_blob || !d_obs_own || !d_obs_opp || !d_status) return fa_internal_fail(-1, "mp_forward: NULL pointer");
+    if (n_own < 1 || n_own > MP_MAX_TEAM || n_opp < 1 || n_opp > MP_MAX_TEAM || n_envs < 1)
+        return fa_internal_fail(-1, "mp_forward: team sizes must be 1..%d and n_envs >= 1", MP_MAX_TEAM);
+    if (mode < 0 || mode > 2 || (mode == MP_MODE_EVAL && !d_action_in)) return fa_internal_fail(-1, "mp_forward: bad mode");
+    if (((uintptr_t)d_blob & 15) || ((uintptr_t)d_obs_own & 7) || ((uintptr_t)d_obs_opp & 7) || ((uintptr_t)d_logits & 15))
+        return fa_internal_fail(-4, "mp_forward: blob/logits must be 16-byte, observations 8-byte aligned");
+    Variant *v = pick_variant();
+    if (int rc = prepare(v)) return rc;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    mp::Params p;
+    p.blob = (const uint8_t *)d_blob; p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.action_in = d_action_in;
+    p.value = d_value; p.logp = d_logp; p.entropy = d_entropy; p.logits = d_logits; p.action = d_action;
+    p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0;
+    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace;
+    p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
+    p.n_tiles = (n_envs + p.ept - 1) / p.ept;
+    const int slots = v->minb * sms;
+    const int grid = p.n_tiles < slots ? p.n_tiles : slots;
+    v->launch(p, grid, (cudaStream_t)stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "mp_forward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int mp_kernel_info(int n_own, int n_opp, int32_t *regs, int32_t *block, int32_t *smem, int32_t *blocks_per_sm,
+                              int32_t *envs_per_tile) {
+    if (n_own < 1 || n_own > MP_MAX_TEAM || n_opp < 1 || n_opp > MP_MAX_TEAM) return fa_internal_fail(-1, "mp_kernel_info: team sizes");
+    Variant *v = pick_variant();
+    if (int rc = prepare(v)) return rc;
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, v->fn);
+    if (e != cudaSuccess) return fa_internal_fail(-2, "mp_kernel_info: %s", cudaGetErrorString(e));
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v->fn, mp::THREADS, mp::smem_bytes(v->ns));
+    if (regs) *regs = at.numRegs;
+    if (block) *block = mp::THREADS;
+    if (smem) *smem = mp::smem_bytes(v->ns) + (int)at.sharedSizeBytes;
+    if (blocks_per_sm) *blocks_per_sm = nb;
+    if (envs_per_tile) *envs_per_tile = 128 / (n_own > n_opp ? n_own : n_opp);
+    return 0;
+}
+
+// Debug aid: device buffer of 96 uint64 that receives clock64() of one row thread at every phase boundary of
+// the first tile of CTA 0 (NULL switches it off).  Not part of the product API.
+extern "C" int mp_set_trace(unsigned long long *d_trace) {
+    g_trace = d_trace;
+    return 0;
+}

@@ -39,13 +39,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as an error code, never as a hung GPU.  try_wait itself
-// sleeps in hardware for a system-dependent time, so the bound is generous (>= seconds).
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *err_flag, uint32_t code) {
-    for (uint32_t it = 0; it < (1u << 22); ++it)
+// Bounded wait: a protocol bug must surface as an error code, never as a hung GPU.  The first waiter
+// that sees 0.25 s pass records `code`; every other waiter then leaves at once.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static __device__ __noinline__ bool mbar_wait_slow(uint64_t *bar, uint32_t parity, uint32_t *err_flag, uint32_t code) {
+    // try_wait suspends the thread in hardware until the phase flips or a system time limit passes, so the
+    // loop body runs rarely; the timeout / abort checks (a global load and a timer read) only every 256 turns
+    const uint64_t t0 = globaltimer_ns();
+    for (uint32_t spin = 1;; ++spin) {
         if (mbar_try_wait(bar, parity)) return true;
-    if (err_flag != nullptr) atomicCAS(err_flag, 0u, code);
-    return false;
+        if ((spin & 255u) == 0u) {
+            if (err_flag != nullptr && *(volatile uint32_t *)err_flag != 0u) return false;
+            if (globaltimer_ns() - t0 > 250000000ull) {
+                if (err_flag != nullptr) atomicCAS(err_flag, 0u, code);
+                return false;
+            }
+        }
+    }
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *err_flag, uint32_t code) {
+#pragma unroll 1
+    for (int i = 0; i < 16; ++i)
+        if (mbar_try_wait(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, err_flag, code);
 }
 
 // ---- proxies / fences ----------------------------------------------------------------------------
@@ -108,6 +128,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
 }

@@ -1,0 +1,171 @@
+"""Host side of the fused MPNN rollout forward (csrc/mp_policy.cu, include/fortattack_policy.h).
+
+`pack_mpnn(module)` turns an MPNN's parameters (the reference's state_dict names, mpnn.py:25-84) into
+the one packed blob the kernel streams; `FusedPolicy` wraps an MPNN and offers the rollout half of its
+call surface -- `act`, `get_value` (mpnn.py:180-205) -- on device tensors in the step kernel's
+agent-major layout.  Training (`evaluate_actions` with autograd) stays on the module itself; call
+`refresh()` after the optimizer changed the weights.
+
+There is no fallback: without the CUDA library these calls raise.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+
+HIDDEN, OBS_DIM, ACTIONS = 128, 6, 8
+BLOB_F16_BYTES, BLOB_CONST_FLOATS = 262144, 2576
+MODE_SAMPLE, MODE_ARGMAX, MODE_EVAL = 0, 1, 2
+
+
+def _canonical(w):
+    """[N][K] -> UMMA canonical K-major core-matrix order [N/8][K/8][8][8] (csrc/mp_umma.cuh)."""
+    n, k = w.shape
+    return w.reshape(n // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().reshape(-1)
+
+
+def check_supported(m):
+    ok = (m.h_dim == HIDDEN and m.embed_dim == HIDDEN and m.input_size == OBS_DIM and m.K == 3 and m.n_heads == 1
+          and not m.entity_mp and m.policy_layers == 1 and m.dist.linear.out_features == ACTIONS
+          and 1 <= m.num_agents <= 5 and 1 <= m.num_opp_agents <= 5)
+    if not ok:
+        raise _capi.FaError("the fused policy kernel covers the reference's FortAttack configuration only: hidden 128, "
+                            "6-float observations, 8 actions, 1 head, policy_layers=1, teams of 1..5 (learner.py:57-69)")
+
+
+@torch.no_grad()
+def pack_mpnn(m, device=None):
+    """MPNN parameters -> uint8 blob of MP_BLOB_BYTES (layout: csrc/mp_policy.cu header)."""
+    check_supported(m)
+    device = device or next(m.parameters()).device
+    d = lambda t: t.detach().to(device=device, dtype=torch.float64)
+    f16 = []
+    oa, ms = m.oppAttn, m.messages
+    # B operands are [N out][K in]; the attention parameters are stored [in][out] (mpnn.py:229-232)
+    for w in (oa.W_key[0], oa.W_query[0], oa.W_val[0], oa.W_out[0]):
+        f16.append(_canonical(d(w).t().contiguous()))
+    for w in (ms.W_query[0], ms.W_key[0], ms.W_val[0]):
+        wt = d(w).t().contiguous()                     # [128 out][128 in]
+        f16 += [_canonical(wt[:64]), _canonical(wt[64:])]
+    U = d(m.update[0].weight)                          # [128 out][256 in] = [U1 | U2] over cat(h, msg)
+    U1, U2 = U[:, :HIDDEN].contiguous(), U[:, HIDDEN:]
+    Wp = (U2 @ d(ms.W_out[0]).t()).contiguous()        # msg = heads @ W_out  ->  heads @ (W_out U2^T)
+    f16 += [_canonical(U1[:64]), _canonical(Wp[:64]), _canonical(U1[64:]), _canonical(Wp[64:])]
+    for w in (m.value_head[0].weight, m.policy_head[0].weight):
+        w = d(w)
+        f16 += [_canonical(w[:64]), _canonical(w[64:])]
+    f16 = torch.cat(f16).to(torch.float16)
+    assert f16.numel() * 2 == BLOB_F16_BYTES, f16.numel()
+
+    c = torch.zeros(BLOB_CONST_FLOATS, dtype=torch.float64, device=device)
+
+    def enc(lin, off):
+        blk = torch.zeros(64, 8, dtype=torch.float64, device=device)
+        blk[:, :6] = d(lin.weight)
+        blk[:, 6] = d(lin.bias)
+        c[off:off + 512] = blk.reshape(-1)
+    enc(m.encoder[0], 0)
+    enc(m.oppEncoder[0], 512)
+    c[1024:1152] = d(m.update[0].bias)
+    c[1152:1280] = d(m.value_head[0].bias)
+    c[1280:1408] = d(m.value_head[2].weight).reshape(-1)
+    c[1408:1536] = d(m.policy_head[0].bias)
+    c[1536:2560] = d(m.dist.linear.weight).t().contiguous().reshape(-1)      # [128][8]
+    c[2560:2568] = d(m.dist.linear.bias)
+    c[2568] = d(m.value_head[2].bias)[0]
+    blob = torch.cat((f16.view(torch.uint8), c.to(torch.float32).view(torch.uint8)))
+    return blob.contiguous()
+
+
+def _bind(L):
+    if getattr(L, "_mp_bound", False):
+        return
+    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, u64] + [vp] * 9
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
+    L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp]
+    L._mp_bound = True
+
+
+class FusedPolicy(object):
+    """Rollout-time forward of one team's MPNN in a single kernel launch."""
+
+    def __init__(self, module, seed=0, env_id0=0):
+        check_supported(module)
+        self.module = module
+        self.device = next(module.parameters()).device
+        if self.device.type != "cuda":
+            raise _capi.FaError("FusedPolicy needs the module on a CUDA device; there is no CPU path")
+        self._lib = _capi.lib()
+        _bind(self._lib)
+        self.n, self.m = module.num_agents, module.num_opp_agents
+        self.seed, self.env_id0, self.calls = int(seed), int(env_id0), 0
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.launches = 0
+        self.refresh()
+
+    def refresh(self):
+        """Re-pack the weights (after an optimizer step / load_state_dict)."""
+        self.blob = pack_mpnn(self.module, self.device)
+
+    def _ptr(self, t):
+        return None if t is None else t.data_ptr()
+
+    def forward(self, own, opp, mode=MODE_SAMPLE, action_in=None, out=None, want_logits=False, want_entropy=False):
+        """own float32 [n, E, 6], opp float32 [m, E, 6] (contiguous, agent-major).
+        Returns dict(value [n,E], action int64 [n,E], action_i32 [n,E], logp [n,E], entropy?, logits?).
+        `out` may hold preallocated tensors under the same keys (e.g. views into the rollout storage)."""
+        n, m = self.n, self.m
+        E = own.shape[1]
+        if own.shape != (n, E, OBS_DIM) or opp.shape != (m, E, OBS_DIM):
+            raise ValueError("own/opp must be [%d,E,6] / [%d,E,6], got %s / %s" % (n, m, tuple(own.shape), tuple(opp.shape)))
+        if own.dtype != torch.float32 or opp.dtype != torch.float32 or not own.is_contiguous() or not opp.is_contiguous():
+            raise ValueError("observations must be contiguous float32")
+        out = dict(out or {})
+        dev = self.device
+        for key, dt, shape in (("value", torch.float32, (n, E)), ("action", torch.int64, (n, E)),
+                               ("action_i32", torch.int32, (n, E)), ("logp", torch.float32, (n, E))):
+            if key not in out:
+                out[key] = torch.empty(shape, dtype=dt, device=dev)
+        if want_entropy and "entropy" not in out:
+            out["entropy"] = torch.empty((n, E), dtype=torch.float32, device=dev)
+        if want_logits and "logits" not in out:
+            out["logits"] = torch.empty((n, E, ACTIONS), dtype=torch.float32, device=dev)
+        for key, t in out.items():
+            if not t.is_contiguous() or t.numel() != n * E * (ACTIONS if key == "logits" else 1):
+                raise ValueError("output %r must be contiguous with %d rows" % (key, n * E))
+        if mode == MODE_EVAL:
+            action_in = action_in.to(device=dev, dtype=torch.int64).contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(self._lib.mp_forward(self.blob.data_ptr(), own.data_ptr(), opp.data_ptr(), n, m, E, mode,
+                                         self.seed, self.calls, self.env_id0, self._ptr(action_in),
+                                         out["value"].data_ptr(), out["action"].data_ptr(), out["action_i32"].data_ptr(),
+                                         out["logp"].data_ptr(), self._ptr(out.get("entropy")), self._ptr(out.get("logits")),
+                                         self.status.data_ptr(), stream))
+        self.calls += 1
+        self.launches += 1
+        return out
+
+    def check_status(self):
+        """Synchronising: raises if any launch so far reported an internal pipeline timeout."""
+        code = int(self.status.item())
+        if code:
+            raise _capi.FaError("mp_policy_kernel pipeline timeout (wait site %d)" % code)
+
+    # -- MPNN's rollout call surface on flat agent-major rows [n*E, 6] (mpnn.py:180-205) ------------------
+    def act(self, inp, state, oppInp, mask=None, deterministic=False):
+        E = inp.shape[0] // self.n
+        o = self.forward(inp.view(self.n, E, OBS_DIM), oppInp.view(self.m, E, OBS_DIM),
+                         MODE_ARGMAX if deterministic else MODE_SAMPLE)
+        return o["value"].view(-1, 1), o["action"].view(-1, 1), o["logp"].view(-1, 1), state
+
+    def get_value(self, inp, state, oppInp, mask=None):
+        E = inp.shape[0] // self.n
+        return self.forward(inp.view(self.n, E, OBS_DIM), oppInp.view(self.m, E, OBS_DIM), MODE_ARGMAX)["value"].view(-1, 1)
+
+    def kernel_info(self):
+        v = [ctypes.c_int32() for _ in range(5)]
+        _capi.check(self._lib.mp_kernel_info(self.n, self.m, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("regs", "block", "smem", "blocks_per_sm", "envs_per_tile"), [x.value for x in v]))

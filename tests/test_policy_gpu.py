@@ -1,0 +1,108 @@
+"""GPU: the fused MPNN rollout forward (csrc/mp_policy.cu) against (a) a torch evaluation of the same
+blob with fp16 rounding at the kernel's rounding points (tight) and (b) the fp32 module (the
+reference's arithmetic, mpnn.py:117-205; loose: fp16 tensor-core operands), plus the sampling contract."""
+import ctypes
+from importlib import import_module
+
+import pytest
+import torch
+
+import policy_util as pu
+from test_policy_cpu import make
+
+pytestmark = pytest.mark.gpu
+PKG = "emergent-multiagent-strategies_b200"
+pk = import_module(PKG + ".policy_kernel")
+_capi = import_module(PKG + "._capi")
+
+
+def test_tcgen05_gemm_probe():
+    """One 128 x N x K tile through tcgen05.mma with the canonical no-swizzle K-major descriptors."""
+    L = _capi.lib()
+    pk._bind(L)
+    g = torch.Generator().manual_seed(0)
+    for K, N in ((64, 64), (128, 64), (128, 256), (256, 128), (64, 16)):
+        a = torch.randn(128, K, generator=g).half().cuda()
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).half().cuda()
+        out = torch.full((128, N), float("nan"), device="cuda")
+        err = torch.zeros(1, dtype=torch.int32, device="cuda")
+        rc = L.mp_probe_gemm(a.data_ptr(), pk._canonical(w).data_ptr(), out.data_ptr(), K, N, 128, K * 16, 0, err.data_ptr(), None)
+        torch.cuda.synchronize()
+        assert rc == 0 and int(err.item()) == 0
+        ref = a.double() @ w.double().t()
+        assert (out.double() - ref).abs().max() < 1e-4, (K, N)
+
+
+@pytest.mark.parametrize("n,m,E", [(3, 3, 4096), (3, 3, 42), (3, 3, 43), (3, 3, 5), (5, 5, 1000), (1, 1, 300), (2, 4, 777),
+                                   (4, 1, 129), (5, 3, 26), (3, 3, 16384)])
+def test_forward_matches_blob_arithmetic(n, m, E):
+    net = make(n, m, seed=n * 10 + m).cuda()
+    fp = pk.FusedPolicy(net, seed=3)
+    gen = torch.Generator().manual_seed(E)
+    own, opp = pu.random_obs(n, E, gen, "cuda"), pu.random_obs(m, E, gen, "cuda")
+    o = fp.forward(own, opp, pk.MODE_ARGMAX, want_logits=True, want_entropy=True)
+    fp.check_status()
+    lg, v = o["logits"].double().cpu(), o["value"].double().cpu()
+    assert torch.isfinite(lg).all() and torch.isfinite(v).all()
+    lgq, vq = pu.emulate(fp.blob, own, opp, quantize=True)
+    s = max(1.0, float(lgq.abs().max()))
+    # same roundings, different fp32 summation order; an fp16 rounding flip costs up to 1 ulp(fp16) of one activation
+    assert (lg - lgq).abs().max() < 4e-3 * s, float((lg - lgq).abs().max())
+    assert (v - vq).abs().max() < 4e-3 * max(1.0, float(vq.abs().max())), float((v - vq).abs().max())
+    lgr, vr = pu.module_forward(net, own, opp)
+    assert (lg - lgr.double().cpu()).abs().max() < 3e-2 * s
+    assert (v - vr.double().cpu()).abs().max() < 3e-2 * max(1.0, float(vr.abs().max()))
+    # log-prob / entropy / argmax are consistent with the kernel's own logits
+    lsm = torch.log_softmax(lg, dim=-1)
+    act = o["action"].cpu()
+    top = lg.max(dim=-1).values
+    assert torch.equal(lg.gather(-1, act.unsqueeze(-1)).squeeze(-1), top)
+    assert (o["logp"].double().cpu() - lsm.gather(-1, act.unsqueeze(-1)).squeeze(-1)).abs().max() < 1e-5
+    assert (o["entropy"].double().cpu() + (lsm.exp() * lsm).sum(-1)).abs().max() < 1e-5
+    assert torch.equal(o["action_i32"].cpu().long(), act)
+
+
+def test_sampling_distribution_and_determinism():
+    n = m = 3
+    E = 60000
+    net = make(n, m, seed=1).cuda()
+    fp = pk.FusedPolicy(net, seed=11)
+    gen = torch.Generator().manual_seed(0)
+    own1, opp1 = pu.random_obs(n, 1, gen, "cuda"), pu.random_obs(m, 1, gen, "cuda")
+    own, opp = own1.expand(n, E, 6).contiguous(), opp1.expand(m, E, 6).contiguous()   # every env identical
+    o = fp.forward(own, opp, pk.MODE_SAMPLE, want_logits=True)
+    fp.check_status()
+    probs = torch.softmax(o["logits"][:, 0].double(), dim=-1).cpu()                  # [n, 8]
+    for a in range(n):
+        freq = torch.bincount(o["action"][a].cpu(), minlength=8).double() / E
+        assert (freq - probs[a]).abs().max() < 5 * (0.25 / E) ** 0.5 + 1e-3, (freq, probs[a])
+    lsm = torch.log_softmax(o["logits"].double(), dim=-1)
+    assert (o["logp"].double() - lsm.gather(-1, o["action"].unsqueeze(-1)).squeeze(-1)).abs().max() < 1e-5
+    # same (seed, call counter) -> same draw; next call -> a different one
+    fp2 = pk.FusedPolicy(net, seed=11)
+    o2 = fp2.forward(own, opp, pk.MODE_SAMPLE)
+    assert torch.equal(o2["action"], o["action"])
+    o3 = fp2.forward(own, opp, pk.MODE_SAMPLE)
+    assert not torch.equal(o3["action"], o["action"])
+    # shard invariance: envs [E/2, E) drawn by a second shard with env_id0 = E/2
+    fp4 = pk.FusedPolicy(net, seed=11, env_id0=E // 2)
+    o4 = fp4.forward(own[:, E // 2:].contiguous(), opp[:, E // 2:].contiguous(), pk.MODE_SAMPLE)
+    assert torch.equal(o4["action"], o["action"][:, E // 2:])
+    # evaluate mode reproduces the log-probs of given actions
+    o5 = fp.forward(own, opp, pk.MODE_EVAL, action_in=o["action"], want_entropy=True)
+    assert (o5["logp"] - o["logp"]).abs().max() < 1e-6
+
+
+def test_act_surface_matches_module_statistics():
+    """FusedPolicy.act has MPNN.act's signature and shapes (mpnn.py:180-188)."""
+    net = make(3, 3, seed=2).cuda()
+    fp = pk.FusedPolicy(net)
+    gen = torch.Generator().manual_seed(5)
+    E = 512
+    own, opp = pu.random_obs(3, E, gen, "cuda"), pu.random_obs(3, E, gen, "cuda")
+    value, action, logp, state = fp.act(own.view(-1, 6), None, opp.view(-1, 6), None, deterministic=True)
+    v_ref, a_ref, lp_ref, _ = net.act(own.view(-1, 6), None, opp.view(-1, 6), None, deterministic=True)
+    assert value.shape == v_ref.shape and action.shape == a_ref.shape and logp.shape == lp_ref.shape and action.dtype == a_ref.dtype
+    assert (value - v_ref).abs().max() < 3e-2 * max(1.0, float(v_ref.abs().max()))
+    assert (action == a_ref).float().mean() > 0.97          # arg-max flips only where two logits nearly tie
+    assert (fp.get_value(own.view(-1, 6), None, opp.view(-1, 6), None) - value).abs().max() == 0
