@@ -3,32 +3,37 @@
 // tensor memory), everything else (input encoders, both attentions, heads, sampling) in fp32 on the
 // CUDA cores of the same CTA.  C ABI: include/fortattack_policy.h.
 //
+// Algebra.  Both attentions are single-head and linear around their softmax, so the projections fold
+// (done once on the host in float64, emergent-multiagent-strategies_b200/policy_kernel.py):
+//   scores   q_a . k_b = (h_a Wq)(h_b Wk)^T = (h_a G) . h_b            G  = Wq Wk^T
+//   message  (sum_b p_ab v_b) Wout U2^T = sum_b p_ab (h_b Wz)           Wz = Wv Wout U2^T
+//   update   ReLU([h, msg] U^T + b) = ReLU(h U1^T + sum_b p_ab z_b + b) z = h Wz,  U = [U1 | U2]
+// so one message round (mpnn.py:156-158) is ONE GEMM  [T | Z | Y] = h [G | Wz | U1^T]  (N = 384, K = 128)
+// followed by a per-row epilogue; the 96 KB of round weights stay resident in shared memory for the whole
+// kernel.  The opponent attention (mpnn.py:409-437) folds the same way into two 64 x 64 products.
+//
 // Tile = 128 rows = EPT environments x up to 5 agents, row r = a * EPT + e (EPT = 128 / max(n_own, n_opp)),
 // so the rows an agent attends to (same e, other a) are in the same tile.  Thread r of the four
 // "row" warps owns row r for the whole network: it is tensor-memory lane r (tcgen05.ld 32x32b gives a
 // thread its own accumulator row), it writes row r of the next layer's fp16 A operand into shared
 // memory, and it reads other rows only for the two attentions.
 //
-// Warp roles (192 threads, two CTAs resident per SM so that one CTA's tensor-core phases overlap the
-// other's CUDA-core phases):
-//   warps 0-3  row threads (epilogues, encoders, attention, heads)
-//   warp 4     weight producer: streams the packed weight chunks global -> shared with cp.async.bulk
-//              into a ring of NS stages (full/empty mbarriers)
-//   warp 5     MMA issuer: one thread issues every tcgen05.mma of the static schedule c_tab[]
-// Synchronisation: a_ready (128 arrivals: "operand written / accumulator columns drained") row -> MMA,
-// acc_ready (tcgen05.commit) MMA -> row, named barrier 1 among the row threads.
+// Warp roles (192 threads, one CTA per SM, persistent over tiles):
+//   warps 0-3  row threads (encoders, epilogues, attention, heads, sampling)
+//   warp 4     weight producer: loads the resident round weights once, then streams the per-tile
+//              weights (opponent attention, heads: 80 KB per tile) with cp.async.bulk into a ring
+//   warp 5     MMA issuer: one thread issues every tcgen05.mma
+// Synchronisation: a_ready (128 arrivals: "operand written / accumulator drained") row -> MMA,
+// acc (tcgen05.commit) MMA -> row, named barrier 1 among the row threads.
 //
-// Shared memory: bufH [128 x 128 fp16] current h (A operand), bufX [128 x 128 fp16] K -> V -> message
-// (exchange between rows, then A operand), NS x 16 KB weight ring, 10 KB fp32 constants.
-// Tensor memory: 256 columns.
+// Shared memory: bufH [128 x 128 fp16] current h (A operand, also read by other rows for the scores),
+// bufX [128 x 128 fp16] z rows (exchange between rows), 96 KB resident round weights, 10 KB fp32
+// constants, NS x 16 KB ring.  Tensor memory: T | Z | Y = 384 of 512 columns.
 //
-// blob layout (fp16 part, byte offsets; every chunk is an N=64 slice in canonical K-major order):
-//        0 oppAttn.W_key^T   [64 x 64]      8192 oppAttn.W_query^T      16384 oppAttn.W_val^T
-//    24576 oppAttn.W_out^T
-//    32768 messages.W_query^T lo/hi [64 x 128] x2     65536 messages.W_key^T lo/hi     98304 messages.W_val^T lo/hi
-//   131072 U1 lo   147456 W' lo   163840 U1 hi   180224 W' hi      (update.0.weight = [U1 | U2],
-//          W' = U2 . messages.W_out^T : the attention's output projection folded into the update layer)
-//   196608 value_head.0.weight lo/hi     229376 policy_head.0.weight lo/hi          (total 262144)
+// blob layout, fp16 part (byte offsets; B operands [N][K] in canonical K-major core-matrix order):
+//        0 oppAttn: (Wkey Wquery^T)^T [64 x 64]      8192 oppAttn: (Wval Wout)^T [64 x 64]
+//    16384 G^T [128 x 128]    49152 Wz^T [128 x 128]    81920 U1 [128 x 128]
+//   114688 value_head.0.weight lo/hi [64 x 128] x2     147456 policy_head.0.weight lo/hi      (total 180224)
 // fp32 part (float index): 0 encoder [64][8]={w0..w5,bias,0}  512 oppEncoder  1024 update.0.bias
 //   1152 value_head.0.bias  1280 value_head.2.weight  1408 policy_head.0.bias  1536 dist.linear.weight^T [128][8]
 //   2560 dist.linear.bias[8]  2568 value_head.2.bias
@@ -45,13 +50,17 @@ int fa_internal_fail(int code, const char *fmt, ...);
 
 namespace mp {
 
-constexpr int STAGE_BYTES = 16384;             // one weight chunk (N = 64 slice, K <= 128)
-constexpr uint32_t A_LBO = 128, A_SBO = 2048; // activation operands: 128 rows x K = 128
-constexpr int OFF_H = 0, OFF_X = 32768, OFF_CONST = 65536, OFF_RING = OFF_CONST + 10368;   // ring last: NS stages
-constexpr int smem_bytes(int ns) { return OFF_RING + ns * STAGE_BYTES; }
-constexpr int N_CHUNKS = 38;
+constexpr int STAGE_BYTES = 16384;             // one streamed weight chunk (N = 64 slice, K <= 128)
+constexpr int NS = 3;                          // ring stages
+constexpr uint32_t A_LBO = 128, A_SBO = 2048;  // [128 rows] x [K = 128] fp16 operands (activations, resident weights)
+constexpr int OFF_H = 0, OFF_X = 32768, OFF_WRES = 65536, RES_BYTES = 98304, OFF_CONST = OFF_WRES + RES_BYTES,
+              OFF_RING = OFF_CONST + 10368, SMEM_BYTES = OFF_RING + NS * STAGE_BYTES;
+constexpr uint32_t BLOB_RES = 16384;           // blob offset of the resident part
+constexpr int N_STREAM = 6;                    // streamed chunks per tile
 constexpr int ROW_THREADS = 128, THREADS = 192;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t COL_T = 0, COL_Z = 128, COL_Y = 256;
+static_assert(MP_BLOB_F16_BYTES == 180224 && MP_BLOB_CONST_FLOATS * 4 <= 10368, "blob layout");
 
 // fp32 constant offsets
 constexpr int C_ENC = 0, C_OENC = 512, C_UB = 1024, C_VB = 1152, C_VW = 1280, C_PB = 1408, C_DW = 1536, C_DB = 2560,
@@ -62,22 +71,15 @@ struct Chunk {
     uint32_t a_off;        // shared-memory byte offset of the A operand
     uint32_t b_sbo;        // SBO of the weight chunk (K * 16)
     uint16_t ksteps, tmem_col;
-    uint8_t acc, wait_a, commit_acc, pad;
+    uint8_t wait_a, commit_acc, pad0, pad1;
 };
-#define CK64(off, abuf, tcol, wa, cm) {off, 8192u, abuf, 1024u, 4, tcol, 0, wa, cm, 0}
-#define CK128(off, abuf, tcol, acc, wa, cm) {off, 16384u, abuf, 2048u, 8, tcol, acc, wa, cm, 0}
-#define ROUND_CHUNKS                                                                                              \
-    CK128(32768u, OFF_H, 0, 0, 1, 0), CK128(49152u, OFF_H, 64, 0, 0, 0), CK128(65536u, OFF_H, 128, 0, 0, 0),       \
-        CK128(81920u, OFF_H, 192, 0, 0, 1), /* Q | K */                                                             \
-        CK128(98304u, OFF_H, 128, 0, 1, 0), CK128(114688u, OFF_H, 192, 0, 0, 1), /* V */                            \
-        CK128(131072u, OFF_H, 0, 0, 1, 0), CK128(147456u, OFF_X, 0, 1, 0, 0), CK128(163840u, OFF_H, 64, 0, 0, 0),  \
-        CK128(180224u, OFF_X, 64, 1, 0, 1) /* update: h.U1 + m.W' */
-__constant__ Chunk c_tab[N_CHUNKS] = {
-    CK64(0u, OFF_H, 0, 1, 0), CK64(8192u, OFF_X, 64, 0, 0), CK64(16384u, OFF_X, 128, 0, 1),   // K_own | Q_opp | V_opp
-    CK64(24576u, OFF_X, 0, 1, 1),                                                             // oppAttn out projection
-    ROUND_CHUNKS, ROUND_CHUNKS, ROUND_CHUNKS,
-    CK128(196608u, OFF_H, 0, 0, 1, 0), CK128(212992u, OFF_H, 64, 0, 0, 0), CK128(229376u, OFF_H, 128, 0, 0, 0),
-    CK128(245760u, OFF_H, 192, 0, 0, 1)};                                                     // value | policy hidden
+__constant__ Chunk c_tab[N_STREAM] = {
+    {0u, 8192u, OFF_H, 1024u, 4, 0, 1, 0, 0, 0},          // T' = h0 (Wkey Wquery^T)
+    {8192u, 8192u, OFF_X, 1024u, 4, 64, 0, 1, 0, 0},      // z' = hOpp (Wval Wout)
+    {114688u, 16384u, OFF_H, 2048u, 8, 0, 1, 0, 0, 0},    // value hidden lo / hi
+    {131072u, 16384u, OFF_H, 2048u, 8, 64, 0, 0, 0, 0},
+    {147456u, 16384u, OFF_H, 2048u, 8, 128, 0, 0, 0, 0},  // policy hidden lo / hi
+    {163840u, 16384u, OFF_H, 2048u, 8, 192, 0, 1, 0, 0}};
 
 struct Params {
     const uint8_t *blob;
@@ -115,8 +117,7 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 
 // tensor-memory columns [col, col+ncols) of this thread's row -> fp16 row segment k0.. of a canonical operand;
 // ncols is a multiple of 64: two 32-column loads are in flight per tcgen05.wait
-template <bool BIAS_RELU>
-__device__ __forceinline__ void drain(uint32_t taddr, int ncols, uint8_t *buf, int r, int k0, const float *bias) {
+__device__ __forceinline__ void drain(uint32_t taddr, int ncols, uint8_t *buf, int r, int k0) {
     for (int c = 0; c < ncols; c += 64) {
         uint32_t v[2][32];
         tmem_ld32(taddr + (uint32_t)c, v[0]);
@@ -128,15 +129,8 @@ __device__ __forceinline__ void drain(uint32_t taddr, int ncols, uint8_t *buf, i
             for (int g = 0; g < 4; ++g) {          // 8 columns -> one 16-byte chunk
                 uint32_t h[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float x = __uint_as_float(v[half][g * 8 + 2 * j]), y = __uint_as_float(v[half][g * 8 + 2 * j + 1]);
-                    if (BIAS_RELU) {
-                        const float2 b = *reinterpret_cast<const float2 *>(bias + c + half * 32 + g * 8 + 2 * j);
-                        x = fmaxf(x + b.x, 0.0f);
-                        y = fmaxf(y + b.y, 0.0f);
-                    }
-                    h[j] = pack_h2(x, y);
-                }
+                for (int j = 0; j < 4; ++j)
+                    h[j] = pack_h2(__uint_as_float(v[half][g * 8 + 2 * j]), __uint_as_float(v[half][g * 8 + 2 * j + 1]));
                 *reinterpret_cast<uint4 *>(buf + canon_off(r, k0 + c + half * 32 + g * 8, A_LBO, A_SBO)) =
                     make_uint4(h[0], h[1], h[2], h[3]);
             }
@@ -178,27 +172,45 @@ __device__ __forceinline__ void load_obs(const float *obs, int n, int a, int E, 
     }
 }
 
-// dot products of 32 fp32 values (this row's accumulator columns) with the fp16 segments (four 16-byte
-// chunks starting at byte offset koff) of up to `cnt` other rows
-__device__ __forceinline__ void dot32(const uint32_t (&v)[32], const uint8_t *buf, const uint32_t (&rowoff)[MP_MAX_TEAM], int cnt,
+// s[b] += <32 fp32 accumulator columns of this row, fp16 segment (four 16-byte chunks from byte offset koff) of row b>
+template <int CNT>
+__device__ __forceinline__ void dot32(const uint32_t (&v)[32], const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM],
                                       uint32_t koff, float (&s)[MP_MAX_TEAM]) {
+    uint4 u[CNT > 0 ? CNT : 1][4];
 #pragma unroll
-    for (int b = 0; b < MP_MAX_TEAM; ++b) {
-        if (b < cnt) {
-            float acc0 = s[b], acc1 = 0.0f;
+    for (int b = 0; b < CNT; ++b)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint4 u = *reinterpret_cast<const uint4 *>(buf + rowoff[b] + koff + (uint32_t)g * A_LBO);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int g = 0; g < 4; ++g) u[b][g] = *reinterpret_cast<const uint4 *>(buf + rows[b] + koff + (uint32_t)g * A_LBO);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack_h2(w[j]);
-                    acc0 = fmaf(__uint_as_float(v[g * 8 + 2 * j]), f.x, acc0);
-                    acc1 = fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), f.y, acc1);
-                }
+    for (int b = 0; b < CNT; ++b) {
+        float acc0 = s[b], acc1 = 0.0f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t w[4] = {u[b][g].x, u[b][g].y, u[b][g].z, u[b][g].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_h2(w[j]);
+                acc0 = fmaf(__uint_as_float(v[g * 8 + 2 * j]), f.x, acc0);
+                acc1 = fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), f.y, acc1);
             }
-            s[b] = acc0 + acc1;
         }
+        s[b] = acc0 + acc1;
+    }
+}
+
+// scores of this row against CNT other rows: NB batches of 64 accumulator columns starting at taddr
+template <int CNT, int NB>
+__device__ __forceinline__ void scores(uint32_t taddr, const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM],
+                                       float (&s)[MP_MAX_TEAM]) {
+    if (CNT == 0) return;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        uint32_t v[2][32];
+        tmem_ld32(taddr + (uint32_t)(c * 64), v[0]);
+        tmem_ld32(taddr + (uint32_t)(c * 64 + 32), v[1]);
+        tmem_ld_wait();
+        dot32<CNT>(v[0], buf, rows, (uint32_t)(c * 8) * A_LBO, s);
+        dot32<CNT>(v[1], buf, rows, (uint32_t)(c * 8 + 4) * A_LBO, s);
     }
 }
 
@@ -221,34 +233,82 @@ __device__ __forceinline__ void softmax_small(float (&s)[MP_MAX_TEAM], int cnt, 
     for (int b = 0; b < MP_MAX_TEAM; ++b) s[b] *= inv;
 }
 
-// 8 columns (one 16-byte chunk at byte offset koff) of sum_b p[b] * row_b, packed to fp16
-__device__ __forceinline__ uint4 mix8(const uint8_t *buf, const uint32_t (&rowoff)[MP_MAX_TEAM], int n, uint32_t koff,
-                                      const float (&p)[MP_MAX_TEAM]) {
-    float acc[8];
+// acc[0..8) += sum_b p[b] * (8 fp16 values at byte offset koff of row b)
+template <int CNT>
+__device__ __forceinline__ void mix8(float (&acc)[8], const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM], uint32_t koff,
+                                     const float (&p)[MP_MAX_TEAM]) {
+    uint4 u[CNT > 0 ? CNT : 1];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    for (int b = 0; b < CNT; ++b) u[b] = *reinterpret_cast<const uint4 *>(buf + rows[b] + koff);
 #pragma unroll
-    for (int b = 0; b < MP_MAX_TEAM; ++b) {
-        if (b < n) {
-            const uint4 u = *reinterpret_cast<const uint4 *>(buf + rowoff[b] + koff);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int b = 0; b < CNT; ++b) {
+        const uint32_t w[4] = {u[b].x, u[b].y, u[b].z, u[b].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_h2(w[j]);
-                acc[2 * j] = fmaf(p[b], f.x, acc[2 * j]);
-                acc[2 * j + 1] = fmaf(p[b], f.y, acc[2 * j + 1]);
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_h2(w[j]);
+            acc[2 * j] = fmaf(p[b], f.x, acc[2 * j]);
+            acc[2 * j + 1] = fmaf(p[b], f.y, acc[2 * j + 1]);
+        }
+    }
+}
+
+// eOpp = sum_b p_b z'_b  (z' rows at bufX k = 64..127) -> this row of bufH, k = 64..127  (mpnn.py:142,432-437)
+template <int CNT>
+__device__ __forceinline__ void opp_message(const uint8_t *bufX, uint8_t *bufH, int r, const uint32_t (&rows)[MP_MAX_TEAM],
+                                            const float (&p)[MP_MAX_TEAM]) {
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        mix8<CNT>(acc, bufX, rows, (uint32_t)(8 + kc) * A_LBO, p);
+        *reinterpret_cast<uint4 *>(bufH + canon_off(r, 64 + kc * 8, A_LBO, A_SBO)) =
+            make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
+    }
+}
+
+// h_new = ReLU(Y + sum_b p_b z_b + bias) -> this row of bufH   (mpnn.py:157-158 with the folded projections)
+template <int CNT>
+__device__ __forceinline__ void update_row(uint32_t t_y, const uint8_t *bufX, uint8_t *bufH, int r,
+                                           const uint32_t (&rows)[MP_MAX_TEAM], const float (&p)[MP_MAX_TEAM], const float *bias) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        uint32_t y[2][32];
+        tmem_ld32(t_y + (uint32_t)(c * 64), y[0]);
+        tmem_ld32(t_y + (uint32_t)(c * 64 + 32), y[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int k = c * 64 + half * 32 + g * 8;
+                const float4 b0 = *reinterpret_cast<const float4 *>(bias + k), b1 = *reinterpret_cast<const float4 *>(bias + k + 4);
+                float acc[8] = {__uint_as_float(y[half][g * 8]) + b0.x,     __uint_as_float(y[half][g * 8 + 1]) + b0.y,
+                                __uint_as_float(y[half][g * 8 + 2]) + b0.z, __uint_as_float(y[half][g * 8 + 3]) + b0.w,
+                                __uint_as_float(y[half][g * 8 + 4]) + b1.x, __uint_as_float(y[half][g * 8 + 5]) + b1.y,
+                                __uint_as_float(y[half][g * 8 + 6]) + b1.z, __uint_as_float(y[half][g * 8 + 7]) + b1.w};
+                mix8<CNT>(acc, bufX, rows, (uint32_t)(k >> 3) * A_LBO, p);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.0f);
+                *reinterpret_cast<uint4 *>(bufH + canon_off(r, k, A_LBO, A_SBO)) =
+                    make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
             }
         }
     }
-    return make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
 }
 
-// NS = weight ring stages.  NS = 2 leaves room for two resident CTAs per SM, NS = 6/7 is one CTA per SM with a
-// deep prefetch queue (the weight stream is L2-latency-bound with a shallow ring).
-template <int NS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p) {
+// run CALL(CNT) with the team size as a compile-time constant (branch-free, fully unrolled inner loops)
+#define MP_DISPATCH(cnt, CALL)            \
+    switch (cnt) {                        \
+        case 0: { CALL(0); } break;       \
+        case 1: { CALL(1); } break;       \
+        case 2: { CALL(2); } break;       \
+        case 3: { CALL(3); } break;       \
+        case 4: { CALL(4); } break;       \
+        default: { CALL(5); } break;      \
+    }
+
+__global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_a_ready, bar_acc;
+    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_a_ready, bar_acc, bar_res;
     __shared__ uint32_t tmem_base_s;
     uint8_t *bufH = smem + OFF_H, *bufX = smem + OFF_X;
     float *C = reinterpret_cast<float *>(smem + OFF_CONST);
@@ -258,6 +318,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p
         for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_a_ready, ROW_THREADS);
         mbar_init(&bar_acc, 1);
+        mbar_init(&bar_res, 1);
         mbar_fence_init();
     }
     if (warp == 4) tmem_alloc<TMEM_COLS>(&tmem_base_s);
@@ -274,9 +335,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p
     if (warp == 4) {
         // ================= weight producer =================
         if (lane == 0) {
+            mbar_expect_tx(&bar_res, RES_BYTES);           // round weights: resident for the whole kernel
+            for (int i = 0; i < RES_BYTES / STAGE_BYTES; ++i)
+                bulk_g2s(smem + OFF_WRES + i * STAGE_BYTES, p.blob + BLOB_RES + i * STAGE_BYTES, STAGE_BYTES, &bar_res);
             uint32_t g = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < N_CHUNKS; ++c, ++g) {
+                for (int c = 0; c < N_STREAM; ++c, ++g) {
                     const uint32_t s = g % NS, ph = (g / NS) & 1u;
                     mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 3);
                     mbar_expect_tx(&bar_full[s], c_tab[c].bytes);
@@ -288,23 +352,40 @@ __global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p
     } else if (warp == 5) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = idesc_f16(128, 64);
+            const uint32_t idesc64 = idesc_f16(128, 64), idesc128 = idesc_f16(128, 128);
             const uint32_t sbase = smem_u32(smem);
             uint32_t g = 0, pa = 0;
+            auto stream_chunk = [&](int c) {
+                const Chunk ch = c_tab[c];
+                const uint32_t s = g % NS, ph = (g / NS) & 1u;
+                if (ch.wait_a) { mbar_wait(&bar_a_ready, pa, p.status, 4); pa ^= 1u; }
+                mbar_wait(&bar_full[s], ph, p.status, 5);
+                tc_fence_after();
+                const uint32_t a0 = sbase + ch.a_off, b0 = sbase + OFF_RING + s * STAGE_BYTES;
+                for (uint32_t k = 0; k < ch.ksteps; ++k)
+                    umma_f16(tmem + ch.tmem_col, smem_desc(a0 + k * 2u * A_LBO, A_LBO, A_SBO),
+                             smem_desc(b0 + k * 2u * A_LBO, A_LBO, ch.b_sbo), idesc64, k > 0);
+                umma_commit(&bar_empty[s]);
+                if (ch.commit_acc) umma_commit(&bar_acc);
+                ++g;
+            };
+            mbar_wait(&bar_res, 0, p.status, 2);
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < N_CHUNKS; ++c, ++g) {
-                    const Chunk ch = c_tab[c];
-                    const uint32_t s = g % NS, ph = (g / NS) & 1u;
-                    if (ch.wait_a) { mbar_wait(&bar_a_ready, pa, p.status, 4); pa ^= 1u; }
-                    mbar_wait(&bar_full[s], ph, p.status, 5);
+                stream_chunk(0);
+                stream_chunk(1);
+                for (int round = 0; round < 3; ++round) {      // [T | Z | Y] = h [G | Wz | U1^T]
+                    mbar_wait(&bar_a_ready, pa, p.status, 4);
+                    pa ^= 1u;
                     tc_fence_after();
-                    const uint32_t a0 = sbase + ch.a_off, b0 = sbase + OFF_RING + s * STAGE_BYTES;
-                    for (uint32_t k = 0; k < ch.ksteps; ++k)
-                        umma_f16(tmem + ch.tmem_col, smem_desc(a0 + k * 2u * A_LBO, A_LBO, A_SBO),
-                                 smem_desc(b0 + k * 2u * A_LBO, A_LBO, ch.b_sbo), idesc, k > 0 || ch.acc);
-                    umma_commit(&bar_empty[s]);
-                    if (ch.commit_acc) umma_commit(&bar_acc);
+#pragma unroll
+                    for (uint32_t j = 0; j < 3; ++j)
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; ++k)
+                            umma_f16(tmem + j * 128u, smem_desc(sbase + OFF_H + k * 2u * A_LBO, A_LBO, A_SBO),
+                                     smem_desc(sbase + OFF_WRES + j * 32768u + k * 2u * A_LBO, A_LBO, A_SBO), idesc128, k > 0);
+                    umma_commit(&bar_acc);
                 }
+                for (int c = 2; c < N_STREAM; ++c) stream_chunk(c);
             }
         }
         __syncwarp();
@@ -315,11 +396,11 @@ __global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p
         const int ept = p.ept, n_own = p.n_own, n_opp = p.n_opp;
         const int a = r / ept, e = r - a * ept;
         // byte offsets of the rows this row attends to: opponents (b, e) for every b; team mates (b, e), b != a
-        uint32_t rowoff[MP_MAX_TEAM], rowoth[MP_MAX_TEAM];
+        uint32_t rowopp[MP_MAX_TEAM], rowoth[MP_MAX_TEAM];
 #pragma unroll
         for (int b = 0; b < MP_MAX_TEAM; ++b) {
             const int rb = min(b * ept + e, 127);
-            rowoff[b] = (uint32_t)(rb >> 3) * A_SBO + (uint32_t)(rb & 7) * 16u;
+            rowopp[b] = (uint32_t)(rb >> 3) * A_SBO + (uint32_t)(rb & 7) * 16u;
             const int ro = min((b + (b >= a ? 1 : 0)) * ept + e, 127);
             rowoth[b] = (uint32_t)(ro >> 3) * A_SBO + (uint32_t)(ro & 7) * 16u;
         }
@@ -343,94 +424,43 @@ __global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p
             }
             ARRIVE_A();
             TS();
-            // ---- attention over the opponents (mpnn.py:409-437): K from the own team, Q and V from the opponents
+            // ---- attention over the opponents (mpnn.py:409-437), folded: T' = h0 G', z' = hOpp Wz' -------
             WAIT_ACC(6);
             TS();
-            drain<false>(trow + 64, 64, bufX, r, 64, nullptr);    // Q_opp -> bufX[:, 64:128)
-            TS();
-            drain<false>(trow + 128, 64, bufX, r, 0, nullptr);    // V_opp -> bufX[:, 0:64)   (hOpp is dead)
-            TS();
+            drain(trow + 64, 64, bufX, r, 64);                    // z' of opponent row r -> bufX[:, 64:128)
             bar_rows();
             TS();
-            uint32_t m[64];
             {
                 float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                uint32_t v[2][32];
-                tmem_ld32(trow, v[0]);
-                tmem_ld32(trow + 32u, v[1]);
-                tmem_ld_wait();
-                dot32(v[0], bufX, rowoff, n_opp, 8u * A_LBO, s);     // Q_opp lives at k = 64..127
-                dot32(v[1], bufX, rowoff, n_opp, 12u * A_LBO, s);
-                softmax_small(s, n_opp, 0.125f);                     // 1/sqrt(64)
+#define CALL(N) scores<N, 1>(trow + COL_T, bufX, rowopp, s)
+                MP_DISPATCH(n_opp, CALL)
+#undef CALL
+                softmax_small(s, n_opp, 0.125f);                  // 1/sqrt(64)
                 TS();
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
-                    const uint4 u = mix8(bufX, rowoff, n_opp, (uint32_t)kc * A_LBO, s);
-                    m[kc * 4] = u.x; m[kc * 4 + 1] = u.y; m[kc * 4 + 2] = u.z; m[kc * 4 + 3] = u.w;
-                }
+#define CALL(N) opp_message<N>(bufX, bufH, r, rowopp, s)
+                MP_DISPATCH(n_opp, CALL)                          // h = [h0 | eOpp]
+#undef CALL
             }
-            bar_rows();
-            TS();
-#pragma unroll
-            for (int kc = 0; kc < 8; ++kc)
-                *reinterpret_cast<uint4 *>(bufX + canon_off(r, kc * 8, A_LBO, A_SBO)) =
-                    make_uint4(m[kc * 4], m[kc * 4 + 1], m[kc * 4 + 2], m[kc * 4 + 3]);
-            ARRIVE_A();
-            TS();
-            WAIT_ACC(7);
-            TS();
-            drain<false>(trow + 0, 64, bufH, r, 64, nullptr);     // eOpp -> bufH[:, 64:128): h = [h0 | eOpp] (mpnn.py:142)
-            TS();
             ARRIVE_A();
             TS();
 
             // ---- three message-passing rounds (mpnn.py:156-158) ------------------------------------------
             for (int round = 0; round < 3; ++round) {
-                WAIT_ACC(8);                                       // Q in columns [0,128), K in [128,256)
+                WAIT_ACC(8);                                      // T | Z | Y ready
                 TS();
-                drain<false>(trow + 128, 128, bufX, r, 0, nullptr);
-                TS();
-                ARRIVE_A();                                        // K columns are free: the V product may start
-                TS();
-                bar_rows();
+                drain(trow + COL_Z, 128, bufX, r, 0);            // z of this row -> bufX
                 TS();
                 float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[2][32];
-                    tmem_ld32(trow + (uint32_t)(c * 64), v[0]);
-                    tmem_ld32(trow + (uint32_t)(c * 64 + 32), v[1]);
-                    tmem_ld_wait();
-                    dot32(v[0], bufX, rowoth, n_oth, (uint32_t)(c * 8) * A_LBO, s);
-                    dot32(v[1], bufX, rowoth, n_oth, (uint32_t)(c * 8 + 4) * A_LBO, s);
-                }
-                softmax_small(s, n_oth, 0.08838834764831845f);     // 1/sqrt(128); no self message (mpnn.py:297-298)
+#define CALL(N) scores<N, 2>(trow + COL_T, bufH, rowoth, s)
+                MP_DISPATCH(n_oth, CALL)                          // (h_a G) . h_b against the team mates' h rows
+#undef CALL
+                softmax_small(s, n_oth, 0.08838834764831845f);    // 1/sqrt(128); no self message (mpnn.py:297-298)
                 TS();
-                bar_rows();                                        // every row has read K
+                bar_rows();                                       // z rows visible; nobody reads bufH any more
                 TS();
-                WAIT_ACC(9);
-                TS();
-                drain<false>(trow + 128, 128, bufX, r, 0, nullptr);   // V
-                TS();
-                bar_rows();
-                TS();
-#pragma unroll
-                for (int kc = 0; kc < 16; ++kc) {
-                    const uint4 u = mix8(bufX, rowoth, n_oth, (uint32_t)kc * A_LBO, s);
-                    m[kc * 4] = u.x; m[kc * 4 + 1] = u.y; m[kc * 4 + 2] = u.z; m[kc * 4 + 3] = u.w;
-                }
-                bar_rows();                                        // every row has read V
-                TS();
-#pragma unroll
-                for (int kc = 0; kc < 16; ++kc)
-                    *reinterpret_cast<uint4 *>(bufX + canon_off(r, kc * 8, A_LBO, A_SBO)) =
-                        make_uint4(m[kc * 4], m[kc * 4 + 1], m[kc * 4 + 2], m[kc * 4 + 3]);
-                ARRIVE_A();
-                TS();
-                WAIT_ACC(10);
-                TS();
-                drain<true>(trow + 0, 128, bufH, r, 0, C + C_UB);  // h = ReLU(update([h, msg]))
-                TS();
+#define CALL(N) update_row<N>(trow + COL_Y, bufX, bufH, r, rowoth, s, C + C_UB)
+                MP_DISPATCH(n_oth, CALL)
+#undef CALL
                 ARRIVE_A();
                 TS();
             }
@@ -525,37 +555,14 @@ __global__ void __launch_bounds__(THREADS, MINB) mp_policy_kernel(const Params p
 
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
-struct Variant {
-    const void *fn;
-    int ns, minb;
-    void (*launch)(const mp::Params &, int grid, cudaStream_t);
-    bool attr_done;
-};
-template <int NS, int MINB> void launch_v(const mp::Params &p, int grid, cudaStream_t st) {
-    mp::mp_policy_kernel<NS, MINB><<<grid, mp::THREADS, mp::smem_bytes(NS), st>>>(p);
-}
-#define MP_VARIANT(NS, MINB) {(const void *)mp::mp_policy_kernel<NS, MINB>, NS, MINB, launch_v<NS, MINB>, false}
-Variant g_variants[] = {MP_VARIANT(2, 2), MP_VARIANT(6, 1), MP_VARIANT(9, 1)};
-constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
-int g_default_variant = 0;
+bool g_attr_done = false;
 unsigned long long *g_trace = nullptr;
 
-// MP_VARIANT=<index> (read once) overrides the default; used by the benchmarks to compare configurations
-Variant *pick_variant() {
-    static int chosen = -1;
-    if (chosen < 0) {
-        chosen = g_default_variant;
-        const char *ev = getenv("MP_VARIANT");
-        if (ev && ev[0] >= '0' && ev[0] < '0' + N_VARIANTS && ev[1] == 0) chosen = ev[0] - '0';
-    }
-    return &g_variants[chosen];
-}
-int prepare(Variant *v) {
-    if (v->attr_done) return 0;
-    cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, mp::smem_bytes(v->ns));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(v->fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+int prepare() {
+    if (g_attr_done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(mp::mp_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mp::SMEM_BYTES);
     if (e != cudaSuccess) return fa_internal_fail(-2, "mp_policy_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    v->attr_done = true;
+    g_attr_done = true;
     return 0;
 }
 }  // namespace
@@ -570,8 +577,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     if (mode < 0 || mode > 2 || (mode == MP_MODE_EVAL && !d_action_in)) return fa_internal_fail(-1, "mp_forward: bad mode");
     if (((uintptr_t)d_blob & 15) || ((uintptr_t)d_obs_own & 7) || ((uintptr_t)d_obs_opp & 7) || ((uintptr_t)d_logits & 15))
         return fa_internal_fail(-4, "mp_forward: blob/logits must be 16-byte, observations 8-byte aligned");
-    Variant *v = pick_variant();
-    if (int rc = prepare(v)) return rc;
+    if (int rc = prepare()) return rc;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -585,9 +591,8 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace;
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;
-    const int slots = v->minb * sms;
-    const int grid = p.n_tiles < slots ? p.n_tiles : slots;
-    v->launch(p, grid, (cudaStream_t)stream);
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    mp::mp_policy_kernel<<<grid, mp::THREADS, mp::SMEM_BYTES, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "mp_forward: launch: %s", cudaGetErrorString(e));
     return 0;
@@ -596,16 +601,15 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
 extern "C" int mp_kernel_info(int n_own, int n_opp, int32_t *regs, int32_t *block, int32_t *smem, int32_t *blocks_per_sm,
                               int32_t *envs_per_tile) {
     if (n_own < 1 || n_own > MP_MAX_TEAM || n_opp < 1 || n_opp > MP_MAX_TEAM) return fa_internal_fail(-1, "mp_kernel_info: team sizes");
-    Variant *v = pick_variant();
-    if (int rc = prepare(v)) return rc;
+    if (int rc = prepare()) return rc;
     cudaFuncAttributes at;
-    cudaError_t e = cudaFuncGetAttributes(&at, v->fn);
+    cudaError_t e = cudaFuncGetAttributes(&at, mp::mp_policy_kernel);
     if (e != cudaSuccess) return fa_internal_fail(-2, "mp_kernel_info: %s", cudaGetErrorString(e));
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v->fn, mp::THREADS, mp::smem_bytes(v->ns));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mp::mp_policy_kernel, mp::THREADS, mp::SMEM_BYTES);
     if (regs) *regs = at.numRegs;
     if (block) *block = mp::THREADS;
-    if (smem) *smem = mp::smem_bytes(v->ns) + (int)at.sharedSizeBytes;
+    if (smem) *smem = mp::SMEM_BYTES + (int)at.sharedSizeBytes;
     if (blocks_per_sm) *blocks_per_sm = nb;
     if (envs_per_tile) *envs_per_tile = 128 / (n_own > n_opp ? n_own : n_opp);
     return 0;

@@ -15,7 +15,7 @@ import torch
 from . import _capi
 
 HIDDEN, OBS_DIM, ACTIONS = 128, 6, 8
-BLOB_F16_BYTES, BLOB_CONST_FLOATS = 262144, 2576
+BLOB_F16_BYTES, BLOB_CONST_FLOATS = 180224, 2576
 MODE_SAMPLE, MODE_ARGMAX, MODE_EVAL = 0, 1, 2
 
 
@@ -40,18 +40,16 @@ def pack_mpnn(m, device=None):
     check_supported(m)
     device = device or next(m.parameters()).device
     d = lambda t: t.detach().to(device=device, dtype=torch.float64)
-    f16 = []
     oa, ms = m.oppAttn, m.messages
-    # B operands are [N out][K in]; the attention parameters are stored [in][out] (mpnn.py:229-232)
-    for w in (oa.W_key[0], oa.W_query[0], oa.W_val[0], oa.W_out[0]):
-        f16.append(_canonical(d(w).t().contiguous()))
-    for w in (ms.W_query[0], ms.W_key[0], ms.W_val[0]):
-        wt = d(w).t().contiguous()                     # [128 out][128 in]
-        f16 += [_canonical(wt[:64]), _canonical(wt[64:])]
+    # attention parameters are stored [in][out] (mpnn.py:229-232); B operands are [N out][K in] = W^T for y = x W.
+    # Folding (float64): scores (h0 Wkey)(hOpp Wquery)^T = (h0 [Wkey Wquery^T]) . hOpp ; eOpp = sum p (hOpp [Wval Wout])
+    f16 = [_canonical((d(oa.W_key[0]) @ d(oa.W_query[0]).t()).t().contiguous()),
+           _canonical((d(oa.W_val[0]) @ d(oa.W_out[0])).t().contiguous())]
     U = d(m.update[0].weight)                          # [128 out][256 in] = [U1 | U2] over cat(h, msg)
     U1, U2 = U[:, :HIDDEN].contiguous(), U[:, HIDDEN:]
-    Wp = (U2 @ d(ms.W_out[0]).t()).contiguous()        # msg = heads @ W_out  ->  heads @ (W_out U2^T)
-    f16 += [_canonical(U1[:64]), _canonical(Wp[:64]), _canonical(U1[64:]), _canonical(Wp[64:])]
+    G = d(ms.W_query[0]) @ d(ms.W_key[0]).t()          # (h_a Wq)(h_b Wk)^T = (h_a G) . h_b
+    Wz = d(ms.W_val[0]) @ d(ms.W_out[0]) @ U2.t()      # msg U2^T = sum_b p_b (h_b Wv Wout U2^T)
+    f16 += [_canonical(G.t().contiguous()), _canonical(Wz.t().contiguous()), _canonical(U1)]
     for w in (m.value_head[0].weight, m.policy_head[0].weight):
         w = d(w)
         f16 += [_canonical(w[:64]), _canonical(w[64:])]

@@ -12,9 +12,10 @@
  * The network is the reference's with hidden_dim = 128, input_size = 6, 8 actions, one attention head,
  * policy_layers = 1, three message rounds (mpnn.py:25-84; learner.py:57-69).  Dense layers run on the
  * 5th-generation tensor cores (tcgen05.mma, fp16 operands, fp32 accumulation in tensor memory); the
- * two input encoders, both attentions, the value / action heads and the sampling run in fp32 on the
- * CUDA cores of the same kernel.  Weights come as ONE packed blob that the host side builds from
- * MPNN.state_dict() (emergent-multiagent-strategies_b200/policy_kernel.py: pack_mpnn()).
+ * two input encoders, both attention soft-maxes, the value / action heads and the sampling run in fp32
+ * on the CUDA cores of the same kernel.  The attention projections are folded on the host (Wq Wk^T,
+ * Wv Wout U2^T: see csrc/mp_policy.cu), which changes rounding but not the function computed.
+ * Weights come as ONE packed blob that the host side builds from MPNN.state_dict() (emergent-multiagent-strategies_b200/policy_kernel.py: pack_mpnn()).
  *
  * Conventions as in fortattack.h: plain C types, caller-owned device memory, explicit stream, 0 or a
  * negative error code, message through fa_last_error().
@@ -37,7 +38,7 @@ extern "C" {
 /* packed weight blob: MP_BLOB_F16_BYTES of fp16 GEMM operands (UMMA canonical K-major core-matrix
  * order, in the order the kernel consumes them) followed by MP_BLOB_CONST_FLOATS fp32 values
  * (encoders, biases, value / action head).  Layout: csrc/mp_policy.cu "blob layout". */
-#define MP_BLOB_F16_BYTES 262144
+#define MP_BLOB_F16_BYTES 180224
 #define MP_BLOB_CONST_FLOATS 2576
 #define MP_BLOB_BYTES (MP_BLOB_F16_BYTES + 4 * MP_BLOB_CONST_FLOATS)
 

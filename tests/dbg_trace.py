@@ -4,25 +4,46 @@ from importlib import import_module
 import policy_util as pu
 from test_policy_cpu import make
 pk = import_module("emergent-multiagent-strategies_b200.policy_kernel")
+gen = torch.Generator().manual_seed(1)
+# correctness over shapes
+for n, m, E in ((3, 3, 42), (3, 3, 4096), (5, 5, 1000), (1, 1, 300), (2, 4, 777), (4, 1, 129), (5, 3, 26)):
+    net = make(n, m, seed=n * 10 + m).cuda()
+    fp = pk.FusedPolicy(net, seed=3)
+    own, opp = pu.random_obs(n, E, gen, "cuda"), pu.random_obs(m, E, gen, "cuda")
+    o = fp.forward(own, opp, pk.MODE_ARGMAX, want_logits=True)
+    torch.cuda.synchronize()
+    lg, v = o["logits"].double().cpu(), o["value"].double().cpu()
+    lgq, vq = pu.emulate(fp.blob, own, opp, quantize=True)
+    lgr, vr = pu.module_forward(net, own, opp)
+    print(n, m, E, "status", int(fp.status.item()), "finite", bool(torch.isfinite(lg).all()), "vs quant-emul: logits %.3e value %.3e | vs fp32 module: logits %.3e value %.3e | scale %.2f %.2f" % (
+        float((lg-lgq).abs().max()), float((v-vq).abs().max()), float((lg-lgr.double().cpu()).abs().max()), float((v-vr.double().cpu()).abs().max()),
+        float(lgq.abs().max()), float(vq.abs().max())), flush=True)
 n = m = 3
 net = make(n, m, seed=33).cuda()
 fp = pk.FusedPolicy(net, seed=3)
+print(fp.kernel_info())
 L = fp._lib
 L.mp_set_trace.argtypes = [ctypes.c_void_p]
-gen = torch.Generator().manual_seed(1)
-head = ["start", "enc+arrive", "wait(oppQKV)", "drainQ", "drainV", "bar", "dot+softmax", "mix+bar", "store+arrive", "wait(oout)", "drain eOpp", "arrive"]
-rnd = ["wait(QK)", "drainK", "arrive", "bar", "dot+softmax", "bar", "wait(V)", "drainV", "bar", "mix+bar", "store+arrive", "wait(upd)", "drain h", "arrive"]
+head = ["start", "enc+arrive", "wait(opp)", "drain z'+bar", "scores+softmax", "opp msg+arrive"]
+rnd = ["wait(TZY)", "drain z", "scores+softmax", "bar", "update+arrive"]
 labels = head + rnd * 3 + ["wait(heads)", "heads math"]
-for EE in (42, 16384):
+t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+for EE in (42, 4096, 16384, 65536, 262144):
     own, opp = pu.random_obs(n, EE, gen, "cuda"), pu.random_obs(m, EE, gen, "cuda")
-    for _ in range(3): fp.forward(own, opp, pk.MODE_SAMPLE)
-    tr = torch.zeros(96, dtype=torch.int64, device="cuda")
-    L.mp_set_trace(tr.data_ptr())
-    fp.forward(own, opp, pk.MODE_SAMPLE)
+    out = fp.forward(own, opp, pk.MODE_SAMPLE)
+    for _ in range(3): fp.forward(own, opp, pk.MODE_SAMPLE, out=out)
     torch.cuda.synchronize()
-    L.mp_set_trace(None)
-    t = tr.cpu().tolist()
-    nz = [x for x in t if x]
-    print("E=%d: %d stamps, total %d cycles" % (EE, len(nz), nz[-1] - nz[0]))
-    for i in range(1, len(nz)):
-        print("  %2d %-14s %7d" % (i, labels[i] if i < len(labels) else "?", nz[i] - nz[i - 1]))
+    t0.record()
+    for _ in range(20): fp.forward(own, opp, pk.MODE_SAMPLE, out=out)
+    t1.record(); torch.cuda.synchronize()
+    us = t0.elapsed_time(t1) / 20 * 1e3
+    print("E=%d: %.1f us per team forward, %.3e agent-forwards/s, %.1f TFLOP/s (0.7 MFLOP/row)  status %d" % (EE, us, n*EE/us*1e6, n*EE*0.7e6/us*1e6/1e12, int(fp.status.item())), flush=True)
+    if EE in (42, 16384):
+        tr = torch.zeros(96, dtype=torch.int64, device="cuda")
+        L.mp_set_trace(tr.data_ptr())
+        fp.forward(own, opp, pk.MODE_SAMPLE, out=out)
+        torch.cuda.synchronize()
+        L.mp_set_trace(None)
+        nz = [x for x in tr.cpu().tolist() if x]
+        print("  trace: %d stamps, total %d cycles" % (len(nz), nz[-1] - nz[0]))
+        print("   " + "  ".join("%s=%d" % (labels[i] if i < len(labels) else "?", nz[i] - nz[i - 1]) for i in range(1, len(nz))))

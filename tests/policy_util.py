@@ -23,12 +23,8 @@ def decode_blob(blob):
         t = _uncanon(f16[pos:pos + n * k], n, k)
         pos += n * k
         return t
-    for name in ("okey", "oquery", "oval", "oout"):
-        w[name] = take(64, 64)
-    for name in ("q", "k", "v"):
-        w[name] = torch.cat((take(64, 128), take(64, 128)))
-    u1l, wpl, u1h, wph = take(64, 128), take(64, 128), take(64, 128), take(64, 128)
-    w["u1"], w["wp"] = torch.cat((u1l, u1h)), torch.cat((wpl, wph))
+    w["og"], w["oz"] = take(64, 64), take(64, 64)                # (Wkey Wquery^T)^T, (Wval Wout)^T
+    w["g"], w["wz"], w["u1"] = take(128, 128), take(128, 128), take(128, 128)
     w["v0"] = torch.cat((take(64, 128), take(64, 128)))
     w["p0"] = torch.cat((take(64, 128), take(64, 128)))
     assert pos * 2 == pk.BLOB_F16_BYTES
@@ -46,23 +42,19 @@ def emulate(blob, own, opp, quantize):
     relu = torch.relu
     h0 = q16(relu(own @ w["enc_w"].t() + w["enc_b"]))            # [n,E,64]
     ho = q16(relu(opp @ w["oenc_w"].t() + w["oenc_b"]))          # [m,E,64]
-    K = h0 @ w["okey"].t()                                       # fp32 accumulators stay unrounded
-    Q, V = q16(ho @ w["oquery"].t()), q16(ho @ w["oval"].t())
-    s = torch.einsum("nek,mek->enm", K, Q) * 0.125
-    p = torch.softmax(s, dim=-1)
-    e = q16(torch.einsum("enm,mek->nek", p, V))
-    h = torch.cat((h0, q16(e @ w["oout"].t())), dim=-1)          # [n,E,128]
+    T = h0 @ w["og"].t()                                         # fp32 accumulators stay unrounded
+    Z = q16(ho @ w["oz"].t())
+    p = torch.softmax(torch.einsum("nek,mek->enm", T, ho) * 0.125, dim=-1)
+    h = torch.cat((h0, q16(torch.einsum("enm,mek->nek", p, Z))), dim=-1)     # [n,E,128]
     n = own.shape[0]
     for _ in range(3):
-        Qs, Ks, Vs = h @ w["q"].t(), q16(h @ w["k"].t()), q16(h @ w["v"].t())
-        s = torch.einsum("aek,bek->eab", Qs, Ks) / 128 ** 0.5
+        T, Z, Y = h @ w["g"].t(), q16(h @ w["wz"].t()), h @ w["u1"].t()
+        s = torch.einsum("aek,bek->eab", T, h) / 128 ** 0.5
         if n > 1:
-            s = s.masked_fill(torch.eye(n, dtype=torch.bool), float("-inf"))
-            p = torch.softmax(s, dim=-1)
+            p = torch.softmax(s.masked_fill(torch.eye(n, dtype=torch.bool), float("-inf")), dim=-1)
         else:
             p = torch.zeros_like(s)
-        msg = q16(torch.einsum("eab,bek->aek", p, Vs))
-        h = q16(relu(h @ w["u1"].t() + msg @ w["wp"].t() + w["ub"]))
+        h = q16(relu(Y + torch.einsum("eab,bek->aek", p, Z) + w["ub"]))
     value = relu(h @ w["v0"].t() + w["vb"]) @ w["vw"] + w["vb2"]
     logits = relu(h @ w["p0"].t() + w["pb"]) @ w["dw"] + w["db"]
     return logits, value
