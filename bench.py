@@ -285,6 +285,10 @@ def run_ours(args):
         extra["roofline_sweep"] = sweep(fab, torch, dev, peak)
         extra["persistent"] = persistent(fab, torch, dev, peak, E, min(K, 1000))
         extra["persistent_thread_per_env"] = persistent(fab, torch, dev, peak, E, min(K, 1000), "env")
+        try:
+            extra["rollout"] = rollout_config3(fab, torch, dev)
+        except Exception as exc:                      # never lose the headline line to the secondary workload
+            extra["rollout"] = {"error": repr(exc)}
     del env
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,6 +318,71 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def rollout_config3(fab, torch, dev, E=16384, T=128):
+    """BASELINE.json configs[2]: 3v3, 16384 envs, full PPO rollout with the MPNN policy (fused tcgen05 forward +
+    fused step + fused GAE), and one JointPPO update (4 epochs x 32 minibatches, torch autograd).  Reported next to
+    the headline line, never mixed into it."""
+    import importlib
+    ro = importlib.import_module("emergent-multiagent-strategies_b200.rollout")
+    pk = importlib.import_module("emergent-multiagent-strategies_b200.policy_kernel")
+    torch.manual_seed(0)
+    tr = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    tr.collect(); tr.wrap_horizon(); tr.after_update()                      # warm-up rollout
+    torch.cuda.synchronize(dev)
+    e0, e1, e2 = ev(), ev(), ev()
+    e0.record(); tr.collect(); e1.record(); tr.wrap_horizon(); e2.record()
+    torch.cuda.synchronize(dev)
+    collect_ms, wrap_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    # the policy kernel alone (guards' team), CUDA events over 20 launches
+    R = tr.roll
+    f = tr.fused[0]
+    out = f.forward(R.obs[0, 0:NG], R.obs[0, NG:A])
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(20):
+        f.forward(R.obs[0, 0:NG], R.obs[0, NG:A], out=out)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    pol_us = e0.elapsed_time(e1) / 20 * 1e3
+    with torch.no_grad():
+        own, opp = R.obs[0, 0:NG].reshape(-1, 6), R.obs[0, NG:A].reshape(-1, 6)
+        for _ in range(2):
+            tr.policies[0].act(own, None, opp)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(5):
+            tr.policies[0].act(own, None, opp)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    torch_us = e0.elapsed_time(e1) / 5 * 1e3
+    e0, e1 = ev(), ev()
+    e0.record(); vals = tr.update(); e1.record()
+    torch.cuda.synchronize(dev)
+    update_ms = e0.elapsed_time(e1)
+    for fz in tr.fused:
+        fz.check_status()
+    flop_row = 2 * (64 * 64 * 2 + 3 * 3 * 128 * 128 + 2 * 128 * 128)       # tensor-core MACs x2 per (agent, env) row
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tpeak = float(mp.get("bf16_tflops", 1590.0))
+    ach = NG * E * flop_row / (pol_us * 1e-6) / 1e12
+    return {"workload": "FortAttack 3v3 (BASELINE.json configs[2]), %d envs, T=%d rollout with the MPNN policy + one JointPPO update" % (E, T),
+            "rollout_agent_steps_per_s": E * A * T / (collect_ms * 1e-3), "collect_ms": collect_ms,
+            "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms,
+            "ppo_update": "4 epochs x 32 minibatches x 2 teams, torch autograd on the MPNN module", "losses": vals,
+            "policy_kernel": {"kernel": "mp::mp_policy_kernel", "us_per_team_forward": pol_us, "rows": NG * E,
+                              "torch_module_act_us": torch_us, "speedup_vs_torch_module": torch_us / pol_us,
+                              "roofline": {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                                           "frac": ach / tpeak, "flop_per_row": flop_row,
+                                           "peak_source": "MEASURED_PEAKS.json bf16_tflops (fp16 runs at the bf16 rate)" if mp else "fallback 1590"},
+                              "info": f.kernel_info()},
+            "gpu_launches": {"policy": sum(fz.launches for fz in tr.fused), "step": tr.env.launch_count()}}
 
 
 def sweep(fab, torch, dev, peak):

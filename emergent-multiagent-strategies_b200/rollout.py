@@ -17,10 +17,14 @@ Checkpoints use the reference's file format ({'models': [state_dict per agent], 
 train_fortattack.py:121-128) and its loading rule (models[0] -> guards, models[-1] -> attackers,
 learner.py:245-249).
 """
+import ctypes
+
 import torch
 
+from . import _capi
 from .batched_env import FortAttackBatch
 from .mpnn import MPNN
+from .policy_kernel import FusedPolicy, MODE_ARGMAX, MODE_SAMPLE
 from .rlcore.algo import JointPPO
 from .rlcore.storage import RolloutStorage
 
@@ -58,6 +62,21 @@ class SharedRollouts(object):
             r.num_steps, r.step = T, 0
             self.agents.append(r)
 
+    def compute_returns(self, next_value, gamma, tau):
+        """Learner.wrap_horizon for every agent and env in ONE launch (rl_gae, include/fortattack_rollout.h):
+        next_value float [A, E]; per-env episode boundaries from `ends`."""
+        L = _capi.lib()
+        if not getattr(L, "_rl_bound", False):
+            vp, i32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+            L.rl_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, vp]
+            L._rl_bound = True
+        T, A, E = self.rewards.shape
+        nv = next_value.to(torch.float32).contiguous()
+        assert nv.shape == (A, E) and self.ends.dtype == torch.bool
+        _capi.check(L.rl_gae(self.rewards.data_ptr(), self.value_preds.data_ptr(), nv.data_ptr(), self.masks.data_ptr(),
+                             self.ends.data_ptr(), self.returns.data_ptr(), T, A, E, float(gamma), float(tau),
+                             torch.cuda.current_stream(self.rewards.device).cuda_stream))
+
     def after_update(self):
         # RolloutStorage.after_update for every agent at once (storage.py:51-56)
         self.obs[0].copy_(self.obs[-1])
@@ -70,7 +89,7 @@ class BatchedTrainer(object):
     def __init__(self, n_envs, n_guards=3, n_attackers=3, num_steps=128, max_episode_steps=100, device="cuda:0",
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
-                 use_clipped_value_loss=True, process_group=None):
+                 use_clipped_value_loss=True, process_group=None, fused_policy="auto"):
         self.device = torch.device(device)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
@@ -89,6 +108,12 @@ class BatchedTrainer(object):
             for p in self.policies:
                 for t in p.parameters():
                     dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0), group=process_group)
+        # rollout-time forwards: the fused tcgen05 kernel (csrc/mp_policy.cu) when the network has the reference's
+        # shape (hidden 128); the torch module otherwise (small test networks).  Training always uses the module.
+        if fused_policy == "auto":
+            fused_policy = hidden_dim == 128
+        self.fused = [FusedPolicy(p, seed=seed * 2 + t, env_id0=env_id0) for t, p in enumerate(self.policies)] \
+            if fused_policy else None
         self.roll = SharedRollouts(num_steps, self.A, n_envs, self.device)
         self.teams = [list(range(0, n_guards)), list(range(n_guards, self.A))]
         self.roll.obs[0].copy_(self.env.reset())
@@ -98,16 +123,25 @@ class BatchedTrainer(object):
     @torch.no_grad()
     def act(self, step):
         R = self.roll
-        for team, opp, policy in ((self.teams[0], self.teams[1], self.policies[0]),
-                                  (self.teams[1], self.teams[0], self.policies[1])):
-            own = R.obs[step, team[0]:team[-1] + 1].reshape(-1, 6)
-            oth = R.obs[step, opp[0]:opp[-1] + 1].reshape(-1, 6)
+        for t, (team, opp, policy) in enumerate(((self.teams[0], self.teams[1], self.policies[0]),
+                                                 (self.teams[1], self.teams[0], self.policies[1]))):
+            lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
+            if self.fused is not None:
+                # one launch: value, sampled action (int64 for the storage, int32 for the step kernel) and its
+                # log-probability are written straight into slot `step` of the shared rollout blocks
+                self.fused[t].forward(R.obs[step, lo:hi], R.obs[step, olo:ohi], MODE_SAMPLE,
+                                      out={"value": R.value_preds[step, lo:hi], "action": R.actions[step, lo:hi],
+                                           "action_i32": R.actions_i32[step, lo:hi],
+                                           "logp": R.action_log_probs[step, lo:hi]})
+                continue
+            own = R.obs[step, lo:hi].reshape(-1, 6)
+            oth = R.obs[step, olo:ohi].reshape(-1, 6)
             value, action, logp, _ = policy.act(own, None, oth, None, deterministic=False)
             n = len(team)
-            R.value_preds[step, team[0]:team[-1] + 1] = value.view(n, self.E, 1)
-            R.actions[step, team[0]:team[-1] + 1] = action.view(n, self.E, 1)
-            R.action_log_probs[step, team[0]:team[-1] + 1] = logp.view(n, self.E, 1)
-        R.actions_i32[step].copy_(R.actions[step, :, :, 0])
+            R.value_preds[step, lo:hi] = value.view(n, self.E, 1)
+            R.actions[step, lo:hi] = action.view(n, self.E, 1)
+            R.action_log_probs[step, lo:hi] = logp.view(n, self.E, 1)
+            R.actions_i32[step, lo:hi].copy_(R.actions[step, lo:hi, :, 0])
         return R.actions_i32[step]
 
     # -- the data-collection loop of train_fortattack.train (:51-104) for E envs ---------------------
@@ -134,13 +168,19 @@ class BatchedTrainer(object):
     @torch.no_grad()
     def wrap_horizon(self):
         R, T = self.roll, self.T
-        for team, opp, policy in ((self.teams[0], self.teams[1], self.policies[0]),
-                                  (self.teams[1], self.teams[0], self.policies[1])):
-            own = R.obs[T, team[0]:team[-1] + 1].reshape(-1, 6)
-            oth = R.obs[T, opp[0]:opp[-1] + 1].reshape(-1, 6)
-            nv = policy.get_value(own, None, oth, None).view(len(team), self.E, 1)
-            for k, i in enumerate(team):
-                R.agents[i].compute_returns_batched(nv[k], R.ends, self.gamma, self.tau)
+        nv = torch.empty(self.A, self.E, device=self.device)
+        for t, (team, opp, policy) in enumerate(((self.teams[0], self.teams[1], self.policies[0]),
+                                                 (self.teams[1], self.teams[0], self.policies[1]))):
+            lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
+            if self.fused is not None:
+                self.fused[t].forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]})
+            else:
+                nv[lo:hi] = policy.get_value(R.obs[T, lo:hi].reshape(-1, 6), None, R.obs[T, olo:ohi].reshape(-1, 6),
+                                             None).view(len(team), self.E)
+        R.compute_returns(nv, self.gamma, self.tau)            # segment GAE of all agents and envs: one launch
+        if self.fused is not None:
+            for f in self.fused:
+                f.check_status()
 
     # -- Learner.update (learner.py:175-188) ---------------------------------------------------------
     def update(self, train_guards_only=False):
@@ -150,6 +190,9 @@ class BatchedTrainer(object):
             own = [self.roll.agents[i] for i in self.teams[t]]
             opp = [self.roll.agents[i] for i in self.teams[1 - t]]
             vals.append(trainer.update(own, opp))
+        if self.fused is not None:                         # the optimizer moved the weights: re-pack the kernel's blob
+            for f in self.fused:
+                f.refresh()
         return vals
 
     def after_update(self):
@@ -173,3 +216,6 @@ class BatchedTrainer(object):
     def load_models(self, models):
         self.policies[0].load_state_dict(models[0])        # learner.py:245-249
         self.policies[1].load_state_dict(models[-1])
+        if self.fused is not None:
+            for f in self.fused:
+                f.refresh()

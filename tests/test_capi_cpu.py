@@ -21,6 +21,27 @@ def test_header_symbols_are_exported():
     assert L.fa_abi_version() == int(re.search(r"#define FA_ABI_VERSION (\d+)", hdr).group(1))
 
 
+def test_policy_and_rollout_headers_are_exported():
+    """Every entry point of include/fortattack_policy.h and include/fortattack_rollout.h is in the library, and
+    they reject bad arguments without a GPU."""
+    L = _capi.lib()
+    for hdr_name, prefix in (("fortattack_policy.h", "mp_"), ("fortattack_rollout.h", "rl_")):
+        hdr = open(os.path.join(ROOT, "include", hdr_name)).read()
+        declared = set(re.findall(r"^int\s+(%s\w+)\(" % prefix, hdr, re.M))
+        assert declared, hdr_name
+        for name in declared:
+            assert hasattr(L, name), name
+    L.mp_forward.restype = ctypes.c_int
+    assert L.mp_forward(*([None] * 3), 3, 3, 8, 0, 0, 0, 0, *([None] * 9)) == -1
+    assert b"NULL" in L.fa_last_error()
+    L.rl_gae.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 3 + [ctypes.c_double] * 2 + [ctypes.c_void_p]
+    assert L.rl_gae(None, None, None, None, None, None, 4, 2, 8, 0.99, 0.95, None) == -1
+    blob_bytes = int(re.search(r"#define MP_BLOB_F16_BYTES (\d+)", open(os.path.join(ROOT, "include", "fortattack_policy.h")).read()).group(1))
+    from importlib import import_module
+    pk = import_module("emergent-multiagent-strategies_b200.policy_kernel")
+    assert pk.BLOB_F16_BYTES == blob_bytes
+
+
 def test_config_validation_and_workspace_size():
     L = _capi.lib()
     n = ctypes.c_size_t()
