@@ -362,6 +362,12 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     e0.record(); vals = tr.update(); e1.record()
     torch.cuda.synchronize(dev)
     update_ms = e0.elapsed_time(e1)
+    for trn in tr.trainers:                                                 # the same update with TF32 tensor-core GEMMs
+        trn.allow_tf32 = True
+    e0, e1 = ev(), ev()
+    e0.record(); tr.update(); e1.record()
+    torch.cuda.synchronize(dev)
+    update_tf32_ms = e0.elapsed_time(e1)
     for fz in tr.fused:
         fz.check_status()
     flop_row = 2 * (64 * 64 * 2 + 3 * 3 * 128 * 128 + 2 * 128 * 128)       # tensor-core MACs x2 per (agent, env) row
@@ -374,7 +380,7 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     ach = NG * E * flop_row / (pol_us * 1e-6) / 1e12
     return {"workload": "FortAttack 3v3 (BASELINE.json configs[2]), %d envs, T=%d rollout with the MPNN policy + one JointPPO update" % (E, T),
             "rollout_agent_steps_per_s": E * A * T / (collect_ms * 1e-3), "collect_ms": collect_ms,
-            "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms,
+            "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_tf32_ms": update_tf32_ms,
             "ppo_update": "4 epochs x 32 minibatches x 2 teams, torch autograd on the MPNN module", "losses": vals,
             "policy_kernel": {"kernel": "mp::mp_policy_kernel", "us_per_team_forward": pol_us, "rows": NG * E,
                               "torch_module_act_us": torch_us, "speedup_vs_torch_module": torch_us / pol_us,

@@ -54,8 +54,13 @@ def magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_l
 
 class JointPPO(object):
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
-                 lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=False, process_group=None):
+                 lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=False, process_group=None,
+                 allow_tf32=False):
         self.actor_critic = actor_critic
+        # allow_tf32 (new, off by default = the reference's fp32 arithmetic): run the update's cuBLAS GEMMs on the
+        # tensor cores in TF32.  On B200 the fp32 path is SIMT sgemm and takes ~70% of the update
+        # (profiles/r1c_ppo_update_torch_profile.txt).
+        self.allow_tf32 = allow_tf32
         self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
         self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
         self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
@@ -95,6 +100,14 @@ class JointPPO(object):
     def update(self, rollouts_list, opp_rollouts_list, index_batches=None):
         """index_batches (optional, testing): per epoch, a list of index tensors to use as the minibatches
         instead of chunks of a fresh random permutation."""
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.allow_tf32)
+        try:
+            return self._update(rollouts_list, opp_rollouts_list, index_batches)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+    def _update(self, rollouts_list, opp_rollouts_list, index_batches=None):
         advantages_list = [self._advantages(r) for r in rollouts_list]
         dev = rollouts_list[0].rewards.device
         totals = torch.zeros(3, device=dev)
