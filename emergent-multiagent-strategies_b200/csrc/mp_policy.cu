@@ -14,16 +14,21 @@
 //
 // Tile = 128 rows = EPT environments x up to 5 agents, row r = a * EPT + e (EPT = 128 / max(n_own, n_opp)),
 // so the rows an agent attends to (same e, other a) are in the same tile.  Thread r of the four
-// "row" warps owns row r for the whole network: it is tensor-memory lane r (tcgen05.ld 32x32b gives a
-// thread its own accumulator row), it writes row r of the next layer's fp16 A operand into shared
-// memory, and it reads other rows only for the two attentions.
+// "row" warps own row r for the whole network: it is tensor-memory lane r (tcgen05.ld 32x32b gives a
+// thread its own accumulator row), they write row r of the next layer's fp16 A operand into shared
+// memory, and they read other rows only for the two attentions.
 //
-// Warp roles (192 threads, one CTA per SM, persistent over tiles):
-//   warps 0-3  row threads (encoders, epilogues, attention, heads, sampling)
-//   warp 4     weight producer: loads the resident round weights once, then streams the per-tile
+// Two threads share a row: warp w and warp w+4 both map to tensor-memory lanes 32*(w%4)..+31 (the hardware's
+// lane window of a warp is 32*(warp%4)), thread "half" h = w/4 handles columns [64h, 64h+64) of every
+// per-row loop; attention scores are summed across the two halves through a small shared-memory exchange,
+// and at the heads half 0 evaluates the value head while half 1 evaluates the action head and samples.
+//
+// Warp roles (320 threads, one CTA per SM, persistent over tiles):
+//   warps 0-7  row threads (encoders, epilogues, attention, heads, sampling)
+//   warp 8     weight producer: loads the resident round weights once, then streams the per-tile
 //              weights (opponent attention, heads: 80 KB per tile) with cp.async.bulk into a ring
-//   warp 5     MMA issuer: one thread issues every tcgen05.mma
-// Synchronisation: a_ready (128 arrivals: "operand written / accumulator drained") row -> MMA,
+//   warp 9     MMA issuer: one thread issues every tcgen05.mma
+// Synchronisation: a_ready (256 arrivals: "operand written / accumulator drained") row -> MMA,
 // acc (tcgen05.commit) MMA -> row, named barrier 1 among the row threads.
 //
 // Shared memory: bufH [128 x 128 fp16] current h (A operand, also read by other rows for the scores),
@@ -57,7 +62,7 @@ constexpr int OFF_H = 0, OFF_X = 32768, OFF_WRES = 65536, RES_BYTES = 98304, OFF
               OFF_RING = OFF_CONST + 10368, SMEM_BYTES = OFF_RING + NS * STAGE_BYTES;
 constexpr uint32_t BLOB_RES = 16384;           // blob offset of the resident part
 constexpr int N_STREAM = 6;                    // streamed chunks per tile
-constexpr int ROW_THREADS = 128, THREADS = 192;
+constexpr int ROW_THREADS = 256, THREADS = 320, PRODUCER_WARP = 8, MMA_WARP = 9;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_T = 0, COL_Z = 128, COL_Y = 256;
 static_assert(MP_BLOB_F16_BYTES == 180224 && MP_BLOB_CONST_FLOATS * 4 <= 10368, "blob layout");
@@ -74,12 +79,12 @@ struct Chunk {
     uint8_t wait_a, commit_acc, pad0, pad1;
 };
 __constant__ Chunk c_tab[N_STREAM] = {
-    {0u, 8192u, OFF_H, 1024u, 4, 0, 1, 0, 0, 0},          // T' = h0 (Wkey Wquery^T)
-    {8192u, 8192u, OFF_X, 1024u, 4, 64, 0, 1, 0, 0},      // z' = hOpp (Wval Wout)
-    {114688u, 16384u, OFF_H, 2048u, 8, 0, 1, 0, 0, 0},    // value hidden lo / hi
-    {131072u, 16384u, OFF_H, 2048u, 8, 64, 0, 0, 0, 0},
-    {147456u, 16384u, OFF_H, 2048u, 8, 128, 0, 0, 0, 0},  // policy hidden lo / hi
-    {163840u, 16384u, OFF_H, 2048u, 8, 192, 0, 1, 0, 0}};
+    {0u, 8192u, OFF_H, 1024u, 4, 0, 1, 1, 0, 0},          // T' = h0 (Wkey Wquery^T)          -> acc
+    {8192u, 8192u, OFF_X, 1024u, 4, 64, 0, 1, 0, 0},      // z' = hOpp (Wval Wout)             -> acc
+    {147456u, 16384u, OFF_H, 2048u, 8, 128, 1, 0, 0, 0},  // policy hidden lo / hi             -> acc
+    {163840u, 16384u, OFF_H, 2048u, 8, 192, 0, 1, 0, 0},
+    {114688u, 16384u, OFF_H, 2048u, 8, 0, 0, 0, 0, 0},    // value hidden lo / hi              -> acc
+    {131072u, 16384u, OFF_H, 2048u, 8, 64, 0, 1, 0, 0}};
 
 struct Params {
     const uint8_t *blob;
@@ -105,7 +110,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     }
 }
 
-__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -115,33 +120,31 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
     return __half22float2(*reinterpret_cast<const __half2 *>(&u));
 }
 
-// tensor-memory columns [col, col+ncols) of this thread's row -> fp16 row segment k0.. of a canonical operand;
-// ncols is a multiple of 64: two 32-column loads are in flight per tcgen05.wait
-__device__ __forceinline__ void drain(uint32_t taddr, int ncols, uint8_t *buf, int r, int k0) {
-    for (int c = 0; c < ncols; c += 64) {
-        uint32_t v[2][32];
-        tmem_ld32(taddr + (uint32_t)c, v[0]);
-        tmem_ld32(taddr + (uint32_t)c + 32u, v[1]);
-        tmem_ld_wait();
+// tensor-memory columns [taddr, taddr+ncols) of this thread's row -> fp16 row segment k0.. of a canonical operand
+// (ncols = 32 or 64: all loads are in flight before the one tcgen05.wait)
+template <int NCOLS>
+__device__ __forceinline__ void drain(uint32_t taddr, uint8_t *buf, int r, int k0) {
+    uint32_t v[NCOLS / 32][32];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+    for (int q = 0; q < NCOLS / 32; ++q) tmem_ld32(taddr + (uint32_t)(q * 32), v[q]);
+    tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {          // 8 columns -> one 16-byte chunk
-                uint32_t h[4];
+    for (int q = 0; q < NCOLS / 32; ++q) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    h[j] = pack_h2(__uint_as_float(v[half][g * 8 + 2 * j]), __uint_as_float(v[half][g * 8 + 2 * j + 1]));
-                *reinterpret_cast<uint4 *>(buf + canon_off(r, k0 + c + half * 32 + g * 8, A_LBO, A_SBO)) =
-                    make_uint4(h[0], h[1], h[2], h[3]);
-            }
+        for (int g = 0; g < 4; ++g) {          // 8 columns -> one 16-byte chunk
+            uint32_t h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                h[j] = pack_h2(__uint_as_float(v[q][g * 8 + 2 * j]), __uint_as_float(v[q][g * 8 + 2 * j + 1]));
+            *reinterpret_cast<uint4 *>(buf + canon_off(r, k0 + q * 32 + g * 8, A_LBO, A_SBO)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
     }
 }
 
-// ReLU(W x + b) for the 6-float observation, 64 outputs -> fp16 row segment [0, 64) of buf (mpnn.py:127-128)
-__device__ __forceinline__ void encode(const float *W8, const float (&o)[6], uint8_t *buf, int r) {
-#pragma unroll 2
-    for (int j0 = 0; j0 < 64; j0 += 8) {
+// ReLU(W x + b) for the 6-float observation, outputs [j_lo, j_lo+32) -> fp16 row segment of buf (mpnn.py:127-128)
+__device__ __forceinline__ void encode(const float *W8, const float (&o)[6], uint8_t *buf, int r, int j_lo) {
+#pragma unroll 1
+    for (int j0 = j_lo; j0 < j_lo + 32; j0 += 8) {
         uint32_t h[4];
 #pragma unroll
         for (int jj = 0; jj < 8; jj += 2) {
@@ -198,20 +201,18 @@ __device__ __forceinline__ void dot32(const uint32_t (&v)[32], const uint8_t *bu
     }
 }
 
-// scores of this row against CNT other rows: NB batches of 64 accumulator columns starting at taddr
+// partial scores of this row against CNT other rows over NB*32 accumulator columns starting at taddr; the
+// other rows' fp16 features start at byte offset koff0 (same columns)
 template <int CNT, int NB>
-__device__ __forceinline__ void scores(uint32_t taddr, const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM],
+__device__ __forceinline__ void scores(uint32_t taddr, const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM], uint32_t koff0,
                                        float (&s)[MP_MAX_TEAM]) {
     if (CNT == 0) return;
+    uint32_t v[NB][32];
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        uint32_t v[2][32];
-        tmem_ld32(taddr + (uint32_t)(c * 64), v[0]);
-        tmem_ld32(taddr + (uint32_t)(c * 64 + 32), v[1]);
-        tmem_ld_wait();
-        dot32<CNT>(v[0], buf, rows, (uint32_t)(c * 8) * A_LBO, s);
-        dot32<CNT>(v[1], buf, rows, (uint32_t)(c * 8 + 4) * A_LBO, s);
-    }
+    for (int c = 0; c < NB; ++c) tmem_ld32(taddr + (uint32_t)(c * 32), v[c]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < NB; ++c) dot32<CNT>(v[c], buf, rows, koff0 + (uint32_t)(c * 4) * A_LBO, s);
 }
 
 // softmax over the first cnt entries (cnt = 0: a lone agent receives a zero message, mpnn.py:262-270)
@@ -255,9 +256,9 @@ __device__ __forceinline__ void mix8(float (&acc)[8], const uint8_t *buf, const 
 // eOpp = sum_b p_b z'_b  (z' rows at bufX k = 64..127) -> this row of bufH, k = 64..127  (mpnn.py:142,432-437)
 template <int CNT>
 __device__ __forceinline__ void opp_message(const uint8_t *bufX, uint8_t *bufH, int r, const uint32_t (&rows)[MP_MAX_TEAM],
-                                            const float (&p)[MP_MAX_TEAM]) {
-#pragma unroll
-    for (int kc = 0; kc < 8; ++kc) {
+                                            const float (&p)[MP_MAX_TEAM], int kc_lo) {
+#pragma unroll 2
+    for (int kc = kc_lo; kc < kc_lo + 4; ++kc) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         mix8<CNT>(acc, bufX, rows, (uint32_t)(8 + kc) * A_LBO, p);
         *reinterpret_cast<uint4 *>(bufH + canon_off(r, 64 + kc * 8, A_LBO, A_SBO)) =
@@ -265,34 +266,40 @@ __device__ __forceinline__ void opp_message(const uint8_t *bufX, uint8_t *bufH, 
     }
 }
 
-// h_new = ReLU(Y + sum_b p_b z_b + bias) -> this row of bufH   (mpnn.py:157-158 with the folded projections)
+// h_new = ReLU(Y + sum_b p_b z_b + bias) for columns [c0, c0+64) -> this row of bufH   (mpnn.py:157-158, folded)
 template <int CNT>
-__device__ __forceinline__ void update_row(uint32_t t_y, const uint8_t *bufX, uint8_t *bufH, int r,
+__device__ __forceinline__ void update_row(uint32_t t_y, const uint8_t *bufX, uint8_t *bufH, int r, int c0,
                                            const uint32_t (&rows)[MP_MAX_TEAM], const float (&p)[MP_MAX_TEAM], const float *bias) {
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-        uint32_t y[2][32];
-        tmem_ld32(t_y + (uint32_t)(c * 64), y[0]);
-        tmem_ld32(t_y + (uint32_t)(c * 64 + 32), y[1]);
+    for (int c = c0; c < c0 + 64; c += 32) {
+        uint32_t y[32];
+        tmem_ld32(t_y + (uint32_t)c, y);
         tmem_ld_wait();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int g = 0; g < 4; ++g) {
+            const int k = c + g * 8;
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias + k), b1 = *reinterpret_cast<const float4 *>(bias + k + 4);
+            float acc[8] = {__uint_as_float(y[g * 8]) + b0.x,     __uint_as_float(y[g * 8 + 1]) + b0.y,
+                            __uint_as_float(y[g * 8 + 2]) + b0.z, __uint_as_float(y[g * 8 + 3]) + b0.w,
+                            __uint_as_float(y[g * 8 + 4]) + b1.x, __uint_as_float(y[g * 8 + 5]) + b1.y,
+                            __uint_as_float(y[g * 8 + 6]) + b1.z, __uint_as_float(y[g * 8 + 7]) + b1.w};
+            mix8<CNT>(acc, bufX, rows, (uint32_t)(k >> 3) * A_LBO, p);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int k = c * 64 + half * 32 + g * 8;
-                const float4 b0 = *reinterpret_cast<const float4 *>(bias + k), b1 = *reinterpret_cast<const float4 *>(bias + k + 4);
-                float acc[8] = {__uint_as_float(y[half][g * 8]) + b0.x,     __uint_as_float(y[half][g * 8 + 1]) + b0.y,
-                                __uint_as_float(y[half][g * 8 + 2]) + b0.z, __uint_as_float(y[half][g * 8 + 3]) + b0.w,
-                                __uint_as_float(y[half][g * 8 + 4]) + b1.x, __uint_as_float(y[half][g * 8 + 5]) + b1.y,
-                                __uint_as_float(y[half][g * 8 + 6]) + b1.z, __uint_as_float(y[half][g * 8 + 7]) + b1.w};
-                mix8<CNT>(acc, bufX, rows, (uint32_t)(k >> 3) * A_LBO, p);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.0f);
-                *reinterpret_cast<uint4 *>(bufH + canon_off(r, k, A_LBO, A_SBO)) =
-                    make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
-            }
+            for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.0f);
+            *reinterpret_cast<uint4 *>(bufH + canon_off(r, k, A_LBO, A_SBO)) =
+                make_uint4(pack_h2(acc[0], acc[1]), pack_h2(acc[2], acc[3]), pack_h2(acc[4], acc[5]), pack_h2(acc[6], acc[7]));
         }
     }
+}
+
+// the two halves of a row add their partial scores: write -> barrier -> read the partner's (the barrier also
+// publishes whatever the row threads wrote to shared memory before it)
+__device__ __forceinline__ void combine_scores(float (&s)[MP_MAX_TEAM], float (*sc)[128][MP_MAX_TEAM], int half, int r) {
+#pragma unroll
+    for (int b = 0; b < MP_MAX_TEAM; ++b) sc[half][r][b] = s[b];
+    bar_rows();
+#pragma unroll
+    for (int b = 0; b < MP_MAX_TEAM; ++b) s[b] += sc[half ^ 1][r][b];
 }
 
 // run CALL(CNT) with the team size as a compile-time constant (branch-free, fully unrolled inner loops)
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_a_ready, bar_acc, bar_res;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float sc[2][128][MP_MAX_TEAM];          // partial attention scores of the two halves of a row
     uint8_t *bufH = smem + OFF_H, *bufX = smem + OFF_X;
     float *C = reinterpret_cast<float *>(smem + OFF_CONST);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         mbar_init(&bar_res, 1);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc<TMEM_COLS>(&tmem_base_s);
+    if (warp == PRODUCER_WARP) tmem_alloc<TMEM_COLS>(&tmem_base_s);
     {   // fp32 constants: plain loads, once per CTA
         const float4 *src = reinterpret_cast<const float4 *>(p.blob + MP_BLOB_F16_BYTES);
         float4 *dst = reinterpret_cast<float4 *>(C);
@@ -332,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
-    if (warp == 4) {
+    if (warp == PRODUCER_WARP) {
         // ================= weight producer =================
         if (lane == 0) {
             mbar_expect_tx(&bar_res, RES_BYTES);           // round weights: resident for the whole kernel
@@ -343,56 +351,73 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 for (int c = 0; c < N_STREAM; ++c, ++g) {
                     const uint32_t s = g % NS, ph = (g / NS) & 1u;
                     mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 3);
+                    if (p.trace != nullptr && blockIdx.x == 0 && tile == 0) p.trace[64 + c] = clock64();
                     mbar_expect_tx(&bar_full[s], c_tab[c].bytes);
                     bulk_g2s(smem + OFF_RING + s * STAGE_BYTES, p.blob + c_tab[c].off, c_tab[c].bytes, &bar_full[s]);
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc64 = idesc_f16(128, 64), idesc128 = idesc_f16(128, 128);
-            const uint32_t sbase = smem_u32(smem);
-            uint32_t g = 0, pa = 0;
-            auto stream_chunk = [&](int c) {
-                const Chunk ch = c_tab[c];
-                const uint32_t s = g % NS, ph = (g / NS) & 1u;
-                if (ch.wait_a) { mbar_wait(&bar_a_ready, pa, p.status, 4); pa ^= 1u; }
-                mbar_wait(&bar_full[s], ph, p.status, 5);
-                tc_fence_after();
-                const uint32_t a0 = sbase + ch.a_off, b0 = sbase + OFF_RING + s * STAGE_BYTES;
-                for (uint32_t k = 0; k < ch.ksteps; ++k)
-                    umma_f16(tmem + ch.tmem_col, smem_desc(a0 + k * 2u * A_LBO, A_LBO, A_SBO),
-                             smem_desc(b0 + k * 2u * A_LBO, A_LBO, ch.b_sbo), idesc64, k > 0);
+        // The whole warp runs this code converged (waits included) and one elected lane issues the tcgen05
+        // instructions: everything around them is warp-uniform, so descriptors live in uniform registers and the
+        // issue rate keeps up with the tensor pipe.
+        const uint32_t idesc64 = idesc_f16(128, 64), idesc128 = idesc_f16(128, 128);
+        const uint32_t sbase = smem_u32(smem);
+        const uint64_t hdesc = smem_desc(sbase + OFF_H, A_LBO, A_SBO), wdesc = smem_desc(sbase + OFF_WRES, A_LBO, A_SBO);
+        uint32_t g = 0, pa = 0;
+        auto stream_chunk = [&](int c) {
+            const Chunk ch = c_tab[c];
+            const uint32_t s = g % NS, ph = (g / NS) & 1u;
+            if (ch.wait_a) { mbar_wait(&bar_a_ready, pa, p.status, 4); pa ^= 1u; }
+            mbar_wait(&bar_full[s], ph, p.status, 5);
+            tc_fence_after();
+            // descriptors differ only in the start-address field (+256 bytes = +16 per K step)
+            const uint64_t ad0 = smem_desc(sbase + ch.a_off, A_LBO, A_SBO);
+            const uint64_t bd0 = smem_desc(sbase + OFF_RING + s * STAGE_BYTES, A_LBO, ch.b_sbo);
+            const uint32_t dcol = tmem + ch.tmem_col;
+            if (elect_one()) {
+                if (ch.ksteps == 8) {
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) umma_f16(dcol, ad0 + k * 16u, bd0 + k * 16u, idesc64, k > 0);
+                } else {
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) umma_f16(dcol, ad0 + k * 16u, bd0 + k * 16u, idesc64, k > 0);
+                }
                 umma_commit(&bar_empty[s]);
                 if (ch.commit_acc) umma_commit(&bar_acc);
-                ++g;
-            };
-            mbar_wait(&bar_res, 0, p.status, 2);
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                stream_chunk(0);
-                stream_chunk(1);
-                for (int round = 0; round < 3; ++round) {      // [T | Z | Y] = h [G | Wz | U1^T]
-                    mbar_wait(&bar_a_ready, pa, p.status, 4);
-                    pa ^= 1u;
-                    tc_fence_after();
+                if (p.trace != nullptr && blockIdx.x == 0 && g < 6) p.trace[72 + c] = clock64();
+            }
+            __syncwarp();
+            ++g;
+        };
+        mbar_wait(&bar_res, 0, p.status, 2);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            stream_chunk(0);
+            stream_chunk(1);
+            for (int round = 0; round < 3; ++round) {      // [T | Z | Y] = h [G | Wz | U1^T]
+                mbar_wait(&bar_a_ready, pa, p.status, 4);
+                pa ^= 1u;
+                tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                    for (uint32_t j = 0; j < 3; ++j)
+                    for (uint32_t j = 0; j < 3; ++j) {
 #pragma unroll
                         for (uint32_t k = 0; k < 8; ++k)
-                            umma_f16(tmem + j * 128u, smem_desc(sbase + OFF_H + k * 2u * A_LBO, A_LBO, A_SBO),
-                                     smem_desc(sbase + OFF_WRES + j * 32768u + k * 2u * A_LBO, A_LBO, A_SBO), idesc128, k > 0);
-                    umma_commit(&bar_acc);
+                            umma_f16(tmem + j * 128u, hdesc + k * 16u, wdesc + (j * 32768u >> 4) + k * 16u, idesc128, k > 0);
+                        if (j != 1) umma_commit(&bar_acc);        // T ready (the rows start the scores), then Z | Y
+                    }
                 }
-                for (int c = 2; c < N_STREAM; ++c) stream_chunk(c);
+                __syncwarp();
             }
+            for (int c = 2; c < N_STREAM; ++c) stream_chunk(c);
         }
-        __syncwarp();
     } else {
-        // ================= row threads =================
-        const int r = tid;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        // ================= row threads: row r, column half `half` =================
+        const int half = warp >> 2, r = (warp & 3) * 32 + lane;
+        const int c0 = half * 64;                                  // this thread's columns of a 128-wide row
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const int ept = p.ept, n_own = p.n_own, n_opp = p.n_opp;
         const int a = r / ept, e = r - a * ept;
         // byte offsets of the rows this row attends to: opponents (b, e) for every b; team mates (b, e), b != a
@@ -408,36 +433,34 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         uint32_t pc = 0;
         int ti = 0;
 #define ARRIVE_A() do { tc_fence_before(); fence_async_smem(); mbar_arrive(&bar_a_ready); } while (0)
-#define TS() do { if (p.trace != nullptr && r == 0 && blockIdx.x == 0 && tile == 0 && ti < 96) p.trace[ti++] = clock64(); } while (0)
+#define TS() do { if (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && tile == 0 && ti < 96) p.trace[ti++] = clock64(); } while (0)
 #define WAIT_ACC(code) do { mbar_wait(&bar_acc, pc, p.status, code); pc ^= 1u; tc_fence_after(); } while (0)
 
+        float o_own[6], o_opp[6];                                  // this tile's observations (prefetched one tile ahead)
+        load_obs(p.obs_own, n_own, a, p.E, blockIdx.x * ept + e, o_own);
+        load_obs(p.obs_opp, n_opp, a, p.E, blockIdx.x * ept + e, o_opp);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int eg = tile * ept + e;
             TS();
-            // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64) ----------
-            {
-                float o[6];
-                load_obs(p.obs_own, n_own, a, p.E, eg, o);
-                encode(C + C_ENC, o, bufH, r);
-                load_obs(p.obs_opp, n_opp, a, p.E, eg, o);
-                encode(C + C_OENC, o, bufX, r);
-            }
+            // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64); 32 outputs per half
+            encode(C + C_ENC, o_own, bufH, r, half * 32);
+            encode(C + C_OENC, o_opp, bufX, r, half * 32);
             ARRIVE_A();
             TS();
             // ---- attention over the opponents (mpnn.py:409-437), folded: T' = h0 G', z' = hOpp Wz' -------
-            WAIT_ACC(6);
-            TS();
-            drain(trow + 64, 64, bufX, r, 64);                    // z' of opponent row r -> bufX[:, 64:128)
-            bar_rows();
-            TS();
             {
                 float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#define CALL(N) scores<N, 1>(trow + COL_T, bufX, rowopp, s)
-                MP_DISPATCH(n_opp, CALL)
+                WAIT_ACC(6);                                      // T'
+                TS();
+#define CALL(N) scores<N, 1>(trow + COL_T + half * 32, bufX, rowopp, (uint32_t)(half * 4) * A_LBO, s)
+                MP_DISPATCH(n_opp, CALL)                          // T' . hOpp_b over this half's 32 features
 #undef CALL
+                WAIT_ACC(7);                                      // z'
+                drain<32>(trow + 64 + half * 32, bufX, r, 64 + half * 32);   // z' of opponent row r -> bufX[:, 64:128)
+                combine_scores(s, sc, half, r);                   // (barrier: every z' row is in bufX)
                 softmax_small(s, n_opp, 0.125f);                  // 1/sqrt(64)
                 TS();
-#define CALL(N) opp_message<N>(bufX, bufH, r, rowopp, s)
+#define CALL(N) opp_message<N>(bufX, bufH, r, rowopp, s, half * 4)
                 MP_DISPATCH(n_opp, CALL)                          // h = [h0 | eOpp]
 #undef CALL
             }
@@ -446,101 +469,125 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
 
             // ---- three message-passing rounds (mpnn.py:156-158) ------------------------------------------
             for (int round = 0; round < 3; ++round) {
-                WAIT_ACC(8);                                      // T | Z | Y ready
-                TS();
-                drain(trow + COL_Z, 128, bufX, r, 0);            // z of this row -> bufX
-                TS();
                 float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#define CALL(N) scores<N, 2>(trow + COL_T, bufH, rowoth, s)
+                WAIT_ACC(8);                                      // T ready; Z | Y are still being computed
+                TS();
+#define CALL(N) scores<N, 2>(trow + COL_T + c0, bufH, rowoth, (uint32_t)(c0 >> 3) * A_LBO, s)
                 MP_DISPATCH(n_oth, CALL)                          // (h_a G) . h_b against the team mates' h rows
 #undef CALL
+                TS();
+                WAIT_ACC(9);                                      // Z | Y ready
+                drain<64>(trow + COL_Z + c0, bufX, r, c0);       // this half of z -> bufX
+                combine_scores(s, sc, half, r);                   // (barrier: z rows visible; nobody reads bufH any more)
                 softmax_small(s, n_oth, 0.08838834764831845f);    // 1/sqrt(128); no self message (mpnn.py:297-298)
                 TS();
-                bar_rows();                                       // z rows visible; nobody reads bufH any more
-                TS();
-#define CALL(N) update_row<N>(trow + COL_Y, bufX, bufH, r, rowoth, s, C + C_UB)
+#define CALL(N) update_row<N>(trow + COL_Y, bufX, bufH, r, c0, rowoth, s, C + C_UB)
                 MP_DISPATCH(n_oth, CALL)
 #undef CALL
                 ARRIVE_A();
                 TS();
             }
+            {   // the next tile's observations: the loads fly while the heads are computed
+                const int nt = tile + gridDim.x;
+                if (nt < p.n_tiles) {
+                    load_obs(p.obs_own, n_own, a, p.E, nt * ept + e, o_own);
+                    load_obs(p.obs_opp, n_opp, a, p.E, nt * ept + e, o_opp);
+                }
+            }
 
-            // ---- heads (mpnn.py:174-205): value_head, policy_head, dist.linear, Categorical --------------
+            // ---- heads (mpnn.py:174-205): half 0 = value_head, half 1 = policy_head + dist.linear + Categorical
+            // The MMA issuer commits the policy hidden layer first, then the value hidden layer: half 1 starts on the
+            // logits while the value weights are still streaming in.
             WAIT_ACC(11);
             TS();
-            float value = C[C_VB2];
-            float lg[MP_ACTIONS];
-#pragma unroll
-            for (int k = 0; k < MP_ACTIONS; ++k) lg[k] = C[C_DB + k];
+            const bool live = a < n_own && eg < p.E;
+            const size_t row = (size_t)a * p.E + eg;
+            if (half == 0) {
+                WAIT_ACC(12);
+                float value = C[C_VB2];
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32], w[32];
-                tmem_ld32(trow + (uint32_t)(c * 32), v);
-                tmem_ld32(trow + (uint32_t)(128 + c * 32), w);
-                tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int k = c * 32 + j;
-                    value = fmaf(fmaxf(__uint_as_float(v[j]) + C[C_VB + k], 0.0f), C[C_VW + k], value);
-                    const float x = fmaxf(__uint_as_float(w[j]) + C[C_PB + k], 0.0f);
-                    const float4 d0 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8);
-                    const float4 d1 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8 + 4);
-                    lg[0] = fmaf(x, d0.x, lg[0]); lg[1] = fmaf(x, d0.y, lg[1]); lg[2] = fmaf(x, d0.z, lg[2]);
-                    lg[3] = fmaf(x, d0.w, lg[3]); lg[4] = fmaf(x, d1.x, lg[4]); lg[5] = fmaf(x, d1.y, lg[5]);
-                    lg[6] = fmaf(x, d1.z, lg[6]); lg[7] = fmaf(x, d1.w, lg[7]);
+                    for (int j = 0; j < 32; ++j) {
+                        const int k = c * 32 + j;
+                        value = fmaf(fmaxf(__uint_as_float(v[j]) + C[C_VB + k], 0.0f), C[C_VW + k], value);
+                    }
                 }
+                if (live && p.value) p.value[row] = value;
+            } else {
+                float lg[MP_ACTIONS];
+#pragma unroll
+                for (int k = 0; k < MP_ACTIONS; ++k) lg[k] = C[C_DB + k];
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[32];
+                    tmem_ld32(trow + (uint32_t)(128 + c * 32), w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int k = c * 32 + j;
+                        const float x = fmaxf(__uint_as_float(w[j]) + C[C_PB + k], 0.0f);
+                        const float4 d0 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8);
+                        const float4 d1 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8 + 4);
+                        lg[0] = fmaf(x, d0.x, lg[0]); lg[1] = fmaf(x, d0.y, lg[1]); lg[2] = fmaf(x, d0.z, lg[2]);
+                        lg[3] = fmaf(x, d0.w, lg[3]); lg[4] = fmaf(x, d1.x, lg[4]); lg[5] = fmaf(x, d1.y, lg[5]);
+                        lg[6] = fmaf(x, d1.z, lg[6]); lg[7] = fmaf(x, d1.w, lg[7]);
+                    }
+                }
+                if (live) {
+                    float mx = lg[0];
+#pragma unroll
+                    for (int k = 1; k < MP_ACTIONS; ++k) mx = fmaxf(mx, lg[k]);
+                    float pr[MP_ACTIONS], sum = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < MP_ACTIONS; ++k) { pr[k] = expf(lg[k] - mx); sum += pr[k]; }
+                    const float lse = mx + logf(sum), inv = 1.0f / sum;
+                    int act = 0;
+                    if (p.mode == MP_MODE_SAMPLE) {
+                        const uint64_t env = p.env_id0 + (uint64_t)eg;
+                        uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)p.offset,
+                                           (uint32_t)(p.offset >> 32) ^ ((uint32_t)a << 24)};
+                        philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), ctr);
+                        const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                        // inverse CDF over softmax(logits): the distribution of dist.sample() (distributions.py:11-13)
+                        float cum = 0.0f;
+                        bool found = false;
+                        act = MP_ACTIONS - 1;
+#pragma unroll
+                        for (int k = 0; k < MP_ACTIONS - 1; ++k) {
+                            cum += pr[k] * inv;
+                            if (!found && u < cum) { act = k; found = true; }
+                        }
+                    } else if (p.mode == MP_MODE_ARGMAX) {
+#pragma unroll
+                        for (int k = 1; k < MP_ACTIONS; ++k) if (lg[k] > lg[act]) act = k;
+                    } else {
+                        act = (int)p.action_in[row];
+                        act = act < 0 ? 0 : (act > MP_ACTIONS - 1 ? MP_ACTIONS - 1 : act);
+                    }
+                    float lp = 0.0f, ent = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < MP_ACTIONS; ++k) {
+                        const float l = lg[k] - lse;
+                        if (k == act) lp = l;
+                        ent -= pr[k] * inv * l;
+                    }
+                    if (p.action) p.action[row] = act;
+                    if (p.action_i32) p.action_i32[row] = act;
+                    if (p.logp) p.logp[row] = lp;
+                    if (p.entropy) p.entropy[row] = ent;
+                    if (p.logits) {
+                        float4 *o = reinterpret_cast<float4 *>(p.logits + row * MP_ACTIONS);
+                        o[0] = make_float4(lg[0], lg[1], lg[2], lg[3]);
+                        o[1] = make_float4(lg[4], lg[5], lg[6], lg[7]);
+                    }
+                }
+                WAIT_ACC(12);   // the value hidden layer still reads bufH: nobody may start the next tile before it is done
             }
             TS();
-            if (a < n_own && eg < p.E) {
-                float mx = lg[0];
-#pragma unroll
-                for (int k = 1; k < MP_ACTIONS; ++k) mx = fmaxf(mx, lg[k]);
-                float pr[MP_ACTIONS], sum = 0.0f;
-#pragma unroll
-                for (int k = 0; k < MP_ACTIONS; ++k) { pr[k] = expf(lg[k] - mx); sum += pr[k]; }
-                const float lse = mx + logf(sum), inv = 1.0f / sum;
-                const size_t row = (size_t)a * p.E + eg;
-                int act = 0;
-                if (p.mode == MP_MODE_SAMPLE) {
-                    const uint64_t env = p.env_id0 + (uint64_t)eg;
-                    uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)p.offset,
-                                       (uint32_t)(p.offset >> 32) ^ ((uint32_t)a << 24)};
-                    philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), ctr);
-                    const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                    // inverse CDF over softmax(logits): the distribution of dist.sample() (distributions.py:11-13)
-                    float cum = 0.0f;
-                    bool found = false;
-                    act = MP_ACTIONS - 1;
-#pragma unroll
-                    for (int k = 0; k < MP_ACTIONS - 1; ++k) {
-                        cum += pr[k] * inv;
-                        if (!found && u < cum) { act = k; found = true; }
-                    }
-                } else if (p.mode == MP_MODE_ARGMAX) {
-#pragma unroll
-                    for (int k = 1; k < MP_ACTIONS; ++k) if (lg[k] > lg[act]) act = k;
-                } else {
-                    act = (int)p.action_in[row];
-                    act = act < 0 ? 0 : (act > MP_ACTIONS - 1 ? MP_ACTIONS - 1 : act);
-                }
-                float lp = 0.0f, ent = 0.0f;
-#pragma unroll
-                for (int k = 0; k < MP_ACTIONS; ++k) {
-                    const float l = lg[k] - lse;
-                    if (k == act) lp = l;
-                    ent -= pr[k] * inv * l;
-                }
-                if (p.value) p.value[row] = value;
-                if (p.action) p.action[row] = act;
-                if (p.action_i32) p.action_i32[row] = act;
-                if (p.logp) p.logp[row] = lp;
-                if (p.entropy) p.entropy[row] = ent;
-                if (p.logits) {
-                    float4 *o = reinterpret_cast<float4 *>(p.logits + row * MP_ACTIONS);
-                    o[0] = make_float4(lg[0], lg[1], lg[2], lg[3]);
-                    o[1] = make_float4(lg[4], lg[5], lg[6], lg[7]);
-                }
-            }
         }
 #undef TS
 #undef ARRIVE_A
@@ -548,7 +595,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem);
+    if (warp == PRODUCER_WARP) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
 }  // namespace mp

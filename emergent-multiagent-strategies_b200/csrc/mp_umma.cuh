@@ -68,6 +68,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32
     return mbar_wait_slow(bar, parity, err_flag, code);
 }
 
+// one lane of a converged warp (the rest of the warp keeps executing the surrounding, warp-uniform code, which
+// lets the compiler keep addresses and descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- proxies / fences ----------------------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -1,5 +1,5 @@
 import sys, os, ctypes, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from importlib import import_module
 import policy_util as pu
 from test_policy_cpu import make
@@ -24,8 +24,8 @@ fp = pk.FusedPolicy(net, seed=3)
 print(fp.kernel_info())
 L = fp._lib
 L.mp_set_trace.argtypes = [ctypes.c_void_p]
-head = ["start", "enc+arrive", "wait(opp)", "drain z'+bar", "scores+softmax", "opp msg+arrive"]
-rnd = ["wait(TZY)", "drain z", "scores+softmax", "bar", "update+arrive"]
+head = ["start", "enc+arrive", "wait(T')", "scores', wait z', drain, combine", "opp msg+arrive"]
+rnd = ["wait(T)", "scores", "wait(ZY)+drain+combine+softmax", "update+arrive"]
 labels = head + rnd * 3 + ["wait(heads)", "heads math"]
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 for EE in (42, 4096, 16384, 65536, 262144):
