@@ -161,3 +161,13 @@ def test_fused_policy_rollout_statistics():
     assert int(R.actions.min()) >= 0 and int(R.actions.max()) <= 7
     assert len(torch.unique(R.actions)) == 8
     assert torch.isfinite(R.returns).all()
+
+
+def test_two_gpu_shards_and_nccl_update():
+    """World size 2 over NCCL (skipped on a one-GPU box; profiles/r1d_dist_train_2gpu.log holds a recorded run)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "dist_train_gpu.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "-> OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
