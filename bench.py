@@ -330,7 +330,8 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     torch.manual_seed(0)
     tr = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    tr.collect(); tr.wrap_horizon(); tr.after_update()                      # warm-up rollout
+    for _ in range(2):                                                      # eager warm-up, then the graph-capturing pass
+        tr.collect(); tr.wrap_horizon(); tr.after_update()
     torch.cuda.synchronize(dev)
     e0, e1, e2 = ev(), ev(), ev()
     e0.record(); tr.collect(); e1.record(); tr.wrap_horizon(); e2.record()
@@ -388,7 +389,8 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
                                            "frac": ach / tpeak, "flop_per_row": flop_row,
                                            "peak_source": "MEASURED_PEAKS.json bf16_tflops (fp16 runs at the bf16 rate)" if mp else "fallback 1590"},
                               "info": f.kernel_info()},
-            "gpu_launches": {"policy": sum(fz.launches for fz in tr.fused), "step": tr.env.launch_count()}}
+            "collect": "one CUDA graph of T x (2 mp_policy_kernel + fa_step + bookkeeping), replayed" if tr._graph is not None else "eager",
+            "gpu_launches_per_collect": {"mp_policy_kernel": 2 * T, "fa_step": T}}
 
 
 def sweep(fab, torch, dev, peak):

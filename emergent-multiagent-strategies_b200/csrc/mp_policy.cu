@@ -95,6 +95,7 @@ struct Params {
     int32_t *action_i32;
     uint32_t *status;
     uint64_t seed, offset, env_id0;
+    unsigned long long *counter;   // optional device call counter {count, ticket}: overrides `offset`, bumped by the last CTA
     int n_own, n_opp, E, ept, n_tiles, mode;
     unsigned long long *trace;   // optional: clock64() of row thread 0 of CTA 0 at every phase boundary of its first tile
 };
@@ -335,6 +336,9 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         float4 *dst = reinterpret_cast<float4 *>(C);
         for (int i = tid; i < MP_BLOB_CONST_FLOATS / 4; i += THREADS) dst[i] = src[i];
     }
+    // call counter of the sampling stream: read before any CTA can have finished (the bump below happens after ALL
+    // CTAs are done), so launches replayed from a CUDA graph still draw fresh numbers
+    const uint64_t call_offset = p.counter != nullptr ? (uint64_t)p.counter[0] : p.offset;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -548,8 +552,8 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                     int act = 0;
                     if (p.mode == MP_MODE_SAMPLE) {
                         const uint64_t env = p.env_id0 + (uint64_t)eg;
-                        uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)p.offset,
-                                           (uint32_t)(p.offset >> 32) ^ ((uint32_t)a << 24)};
+                        uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)call_offset,
+                                           (uint32_t)(call_offset >> 32) ^ ((uint32_t)a << 24)};
                         philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), ctr);
                         const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
                         // inverse CDF over softmax(logits): the distribution of dist.sample() (distributions.py:11-13)
@@ -596,6 +600,13 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     tc_fence_before();
     __syncthreads();
     if (warp == PRODUCER_WARP) tmem_dealloc<TMEM_COLS>(tmem);
+    if (p.counter != nullptr && tid == 0) {           // the last CTA to finish advances the call counter
+        __threadfence();
+        if (atomicAdd(&p.counter[1], 1ull) == (unsigned long long)gridDim.x - 1ull) {
+            p.counter[1] = 0ull;
+            p.counter[0] = call_offset + 1ull;
+        }
+    }
 }
 
 }  // namespace mp
@@ -615,7 +626,8 @@ int prepare() {
 }  // namespace
 
 extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const float *d_obs_opp, int n_own, int n_opp,
-                          int n_envs, int mode, uint64_t seed, uint64_t offset, uint64_t env_id0, const int64_t *d_action_in,
+                          int n_envs, int mode, uint64_t seed, uint64_t offset, uint64_t *d_counter, uint64_t env_id0,
+                          const int64_t *d_action_in,
                           float *d_value, int64_t *d_action, int32_t *d_action_i32, float *d_logp, float *d_entropy,
                           float *d_logits, uint32_t *d_status, void *stream) {
     if (!d_blob || !d_obs_own || !d_obs_opp || !d_status) return fa_internal_fail(-1, "mp_forward: NULL pointer");
@@ -634,7 +646,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     mp::Params p;
     p.blob = (const uint8_t *)d_blob; p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.action_in = d_action_in;
     p.value = d_value; p.logp = d_logp; p.entropy = d_entropy; p.logits = d_logits; p.action = d_action;
-    p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0;
+    p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0; p.counter = (unsigned long long *)d_counter;
     p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace;
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;

@@ -80,7 +80,7 @@ def _bind(L):
     if getattr(L, "_mp_bound", False):
         return
     vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
-    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, u64] + [vp] * 9
+    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 9
     i32p = ctypes.POINTER(ctypes.c_int32)
     L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
     L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp]
@@ -101,12 +101,19 @@ class FusedPolicy(object):
         self.n, self.m = module.num_agents, module.num_opp_agents
         self.seed, self.env_id0, self.calls = int(seed), int(env_id0), 0
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # device-resident call counter {count, ticket}: the kernel advances it, so CUDA-graph replays stay fresh
+        self.counter = torch.zeros(2, dtype=torch.int64, device=self.device)
         self.launches = 0
         self.refresh()
 
     def refresh(self):
-        """Re-pack the weights (after an optimizer step / load_state_dict)."""
-        self.blob = pack_mpnn(self.module, self.device)
+        """Re-pack the weights (after an optimizer step / load_state_dict) IN PLACE: launches captured in a CUDA
+        graph keep pointing at the same blob."""
+        blob = pack_mpnn(self.module, self.device)
+        if getattr(self, "blob", None) is None:
+            self.blob = blob
+        else:
+            self.blob.copy_(blob)
 
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
@@ -138,7 +145,7 @@ class FusedPolicy(object):
             action_in = action_in.to(device=dev, dtype=torch.int64).contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _capi.check(self._lib.mp_forward(self.blob.data_ptr(), own.data_ptr(), opp.data_ptr(), n, m, E, mode,
-                                         self.seed, self.calls, self.env_id0, self._ptr(action_in),
+                                         self.seed, self.calls, self.counter.data_ptr(), self.env_id0, self._ptr(action_in),
                                          out["value"].data_ptr(), out["action"].data_ptr(), out["action_i32"].data_ptr(),
                                          out["logp"].data_ptr(), self._ptr(out.get("entropy")), self._ptr(out.get("logits")),
                                          self.status.data_ptr(), stream))

@@ -89,7 +89,8 @@ class BatchedTrainer(object):
     def __init__(self, n_envs, n_guards=3, n_attackers=3, num_steps=128, max_episode_steps=100, device="cuda:0",
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
-                 use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False):
+                 use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False,
+                 graph_rollouts=True):
         self.device = torch.device(device)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
@@ -114,6 +115,10 @@ class BatchedTrainer(object):
             fused_policy = hidden_dim == 128
         self.fused = [FusedPolicy(p, seed=seed * 2 + t, env_id0=env_id0) for t, p in enumerate(self.policies)] \
             if fused_policy else None
+        # the T-step collection loop is captured into ONE CUDA graph on its second use and replayed afterwards
+        # (3 kernels of ours + ~8 small bookkeeping kernels per step; the sampling counter lives on the device)
+        self.graph_rollouts = bool(graph_rollouts) and self.fused is not None
+        self._collect_calls, self._graph = 0, None
         self.roll = SharedRollouts(num_steps, self.A, n_envs, self.device)
         self.teams = [list(range(0, n_guards)), list(range(n_guards, self.A))]
         self.roll.obs[0].copy_(self.env.reset())
@@ -147,6 +152,23 @@ class BatchedTrainer(object):
     # -- the data-collection loop of train_fortattack.train (:51-104) for E envs ---------------------
     @torch.no_grad()
     def collect(self):
+        self._collect_calls += 1
+        if not self.graph_rollouts or self._collect_calls == 1:       # first pass eager: lazy initialisation happens here
+            return self._collect()
+        if self._graph is None:
+            torch.cuda.synchronize(self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(self._graph, stream=side):
+                    self._collect()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph.replay()
+        return self.episode_rewards
+
+    @torch.no_grad()
+    def _collect(self):
         R = self.roll
         self.episode_rewards.zero_()
         for step in range(self.T):

@@ -54,13 +54,15 @@ enum {
  *   d_obs_opp   float [n_opp][E][6]  observations of the opposing team
  *   mode        MP_MODE_*
  *   seed, offset  Philox key / call counter for MP_MODE_SAMPLE (row r of call `offset` always draws the same number)
+ *   d_counter   optional uint64[2] on the device {call counter, 0}: when given it replaces `offset` and the kernel
+ *               advances it by one per launch, so launches replayed from a CUDA graph keep drawing fresh numbers
  *   env_id0     global id of env 0 of this shard (keeps samples identical under any sharding)
  *   d_action_in int64 [n_own][E], MP_MODE_EVAL only
  * Outputs (any may be NULL): d_value float [n_own][E]; d_action int64 [n_own][E]; d_action_i32 int32 [n_own][E]
  * (what fa_step reads); d_logp float [n_own][E]; d_entropy float [n_own][E]; d_logits float [n_own][E][8].
  * d_status: uint32 on the device, set non-zero if the kernel's internal pipeline timed out (a bug, never expected). */
 int mp_forward(const void *d_blob, const float *d_obs_own, const float *d_obs_opp, int n_own, int n_opp, int n_envs,
-               int mode, uint64_t seed, uint64_t offset, uint64_t env_id0, const int64_t *d_action_in, float *d_value,
+               int mode, uint64_t seed, uint64_t offset, uint64_t *d_counter, uint64_t env_id0, const int64_t *d_action_in, float *d_value,
                int64_t *d_action, int32_t *d_action_i32, float *d_logp, float *d_entropy, float *d_logits,
                uint32_t *d_status, void *stream);
 

@@ -163,6 +163,33 @@ def test_fused_policy_rollout_statistics():
     assert torch.isfinite(R.returns).all()
 
 
+def test_graph_replayed_rollouts_equal_eager():
+    """collect() replayed from one CUDA graph == the same loop launched eagerly, bit for bit, across updates
+    (sampling counter on the device, weight blob refreshed in place)."""
+    ro = import_module(PKG + ".rollout")
+    trs = []
+    for graphed in (True, False):
+        torch.manual_seed(11)
+        trs.append(ro.BatchedTrainer(128, 3, 3, num_steps=12, max_episode_steps=9, hidden_dim=128, seed=3, ppo_epoch=1,
+                                     num_mini_batch=2, graph_rollouts=graphed))
+    for it in range(4):
+        for tr in trs:
+            tr.collect()
+            tr.wrap_horizon()
+        a, b = trs[0].roll, trs[1].roll
+        for name in ("obs", "rewards", "actions", "actions_i32", "value_preds", "action_log_probs", "masks", "returns", "ends"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), (it, name)
+        assert torch.equal(trs[0].episode_rewards, trs[1].episode_rewards)
+        if it == 1:                                   # weights change under the captured graph
+            torch.manual_seed(5)
+            trs[0].update()
+            torch.manual_seed(5)
+            trs[1].update()
+        for tr in trs:
+            tr.after_update()
+    assert trs[0]._graph is not None and trs[1]._graph is None
+
+
 def test_two_gpu_shards_and_nccl_update():
     """World size 2 over NCCL (skipped on a one-GPU box; profiles/r1d_dist_train_2gpu.log holds a recorded run)."""
     if torch.cuda.device_count() < 2:
