@@ -95,6 +95,8 @@ struct Params {
     int32_t *action_i32;
     uint32_t *status;
     uint64_t seed, offset, env_id0;
+    const int32_t *env_sel;        // optional int32 [E]: outputs are written only for envs with env_sel[e] == sel_value
+    int32_t sel_value;
     unsigned long long *counter;   // optional device call counter {count, ticket}: overrides `offset`, bumped by the last CTA
     int n_own, n_opp, E, ept, n_tiles, mode;
     unsigned long long *trace;   // optional: clock64() of row thread 0 of CTA 0 at every phase boundary of its first tile
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             // logits while the value weights are still streaming in.
             WAIT_ACC(11);
             TS();
-            const bool live = a < n_own && eg < p.E;
+            const bool live = a < n_own && eg < p.E && (p.env_sel == nullptr || p.env_sel[eg] == p.sel_value);
             const size_t row = (size_t)a * p.E + eg;
             if (half == 0) {
                 WAIT_ACC(12);
@@ -629,7 +631,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
                           int n_envs, int mode, uint64_t seed, uint64_t offset, uint64_t *d_counter, uint64_t env_id0,
                           const int64_t *d_action_in,
                           float *d_value, int64_t *d_action, int32_t *d_action_i32, float *d_logp, float *d_entropy,
-                          float *d_logits, uint32_t *d_status, void *stream) {
+                          float *d_logits, const int32_t *d_env_sel, int32_t sel_value, uint32_t *d_status, void *stream) {
     if (!d_blob || !d_obs_own || !d_obs_opp || !d_status) return fa_internal_fail(-1, "mp_forward: NULL pointer");
     if (n_own < 1 || n_own > MP_MAX_TEAM || n_opp < 1 || n_opp > MP_MAX_TEAM || n_envs < 1)
         return fa_internal_fail(-1, "mp_forward: team sizes must be 1..%d and n_envs >= 1", MP_MAX_TEAM);
@@ -646,7 +648,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     mp::Params p;
     p.blob = (const uint8_t *)d_blob; p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.action_in = d_action_in;
     p.value = d_value; p.logp = d_logp; p.entropy = d_entropy; p.logits = d_logits; p.action = d_action;
-    p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0; p.counter = (unsigned long long *)d_counter;
+    p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0; p.counter = (unsigned long long *)d_counter; p.env_sel = d_env_sel; p.sel_value = sel_value;
     p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace;
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;

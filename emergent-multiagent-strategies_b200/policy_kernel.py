@@ -80,7 +80,7 @@ def _bind(L):
     if getattr(L, "_mp_bound", False):
         return
     vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
-    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 9
+    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 7 + [vp, i32, vp, vp]
     i32p = ctypes.POINTER(ctypes.c_int32)
     L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
     L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp]
@@ -118,10 +118,12 @@ class FusedPolicy(object):
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
 
-    def forward(self, own, opp, mode=MODE_SAMPLE, action_in=None, out=None, want_logits=False, want_entropy=False):
+    def forward(self, own, opp, mode=MODE_SAMPLE, action_in=None, out=None, want_logits=False, want_entropy=False,
+                env_sel=None, sel_value=0):
         """own float32 [n, E, 6], opp float32 [m, E, 6] (contiguous, agent-major).
         Returns dict(value [n,E], action int64 [n,E], action_i32 [n,E], logp [n,E], entropy?, logits?).
-        `out` may hold preallocated tensors under the same keys (e.g. views into the rollout storage)."""
+        `out` may hold preallocated tensors under the same keys (e.g. views into the rollout storage).
+        env_sel (int32 [E]) / sel_value: write outputs only for environments with env_sel[e] == sel_value."""
         n, m = self.n, self.m
         E = own.shape[1]
         if own.shape != (n, E, OBS_DIM) or opp.shape != (m, E, OBS_DIM):
@@ -143,12 +145,14 @@ class FusedPolicy(object):
                 raise ValueError("output %r must be contiguous with %d rows" % (key, n * E))
         if mode == MODE_EVAL:
             action_in = action_in.to(device=dev, dtype=torch.int64).contiguous()
+        if env_sel is not None and (env_sel.dtype != torch.int32 or env_sel.numel() != E or not env_sel.is_contiguous()):
+            raise ValueError("env_sel must be a contiguous int32 tensor with one entry per environment")
         stream = torch.cuda.current_stream(dev).cuda_stream
         _capi.check(self._lib.mp_forward(self.blob.data_ptr(), own.data_ptr(), opp.data_ptr(), n, m, E, mode,
                                          self.seed, self.calls, self.counter.data_ptr(), self.env_id0, self._ptr(action_in),
                                          out["value"].data_ptr(), out["action"].data_ptr(), out["action_i32"].data_ptr(),
                                          out["logp"].data_ptr(), self._ptr(out.get("entropy")), self._ptr(out.get("logits")),
-                                         self.status.data_ptr(), stream))
+                                         self._ptr(env_sel), int(sel_value), self.status.data_ptr(), stream))
         self.calls += 1
         self.launches += 1
         return out

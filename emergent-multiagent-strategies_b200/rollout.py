@@ -90,7 +90,7 @@ class BatchedTrainer(object):
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
                  use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False,
-                 graph_rollouts=True):
+                 graph_rollouts=True, attacker_ensemble=None):
         self.device = torch.device(device)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
@@ -115,6 +115,26 @@ class BatchedTrainer(object):
             fused_policy = hidden_dim == 128
         self.fused = [FusedPolicy(p, seed=seed * 2 + t, env_id0=env_id0) for t, p in enumerate(self.policies)] \
             if fused_policy else None
+        # Ensemble play (train_fortattack_v2.py:34-35,110-111; Learner.sample_attacker / select_attacker,
+        # learner.py:119-140): K frozen attacker checkpoints; every env draws one uniformly at each of its episode
+        # starts.  One forward per checkpoint over all envs, each writing only the envs assigned to it.
+        self.ensemble = None
+        if attacker_ensemble is not None:
+            if not fused_policy:
+                raise ValueError("attacker_ensemble needs the fused policy kernel (hidden_dim 128)")
+            self.ensemble = []
+            for k, sd in enumerate(attacker_ensemble):
+                pol = mk(n_attackers, n_guards)
+                pol.load_state_dict(sd)
+                pol.requires_grad_(False)
+                self.ensemble.append(FusedPolicy(pol, seed=seed * 2 + 1, env_id0=env_id0))
+            for f in self.ensemble[1:]:                    # one sampling stream for the attacker team
+                f.counter = self.ensemble[0].counter
+            K = len(self.ensemble)
+            self.att_id = torch.randint(0, K, (n_envs,), device=self.device, dtype=torch.int32)
+            # per checkpoint: episodes ended by [attackers all dead, time limit, fort reached] (world.gameResult),
+            # and the sums needed for the reference's test_fortattack_v2.py table (:94-124)
+            self.ensemble_results = torch.zeros(K, 4, device=self.device, dtype=torch.int64)
         # the T-step collection loop is captured into ONE CUDA graph on its second use and replayed afterwards
         # (3 kernels of ours + ~8 small bookkeeping kernels per step; the sampling counter lives on the device)
         self.graph_rollouts = bool(graph_rollouts) and self.fused is not None
@@ -131,6 +151,12 @@ class BatchedTrainer(object):
         for t, (team, opp, policy) in enumerate(((self.teams[0], self.teams[1], self.policies[0]),
                                                  (self.teams[1], self.teams[0], self.policies[1]))):
             lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
+            if t == 1 and self.ensemble is not None:
+                out = {"value": R.value_preds[step, lo:hi], "action": R.actions[step, lo:hi],
+                       "action_i32": R.actions_i32[step, lo:hi], "logp": R.action_log_probs[step, lo:hi]}
+                for k, f in enumerate(self.ensemble):
+                    f.forward(R.obs[step, lo:hi], R.obs[step, olo:ohi], MODE_SAMPLE, out=out, env_sel=self.att_id, sel_value=k)
+                continue
             if self.fused is not None:
                 # one launch: value, sampled action (int64 for the storage, int32 for the step kernel) and its
                 # log-probability are written straight into slot `step` of the shared rollout blocks
@@ -183,6 +209,12 @@ class BatchedTrainer(object):
             # the new episode's alive flags (= 1)                         (train_fortattack.py:100-104)
             R.masks[step + 1, :, :, 0] = torch.where(finished[None, :], R.obs[step + 1, :, :, 0], R.masks[step + 1, :, :, 0])
             self.episode_rewards += R.rewards[step] * masks
+            if self.ensemble is not None:
+                K = len(self.ensemble)
+                code = R.result[step].long()                                  # 0 running, 1 all dead, 2 time limit, 3 reached
+                self.ensemble_results.view(-1).index_add_(0, self.att_id.long() * 4 + code, finished.long())
+                self.att_id.copy_(torch.where(finished, torch.randint(0, K, (self.E,), device=self.device, dtype=torch.int32),
+                                              self.att_id))
         R.ends[self.T] = True                                              # (:108-109)
         return self.episode_rewards
 
@@ -194,18 +226,24 @@ class BatchedTrainer(object):
         for t, (team, opp, policy) in enumerate(((self.teams[0], self.teams[1], self.policies[0]),
                                                  (self.teams[1], self.teams[0], self.policies[1]))):
             lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
-            if self.fused is not None:
+            if t == 1 and self.ensemble is not None:
+                for k, f in enumerate(self.ensemble):
+                    f.forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]},
+                              env_sel=self.att_id, sel_value=k)
+            elif self.fused is not None:
                 self.fused[t].forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]})
             else:
                 nv[lo:hi] = policy.get_value(R.obs[T, lo:hi].reshape(-1, 6), None, R.obs[T, olo:ohi].reshape(-1, 6),
                                              None).view(len(team), self.E)
         R.compute_returns(nv, self.gamma, self.tau)            # segment GAE of all agents and envs: one launch
         if self.fused is not None:
-            for f in self.fused:
+            for f in self.fused + (self.ensemble or []):
                 f.check_status()
 
     # -- Learner.update (learner.py:175-188) ---------------------------------------------------------
-    def update(self, train_guards_only=False):
+    def update(self, train_guards_only=None):
+        if train_guards_only is None:                      # an attacker ensemble is frozen by construction
+            train_guards_only = self.ensemble is not None
         vals = []
         trainers = self.trainers[:1] if train_guards_only else self.trainers
         for t, trainer in enumerate(trainers):
@@ -220,7 +258,7 @@ class BatchedTrainer(object):
     def after_update(self):
         self.roll.after_update()
 
-    def train_once(self, train_guards_only=False):
+    def train_once(self, train_guards_only=None):
         rewards = self.collect()
         self.wrap_horizon()
         vals = self.update(train_guards_only)

@@ -190,6 +190,44 @@ def test_graph_replayed_rollouts_equal_eager():
     assert trs[0]._graph is not None and trs[1]._graph is None
 
 
+def test_attacker_ensemble_play():
+    """K frozen attacker checkpoints, one drawn per env at every episode start (learner.py:119-140,
+    train_fortattack_v2.py:34-35,110-111): each env's attacker rows come from the checkpoint it is assigned to."""
+    ro = import_module(PKG + ".rollout")
+    pk = import_module(PKG + ".policy_kernel")
+    mp = import_module(PKG + ".mpnn")
+    sds = []
+    for k in range(3):
+        torch.manual_seed(100 + k)
+        sds.append(mp.MPNN(action_space=ro._Shape(8), num_agents=3, num_opp_agents=3, input_size=6, hidden_dim=128).state_dict())
+    torch.manual_seed(0)
+    tr = ro.BatchedTrainer(300, 3, 3, num_steps=20, max_episode_steps=7, seed=2, attacker_ensemble=sds, ppo_epoch=1,
+                           num_mini_batch=2, graph_rollouts=False)
+    ids0 = tr.att_id.clone()
+    seen = [ids0.clone()]
+    R = tr.roll
+    tr.collect()
+    tr.wrap_horizon()
+    # step 0: attacker values of env e equal checkpoint ids0[e]'s own forward on the same observations
+    for k in range(3):
+        o = tr.ensemble[k].forward(R.obs[0, 3:6].contiguous(), R.obs[0, 0:3].contiguous(), pk.MODE_ARGMAX)
+        sel = ids0 == k
+        assert sel.any()
+        assert torch.equal(o["value"][:, sel], R.value_preds[0, 3:6, :, 0][:, sel])
+    assert not torch.equal(ids0, tr.att_id)                          # episodes ended (cap 7): new draws
+    n_done = int((R.done != 0).sum())
+    assert int(tr.ensemble_results.sum()) == n_done and int(tr.ensemble_results[:, 0].sum()) == 0
+    assert (tr.ensemble_results.sum(1) > 0).all()
+    before = [p.detach().clone() for p in tr.policies[1].parameters()]
+    vals = tr.update()                                               # guards only
+    assert len(vals) == 1 and all(torch.equal(a, b) for a, b in zip(before, tr.policies[1].parameters()))
+    # graph-replayed ensemble rollouts run and keep resampling
+    tr2 = ro.BatchedTrainer(300, 3, 3, num_steps=20, max_episode_steps=7, seed=2, attacker_ensemble=sds)
+    for _ in range(3):
+        tr2.collect(); tr2.wrap_horizon(); tr2.after_update()
+    assert tr2._graph is not None and int(tr2.ensemble_results.sum()) > 2 * n_done
+
+
 def test_two_gpu_shards_and_nccl_update():
     """World size 2 over NCCL (skipped on a one-GPU box; profiles/r1d_dist_train_2gpu.log holds a recorded run)."""
     if torch.cuda.device_count() < 2:
