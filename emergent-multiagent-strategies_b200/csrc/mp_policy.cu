@@ -58,18 +58,27 @@ namespace mp {
 constexpr int STAGE_BYTES = 16384;             // one streamed weight chunk (N = 64 slice, K <= 128)
 constexpr int NS = 3;                          // ring stages
 constexpr uint32_t A_LBO = 128, A_SBO = 2048;  // [128 rows] x [K = 128] fp16 operands (activations, resident weights)
+constexpr int NQ = 2;                          // threads per accumulator row (warps w, w+4, ... share a lane window);
+                                               // measured: 4 is slower (68 vs 54 us at 3v3 x 16384): the phases are latency-bound
+constexpr int ROW_WARPS = 4 * NQ, ROW_THREADS = 128 * NQ, THREADS = ROW_THREADS + 64, PRODUCER_WARP = ROW_WARPS,
+              MMA_WARP = ROW_WARPS + 1;
+constexpr int QC = 128 / NQ, QC64 = 64 / NQ;   // columns per thread of a 128-wide / 64-wide row segment
+static_assert(NQ == 2 || NQ == 4, "two or four threads per row");
+constexpr bool DW_IN_SMEM = NQ == 2;            // dist.linear.weight^T (4 KB): shared memory if it fits, else L1-cached global
+constexpr int CONST_SMEM_FLOATS = DW_IN_SMEM ? MP_BLOB_CONST_FLOATS : 1552;
 constexpr int OFF_H = 0, OFF_X = 32768, OFF_WRES = 65536, RES_BYTES = 98304, OFF_CONST = OFF_WRES + RES_BYTES,
-              OFF_RING = OFF_CONST + 10368, SMEM_BYTES = OFF_RING + NS * STAGE_BYTES;
+              OFF_RING = OFF_CONST + (DW_IN_SMEM ? 10368 : 6272), SMEM_BYTES = OFF_RING + NS * STAGE_BYTES;
 constexpr uint32_t BLOB_RES = 16384;           // blob offset of the resident part
 constexpr int N_STREAM = 6;                    // streamed chunks per tile
-constexpr int ROW_THREADS = 256, THREADS = 320, PRODUCER_WARP = 8, MMA_WARP = 9;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_T = 0, COL_Z = 128, COL_Y = 256;
-static_assert(MP_BLOB_F16_BYTES == 180224 && MP_BLOB_CONST_FLOATS * 4 <= 10368, "blob layout");
+static_assert(MP_BLOB_F16_BYTES == 180224 && CONST_SMEM_FLOATS * 4 <= OFF_RING - OFF_CONST, "blob layout");
 
 // fp32 constant offsets
 constexpr int C_ENC = 0, C_OENC = 512, C_UB = 1024, C_VB = 1152, C_VW = 1280, C_PB = 1408, C_DW = 1536, C_DB = 2560,
-              C_VB2 = 2568;
+              C_VB2 = 2568;                      // blob indices
+static_assert(C_VB2 == C_DB + 8, "value_head.2.bias follows dist.linear.bias");
+constexpr int S_DB = DW_IN_SMEM ? C_DB : 1536, S_VB2 = S_DB + 8;   // shared-memory indices of dist.linear.bias, value_head.2.bias
 
 struct Chunk {
     uint32_t off, bytes;   // in the blob
@@ -113,7 +122,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     }
 }
 
-__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -123,31 +132,31 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
     return __half22float2(*reinterpret_cast<const __half2 *>(&u));
 }
 
-// tensor-memory columns [taddr, taddr+ncols) of this thread's row -> fp16 row segment k0.. of a canonical operand
-// (ncols = 32 or 64: all loads are in flight before the one tcgen05.wait)
+// tensor-memory columns [taddr, taddr+NCOLS) of this thread's row -> fp16 row segment k0.. of a canonical operand
+// (NCOLS = 16, 32 or 64: all loads are in flight before the one tcgen05.wait)
 template <int NCOLS>
 __device__ __forceinline__ void drain(uint32_t taddr, uint8_t *buf, int r, int k0) {
-    uint32_t v[NCOLS / 32][32];
+    uint32_t v[NCOLS / 16][16];
 #pragma unroll
-    for (int q = 0; q < NCOLS / 32; ++q) tmem_ld32(taddr + (uint32_t)(q * 32), v[q]);
+    for (int q = 0; q < NCOLS / 16; ++q) tmem_ld16(taddr + (uint32_t)(q * 16), v[q]);
     tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < NCOLS / 32; ++q) {
+    for (int q = 0; q < NCOLS / 16; ++q) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {          // 8 columns -> one 16-byte chunk
+        for (int g = 0; g < 2; ++g) {          // 8 columns -> one 16-byte chunk
             uint32_t h[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 h[j] = pack_h2(__uint_as_float(v[q][g * 8 + 2 * j]), __uint_as_float(v[q][g * 8 + 2 * j + 1]));
-            *reinterpret_cast<uint4 *>(buf + canon_off(r, k0 + q * 32 + g * 8, A_LBO, A_SBO)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(buf + canon_off(r, k0 + q * 16 + g * 8, A_LBO, A_SBO)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
     }
 }
 
-// ReLU(W x + b) for the 6-float observation, outputs [j_lo, j_lo+32) -> fp16 row segment of buf (mpnn.py:127-128)
+// ReLU(W x + b) for the 6-float observation, outputs [j_lo, j_lo+QC64) -> fp16 row segment of buf (mpnn.py:127-128)
 __device__ __forceinline__ void encode(const float *W8, const float (&o)[6], uint8_t *buf, int r, int j_lo) {
 #pragma unroll 1
-    for (int j0 = j_lo; j0 < j_lo + 32; j0 += 8) {
+    for (int j0 = j_lo; j0 < j_lo + QC64; j0 += 8) {
         uint32_t h[4];
 #pragma unroll
         for (int jj = 0; jj < 8; jj += 2) {
@@ -178,20 +187,21 @@ __device__ __forceinline__ void load_obs(const float *obs, int n, int a, int E, 
     }
 }
 
-// s[b] += <32 fp32 accumulator columns of this row, fp16 segment (four 16-byte chunks from byte offset koff) of row b>
+// s[b] += <16 fp32 accumulator columns of this row, fp16 segment (two 16-byte chunks from byte offset koff) of row b>
 template <int CNT>
-__device__ __forceinline__ void dot32(const uint32_t (&v)[32], const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM],
+__device__ __forceinline__ void dot16(const uint32_t (&v)[16], const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM],
                                       uint32_t koff, float (&s)[MP_MAX_TEAM]) {
-    uint4 u[CNT > 0 ? CNT : 1][4];
+    uint4 u[CNT > 0 ? CNT : 1][2];
 #pragma unroll
     for (int b = 0; b < CNT; ++b)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) u[b][g] = *reinterpret_cast<const uint4 *>(buf + rows[b] + koff + (uint32_t)g * A_LBO);
+        for (int g = 0; g < 2; ++g) u[b][g] = *reinterpret_cast<const uint4 *>(buf + rows[b] + koff + (uint32_t)g * A_LBO);
 #pragma unroll
     for (int b = 0; b < CNT; ++b) {
+        // two scalar chains (even / odd columns); the packed FFMA2 form measured slower (56 vs 54 us at 3v3 x 16384)
         float acc0 = s[b], acc1 = 0.0f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
             const uint32_t w[4] = {u[b][g].x, u[b][g].y, u[b][g].z, u[b][g].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -204,18 +214,18 @@ __device__ __forceinline__ void dot32(const uint32_t (&v)[32], const uint8_t *bu
     }
 }
 
-// partial scores of this row against CNT other rows over NB*32 accumulator columns starting at taddr; the
+// partial scores of this row against CNT other rows over NB*16 accumulator columns starting at taddr; the
 // other rows' fp16 features start at byte offset koff0 (same columns)
 template <int CNT, int NB>
 __device__ __forceinline__ void scores(uint32_t taddr, const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM], uint32_t koff0,
                                        float (&s)[MP_MAX_TEAM]) {
     if (CNT == 0) return;
-    uint32_t v[NB][32];
+    uint32_t v[NB][16];
 #pragma unroll
-    for (int c = 0; c < NB; ++c) tmem_ld32(taddr + (uint32_t)(c * 32), v[c]);
+    for (int c = 0; c < NB; ++c) tmem_ld16(taddr + (uint32_t)(c * 16), v[c]);
     tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < NB; ++c) dot32<CNT>(v[c], buf, rows, koff0 + (uint32_t)(c * 4) * A_LBO, s);
+    for (int c = 0; c < NB; ++c) dot16<CNT>(v[c], buf, rows, koff0 + (uint32_t)(c * 2) * A_LBO, s);
 }
 
 // softmax over the first cnt entries (cnt = 0: a lone agent receives a zero message, mpnn.py:262-270)
@@ -260,8 +270,8 @@ __device__ __forceinline__ void mix8(float (&acc)[8], const uint8_t *buf, const 
 template <int CNT>
 __device__ __forceinline__ void opp_message(const uint8_t *bufX, uint8_t *bufH, int r, const uint32_t (&rows)[MP_MAX_TEAM],
                                             const float (&p)[MP_MAX_TEAM], int kc_lo) {
-#pragma unroll 2
-    for (int kc = kc_lo; kc < kc_lo + 4; ++kc) {
+#pragma unroll
+    for (int kc = kc_lo; kc < kc_lo + 8 / NQ; ++kc) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         mix8<CNT>(acc, bufX, rows, (uint32_t)(8 + kc) * A_LBO, p);
         *reinterpret_cast<uint4 *>(bufH + canon_off(r, 64 + kc * 8, A_LBO, A_SBO)) =
@@ -269,23 +279,24 @@ __device__ __forceinline__ void opp_message(const uint8_t *bufX, uint8_t *bufH, 
     }
 }
 
-// h_new = ReLU(Y + sum_b p_b z_b + bias) for columns [c0, c0+64) -> this row of bufH   (mpnn.py:157-158, folded)
+// h_new = ReLU(Y + sum_b p_b z_b + bias) for columns [c0, c0+QC) -> this row of bufH   (mpnn.py:157-158, folded)
 template <int CNT>
 __device__ __forceinline__ void update_row(uint32_t t_y, const uint8_t *bufX, uint8_t *bufH, int r, int c0,
                                            const uint32_t (&rows)[MP_MAX_TEAM], const float (&p)[MP_MAX_TEAM], const float *bias) {
-#pragma unroll 1
-    for (int c = c0; c < c0 + 64; c += 32) {
-        uint32_t y[32];
-        tmem_ld32(t_y + (uint32_t)c, y);
-        tmem_ld_wait();
+    uint32_t y[QC / 16][16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int k = c + g * 8;
+    for (int q = 0; q < QC / 16; ++q) tmem_ld16(t_y + (uint32_t)(c0 + q * 16), y[q]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < QC / 16; ++q) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int k = c0 + q * 16 + g * 8;
             const float4 b0 = *reinterpret_cast<const float4 *>(bias + k), b1 = *reinterpret_cast<const float4 *>(bias + k + 4);
-            float acc[8] = {__uint_as_float(y[g * 8]) + b0.x,     __uint_as_float(y[g * 8 + 1]) + b0.y,
-                            __uint_as_float(y[g * 8 + 2]) + b0.z, __uint_as_float(y[g * 8 + 3]) + b0.w,
-                            __uint_as_float(y[g * 8 + 4]) + b1.x, __uint_as_float(y[g * 8 + 5]) + b1.y,
-                            __uint_as_float(y[g * 8 + 6]) + b1.z, __uint_as_float(y[g * 8 + 7]) + b1.w};
+            float acc[8] = {__uint_as_float(y[q][g * 8]) + b0.x,     __uint_as_float(y[q][g * 8 + 1]) + b0.y,
+                            __uint_as_float(y[q][g * 8 + 2]) + b0.z, __uint_as_float(y[q][g * 8 + 3]) + b0.w,
+                            __uint_as_float(y[q][g * 8 + 4]) + b1.x, __uint_as_float(y[q][g * 8 + 5]) + b1.y,
+                            __uint_as_float(y[q][g * 8 + 6]) + b1.z, __uint_as_float(y[q][g * 8 + 7]) + b1.w};
             mix8<CNT>(acc, bufX, rows, (uint32_t)(k >> 3) * A_LBO, p);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.0f);
@@ -295,14 +306,19 @@ __device__ __forceinline__ void update_row(uint32_t t_y, const uint8_t *bufX, ui
     }
 }
 
-// the two halves of a row add their partial scores: write -> barrier -> read the partner's (the barrier also
+// the NQ threads of a row add their partial scores: write -> barrier -> read the partners' (the barrier also
 // publishes whatever the row threads wrote to shared memory before it)
-__device__ __forceinline__ void combine_scores(float (&s)[MP_MAX_TEAM], float (*sc)[128][MP_MAX_TEAM], int half, int r) {
+__device__ __forceinline__ void combine_scores(float (&s)[MP_MAX_TEAM], float (*sc)[128][MP_MAX_TEAM], int q, int r) {
 #pragma unroll
-    for (int b = 0; b < MP_MAX_TEAM; ++b) sc[half][r][b] = s[b];
+    for (int b = 0; b < MP_MAX_TEAM; ++b) sc[q][r][b] = s[b];
     bar_rows();
 #pragma unroll
-    for (int b = 0; b < MP_MAX_TEAM; ++b) s[b] += sc[half ^ 1][r][b];
+    for (int b = 0; b < MP_MAX_TEAM; ++b) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) t += sc[k][r][b];     // same order in every thread of the row: identical sums
+        s[b] = t;
+    }
 }
 
 // run CALL(CNT) with the team size as a compile-time constant (branch-free, fully unrolled inner loops)
@@ -320,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_a_ready, bar_acc, bar_res;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float sc[2][128][MP_MAX_TEAM];          // partial attention scores of the two halves of a row
+    __shared__ float sc[NQ][128][MP_MAX_TEAM];         // partial sums exchanged between the NQ threads of a row
     uint8_t *bufH = smem + OFF_H, *bufX = smem + OFF_X;
     float *C = reinterpret_cast<float *>(smem + OFF_CONST);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -336,7 +352,12 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     {   // fp32 constants: plain loads, once per CTA
         const float4 *src = reinterpret_cast<const float4 *>(p.blob + MP_BLOB_F16_BYTES);
         float4 *dst = reinterpret_cast<float4 *>(C);
-        for (int i = tid; i < MP_BLOB_CONST_FLOATS / 4; i += THREADS) dst[i] = src[i];
+        if (DW_IN_SMEM) {
+            for (int i = tid; i < MP_BLOB_CONST_FLOATS / 4; i += THREADS) dst[i] = src[i];
+        } else {
+            for (int i = tid; i < C_DW / 4; i += THREADS) dst[i] = src[i];                   // encoders, biases, value_head.2
+            if (tid < 4) dst[S_DB / 4 + tid] = src[C_DB / 4 + tid];                           // dist.linear.bias, value_head.2.bias
+        }
     }
     // call counter of the sampling stream: read before any CTA can have finished (the bump below happens after ALL
     // CTAs are done), so launches replayed from a CUDA graph still draw fresh numbers
@@ -420,9 +441,9 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             for (int c = 2; c < N_STREAM; ++c) stream_chunk(c);
         }
     } else {
-        // ================= row threads: row r, column half `half` =================
-        const int half = warp >> 2, r = (warp & 3) * 32 + lane;
-        const int c0 = half * 64;                                  // this thread's columns of a 128-wide row
+        // ================= row threads: row r, column slice q of NQ =================
+        const int q = warp >> 2, r = (warp & 3) * 32 + lane;
+        const int c0 = q * QC;                                     // this thread's columns of a 128-wide row
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const int ept = p.ept, n_own = p.n_own, n_opp = p.n_opp;
         const int a = r / ept, e = r - a * ept;
@@ -436,6 +457,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             rowoth[b] = (uint32_t)(ro >> 3) * A_SBO + (uint32_t)(ro & 7) * 16u;
         }
         const int n_oth = n_own - 1;
+        const float *DW = DW_IN_SMEM ? C + C_DW : reinterpret_cast<const float *>(p.blob + MP_BLOB_F16_BYTES) + C_DW;   // [128][8]
         uint32_t pc = 0;
         int ti = 0;
 #define ARRIVE_A() do { tc_fence_before(); fence_async_smem(); mbar_arrive(&bar_a_ready); } while (0)
@@ -448,9 +470,9 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int eg = tile * ept + e;
             TS();
-            // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64); 32 outputs per half
-            encode(C + C_ENC, o_own, bufH, r, half * 32);
-            encode(C + C_OENC, o_opp, bufX, r, half * 32);
+            // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64); QC64 outputs per thread
+            encode(C + C_ENC, o_own, bufH, r, q * QC64);
+            encode(C + C_OENC, o_opp, bufX, r, q * QC64);
             ARRIVE_A();
             TS();
             // ---- attention over the opponents (mpnn.py:409-437), folded: T' = h0 G', z' = hOpp Wz' -------
@@ -458,15 +480,15 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
                 WAIT_ACC(6);                                      // T'
                 TS();
-#define CALL(N) scores<N, 1>(trow + COL_T + half * 32, bufX, rowopp, (uint32_t)(half * 4) * A_LBO, s)
-                MP_DISPATCH(n_opp, CALL)                          // T' . hOpp_b over this half's 32 features
+#define CALL(N) scores<N, QC64 / 16>(trow + COL_T + q * QC64, bufX, rowopp, (uint32_t)(q * QC64 >> 3) * A_LBO, s)
+                MP_DISPATCH(n_opp, CALL)                          // T' . hOpp_b over this thread's QC64 features
 #undef CALL
                 WAIT_ACC(7);                                      // z'
-                drain<32>(trow + 64 + half * 32, bufX, r, 64 + half * 32);   // z' of opponent row r -> bufX[:, 64:128)
-                combine_scores(s, sc, half, r);                   // (barrier: every z' row is in bufX)
+                drain<QC64>(trow + 64 + q * QC64, bufX, r, 64 + q * QC64);   // z' of opponent row r -> bufX[:, 64:128)
+                combine_scores(s, sc, q, r);                      // (barrier: every z' row is in bufX)
                 softmax_small(s, n_opp, 0.125f);                  // 1/sqrt(64)
                 TS();
-#define CALL(N) opp_message<N>(bufX, bufH, r, rowopp, s, half * 4)
+#define CALL(N) opp_message<N>(bufX, bufH, r, rowopp, s, q * (8 / NQ))
                 MP_DISPATCH(n_opp, CALL)                          // h = [h0 | eOpp]
 #undef CALL
             }
@@ -478,13 +500,13 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
                 WAIT_ACC(8);                                      // T ready; Z | Y are still being computed
                 TS();
-#define CALL(N) scores<N, 2>(trow + COL_T + c0, bufH, rowoth, (uint32_t)(c0 >> 3) * A_LBO, s)
+#define CALL(N) scores<N, QC / 16>(trow + COL_T + c0, bufH, rowoth, (uint32_t)(c0 >> 3) * A_LBO, s)
                 MP_DISPATCH(n_oth, CALL)                          // (h_a G) . h_b against the team mates' h rows
 #undef CALL
                 TS();
                 WAIT_ACC(9);                                      // Z | Y ready
-                drain<64>(trow + COL_Z + c0, bufX, r, c0);       // this half of z -> bufX
-                combine_scores(s, sc, half, r);                   // (barrier: z rows visible; nobody reads bufH any more)
+                drain<QC>(trow + COL_Z + c0, bufX, r, c0);       // this slice of z -> bufX
+                combine_scores(s, sc, q, r);                      // (barrier: z rows visible; nobody reads bufH any more)
                 softmax_small(s, n_oth, 0.08838834764831845f);    // 1/sqrt(128); no self message (mpnn.py:297-298)
                 TS();
 #define CALL(N) update_row<N>(trow + COL_Y, bufX, bufH, r, c0, rowoth, s, C + C_UB)
@@ -501,97 +523,111 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 }
             }
 
-            // ---- heads (mpnn.py:174-205): half 0 = value_head, half 1 = policy_head + dist.linear + Categorical
-            // The MMA issuer commits the policy hidden layer first, then the value hidden layer: half 1 starts on the
-            // logits while the value weights are still streaming in.
+            // ---- heads (mpnn.py:174-205).  Threads q < NQ/2 evaluate the value head, the others policy_head +
+            // dist.linear, each over a slice of the 128 hidden units; partial sums meet in `sc`, thread NQ/2 of the row
+            // then finishes the Categorical.  The MMA issuer commits the policy hidden layer first, then the value
+            // hidden layer: the logits are computed while the value weights are still streaming in.
+            constexpr int HG = NQ / 2, HC = 128 / HG;             // threads per head, hidden units per thread
             WAIT_ACC(11);
             TS();
             const bool live = a < n_own && eg < p.E && (p.env_sel == nullptr || p.env_sel[eg] == p.sel_value);
             const size_t row = (size_t)a * p.E + eg;
-            if (half == 0) {
-                WAIT_ACC(12);
-                float value = C[C_VB2];
+            float value = 0.0f, lg[MP_ACTIONS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (q >= HG) {
+                const int k0 = (q - HG) * HC;
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(trow + (uint32_t)(c * 32), v);
+                for (int c = 0; c < HC; c += 16) {
+                    uint32_t w[16];
+                    tmem_ld16(trow + (uint32_t)(128 + k0 + c), w);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int k = c * 32 + j;
-                        value = fmaf(fmaxf(__uint_as_float(v[j]) + C[C_VB + k], 0.0f), C[C_VW + k], value);
-                    }
-                }
-                if (live && p.value) p.value[row] = value;
-            } else {
-                float lg[MP_ACTIONS];
-#pragma unroll
-                for (int k = 0; k < MP_ACTIONS; ++k) lg[k] = C[C_DB + k];
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t w[32];
-                    tmem_ld32(trow + (uint32_t)(128 + c * 32), w);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int k = c * 32 + j;
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = k0 + c + j;
                         const float x = fmaxf(__uint_as_float(w[j]) + C[C_PB + k], 0.0f);
-                        const float4 d0 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8);
-                        const float4 d1 = *reinterpret_cast<const float4 *>(C + C_DW + k * 8 + 4);
+                        const float4 d0 = *reinterpret_cast<const float4 *>(DW + k * 8);
+                        const float4 d1 = *reinterpret_cast<const float4 *>(DW + k * 8 + 4);
                         lg[0] = fmaf(x, d0.x, lg[0]); lg[1] = fmaf(x, d0.y, lg[1]); lg[2] = fmaf(x, d0.z, lg[2]);
                         lg[3] = fmaf(x, d0.w, lg[3]); lg[4] = fmaf(x, d1.x, lg[4]); lg[5] = fmaf(x, d1.y, lg[5]);
                         lg[6] = fmaf(x, d1.z, lg[6]); lg[7] = fmaf(x, d1.w, lg[7]);
                     }
                 }
-                if (live) {
-                    float mx = lg[0];
+                if (q > HG) {                                     // (NQ = 4) second policy thread: hand the partial logits over
 #pragma unroll
-                    for (int k = 1; k < MP_ACTIONS; ++k) mx = fmaxf(mx, lg[k]);
-                    float pr[MP_ACTIONS], sum = 0.0f;
+                    for (int k = 0; k < MP_ACTIONS; ++k) sc[2 + k / MP_MAX_TEAM][r][k % MP_MAX_TEAM] = lg[k];
+                }
+            }
+            WAIT_ACC(12);    // value hidden layer; also: it still reads bufH, nobody may start the next tile before it is done
+            if (q < HG) {
+                const int k0 = q * HC;
+#pragma unroll 1
+                for (int c = 0; c < HC; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(trow + (uint32_t)(k0 + c), v);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < MP_ACTIONS; ++k) { pr[k] = expf(lg[k] - mx); sum += pr[k]; }
-                    const float lse = mx + logf(sum), inv = 1.0f / sum;
-                    int act = 0;
-                    if (p.mode == MP_MODE_SAMPLE) {
-                        const uint64_t env = p.env_id0 + (uint64_t)eg;
-                        uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)call_offset,
-                                           (uint32_t)(call_offset >> 32) ^ ((uint32_t)a << 24)};
-                        philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), ctr);
-                        const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                        // inverse CDF over softmax(logits): the distribution of dist.sample() (distributions.py:11-13)
-                        float cum = 0.0f;
-                        bool found = false;
-                        act = MP_ACTIONS - 1;
-#pragma unroll
-                        for (int k = 0; k < MP_ACTIONS - 1; ++k) {
-                            cum += pr[k] * inv;
-                            if (!found && u < cum) { act = k; found = true; }
-                        }
-                    } else if (p.mode == MP_MODE_ARGMAX) {
-#pragma unroll
-                        for (int k = 1; k < MP_ACTIONS; ++k) if (lg[k] > lg[act]) act = k;
-                    } else {
-                        act = (int)p.action_in[row];
-                        act = act < 0 ? 0 : (act > MP_ACTIONS - 1 ? MP_ACTIONS - 1 : act);
-                    }
-                    float lp = 0.0f, ent = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < MP_ACTIONS; ++k) {
-                        const float l = lg[k] - lse;
-                        if (k == act) lp = l;
-                        ent -= pr[k] * inv * l;
-                    }
-                    if (p.action) p.action[row] = act;
-                    if (p.action_i32) p.action_i32[row] = act;
-                    if (p.logp) p.logp[row] = lp;
-                    if (p.entropy) p.entropy[row] = ent;
-                    if (p.logits) {
-                        float4 *o = reinterpret_cast<float4 *>(p.logits + row * MP_ACTIONS);
-                        o[0] = make_float4(lg[0], lg[1], lg[2], lg[3]);
-                        o[1] = make_float4(lg[4], lg[5], lg[6], lg[7]);
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = k0 + c + j;
+                        value = fmaf(fmaxf(__uint_as_float(v[j]) + C[C_VB + k], 0.0f), C[C_VW + k], value);
                     }
                 }
-                WAIT_ACC(12);   // the value hidden layer still reads bufH: nobody may start the next tile before it is done
+                if (q > 0) sc[1][r][0] = value;
+            }
+            if (NQ > 2) bar_rows();
+            if (q == 0) {
+                if (NQ > 2) value += sc[1][r][0];
+                if (live && p.value) p.value[row] = value + C[S_VB2];
+            } else if (q == HG && live) {
+#pragma unroll
+                for (int k = 0; k < MP_ACTIONS; ++k) {
+                    if (NQ > 2) lg[k] += sc[2 + k / MP_MAX_TEAM][r][k % MP_MAX_TEAM];
+                    lg[k] += C[S_DB + k];
+                }
+                float mx = lg[0];
+#pragma unroll
+                for (int k = 1; k < MP_ACTIONS; ++k) mx = fmaxf(mx, lg[k]);
+                float pr[MP_ACTIONS], sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < MP_ACTIONS; ++k) { pr[k] = expf(lg[k] - mx); sum += pr[k]; }
+                const float lse = mx + logf(sum), inv = 1.0f / sum;
+                int act = 0;
+                if (p.mode == MP_MODE_SAMPLE) {
+                    const uint64_t env = p.env_id0 + (uint64_t)eg;
+                    uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)call_offset,
+                                       (uint32_t)(call_offset >> 32) ^ ((uint32_t)a << 24)};
+                    philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), ctr);
+                    const float u = ((float)(ctr[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                    // inverse CDF over softmax(logits): the distribution of dist.sample() (distributions.py:11-13)
+                    float cum = 0.0f;
+                    bool found = false;
+                    act = MP_ACTIONS - 1;
+#pragma unroll
+                    for (int k = 0; k < MP_ACTIONS - 1; ++k) {
+                        cum += pr[k] * inv;
+                        if (!found && u < cum) { act = k; found = true; }
+                    }
+                } else if (p.mode == MP_MODE_ARGMAX) {
+#pragma unroll
+                    for (int k = 1; k < MP_ACTIONS; ++k) if (lg[k] > lg[act]) act = k;
+                } else {
+                    act = (int)p.action_in[row];
+                    act = act < 0 ? 0 : (act > MP_ACTIONS - 1 ? MP_ACTIONS - 1 : act);
+                }
+                float lp = 0.0f, ent = 0.0f;
+#pragma unroll
+                for (int k = 0; k < MP_ACTIONS; ++k) {
+                    const float l = lg[k] - lse;
+                    if (k == act) lp = l;
+                    ent -= pr[k] * inv * l;
+                }
+                if (p.action) p.action[row] = act;
+                if (p.action_i32) p.action_i32[row] = act;
+                if (p.logp) p.logp[row] = lp;
+                if (p.entropy) p.entropy[row] = ent;
+                if (p.logits) {
+                    float4 *o = reinterpret_cast<float4 *>(p.logits + row * MP_ACTIONS);
+                    o[0] = make_float4(lg[0], lg[1], lg[2], lg[3]);
+                    o[1] = make_float4(lg[4], lg[5], lg[6], lg[7]);
+                }
             }
             TS();
         }
