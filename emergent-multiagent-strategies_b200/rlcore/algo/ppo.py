@@ -97,15 +97,76 @@ class JointPPO(object):
         var = (s[1] - n * mean * mean) / (n - 1)
         return ((adv - mean.to(adv.dtype)) / (var.clamp_min(0).sqrt().to(adv.dtype) + 1e-5))
 
-    def update(self, rollouts_list, opp_rollouts_list, index_batches=None):
+    def update(self, rollouts_list, opp_rollouts_list, index_batches=None, shared=None):
         """index_batches (optional, testing): per epoch, a list of index tensors to use as the minibatches
-        instead of chunks of a fresh random permutation."""
+        instead of chunks of a fresh random permutation.
+        shared (optional): (SharedRollouts, a0, n, o0, m) when the per-agent storages are views of the shared rollout
+        blocks -- minibatches are then gathered by ONE kernel and the clipped-PPO loss and its gradient are evaluated
+        by ONE kernel (rlcore/fused.py), instead of ~60 index/cat and ~30 elementwise launches per minibatch."""
+        self._shared = shared
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(self.allow_tf32)
         try:
+            if shared is not None and self.use_clipped_value_loss and rollouts_list[0].rewards.is_cuda:
+                return self._update_fused(rollouts_list, index_batches)
             return self._update(rollouts_list, opp_rollouts_list, index_batches)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+    def _update_fused(self, rollouts_list, index_batches=None):
+        try:
+            from .. import fused
+        except ImportError:
+            from rlcore import fused
+        R, a0, n, o0, m = self._shared
+        advantages = torch.stack([self._advantages(r)[..., 0] for r in rollouts_list]).contiguous()      # [n, T, E]
+        T, P = rollouts_list[0].rewards.size()[0:2]
+        dev = advantages.device
+        batch_size = T * P
+        mini_batch_size = int(batch_size / self.num_mini_batch)
+        totals = torch.zeros(3, device=dev)
+        params = [p for p in self.actor_critic.parameters()]
+        world = self._world()
+        n_updates = 0
+        for epoch in range(self.ppo_epoch):
+            if index_batches is not None:
+                batches = index_batches[epoch]
+            else:
+                perm = self._perm(rollouts_list[0])
+                batches = [perm[i:i + mini_batch_size] for i in range(0, batch_size, mini_batch_size)]
+            for idx in batches:
+                idx = idx.to(dev).contiguous()
+                (obs_batch, mask, obs_opp_batch, actions_batch, value_preds_batch, return_batch, masks_batch,
+                 old_log_probs_batch, adv_targ, alive_sum) = fused.gather_minibatch(R, idx, a0, n, o0, m, advantages)
+                values, action_log_probs, dist_entropy, _ = self.actor_critic.evaluate_actions(
+                    obs_batch, None, obs_opp_batch, masks_batch, actions_batch)
+                count = mask.new_full((1,), float(mask.numel()))
+                if world == 1:
+                    norm = torch.where(alive_sum != 0, alive_sum, count)          # mask.mean() != 0 else 1 (ppo.py:150-187)
+                else:
+                    g = self._allreduce(torch.cat([alive_sum, count]))
+                    norm = torch.where(g[0:1] != 0, g[0:1], g[1:2]) / world
+                loss, stats = fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch,
+                                             old_log_probs_batch, adv_targ, mask, norm, self.clip_param,
+                                             self.value_loss_coef, self.entropy_coef)
+                self.optimizer.zero_grad()
+                loss.backward()
+                if world > 1:
+                    grads = [p.grad for p in params if p.grad is not None]
+                    flat = torch.cat([g_.reshape(-1) for g_ in grads])
+                    self._allreduce(flat).div_(world)
+                    off = 0
+                    for g_ in grads:
+                        g_.copy_(flat[off:off + g_.numel()].view_as(g_))
+                        off += g_.numel()
+                nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
+                self.optimizer.step()
+                totals += stats[:3]
+                n_updates += 1
+        if world > 1:
+            totals = self._allreduce(totals) / world
+        v, a, e = (totals / max(n_updates, 1)).tolist()
+        return v, a, e
 
     def _update(self, rollouts_list, opp_rollouts_list, index_batches=None):
         advantages_list = [self._advantages(r) for r in rollouts_list]

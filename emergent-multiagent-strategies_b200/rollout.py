@@ -90,7 +90,7 @@ class BatchedTrainer(object):
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
                  use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False,
-                 graph_rollouts=True, attacker_ensemble=None):
+                 graph_rollouts=True, attacker_ensemble=None, fused_update=True):
         self.device = torch.device(device)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
@@ -104,6 +104,7 @@ class BatchedTrainer(object):
                                   max_grad_norm=max_grad_norm, use_clipped_value_loss=use_clipped_value_loss,
                                   process_group=process_group, allow_tf32=allow_tf32) for p in self.policies]
         self.process_group = process_group
+        self.fused_update = bool(fused_update)      # minibatch gather + clipped-PPO loss kernels (rlcore/fused.py)
         if process_group is not None:                    # replicas start from rank 0's weights
             import torch.distributed as dist
             for p in self.policies:
@@ -249,7 +250,9 @@ class BatchedTrainer(object):
         for t, trainer in enumerate(trainers):
             own = [self.roll.agents[i] for i in self.teams[t]]
             opp = [self.roll.agents[i] for i in self.teams[1 - t]]
-            vals.append(trainer.update(own, opp))
+            lo, olo = self.teams[t][0], self.teams[1 - t][0]
+            shared = (self.roll, lo, len(own), olo, len(opp)) if self.fused_update else None
+            vals.append(trainer.update(own, opp, shared=shared))
         if self.fused is not None:                         # the optimizer moved the weights: re-pack the kernel's blob
             for f in self.fused:
                 f.refresh()

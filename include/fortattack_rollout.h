@@ -34,6 +34,34 @@ extern "C" {
 int rl_gae(const float *d_rewards, float *d_value_preds, const float *d_next_value, const float *d_masks,
            const uint8_t *d_ends, float *d_returns, int T, int A, int E, double gamma, double tau, void *stream);
 
+/* Team minibatch gather (replaces magent_feed_forward_generator's per-agent index + cat,
+ * rlcore/algo/ppo.py:207-246): for mb sample indices idx[j] = t * E + e and the team's agents a0 .. a0+n-1 (opponents
+ * o0 .. o0+m-1), rows are emitted agent-major (row = k * mb + j), exactly the order torch.cat([x[i][idx] ...]) gives.
+ *   inputs  (shared rollout blocks, SharedRollouts): d_obs float [T+1][A][E][6]; d_actions int64 [T][A][E];
+ *           d_value_preds / d_returns / d_masks float [T+1][A][E]; d_old_logp float [T][A][E]; d_adv float [n][T][E]
+ *   outputs: obs_own float [n*mb][6], obs_opp float [m*mb][6], actions int64 [n*mb], value_preds, returns, masks,
+ *            old_logp, adv, alive float [n*mb] (alive = obs_own[:, 0], the loss mask of ppo.py:224), and
+ *            d_alive_sum float [1] += sum(alive)  (zero it first; it is the loss normaliser) */
+int rl_gather_minibatch(const int64_t *d_idx, int mb, int T, int A, int E, int a0, int n, int o0, int m,
+                        const float *d_obs, const int64_t *d_actions, const float *d_value_preds, const float *d_returns,
+                        const float *d_masks, const float *d_old_logp, const float *d_adv, float *obs_own, float *obs_opp,
+                        int64_t *actions, float *value_preds, float *returns, float *masks, float *old_logp, float *adv,
+                        float *alive, float *d_alive_sum, void *stream);
+
+/* Masked clipped-PPO loss, forward and gradient in one pass (rlcore/algo/ppo.py:150-187 with
+ * use_clipped_value_loss=True):  with S = *d_norm (sum of the alive mask, or N if that is 0; made global by the caller
+ * in multi-rank runs),
+ *   entropy     = sum(ent * mask) / S
+ *   action_loss = sum(mask * -min(r * adv, clamp(r, 1-c, 1+c) * adv)) / S,   r = mask * exp(logp - old_logp)
+ *   value_loss  = sum(mask * 0.5 * max((v - ret)^2, (old_v + clamp(v - old_v, -c, c) - ret)^2)) / S
+ *   total       = value_loss * vcoef + action_loss - entropy * ecoef
+ * d_out float [4] += {value_loss, action_loss, entropy, total} (zero it first); d_gvalues / d_glogp / d_gentropy
+ * float [N] receive d total / d input (torch's tie rule for min/max: the gradient is split evenly). */
+int rl_ppo_loss(const float *d_values, const float *d_logp, const float *d_entropy, const float *d_old_values,
+                const float *d_returns, const float *d_old_logp, const float *d_adv, const float *d_mask,
+                const float *d_norm, int N, float clip, float vcoef, float ecoef, float *d_out, float *d_gvalues,
+                float *d_glogp, float *d_gentropy, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

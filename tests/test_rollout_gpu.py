@@ -190,6 +190,64 @@ def test_graph_replayed_rollouts_equal_eager():
     assert trs[0]._graph is not None and trs[1]._graph is None
 
 
+def test_fused_gather_and_loss_match_torch_path():
+    """rl_gather_minibatch == magent_feed_forward_generator (bit-equal rows); rl_ppo_loss == the torch expressions of
+    ppo.py:150-187 (values and autograd gradients); a fused update tracks the unfused one."""
+    ro = import_module(PKG + ".rollout")
+    ppo = import_module(PKG + ".rlcore.algo.ppo")
+    fused = import_module(PKG + ".rlcore.fused")
+    torch.manual_seed(3)
+    tr = ro.BatchedTrainer(200, 3, 2, num_steps=24, max_episode_steps=9, seed=4, ppo_epoch=1, num_mini_batch=4)
+    tr.collect(); tr.wrap_horizon()
+    R = tr.roll
+    own, opp = [R.agents[i] for i in (0, 1, 2)], [R.agents[i] for i in (3, 4)]
+    trainer = tr.trainers[0]
+    adv_list = [trainer._advantages(r) for r in own]
+    idx = torch.randperm(24 * 200)[:1111].cuda()
+    ref = next(ppo.magent_feed_forward_generator(own, opp, adv_list, 4, index_batches=[idx]))
+    (obs_b, mask_b, opp_b, hid_b, act_b, val_b, ret_b, msk_b, olp_b, adv_b) = ref
+    adv = torch.stack([a[..., 0] for a in adv_list]).contiguous()
+    g = fused.gather_minibatch(R, idx, 0, 3, 3, 2, adv)
+    for got, want in zip(g[:9], (obs_b, mask_b, opp_b, act_b, val_b, ret_b, msk_b, olp_b, adv_b)):
+        assert got.shape == want.shape and torch.equal(got, want)
+    assert float(g[9]) == float(mask_b.sum())
+    # loss + gradients
+    gen = torch.Generator().manual_seed(0)
+    N = mask_b.numel()
+    values = (val_b + 0.3 * torch.randn(N, 1, generator=gen).cuda()).requires_grad_()
+    logp = (olp_b + 0.3 * torch.randn(N, 1, generator=gen).cuda()).requires_grad_()
+    ent = (1.5 + 0.2 * torch.randn(N, generator=gen).cuda()).requires_grad_()
+    clip, vc, ec = 0.2, 0.5, 0.01
+    norm = mask_b.sum().view(1)
+    total, stats = fused.ppo_loss(values, logp, ent, val_b, ret_b, olp_b, adv_b, mask_b, norm, clip, vc, ec)
+    total.backward()
+    got_grads = [values.grad.clone(), logp.grad.clone(), ent.grad.clone()]
+    for t in (values, logp, ent):
+        t.grad = None
+    mm = lambda x: x.mean() / mask_b.mean()
+    entropy = mm(ent * mask_b[:, 0])
+    ratio = mask_b * torch.exp(logp - olp_b)
+    action_loss = mm(mask_b * -torch.min(ratio * adv_b, torch.clamp(ratio, 1 - clip, 1 + clip) * adv_b))
+    clipped = val_b + (values - val_b).clamp(-clip, clip)
+    value_loss = mm(0.5 * torch.max((values - ret_b).pow(2), (clipped - ret_b).pow(2)) * mask_b)
+    ref_total = value_loss * vc + action_loss - entropy * ec
+    ref_total.backward()
+    assert torch.allclose(stats[:3], torch.stack([value_loss, action_loss, entropy]).detach(), rtol=2e-5, atol=1e-6)
+    assert abs(float(total) - float(ref_total)) < 2e-5 * max(1.0, abs(float(ref_total)))
+    for got, t in zip(got_grads, (values, logp, ent)):
+        assert torch.allclose(got, t.grad, rtol=1e-4, atol=1e-9)
+    # whole update: fused and unfused trainers see the same rollouts and permutations
+    trs = []
+    for fu in (True, False):
+        torch.manual_seed(8)
+        t2 = ro.BatchedTrainer(128, 3, 3, num_steps=16, max_episode_steps=9, seed=6, ppo_epoch=2, num_mini_batch=4, fused_update=fu)
+        t2.collect(); t2.wrap_horizon()
+        torch.manual_seed(9)
+        trs.append(t2.update())
+    for a, b in zip(trs[0], trs[1]):
+        assert np.allclose(a, b, rtol=2e-3, atol=2e-4), (trs[0], trs[1])
+
+
 def test_attacker_ensemble_play():
     """K frozen attacker checkpoints, one drawn per env at every episode start (learner.py:119-140,
     train_fortattack_v2.py:34-35,110-111): each env's attacker rows come from the checkpoint it is assigned to."""
