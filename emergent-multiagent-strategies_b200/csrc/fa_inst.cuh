@@ -6,24 +6,42 @@ namespace fa {
 
 #define FA_FOR_NA(X) X(1) X(2) X(3) X(4) X(5)
 
+// p.pdl: launch with programmatic stream serialization, so that consecutive steps overlap their launch latency and
+// action fetch with the predecessor's tail (see pdl_wait() in fa_kernels.cuh)
+template <typename K, typename R>
+static cudaError_t launch_one(K kernel, const StepParams<R> &p, int grid, int block, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 template <int NG, typename R>
 cudaError_t launch_step_g(int na, bool many, bool wide, const StepParams<R> &p, int grid, int block, cudaStream_t stream) {
+    cudaError_t e = cudaSuccess;
     switch (na) {
-#define FA_CASE(NA)                                                                          \
-    case NA:                                                                                 \
-        if (wide) {                                                                          \
-            if (many) fa_step_wide_kernel<NG, NA, R, true><<<grid, block, 0, stream>>>(p);   \
-            else fa_step_wide_kernel<NG, NA, R, false><<<grid, block, 0, stream>>>(p);       \
-        } else {                                                                             \
-            if (many) fa_step_kernel<NG, NA, R, true><<<grid, block, 0, stream>>>(p);        \
-            else fa_step_kernel<NG, NA, R, false><<<grid, block, 0, stream>>>(p);            \
-        }                                                                                    \
+#define FA_CASE(NA)                                                                                   \
+    case NA:                                                                                          \
+        if (wide) {                                                                                   \
+            if (many) e = launch_one(fa_step_wide_kernel<NG, NA, R, true>, p, grid, block, stream);   \
+            else e = launch_one(fa_step_wide_kernel<NG, NA, R, false>, p, grid, block, stream);       \
+        } else {                                                                                      \
+            if (many) e = launch_one(fa_step_kernel<NG, NA, R, true>, p, grid, block, stream);        \
+            else e = launch_one(fa_step_kernel<NG, NA, R, false>, p, grid, block, stream);            \
+        }                                                                                             \
         break;
         FA_FOR_NA(FA_CASE)
 #undef FA_CASE
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <int NG, typename R>

@@ -69,6 +69,7 @@ template <typename R> struct StepParams {
     uint8_t *done;        // [T][E]        (may be null)
     uint8_t *result;      // [T][E]        (may be null)
     int E, T, max_steps, auto_reset, obs_vec_ok;
+    int pdl;              // launched with programmatic stream serialization: the state is read after griddepcontrol.wait
     uint64_t seed, env_id0;
 };
 
@@ -182,6 +183,13 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
 __device__ __forceinline__ double u01(uint32_t r) {
     return __dmul_rn(__dadd_rn((double)r, 0.5), 1.0 / 4294967296.0);
 }
+
+// Programmatic dependent launch (sm_90+): a step launched with the attribute may start while the previous step of
+// the same stream is still running; everything it does before pdl_wait() (index arithmetic, fetching this step's
+// actions, which no step kernel writes) overlaps the predecessor's tail and the launch latency.  pdl_wait() returns
+// once the predecessor grid has completed and its writes are visible.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 template <int A, typename R> struct Env {
@@ -458,14 +466,16 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) fa_step_kernel(const StepParam
     const size_t E = (size_t)p.E;
     const bool vec = p.obs_vec_ok && (e - lane + 32 <= p.E);
 
+    pdl_launch_dependents();
+    int act[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) act[i] = p.act[i * E + ec];
+    pdl_wait();
+
     Env<A, R> s;
     load_env<A, R>(s, p.st, E, ec);
     uint32_t ep = 0;
     if (MANY) ep = p.st.episode[ec];
-
-    int act[A];
-#pragma unroll
-    for (int i = 0; i < A; ++i) act[i] = p.act[i * E + ec];
 
     const int T = MANY ? p.T : 1;
     for (int t = 0; t < T; ++t) {
@@ -533,6 +543,9 @@ __global__ void __launch_bounds__(32 * (NG + NA)) fa_step_wide_kernel(const Step
     const bool attacker = i >= NG;                                     // warp-uniform
     const int j0 = attacker ? 0 : NG, nopp = attacker ? NG : NA;      // the other team
 
+    pdl_launch_dependents();
+    int act = p.act[i * E + ec];
+    pdl_wait();
     Env<1, R> s;                                                       // this thread's agent
     {
         const typename VecT<R>::T4 v = p.st.pv[i * E + ec];
@@ -542,7 +555,6 @@ __global__ void __launch_bounds__(32 * (NG + NA)) fa_step_wide_kernel(const Step
         s.t = p.st.tstep[ec];
     }
     uint32_t ep = p.st.episode[ec];
-    int act = p.act[i * E + ec];
     const int T = MANY ? p.T : 1;
     for (int t = 0; t < T; ++t) {
         int nxt = 0;
