@@ -277,7 +277,11 @@ def run_ours(args):
     achieved = bytes_launch / (ms_total * 1e-3 / K) / 1e9
     info = env.kernel_info()
     roofline = {"kernel": "fa::fa_step_wide_kernel<3,3,float,false>" if info["mapping"] == "agent" else "fa::fa_step_kernel<3,3,float,false>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch under `ncu --set full` (profiles/): at 4096 envs the
+                # state and actions are read from DRAM once, the 1.4 MB of results are still in L2 when the launch ends
+                "traffic": 834048 if (E == 4096 and info["mapping"] == "agent") else None,
+                "traffic_source": "profiles/r1c_step_3v3_E4096_ncu_full.txt", "peak_source": peak_src,
                 "bytes_per_launch": bytes_launch, "launch_us": 1e3 * ms_total / K,
                 "regs": info["regs"], "block": info["block"], "grid": info["grid"], "mapping": info["mapping"]}
     extra = {}
