@@ -141,7 +141,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm runs one shard of %d envs on the host cores whatever N is" % E_PER_GPU},
+            "config": {"workload": WORKLOAD, "note": "CPU arm runs one shard of %d envs on the host cores whatever N is" % E_PER_GPU,
+                       "what_runs": "oracle/fa_oracle.c: the reference's float64 arithmetic restated in C with one pthread per core "
+                                    "(the reference itself is Python and cannot travel to the GPU box; through the import shim it "
+                                    "steps ~1 450 envs/s per core at 3v3 = ~8.7e3 agent-steps/s per core, SURVEY.md section 6)"},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -386,7 +389,9 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     return {"workload": "FortAttack 3v3 (BASELINE.json configs[2]), %d envs, T=%d rollout with the MPNN policy + one JointPPO update" % (E, T),
             "rollout_agent_steps_per_s": E * A * T / (collect_ms * 1e-3), "collect_ms": collect_ms,
             "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_tf32_ms": update_tf32_ms,
-            "ppo_update": "4 epochs x 32 minibatches x 2 teams, torch autograd on the MPNN module", "losses": vals,
+            "ppo_update": "4 epochs x 32 minibatches x 2 teams: torch autograd for the dense layers; attention forward/backward, "
+                          "minibatch gather and clipped-PPO loss are this repo's kernels (rl_attn_*, rl_gather_minibatch, rl_ppo_loss)",
+            "losses": vals,
             "policy_kernel": {"kernel": "mp::mp_policy_kernel", "us_per_team_forward": pol_us, "rows": NG * E,
                               "torch_module_act_us": torch_us, "speedup_vs_torch_module": torch_us / pol_us,
                               "roofline": {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",

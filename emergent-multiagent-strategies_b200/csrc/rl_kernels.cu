@@ -4,6 +4,7 @@
 // consecutive envs of one agent, so every load/store is a coalesced 128-byte request.  HBM-bound streaming:
 // 4 floats read (reward, V[t+1] is carried in a register, V[t], mask) + 1 written per (t, agent, env).
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/fortattack_rollout.h"
@@ -142,7 +143,197 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
     }
 }
 
+// ---- tiny attention: one warp per batch element, the 32 lanes split the feature dimension (VEC floats each) --------
+constexpr int ATT_MAX = 5;
+struct Opnd { float *p; long long bs, rs; };
+
+template <int VEC> struct VecLoad;
+template <> struct VecLoad<1> { static __device__ __forceinline__ void ld(const float *p, float (&v)[1]) { v[0] = *p; }
+                                static __device__ __forceinline__ void st(float *p, const float (&v)[1]) { *p = v[0]; } };
+template <> struct VecLoad<2> { static __device__ __forceinline__ void ld(const float *p, float (&v)[2]) { const float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y; }
+                                static __device__ __forceinline__ void st(float *p, const float (&v)[2]) { *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]); } };
+template <> struct VecLoad<3> { static __device__ __forceinline__ void ld(const float *p, float (&v)[3]) { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; }
+                                static __device__ __forceinline__ void st(float *p, const float (&v)[3]) { p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; } };
+template <> struct VecLoad<4> { static __device__ __forceinline__ void ld(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+                                static __device__ __forceinline__ void st(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); } };
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+    return x;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(Opnd A, Opnd B, Opnd V, Opnd O, float *attn, int batch, int n, int m,
+                                                       float norm, int mask_diag) {
+    const int lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const int c = lane * VEC;
+    float bb[ATT_MAX][VEC], vv[ATT_MAX][VEC];
+#pragma unroll
+    for (int j = 0; j < ATT_MAX; ++j)
+        if (j < m) {
+            VecLoad<VEC>::ld(B.p + b * B.bs + j * B.rs + c, bb[j]);
+            VecLoad<VEC>::ld(V.p + b * V.bs + j * V.rs + c, vv[j]);
+        }
+#pragma unroll
+    for (int i = 0; i < ATT_MAX; ++i) {
+        if (i < n) {
+            float a[VEC];
+            VecLoad<VEC>::ld(A.p + b * A.bs + i * A.rs + c, a);
+            float s[ATT_MAX], mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < ATT_MAX; ++j) {
+                s[j] = -INFINITY;
+                if (j < m) {
+                    float d = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) d = fmaf(a[q], bb[j][q], d);
+                    d = warp_sum(d) * norm;
+                    s[j] = (mask_diag && i == j) ? -INFINITY : d;
+                    mx = fmaxf(mx, s[j]);
+                }
+            }
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < ATT_MAX; ++j) {
+                s[j] = (j < m && s[j] != -INFINITY) ? expf(s[j] - mx) : 0.0f;
+                sum += s[j];
+            }
+            const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+            float o[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o[q] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < ATT_MAX; ++j)
+                if (j < m) {
+                    s[j] *= inv;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) o[q] = fmaf(s[j], vv[j][q], o[q]);
+                    if (lane == j) attn[(b * n + i) * m + j] = s[j];
+                }
+            VecLoad<VEC>::st(O.p + b * O.bs + i * O.rs + c, o);
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(128) attn_bwd_kernel(Opnd G, Opnd A, Opnd B, Opnd V, const float *attn, Opnd dA, Opnd dB,
+                                                       Opnd dV, int batch, int n, int m, float norm) {
+    const int lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const int c = lane * VEC;
+    float bb[ATT_MAX][VEC], vv[ATT_MAX][VEC], db[ATT_MAX][VEC], dv[ATT_MAX][VEC];
+#pragma unroll
+    for (int j = 0; j < ATT_MAX; ++j)
+        if (j < m) {
+            VecLoad<VEC>::ld(B.p + b * B.bs + j * B.rs + c, bb[j]);
+            VecLoad<VEC>::ld(V.p + b * V.bs + j * V.rs + c, vv[j]);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) { db[j][q] = 0.0f; dv[j][q] = 0.0f; }
+        }
+#pragma unroll
+    for (int i = 0; i < ATT_MAX; ++i) {
+        if (i < n) {
+            float a[VEC], g[VEC], p[ATT_MAX], dp[ATT_MAX];
+            VecLoad<VEC>::ld(A.p + b * A.bs + i * A.rs + c, a);
+            VecLoad<VEC>::ld(G.p + b * G.bs + i * G.rs + c, g);
+            float dot = 0.0f;                       // sum_j p_ij dp_ij
+#pragma unroll
+            for (int j = 0; j < ATT_MAX; ++j) {
+                p[j] = 0.0f; dp[j] = 0.0f;
+                if (j < m) {
+                    p[j] = attn[(b * n + i) * m + j];
+                    float d = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        d = fmaf(g[q], vv[j][q], d);
+                        dv[j][q] = fmaf(p[j], g[q], dv[j][q]);
+                    }
+                    dp[j] = warp_sum(d);
+                    dot = fmaf(p[j], dp[j], dot);
+                }
+            }
+            float da[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) da[q] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < ATT_MAX; ++j)
+                if (j < m) {
+                    const float ds = p[j] * (dp[j] - dot) * norm;     // softmax backward; masked entries have p = 0
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        da[q] = fmaf(ds, bb[j][q], da[q]);
+                        db[j][q] = fmaf(ds, a[q], db[j][q]);
+                    }
+                }
+            VecLoad<VEC>::st(dA.p + b * dA.bs + i * dA.rs + c, da);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < ATT_MAX; ++j)
+        if (j < m) {
+            VecLoad<VEC>::st(dB.p + b * dB.bs + j * dB.rs + c, db[j]);
+            VecLoad<VEC>::st(dV.p + b * dV.bs + j * dV.rs + c, dv[j]);
+        }
+}
+
 }  // namespace rl
+
+static int attn_check(const char *who, int batch, int n, int m, int k, const RlAttnOperand *const *ops, int nops) {
+    if (batch < 1 || n < 1 || m < 1 || n > rl::ATT_MAX || m > rl::ATT_MAX || k < 32 || k > 128 || k % 32 != 0)
+        return fa_internal_fail(-1, "%s: need 1 <= n, m <= %d and k in {32, 64, 96, 128}", who, rl::ATT_MAX);
+    const int vec = k / 32;
+    for (int i = 0; i < nops; ++i) {
+        if (!ops[i] || !ops[i]->ptr) return fa_internal_fail(-1, "%s: NULL operand", who);
+        if (vec == 2 || vec == 4) {     // vector loads: every row must start on a VEC * 4 byte boundary
+            const uintptr_t al = (uintptr_t)vec * 4;
+            if (((uintptr_t)ops[i]->ptr % al) || (ops[i]->batch_stride % vec) || (ops[i]->row_stride % vec))
+                return fa_internal_fail(-4, "%s: operand %d is not aligned for %d-float vector access", who, i, vec);
+        }
+    }
+    return 0;
+}
+static rl::Opnd opnd(const RlAttnOperand *o) { return rl::Opnd{o->ptr, (long long)o->batch_stride, (long long)o->row_stride}; }
+
+extern "C" int rl_attn_forward(const RlAttnOperand *A, const RlAttnOperand *B, const RlAttnOperand *V, const RlAttnOperand *out,
+                               float *d_attn, int batch, int n, int m, int k, float norm, int mask_diag, void *stream) {
+    const RlAttnOperand *ops[4] = {A, B, V, out};
+    if (int rc = attn_check("rl_attn_forward", batch, n, m, k, ops, 4)) return rc;
+    if (!d_attn) return fa_internal_fail(-1, "rl_attn_forward: NULL attention output");
+    const int grid = (batch + 3) / 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (k / 32) {
+        case 1: rl::attn_fwd_kernel<1><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
+        case 2: rl::attn_fwd_kernel<2><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
+        case 3: rl::attn_fwd_kernel<3><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
+        default: rl::attn_fwd_kernel<4><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_forward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rl_attn_backward(const RlAttnOperand *dout, const RlAttnOperand *A, const RlAttnOperand *B, const RlAttnOperand *V,
+                                const float *d_attn, const RlAttnOperand *dA, const RlAttnOperand *dB, const RlAttnOperand *dV,
+                                int batch, int n, int m, int k, float norm, void *stream) {
+    const RlAttnOperand *ops[7] = {dout, A, B, V, dA, dB, dV};
+    if (int rc = attn_check("rl_attn_backward", batch, n, m, k, ops, 7)) return rc;
+    if (!d_attn) return fa_internal_fail(-1, "rl_attn_backward: NULL attention input");
+    const int grid = (batch + 3) / 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (k / 32) {
+        case 1: rl::attn_bwd_kernel<1><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
+        case 2: rl::attn_bwd_kernel<2><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
+        case 3: rl::attn_bwd_kernel<3><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
+        default: rl::attn_bwd_kernel<4><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_backward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 extern "C" int rl_gather_minibatch(const int64_t *d_idx, int mb, int T, int A, int E, int a0, int n, int o0, int m,
                                    const float *d_obs, const int64_t *d_actions, const float *d_value_preds,

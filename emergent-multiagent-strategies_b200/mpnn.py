@@ -144,7 +144,43 @@ class MPNN(nn.Module):
     def opp_attn_mat(self):
         return None if self._opp_attn is None else self._opp_attn.squeeze(0).squeeze(0).detach().cpu().numpy()
 
+    # Training-time forward on CUDA with the two attentions as fused kernels (rlcore/fused.py, csrc/rl_kernels.cu): same
+    # function as _fwd, but everything stays in the agent-major row layout (no transposes), Q|K|V come from one product,
+    # the [batch, n, n] bmm -> mask -> softmax -> bmm chains (42 % of the TF32 update, profiles/) are one kernel each way,
+    # and update(cat(h, msg)) is two accumulating GEMMs instead of cat + GEMM.  Opt-in: `fused_attention = True`.
+    fused_attention = False
+
+    def _fwd_fused(self, inp, oppInp):
+        try:
+            from .rlcore import fused
+        except ImportError:
+            from rlcore import fused
+        n, m = self.num_agents, self.num_opp_agents
+        oa, ms = self.oppAttn, self.messages
+        h0 = self.encoder(inp)                                                     # [n*B, 64] agent-major rows
+        hO = self.oppEncoder(oppInp)                                               # [m*B, 64]
+        e, oattn = fused.cross_attention(h0 @ oa.W_key[0], hO @ torch.cat((oa.W_query[0], oa.W_val[0]), dim=1),
+                                         n, m, oa.norm_factor)
+        h = torch.cat((h0, e @ oa.W_out[0]), dim=1)                                # [n*B, 128]
+        wqkv = torch.cat((ms.W_query[0], ms.W_key[0], ms.W_val[0]), dim=1)
+        W, bias = self.update[0].weight, self.update[0].bias
+        U1t, U2t = W[:, :self.h_dim].t(), W[:, self.h_dim:].t()
+        attn = None
+        for _ in range(self.K):
+            if n > 1:
+                msg, attn = fused.self_attention(h @ wqkv, n, ms.norm_factor)
+                h = torch.relu(torch.addmm(torch.addmm(bias, h, U1t), msg @ ms.W_out[0], U2t))
+            else:                                                                  # a lone agent receives a zero message
+                h = torch.relu(torch.addmm(bias, h, U1t))
+        self._opp_attn = oattn
+        # a lone agent: the reference reports a zero attention matrix (mpnn.py:262-270)
+        self._attn = attn.unsqueeze(0) if attn is not None else h.new_zeros(1, h.shape[0] // n, 1, 1)
+        return h
+
     def _fwd(self, inp, oppInp, masks=None):
+        if (self.fused_attention and inp.is_cuda and inp.dtype == torch.float32 and self.h_dim % 64 == 0
+                and self.h_dim <= 256 and self.num_agents <= 5 and self.num_opp_agents <= 5):
+            return self._fwd_fused(inp, oppInp)
         n, m, half = self.num_agents, self.num_opp_agents, self.h_dim // 2
         h = self.encoder(inp).view(n, -1, half).transpose(0, 1)                    # [B, n, 64]
         hOpp = self.oppEncoder(oppInp).view(m, -1, half).transpose(0, 1)           # [B, m, 64]

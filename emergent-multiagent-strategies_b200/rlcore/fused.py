@@ -70,3 +70,95 @@ class _PPOLoss(torch.autograd.Function):
 def ppo_loss(values, logp, entropy, old_values, returns, old_logp, adv, mask, norm, clip, vcoef, ecoef):
     """-> (total loss with autograd, stats [value_loss, action_loss, entropy, total] detached)."""
     return _PPOLoss.apply(values, logp, entropy, old_values, returns, old_logp, adv, mask, norm, clip, vcoef, ecoef)
+
+
+# ---- attention over a handful of agents: forward + backward kernels behind autograd ---------------------------------
+class _Opnd(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("batch_stride", ctypes.c_int64), ("row_stride", ctypes.c_int64)]
+
+
+def _attn_lib():
+    L = _lib()
+    if not getattr(L, "_rl3_bound", False):
+        P, vp, i32, f32 = ctypes.POINTER(_Opnd), ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        L.rl_attn_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
+        L.rl_attn_backward.argtypes = [P, P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
+        L._rl3_bound = True
+    return L
+
+
+def _op(t, col, width, batch):
+    """Agent-major flat rows [agents * batch, width]: agent i of batch entry b is row i * batch + b; take the columns
+    from `col` on."""
+    return _Opnd(t.data_ptr() + 4 * col, width, batch * width)
+
+
+class _SelfAttention(torch.autograd.Function):
+    """qkv [n*B, 3k] (agent-major rows, Q | K | V) -> out [n*B, k], attn [B, n, n]; no self-messages (mpnn.py:297-298)."""
+
+    @staticmethod
+    def forward(ctx, qkv, n, norm):
+        qkv = qkv.contiguous()
+        B, k = qkv.shape[0] // n, qkv.shape[1] // 3
+        out = torch.empty(n * B, k, device=qkv.device)
+        attn = torch.empty(B, n, n, device=qkv.device)
+        st = torch.cuda.current_stream(qkv.device).cuda_stream
+        _capi.check(_attn_lib().rl_attn_forward(_op(qkv, 0, 3 * k, B), _op(qkv, k, 3 * k, B), _op(qkv, 2 * k, 3 * k, B),
+                                                _op(out, 0, k, B), attn.data_ptr(), B, n, n, k, float(norm), 1, st))
+        ctx.save_for_backward(qkv, attn)
+        ctx.meta = (n, float(norm))
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, g, _ga):
+        qkv, attn = ctx.saved_tensors
+        n, norm = ctx.meta
+        B, k = qkv.shape[0] // n, qkv.shape[1] // 3
+        g = g.contiguous()
+        d = torch.empty_like(qkv)
+        st = torch.cuda.current_stream(qkv.device).cuda_stream
+        _capi.check(_attn_lib().rl_attn_backward(_op(g, 0, k, B), _op(qkv, 0, 3 * k, B), _op(qkv, k, 3 * k, B),
+                                                 _op(qkv, 2 * k, 3 * k, B), attn.data_ptr(), _op(d, 0, 3 * k, B),
+                                                 _op(d, k, 3 * k, B), _op(d, 2 * k, 3 * k, B), B, n, n, k, norm, st))
+        return d, None, None
+
+
+class _CrossAttention(torch.autograd.Function):
+    """a [n*B, k] (rows of the own team), bv [m*B, 2k] (B | V of the other team) -> out [n*B, k], attn [B, n, m]
+    (mpnn.py:409-437: compatibility = K(own) . Q(opp), values from the opponents)."""
+
+    @staticmethod
+    def forward(ctx, a, bv, n, m, norm):
+        a, bv = a.contiguous(), bv.contiguous()
+        B, k = a.shape[0] // n, a.shape[1]
+        out = torch.empty(n * B, k, device=a.device)
+        attn = torch.empty(B, n, m, device=a.device)
+        st = torch.cuda.current_stream(a.device).cuda_stream
+        _capi.check(_attn_lib().rl_attn_forward(_op(a, 0, k, B), _op(bv, 0, 2 * k, B), _op(bv, k, 2 * k, B), _op(out, 0, k, B),
+                                                attn.data_ptr(), B, n, m, k, float(norm), 0, st))
+        ctx.save_for_backward(a, bv, attn)
+        ctx.meta = (n, m, float(norm))
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, g, _ga):
+        a, bv, attn = ctx.saved_tensors
+        n, m, norm = ctx.meta
+        B, k = a.shape[0] // n, a.shape[1]
+        g = g.contiguous()
+        da, dbv = torch.empty_like(a), torch.empty_like(bv)
+        st = torch.cuda.current_stream(a.device).cuda_stream
+        _capi.check(_attn_lib().rl_attn_backward(_op(g, 0, k, B), _op(a, 0, k, B), _op(bv, 0, 2 * k, B), _op(bv, k, 2 * k, B),
+                                                 attn.data_ptr(), _op(da, 0, k, B), _op(dbv, 0, 2 * k, B), _op(dbv, k, 2 * k, B),
+                                                 B, n, m, k, norm, st))
+        return da, dbv, None, None, None
+
+
+def self_attention(qkv, n, norm):
+    return _SelfAttention.apply(qkv, n, norm)
+
+
+def cross_attention(a, bv, n, m, norm):
+    return _CrossAttention.apply(a, bv, n, m, norm)

@@ -104,6 +104,8 @@ class BatchedTrainer(object):
                                   max_grad_norm=max_grad_norm, use_clipped_value_loss=use_clipped_value_loss,
                                   process_group=process_group, allow_tf32=allow_tf32) for p in self.policies]
         self.process_group = process_group
+        for pol in self.policies:                     # training forward: attention kernels instead of bmm chains (mpnn.py)
+            pol.fused_attention = bool(fused_update) and self.device.type == "cuda"
         self.fused_update = bool(fused_update)      # minibatch gather + clipped-PPO loss kernels (rlcore/fused.py)
         if process_group is not None:                    # replicas start from rank 0's weights
             import torch.distributed as dist

@@ -62,6 +62,29 @@ int rl_ppo_loss(const float *d_values, const float *d_logp, const float *d_entro
                 const float *d_norm, int N, float clip, float vcoef, float ecoef, float *d_out, float *d_gvalues,
                 float *d_glogp, float *d_gentropy, void *stream);
 
+/* Single-head attention over a handful of agents, forward and backward, for the TRAINING forward of the MPNN
+ * (mpnn.py:249-331 MultiHeadAttention without self-messages, mpnn.py:376-443 MultiHeadOppAttention): replaces
+ * bmm -> mask -> softmax -> bmm (and their four backward bmm's) over [batch, <=5, <=5] matrices by one warp per
+ * environment.  For every batch element b:   s_ij = norm * <A_i, B_j>  (s_ii = -inf if mask_diag),
+ * p_i. = softmax_j s_ij (all-masked rows give p = 0),  out_i = sum_j p_ij V_j.
+ * Operands are addressed as  X[b][i][c] = X + b * batch_stride + i * row_stride + c  (element strides), so the
+ * agent-major activations of the reference ([n * batch, d] rows) and packed Q|K|V products are read in place.
+ *   n rows of A / out, m rows of B / V, feature size k in {32, 64, 96, 128}; d_attn float [batch][n][m]. */
+typedef struct RlAttnOperand {
+    float *ptr;              /* first element */
+    int64_t batch_stride;    /* elements between consecutive batch entries */
+    int64_t row_stride;      /* elements between consecutive agents */
+} RlAttnOperand;
+
+int rl_attn_forward(const RlAttnOperand *A, const RlAttnOperand *B, const RlAttnOperand *V, const RlAttnOperand *out,
+                    float *d_attn, int batch, int n, int m, int k, float norm, int mask_diag, void *stream);
+
+/* Gradients of the same op: given d(out), the saved attention matrix and the forward operands, writes dA, dB, dV
+ * (each with its own strides; they may alias slices of one packed gradient tensor). */
+int rl_attn_backward(const RlAttnOperand *dout, const RlAttnOperand *A, const RlAttnOperand *B, const RlAttnOperand *V,
+                     const float *d_attn, const RlAttnOperand *dA, const RlAttnOperand *dB, const RlAttnOperand *dV,
+                     int batch, int n, int m, int k, float norm, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

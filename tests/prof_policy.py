@@ -8,7 +8,8 @@ pk = import_module("emergent-multiagent-strategies_b200.policy_kernel")
 E = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 16384
 if "--ppo" in sys.argv:
     ro = import_module("emergent-multiagent-strategies_b200.rollout")
-    tr = ro.BatchedTrainer(E, 3, 3, num_steps=32, max_episode_steps=100, seed=0, ppo_epoch=1, num_mini_batch=8)
+    tr = ro.BatchedTrainer(E, 3, 3, num_steps=32, max_episode_steps=100, seed=0, ppo_epoch=1, num_mini_batch=8,
+                           allow_tf32="--tf32" in sys.argv)
     tr.collect(); tr.wrap_horizon()
     tr.update()
     torch.cuda.synchronize()

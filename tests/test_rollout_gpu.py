@@ -248,6 +248,40 @@ def test_fused_gather_and_loss_match_torch_path():
         assert np.allclose(a, b, rtol=2e-3, atol=2e-4), (trs[0], trs[1])
 
 
+@pytest.mark.parametrize("n,m,hid", [(3, 3, 128), (5, 4, 128), (1, 2, 128), (2, 5, 64)])
+def test_fused_training_attention_matches_bmm_path(n, m, hid):
+    """MPNN.evaluate_actions with the attention kernels (rl_attn_forward / rl_attn_backward) == the bmm/softmax mirror
+    of mpnn.py:249-331,376-443: outputs, attention matrices and every parameter gradient."""
+    mp = import_module(PKG + ".mpnn")
+    ro = import_module(PKG + ".rollout")
+    torch.manual_seed(n * 7 + m)
+    net = mp.MPNN(action_space=ro._Shape(8), num_agents=n, num_opp_agents=m, input_size=6, hidden_dim=hid).cuda()
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.3, 0.3)
+    B = 777
+    own, opp = torch.randn(n * B, 6, device="cuda"), torch.randn(m * B, 6, device="cuda")
+    act = torch.randint(0, 8, (n * B, 1), device="cuda")
+    w = torch.randn(n * B, 1, device="cuda")
+    res = []
+    for fused_on in (False, True):
+        net.fused_attention = fused_on
+        net.zero_grad()
+        v, lp, ent, _ = net.evaluate_actions(own, None, opp, None, act)
+        ((v * w).sum() + (lp * w).sum() * 0.7 + ent.sum() * 0.3).backward()
+        grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        res.append((v.detach(), lp.detach(), ent.detach(), net.attn_mat, net.opp_attn_mat, grads))
+    a, b = res
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.allclose(x, y, rtol=1e-4, atol=2e-5)
+    assert np.allclose(a[3], b[3], atol=1e-5) and np.allclose(a[4], b[4], atol=1e-5)
+    assert set(a[5]) == set(b[5])
+    for k in a[5]:
+        scale = float(a[5][k].abs().max()) + 1e-6
+        assert float((a[5][k] - b[5][k]).abs().max()) < 2e-4 * scale, (k, float((a[5][k] - b[5][k]).abs().max()), scale)
+
+
 def test_attacker_ensemble_play():
     """K frozen attacker checkpoints, one drawn per env at every episode start (learner.py:119-140,
     train_fortattack_v2.py:34-35,110-111): each env's attacker rows come from the checkpoint it is assigned to."""
