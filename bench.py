@@ -296,6 +296,10 @@ def run_ours(args):
             extra["rollout"] = rollout_config3(fab, torch, dev)
         except Exception as exc:                      # never lose the headline line to the secondary workload
             extra["rollout"] = {"error": repr(exc)}
+        try:
+            extra["rollout_5v5"] = rollout_config4_share(fab, torch, dev)
+        except Exception as exc:
+            extra["rollout_5v5"] = {"error": repr(exc)}
     del env
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -400,6 +404,27 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
                               "info": f.kernel_info()},
             "collect": "one CUDA graph of T x (2 mp_policy_kernel + fa_step + bookkeeping), replayed" if tr._graph is not None else "eager",
             "gpu_launches_per_collect": {"mp_policy_kernel": 2 * T, "fa_step": T}}
+
+
+def rollout_config4_share(fab, torch, dev, E=8192, T=32):
+    """One GPU's share of BASELINE.json configs[3] (5v5, 65536 envs over 8 GPUs = 8192 envs per GPU): graph-replayed
+    rollout collection with the MPNN policy; the gradient all-reduce of the update is exercised by tests/dist_train_gpu.py."""
+    import importlib
+    ro = importlib.import_module("emergent-multiagent-strategies_b200.rollout")
+    torch.manual_seed(0)
+    tr = ro.BatchedTrainer(E, 5, 5, num_steps=T, max_episode_steps=CAP, device=dev, seed=0)
+    for _ in range(2):
+        tr.collect(); tr.wrap_horizon(); tr.after_update()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); tr.collect(); e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    for fz in tr.fused:
+        fz.check_status()
+    return {"workload": "FortAttack 5v5, %d envs (one GPU's share of BASELINE.json configs[3]), T=%d rollout with the MPNN policy" % (E, T),
+            "rollout_agent_steps_per_s": E * 10 * T / (ms * 1e-3), "us_per_rollout_step": ms * 1e3 / T,
+            "envs_per_tile": tr.fused[0].kernel_info()["envs_per_tile"]}
 
 
 def sweep(fab, torch, dev, peak):
