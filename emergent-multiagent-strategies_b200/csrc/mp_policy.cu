@@ -77,7 +77,7 @@ static_assert(MP_BLOB_F16_BYTES == 180224 && CONST_SMEM_FLOATS * 4 <= OFF_RING -
 // fp32 constant offsets
 constexpr int C_ENC = 0, C_OENC = 512, C_UB = 1024, C_VB = 1152, C_VW = 1280, C_PB = 1408, C_DW = 1536, C_DB = 2560,
               C_VB2 = 2568;                      // blob indices
-static_assert(C_VB2 == C_DB + 8, "value_head.2.bias follows dist.linear.bias");
+static_assert(C_VB2 == C_DB + 8 && C_VB2 < MP_BLOB_CONST_FLOATS, "value_head.2.bias follows dist.linear.bias");
 constexpr int S_DB = DW_IN_SMEM ? C_DB : 1536, S_VB2 = S_DB + 8;   // shared-memory indices of dist.linear.bias, value_head.2.bias
 
 struct Chunk {
