@@ -108,7 +108,8 @@ struct Params {
     int32_t sel_value;
     unsigned long long *counter;   // optional device call counter {count, ticket}: overrides `offset`, bumped by the last CTA
     int n_own, n_opp, E, ept, n_tiles, mode;
-    unsigned long long *trace;   // optional: clock64() of row thread 0 of CTA 0 at every phase boundary of its first tile
+    unsigned long long *trace;   // optional: clock64() of row thread 0 of CTA 0 at every phase boundary of one of its tiles
+    int trace_tile;              // which of CTA 0's tiles (0 = first)
 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c[4]) {
@@ -219,13 +220,14 @@ __device__ __forceinline__ void dot16(const uint32_t (&v)[16], const uint8_t *bu
 template <int CNT, int NB>
 __device__ __forceinline__ void scores(uint32_t taddr, const uint8_t *buf, const uint32_t (&rows)[MP_MAX_TEAM], uint32_t koff0,
                                        float (&s)[MP_MAX_TEAM]) {
-    if (CNT == 0) return;
+    if constexpr (CNT > 0) {
     uint32_t v[NB][16];
 #pragma unroll
     for (int c = 0; c < NB; ++c) tmem_ld16(taddr + (uint32_t)(c * 16), v[c]);
     tmem_ld_wait();
 #pragma unroll
     for (int c = 0; c < NB; ++c) dot16<CNT>(v[c], buf, rows, koff0 + (uint32_t)(c * 2) * A_LBO, s);
+    }
 }
 
 // softmax over the first cnt entries (cnt = 0: a lone agent receives a zero message, mpnn.py:262-270)
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         uint32_t pc = 0;
         int ti = 0;
 #define ARRIVE_A() do { tc_fence_before(); fence_async_smem(); mbar_arrive(&bar_a_ready); } while (0)
-#define TS() do { if (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && tile == 0 && ti < 96) p.trace[ti++] = clock64(); } while (0)
+#define TS() do { if (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && tile == p.trace_tile * (int)gridDim.x && ti < 96) p.trace[ti++] = clock64(); } while (0)
 #define WAIT_ACC(code) do { mbar_wait(&bar_acc, pc, p.status, code); pc ^= 1u; tc_fence_after(); } while (0)
 
         float o_own[6], o_opp[6];                                  // this tile's observations (prefetched one tile ahead)
@@ -653,6 +655,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
 namespace {
 bool g_attr_done = false;
 unsigned long long *g_trace = nullptr;
+int g_trace_tile = 0;
 
 int prepare() {
     if (g_attr_done) return 0;
@@ -685,7 +688,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     p.blob = (const uint8_t *)d_blob; p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.action_in = d_action_in;
     p.value = d_value; p.logp = d_logp; p.entropy = d_entropy; p.logits = d_logits; p.action = d_action;
     p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0; p.counter = (unsigned long long *)d_counter; p.env_sel = d_env_sel; p.sel_value = sel_value;
-    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace;
+    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace; p.trace_tile = g_trace_tile;
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
@@ -716,5 +719,7 @@ extern "C" int mp_kernel_info(int n_own, int n_opp, int32_t *regs, int32_t *bloc
 // the first tile of CTA 0 (NULL switches it off).  Not part of the product API.
 extern "C" int mp_set_trace(unsigned long long *d_trace) {
     g_trace = d_trace;
+    g_trace_tile = 0;
+    if (const char *ev = getenv("MP_TRACE_TILE")) g_trace_tile = atoi(ev);
     return 0;
 }
