@@ -148,7 +148,7 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -326,7 +326,7 @@ def run_ours(args):
                                 "sample": "%d env.step() calls of %d envs, oracle/fa_oracle.c (float64, %d pthreads), %.1f s"
                                           % (n, E_PER_GPU, cores, dt)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -491,10 +491,29 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the K steps eagerly instead of from a CUDA graph")
     ap.add_argument("--quick", action="store_true", help="skip the batch-size sweep, persistent kernel and CPU baseline")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes "NCCL version ..." to fd 1 when the
+    # process group comes up), so fd 1 is pointed at stderr for the whole run and the line is written to the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 if __name__ == "__main__":
