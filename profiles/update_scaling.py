@@ -1,0 +1,41 @@
+"""PPO update time per GPU at fixed per-GPU work (weak scaling of BASELINE configs[3]'s update: 5v5, 8192 envs per GPU,
+T=128, 4 epochs x 32 minibatches x 2 teams, one gradient all-reduce per optimizer step).  Run with and without torchrun:
+  python profiles/update_scaling.py
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29561 profiles/update_scaling.py"""
+import os
+import sys
+from importlib import import_module
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ro = import_module("emergent-multiagent-strategies_b200.rollout")
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+pg = None
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD
+E, T = 8192, 128
+torch.manual_seed(0)
+tr = ro.BatchedTrainer(E, 5, 5, num_steps=T, device=dev, seed=0, env_id0=rank * E, process_group=pg, allow_tf32=True)
+for _ in range(2):
+    tr.collect(); tr.wrap_horizon(); tr.after_update()
+tr.collect(); tr.wrap_horizon()
+tr.update()
+torch.cuda.synchronize(dev)
+e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+if world > 1:
+    dist.barrier()
+e[0].record(); tr.collect(); tr.wrap_horizon(); e[1].record(); vals = tr.update(); e[2].record()
+torch.cuda.synchronize(dev)
+t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], device=dev, dtype=torch.float64)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("update_scaling: world %d, 5v5 x %d envs per GPU, T=%d: rollout+GAE %.1f ms, PPO update (TF32) %.0f ms -> %.3e agent-steps/s trained per GPU-set"
+          % (world, E, T, t[0].item(), t[1].item(), world * E * 10 * T / ((t[0].item() + t[1].item()) * 1e-3)), flush=True)
+if world > 1:
+    dist.destroy_process_group()
