@@ -25,7 +25,7 @@ def test_policy_and_rollout_headers_are_exported():
     """Every entry point of include/fortattack_policy.h and include/fortattack_rollout.h is in the library, and
     they reject bad arguments without a GPU."""
     L = _capi.lib()
-    for hdr_name, prefix in (("fortattack_policy.h", "mp_"), ("fortattack_rollout.h", "rl_")):
+    for hdr_name, prefix in (("fortattack_policy.h", "mp_"), ("fortattack_rollout.h", "rl_"), ("mape_world.h", "mw_")):
         hdr = open(os.path.join(ROOT, "include", hdr_name)).read()
         declared = set(re.findall(r"^int\s+(%s\w+)\(" % prefix, hdr, re.M))
         assert declared, hdr_name
