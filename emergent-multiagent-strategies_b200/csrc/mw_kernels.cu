@@ -36,17 +36,18 @@ __device__ __forceinline__ double pen(double x, double k) {
 __device__ __forceinline__ float sqrt_r(float v) { return sqrtf(v); }
 __device__ __forceinline__ double sqrt_r(double v) { return sqrt(v); }
 
-template <typename R>
+// NE (entities per world) is a template parameter: the loops below unroll exactly, the per-entity state stays in registers
+template <typename R, int NE>
 __global__ void __launch_bounds__(128) step_kernel(const Par<R> p, typename V2<R>::T *pos, typename V2<R>::T *vel,
                                                    const typename V2<R>::T *u) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.E) return;
     const size_t E = (size_t)p.E;
-    R x[MAXE], y[MAXE], fx[MAXE], fy[MAXE];
+    R x[NE], y[NE], fx[NE], fy[NE];
 #pragma unroll
-    for (int i = 0; i < MAXE; ++i) {
-        fx[i] = R(0); fy[i] = R(0); x[i] = R(0); y[i] = R(0);
-        if (i < p.ne) {
+    for (int i = 0; i < NE; ++i) {
+        fx[i] = R(0); fy[i] = R(0);
+        {
             const typename V2<R>::T q = pos[i * E + e];
             x[i] = q.x; y[i] = q.y;
         }
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(128) step_kernel(const Par<R> p, typename V2<R
         }
     }
 #pragma unroll
-    for (int a = 0; a < MAXE; ++a) {                                   // apply_environment_force (core.py:148-160,196-210)
+    for (int a = 0; a < NE; ++a) {                                     // apply_environment_force (core.py:148-160,196-210)
 #pragma unroll
-        for (int b = a + 1; b < MAXE; ++b) {
-            if (b < p.ne && (p.collide >> a & 1u) && (p.collide >> b & 1u)) {
+        for (int b = a + 1; b < NE; ++b) {
+            if ((p.collide >> a & 1u) && (p.collide >> b & 1u)) {
                 const R dx = x[a] - x[b], dy = y[a] - y[b];
                 const R dist = sqrt_r(dx * dx + dy * dy);
                 const R g = p.cf * pen(dist - (p.size[a] + p.size[b]), p.k) / dist;     // dist == 0 -> NaN like the reference
@@ -69,8 +70,8 @@ __global__ void __launch_bounds__(128) step_kernel(const Par<R> p, typename V2<R
         }
     }
 #pragma unroll
-    for (int i = 0; i < MAXE; ++i) {
-        if (i < p.ne && (p.movable >> i & 1u)) {
+    for (int i = 0; i < NE; ++i) {
+        if (p.movable >> i & 1u) {
             if (i < p.na && (p.collide >> i & 1u)) {                   // apply_wall_collision_force (core.py:163-169,212-225)
                 const R s = p.size[i];
                 fx[i] += p.cf * (pen(x[i] - s - p.xmin, p.k) - pen(p.xmax - x[i] - s, p.k));
@@ -105,8 +106,16 @@ template <typename R> static cudaError_t launch(const MwConfig &c, void *pos, vo
         if (in && c.collide[i]) p.collide |= 1u << i;
         if (in && c.movable[i]) p.movable |= 1u << i;
     }
-    step_kernel<R><<<(c.n_envs + 127) / 128, 128, 0, st>>>(p, (typename V2<R>::T *)pos, (typename V2<R>::T *)vel,
-                                                        (const typename V2<R>::T *)u);
+    const int grid = (c.n_envs + 127) / 128;
+    typename V2<R>::T *pp = (typename V2<R>::T *)pos, *vv = (typename V2<R>::T *)vel;
+    const typename V2<R>::T *uu = (const typename V2<R>::T *)u;
+    switch (c.n_entities) {
+#define MW_CASE(N) case N: step_kernel<R, N><<<grid, 128, 0, st>>>(p, pp, vv, uu); break;
+        MW_CASE(1) MW_CASE(2) MW_CASE(3) MW_CASE(4) MW_CASE(5) MW_CASE(6) MW_CASE(7) MW_CASE(8) MW_CASE(9) MW_CASE(10)
+        MW_CASE(11) MW_CASE(12)
+#undef MW_CASE
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
