@@ -380,6 +380,16 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     e0.record(); tr.update(); e1.record()
     torch.cuda.synchronize(dev)
     update_tf32_ms = e0.elapsed_time(e1)
+    # ... and with the optimizer step replayed from a CUDA graph (opt-in JointPPO(graph_update=True))
+    tr2 = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, allow_tf32=True, graph_update=True)
+    tr2.collect(); tr2.wrap_horizon()
+    tr2.update()                                                            # three eager steps, capture, replays
+    torch.cuda.synchronize(dev)
+    e0, e1 = ev(), ev()
+    e0.record(); tr2.update(); e1.record()
+    torch.cuda.synchronize(dev)
+    update_tf32_graph_ms = e0.elapsed_time(e1)
+    del tr2
     for fz in tr.fused:
         fz.check_status()
     flop_row = 2 * (64 * 64 * 2 + 3 * 3 * 128 * 128 + 2 * 128 * 128)       # tensor-core MACs x2 per (agent, env) row
@@ -392,7 +402,7 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     ach = NG * E * flop_row / (pol_us * 1e-6) / 1e12
     return {"workload": "FortAttack 3v3 (BASELINE.json configs[2]), %d envs, T=%d rollout with the MPNN policy + one JointPPO update" % (E, T),
             "rollout_agent_steps_per_s": E * A * T / (collect_ms * 1e-3), "collect_ms": collect_ms,
-            "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_tf32_ms": update_tf32_ms,
+            "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_tf32_ms": update_tf32_ms, "ppo_update_tf32_graph_ms": update_tf32_graph_ms,
             "ppo_update": "4 epochs x 32 minibatches x 2 teams: torch autograd for the dense layers; attention forward/backward, "
                           "minibatch gather and clipped-PPO loss are this repo's kernels (rl_attn_*, rl_gather_minibatch, rl_ppo_loss)",
             "losses": vals,

@@ -55,8 +55,13 @@ def magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_l
 class JointPPO(object):
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
                  lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=False, process_group=None,
-                 allow_tf32=False):
+                 allow_tf32=False, graph_update=False):
         self.actor_critic = actor_critic
+        # graph_update (new, fused path on one rank only): after three eager minibatch steps the whole optimizer step
+        # (gather -> forward -> loss -> backward -> clip -> Adam) is captured in a CUDA graph and replayed; with TF32
+        # GEMMs the eager step is CPU-launch-bound (~9 ms of Python/autograd dispatch vs ~7 ms of GPU work at config 3)
+        self.graph_update = bool(graph_update)
+        self._g = None
         # allow_tf32 (new, off by default = the reference's fp32 arithmetic): run the update's cuBLAS GEMMs on the
         # tensor cores in TF32.  On B200 the fp32 path is SIMT sgemm and takes ~70% of the update
         # (profiles/r1c_ppo_update_torch_profile.txt).
@@ -64,7 +69,9 @@ class JointPPO(object):
         self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
         self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
         self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
-        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr)     # eps is ignored by the reference too (:114)
+        on_cuda = next(actor_critic.parameters()).is_cuda
+        # eps is ignored by the reference too (:114); capturable keeps Adam's step counters on the device (graph capture)
+        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, capturable=bool(graph_update) and on_cuda)
         self.process_group = process_group
 
     # -- distributed helpers (identity on one rank) ------------------------------------------------
@@ -136,37 +143,77 @@ class JointPPO(object):
                 batches = [perm[i:i + mini_batch_size] for i in range(0, batch_size, mini_batch_size)]
             for idx in batches:
                 idx = idx.to(dev).contiguous()
-                (obs_batch, mask, obs_opp_batch, actions_batch, value_preds_batch, return_batch, masks_batch,
-                 old_log_probs_batch, adv_targ, alive_sum) = fused.gather_minibatch(R, idx, a0, n, o0, m, advantages)
-                values, action_log_probs, dist_entropy, _ = self.actor_critic.evaluate_actions(
-                    obs_batch, None, obs_opp_batch, masks_batch, actions_batch)
-                count = mask.new_full((1,), float(mask.numel()))
-                if world == 1:
-                    norm = torch.where(alive_sum != 0, alive_sum, count)          # mask.mean() != 0 else 1 (ppo.py:150-187)
-                else:
-                    g = self._allreduce(torch.cat([alive_sum, count]))
-                    norm = torch.where(g[0:1] != 0, g[0:1], g[1:2]) / world
-                loss, stats = fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch,
-                                             old_log_probs_batch, adv_targ, mask, norm, self.clip_param,
-                                             self.value_loss_coef, self.entropy_coef)
-                self.optimizer.zero_grad()
-                loss.backward()
-                if world > 1:
-                    grads = [p.grad for p in params if p.grad is not None]
-                    flat = torch.cat([g_.reshape(-1) for g_ in grads])
-                    self._allreduce(flat).div_(world)
-                    off = 0
-                    for g_ in grads:
-                        g_.copy_(flat[off:off + g_.numel()].view_as(g_))
-                        off += g_.numel()
-                nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
-                self.optimizer.step()
-                totals += stats[:3]
+                if self._graphed_step(fused, R, (a0, n, o0, m), idx, advantages, totals, mini_batch_size, world):
+                    n_updates += 1
+                    continue
+                self._minibatch_step(fused, R, (a0, n, o0, m), idx, advantages, totals, params, world)
                 n_updates += 1
         if world > 1:
             totals = self._allreduce(totals) / world
         v, a, e = (totals / max(n_updates, 1)).tolist()
         return v, a, e
+
+    def _minibatch_step(self, fused, R, team, idx, advantages, totals, params, world):
+        a0, n, o0, m = team
+        (obs_batch, mask, obs_opp_batch, actions_batch, value_preds_batch, return_batch, masks_batch,
+         old_log_probs_batch, adv_targ, alive_sum) = fused.gather_minibatch(R, idx, a0, n, o0, m, advantages)
+        values, action_log_probs, dist_entropy, _ = self.actor_critic.evaluate_actions(
+            obs_batch, None, obs_opp_batch, masks_batch, actions_batch)
+        count = mask.new_full((1,), float(mask.numel()))
+        if world == 1:
+            norm = torch.where(alive_sum != 0, alive_sum, count)          # mask.mean() != 0 else 1 (ppo.py:150-187)
+        else:
+            g = self._allreduce(torch.cat([alive_sum, count]))
+            norm = torch.where(g[0:1] != 0, g[0:1], g[1:2]) / world
+        loss, stats = fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch,
+                                     old_log_probs_batch, adv_targ, mask, norm, self.clip_param,
+                                     self.value_loss_coef, self.entropy_coef)
+        self.optimizer.zero_grad()
+        loss.backward()
+        if world > 1:
+            grads = [p.grad for p in params if p.grad is not None]
+            flat = torch.cat([g_.reshape(-1) for g_ in grads])
+            self._allreduce(flat).div_(world)
+            off = 0
+            for g_ in grads:
+                g_.copy_(flat[off:off + g_.numel()].view_as(g_))
+                off += g_.numel()
+        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
+        self.optimizer.step()
+        totals += stats[:3]
+
+    def _graphed_step(self, fused, R, team, idx, advantages, totals, mini_batch_size, world):
+        """Replay (or, on its fourth call, capture) the optimizer step as one CUDA graph.  Returns False when the step
+        has to run eagerly (option off, several ranks, a ragged last minibatch, or still warming up)."""
+        if not self.graph_update or world != 1 or idx.numel() != mini_batch_size or not idx.is_cuda:
+            return False
+        g = self._g
+        if g is None or g["key"] != (id(R), team, mini_batch_size, tuple(advantages.shape)):
+            g = self._g = {"key": (id(R), team, mini_batch_size, tuple(advantages.shape)), "eager": 0, "graph": None,
+                           "idx": torch.empty_like(idx), "adv": torch.empty_like(advantages), "totals": torch.zeros_like(totals)}
+        if g["graph"] is None:
+            if g["eager"] < 3:                      # real training steps double as the warm-up torch asks for before a capture
+                g["eager"] += 1
+                return False
+            params = [p for p in self.actor_critic.parameters()]
+            g["idx"].copy_(idx)
+            g["adv"].copy_(advantages)
+            torch.cuda.synchronize(idx.device)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(idx.device)
+            side.wait_stream(torch.cuda.current_stream(idx.device))
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    self._minibatch_step(fused, R, team, g["idx"], g["adv"], g["totals"], params, 1)
+            torch.cuda.current_stream(idx.device).wait_stream(side)
+            g["graph"] = graph
+        g["idx"].copy_(idx)
+        g["adv"].copy_(advantages)              # (same tensor for a whole update; 2 % of a step)
+        g["totals"].zero_()
+        g["graph"].replay()
+        totals += g["totals"]
+        return True
 
     def _update(self, rollouts_list, opp_rollouts_list, index_batches=None):
         advantages_list = [self._advantages(r) for r in rollouts_list]

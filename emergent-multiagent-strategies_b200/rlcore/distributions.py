@@ -26,4 +26,8 @@ class Categorical(nn.Module):
         nn.init.constant_(self.linear.bias.data, 0)
 
     def forward(self, x):
-        return FixedCategorical(logits=self.linear(x))
+        x = self.linear(x)
+        # argument validation synchronises the device (constraint checks end in .all()): skip it while a CUDA graph is
+        # being captured (JointPPO(graph_update=True))
+        capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
+        return FixedCategorical(logits=x, validate_args=False if capturing else None)

@@ -90,7 +90,7 @@ class BatchedTrainer(object):
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
                  use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False,
-                 graph_rollouts=True, attacker_ensemble=None, fused_update=True):
+                 graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=False):
         self.device = torch.device(device)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
@@ -102,7 +102,8 @@ class BatchedTrainer(object):
         self.policies = [mk(n_guards, n_attackers), mk(n_attackers, n_guards)]     # guards first (learner.py:57-69)
         self.trainers = [JointPPO(p, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef, lr=lr,
                                   max_grad_norm=max_grad_norm, use_clipped_value_loss=use_clipped_value_loss,
-                                  process_group=process_group, allow_tf32=allow_tf32) for p in self.policies]
+                                  process_group=process_group, allow_tf32=allow_tf32, graph_update=graph_update)
+                         for p in self.policies]
         self.process_group = process_group
         for pol in self.policies:                     # training forward: attention kernels instead of bmm chains (mpnn.py)
             pol.fused_attention = bool(fused_update) and self.device.type == "cuda"

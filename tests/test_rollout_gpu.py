@@ -282,6 +282,28 @@ def test_fused_training_attention_matches_bmm_path(n, m, hid):
         assert float((a[5][k] - b[5][k]).abs().max()) < 2e-4 * scale, (k, float((a[5][k] - b[5][k]).abs().max()), scale)
 
 
+def test_graph_captured_update_tracks_eager_update():
+    """JointPPO(graph_update=True): three eager steps, then the optimizer step replayed from one CUDA graph; losses and
+    weights follow the eager fused update (Adam's capturable code path rounds its bias correction on the device)."""
+    ro = import_module(PKG + ".rollout")
+    out = []
+    for gu in (True, False):
+        torch.manual_seed(21)
+        tr = ro.BatchedTrainer(256, 3, 3, num_steps=16, max_episode_steps=9, seed=2, ppo_epoch=2, num_mini_batch=8, graph_update=gu)
+        vals = []
+        for it in range(2):
+            tr.collect(); tr.wrap_horizon()
+            torch.manual_seed(40 + it)
+            vals.append(tr.update())
+            tr.after_update()
+        out.append((vals, [p.detach().clone() for pol in tr.policies for p in pol.parameters()], tr))
+    assert out[0][2].trainers[0]._g is not None and out[0][2].trainers[0]._g["graph"] is not None
+    for va, vb in zip(out[0][0], out[1][0]):
+        assert np.allclose(va, vb, rtol=5e-3, atol=5e-4), (va, vb)
+    worst = max(float((a - b).abs().max()) for a, b in zip(out[0][1], out[1][1]))
+    assert worst < 2e-3, worst
+
+
 def test_attacker_ensemble_play():
     """K frozen attacker checkpoints, one drawn per env at every episode start (learner.py:119-140,
     train_fortattack_v2.py:34-35,110-111): each env's attacker rows come from the checkpoint it is assigned to."""
