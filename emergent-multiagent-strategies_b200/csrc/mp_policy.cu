@@ -156,7 +156,7 @@ __device__ __forceinline__ void drain(uint32_t taddr, uint8_t *buf, int r, int k
 
 // ReLU(W x + b) for the 6-float observation, outputs [j_lo, j_lo+QC64) -> fp16 row segment of buf (mpnn.py:127-128)
 __device__ __forceinline__ void encode(const float *W8, const float (&o)[6], uint8_t *buf, int r, int j_lo) {
-#pragma unroll 1
+#pragma unroll
     for (int j0 = j_lo; j0 < j_lo + QC64; j0 += 8) {
         uint32_t h[4];
 #pragma unroll
@@ -653,15 +653,24 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
 
 // ---- host side ------------------------------------------------------------------------------------
 namespace {
-bool g_attr_done = false;
+// per-device one-time setup (cudaFuncSetAttribute is a per-device setting; the SM count sizes the persistent grid)
+constexpr int MAX_DEVICES = 64;
+bool g_attr_done[MAX_DEVICES] = {};
+int g_sms[MAX_DEVICES] = {};
 unsigned long long *g_trace = nullptr;
 int g_trace_tile = 0;
 
-int prepare() {
-    if (g_attr_done) return 0;
-    cudaError_t e = cudaFuncSetAttribute(mp::mp_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mp::SMEM_BYTES);
-    if (e != cudaSuccess) return fa_internal_fail(-2, "mp_policy_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    g_attr_done = true;
+int prepare(int *sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return fa_internal_fail(-3, "mp_policy_kernel: no usable CUDA device");
+    if (!g_attr_done[dev]) {
+        e = cudaFuncSetAttribute(mp::mp_policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mp::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return fa_internal_fail(-2, "mp_policy_kernel: device setup: %s", cudaGetErrorString(e));
+        g_attr_done[dev] = true;
+    }
+    if (sms) *sms = g_sms[dev];
     return 0;
 }
 }  // namespace
@@ -677,13 +686,8 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     if (mode < 0 || mode > 2 || (mode == MP_MODE_EVAL && !d_action_in)) return fa_internal_fail(-1, "mp_forward: bad mode");
     if (((uintptr_t)d_blob & 15) || ((uintptr_t)d_obs_own & 7) || ((uintptr_t)d_obs_opp & 7) || ((uintptr_t)d_logits & 15))
         return fa_internal_fail(-4, "mp_forward: blob/logits must be 16-byte, observations 8-byte aligned");
-    if (int rc = prepare()) return rc;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    int sms = 0;
+    if (int rc = prepare(&sms)) return rc;
     mp::Params p;
     p.blob = (const uint8_t *)d_blob; p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.action_in = d_action_in;
     p.value = d_value; p.logp = d_logp; p.entropy = d_entropy; p.logits = d_logits; p.action = d_action;
@@ -701,7 +705,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
 extern "C" int mp_kernel_info(int n_own, int n_opp, int32_t *regs, int32_t *block, int32_t *smem, int32_t *blocks_per_sm,
                               int32_t *envs_per_tile) {
     if (n_own < 1 || n_own > MP_MAX_TEAM || n_opp < 1 || n_opp > MP_MAX_TEAM) return fa_internal_fail(-1, "mp_kernel_info: team sizes");
-    if (int rc = prepare()) return rc;
+    if (int rc = prepare(nullptr)) return rc;
     cudaFuncAttributes at;
     cudaError_t e = cudaFuncGetAttributes(&at, mp::mp_policy_kernel);
     if (e != cudaSuccess) return fa_internal_fail(-2, "mp_kernel_info: %s", cudaGetErrorString(e));

@@ -197,6 +197,11 @@ class BatchedTrainer(object):
         self._graph.replay()
         return self.episode_rewards
 
+    def invalidate_graph(self):
+        """Drop the captured rollout graph (it bakes in kernel parameters such as the episode cap and the tensors'
+        addresses): call after changing anything collect() depends on; the next collect() captures again."""
+        self._graph = None
+
     @torch.no_grad()
     def _collect(self):
         R = self.roll
