@@ -159,6 +159,14 @@ class FortAttackBatch(object):
         _capi.check(self._lib.fa_set_max_steps(self._h, int(max_steps)))
         self.max_steps = int(max_steps)
 
+    def set_alive_end_buffer(self, buf):
+        """uint8 [E] (or [T, E] for step_many) device tensor that every later step fills with
+        numAliveGuards | numAliveAttackers << 4 as the step leaves them (before an auto-reset); None switches it off."""
+        if buf is not None and (buf.dtype != torch.uint8 or not buf.is_contiguous() or buf.device != self.workspace.device):
+            raise ValueError("alive-end buffer must be a contiguous uint8 tensor on %s" % self.device)
+        self._alive_end = buf                     # keep it alive
+        _capi.check(self._lib.fa_set_alive_end_buffer(self._h, None if buf is None else buf.data_ptr()))
+
     def launch_count(self):
         n = ctypes.c_uint64()
         _capi.check(self._lib.fa_launch_count(self._h, ctypes.byref(n)))

@@ -105,6 +105,7 @@ struct FaHandle {
     uint8_t *s_done, *s_result;
     int block, grid;
     int pdl;            // launch fa_step with programmatic stream serialization (FA_PDL=1 enables)
+    uint8_t *alive_end; // optional extra output of every step (fa_set_alive_end_buffer)
     bool wide;          // one thread per agent (small batches) instead of one thread per env
     int sm_count;
     uint64_t launches;
@@ -207,6 +208,7 @@ static cudaError_t do_step(FaHandle *h, bool many, int T, const int32_t *act, vo
     p.obs_vec_ok = ((size_t)c.n_envs * 6 * sizeof(R)) % 16 == 0 && ((uintptr_t)obs % 16) == 0;
     p.seed = c.seed;
     p.env_id0 = c.env_id0;
+    p.alive_end = h->alive_end;
     p.pdl = h->pdl && !many;     // single-step launches chain through programmatic dependent launch
     return fa::launch_step<R>(c.n_guards, c.n_attackers, many, h->wide, p, h->grid, h->block, s);
 }
@@ -281,6 +283,7 @@ int fa_create(const FaConfig *cfg, void *d_workspace, FaHandle **out) {
     // 2 % for eager launches (13.3 vs 13.6 us/step, CPU-launch-bound) and LOSES inside a replayed CUDA graph
     // (5.7 vs 3.7 us/step).
     h->pdl = 0;
+    h->alive_end = nullptr;
     if (const char *ev = getenv("FA_PDL")) h->pdl = ev[0] == '1';
     if (const char *hp = getenv("FA_HOST_PATH")) h->host_path = !strcmp(hp, "staged") ? 1 : (!strcmp(hp, "mapped") ? 2 : 0);
     pick_launch(h);
@@ -450,6 +453,12 @@ int fa_set_max_steps(FaHandle *h, int32_t max_steps) {
     NEED_HANDLE(h);
     if (max_steps < 1) return fail(FA_EINVAL, "max_steps must be >= 1 (got %d)", max_steps);
     h->cfg.max_steps = max_steps;
+    return FA_OK;
+}
+
+int fa_set_alive_end_buffer(FaHandle *h, uint8_t *d_alive_end) {
+    NEED_HANDLE(h);
+    h->alive_end = d_alive_end;
     return FA_OK;
 }
 

@@ -69,6 +69,7 @@ template <typename R> struct StepParams {
     uint8_t *done;        // [T][E]        (may be null)
     uint8_t *result;      // [T][E]        (may be null)
     int E, T, max_steps, auto_reset, obs_vec_ok;
+    uint8_t *alive_end;   // [T][E] (may be null): alive guards | alive attackers << 4 at the END of the step, before any reset
     int pdl;              // launched with programmatic stream serialization: the state is read after griddepcontrol.wait
     uint64_t seed, env_id0;
 };
@@ -487,6 +488,14 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) fa_step_kernel(const StepParam
         R rew[A];
         int result;
         const bool dn = step_env<NG, NA, R>(s, act, p.max_steps, rew, result);
+        if (p.alive_end != nullptr && valid) {         // world.numAliveGuards / numAliveAttackers as the episode's last step leaves them
+            int ag = 0, aa = 0;
+#pragma unroll
+            for (int i = 0; i < A; ++i) {
+                if (s.fl[i] & F_ALIVE) { if (i < NG) ++ag; else ++aa; }
+            }
+            p.alive_end[(size_t)t * E + e] = (uint8_t)(ag | (aa << 4));
+        }
         if (dn && (MANY || p.auto_reset)) {
             if (!MANY) ep = p.st.episode[ec];
             reset_env<NG, NA, R>(s, p.seed, p.env_id0 + (uint64_t)ec, ep);
@@ -706,6 +715,14 @@ __global__ void __launch_bounds__(32 * (NG + NA)) fa_step_wide_kernel(const Step
         if (i == 0 && valid) {
             if (p.done != nullptr) p.done[(size_t)t * E + e] = dn ? 1 : 0;
             if (p.result != nullptr) p.result[(size_t)t * E + e] = (uint8_t)result;
+            if (p.alive_end != nullptr) {
+                int ag = 0, aa = 0;
+#pragma unroll
+                for (int j = 0; j < A; ++j) {
+                    if (sh.a1[j][lane]) { if (j < NG) ++ag; else ++aa; }
+                }
+                p.alive_end[(size_t)t * E + e] = (uint8_t)(ag | (aa << 4));
+            }
         }
         if (p.obs != nullptr) {
             typedef typename VecT<R>::T2 T2;

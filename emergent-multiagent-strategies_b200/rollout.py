@@ -139,6 +139,12 @@ class BatchedTrainer(object):
             # per checkpoint: episodes ended by [attackers all dead, time limit, fort reached] (world.gameResult),
             # and the sums needed for the reference's test_fortattack_v2.py table (:94-124)
             self.ensemble_results = torch.zeros(K, 4, device=self.device, dtype=torch.int64)
+            # sums behind the reference's evaluation table (test_fortattack_v2.py:94-124), per checkpoint:
+            # episodes, alive guards / attackers when the episode ended, mean per-agent return of guards / attackers
+            self.ensemble_sums = torch.zeros(K, 5, device=self.device, dtype=torch.float64)
+            self.alive_end = torch.zeros(n_envs, dtype=torch.uint8, device=self.device)
+            self.env.set_alive_end_buffer(self.alive_end)
+            self.ep_return = torch.zeros(self.A, n_envs, device=self.device)
         # the T-step collection loop is captured into ONE CUDA graph on its second use and replayed afterwards
         # (3 kernels of ours + ~8 small bookkeeping kernels per step; the sampling counter lives on the device)
         self.graph_rollouts = bool(graph_rollouts) and self.fused is not None
@@ -197,6 +203,15 @@ class BatchedTrainer(object):
         self._graph.replay()
         return self.episode_rewards
 
+    def ensemble_table(self):
+        """The reference's evaluation table (test_fortattack_v2.py:50,94-124), one row per attacker checkpoint, averaged
+        over the episodes finished so far: [P(all attackers dead), P(time limit), their sum = guards win, P(fort reached),
+        alive guards, alive attackers, mean guard return, mean attacker return]."""
+        n = self.ensemble_sums[:, 0].clamp_min(1.0)
+        r = self.ensemble_results.double()
+        cols = [r[:, 1] / n, r[:, 2] / n, (r[:, 1] + r[:, 2]) / n, r[:, 3] / n] + [self.ensemble_sums[:, k] / n for k in (1, 2, 3, 4)]
+        return torch.stack(cols, dim=1).cpu().numpy()
+
     def invalidate_graph(self):
         """Drop the captured rollout graph (it bakes in kernel parameters such as the episode cap and the tensors'
         addresses): call after changing anything collect() depends on; the next collect() captures again."""
@@ -222,6 +237,13 @@ class BatchedTrainer(object):
                 K = len(self.ensemble)
                 code = R.result[step].long()                                  # 0 running, 1 all dead, 2 time limit, 3 reached
                 self.ensemble_results.view(-1).index_add_(0, self.att_id.long() * 4 + code, finished.long())
+                self.ep_return += R.rewards[step] * masks
+                fin = finished.double()
+                ae = self.alive_end.long()
+                rows = torch.stack((fin, fin * (ae & 15), fin * (ae >> 4), fin * self.ep_return[:self.ng].mean(0),
+                                    fin * self.ep_return[self.ng:].mean(0)), dim=1)           # [E, 5]
+                self.ensemble_sums.index_add_(0, self.att_id.long(), rows)
+                self.ep_return *= (~finished).float()
                 self.att_id.copy_(torch.where(finished, torch.randint(0, K, (self.E,), device=self.device, dtype=torch.int32),
                                               self.att_id))
         R.ends[self.T] = True                                              # (:108-109)

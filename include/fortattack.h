@@ -156,6 +156,12 @@ int fa_alive_counts(FaHandle *h, int32_t *d_counts, void *stream);
 /* Change world.max_time_steps for subsequent steps (the reference's scripts assign it directly). */
 int fa_set_max_steps(FaHandle *h, int32_t max_steps);
 
+/* Optional extra output of every subsequent step: d_alive_end uint8 [E] (fa_step) or [T][E] (fa_step_many) receives
+ * numAliveGuards | numAliveAttackers << 4 as the step leaves them, i.e. before an auto-reset -- what the reference's
+ * evaluation script reads off the world when an episode ends (test_fortattack_v2.py:98-99, core.py:113-114).
+ * NULL (the default) switches it off. */
+int fa_set_alive_end_buffer(FaHandle *h, uint8_t *d_alive_end);
+
 /* Number of kernel launches this handle has enqueued so far (bench.py's gpu_launches). */
 int fa_launch_count(const FaHandle *h, uint64_t *out);
 

@@ -332,6 +332,10 @@ def test_attacker_ensemble_play():
     n_done = int((R.done != 0).sum())
     assert int(tr.ensemble_results.sum()) == n_done and int(tr.ensemble_results[:, 0].sum()) == 0
     assert (tr.ensemble_results.sum(1) > 0).all()
+    tab = tr.ensemble_table()                                        # test_fortattack_v2.py's stats, per checkpoint
+    assert tab.shape == (3, 8) and np.allclose(tab[:, 0] + tab[:, 1] + tab[:, 3], 1.0) and np.allclose(tab[:, 2], tab[:, 0] + tab[:, 1])
+    assert (tab[:, 4] >= 0).all() and (tab[:, 4] <= 3).all() and (tab[:, 5] >= 0).all() and (tab[:, 5] <= 3).all()
+    assert (tab[tab[:, 0] == 1.0, 5] == 0).all() and np.isfinite(tab).all()
     before = [p.detach().clone() for p in tr.policies[1].parameters()]
     vals = tr.update()                                               # guards only
     assert len(vals) == 1 and all(torch.equal(a, b) for a, b in zip(before, tr.policies[1].parameters()))

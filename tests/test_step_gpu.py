@@ -285,6 +285,36 @@ def test_episode_statistics_match_oracle_at_scale(ng, na):
         assert 0.05 < res_g[1] / n_g < 0.14 and 0.84 < res_g[2] / n_g < 0.94 and res_g[3] / n_g < 0.03
 
 
+@pytest.mark.parametrize("mapping", MAPPINGS)
+def test_alive_counts_at_step_end(mapping):
+    """fa_set_alive_end_buffer: numAliveGuards | numAliveAttackers << 4 as every step leaves them (before the auto-reset),
+    against the alive flags of the double-precision oracle run on the same actions (core.py:113-114,293-302)."""
+    E, ng, na = 512, 3, 2
+    env = make(E, ng, na, torch.float64, max_steps=20, seed=3, mapping=mapping)
+    ora = fa_oracle.OracleEnv(E, ng, na, max_steps=20, seed=3)
+    env.reset(); ora.reset()
+    buf = torch.full((E,), 255, dtype=torch.uint8, device="cuda")
+    env.set_alive_end_buffer(buf)
+    rng = np.random.RandomState(1)
+    seen_kill = False
+    for t in range(60):
+        act = rng.choice(8, size=(E, ng + na), p=[.1] * 7 + [.3]).astype(np.int32)
+        env.step(acts_dev(act), auto_reset=True)
+        # the oracle without auto-reset shows the terminal state; then reset the finished envs by hand
+        obs, rew, done, res = ora.step(act, auto_reset=False)
+        alive = ora.st_i[:, :, 0]
+        want = alive[:, :ng].sum(1) | (alive[:, ng:].sum(1) << 4)
+        assert np.array_equal(buf.cpu().numpy(), want.astype(np.uint8)), t
+        seen_kill |= bool((want != (ng | na << 4)).any())
+        ora.reset(mask=done.astype(np.uint8))
+    assert seen_kill
+    many = torch.zeros(7, E, dtype=torch.uint8, device="cuda")
+    env.set_alive_end_buffer(many)
+    env.step_many(torch.randint(0, 8, (7, ng + na, E), device="cuda", dtype=torch.int32))
+    assert int(many.max()) <= (ng | na << 4) and int((many & 15).max()) == ng
+    env.set_alive_end_buffer(None)
+
+
 def test_both_mappings_agree_and_auto_picks_by_batch_size():
     """Thread-per-env and thread-per-agent run the same physics: 200 free-running steps stay within float
     rounding of each other (contact forces are summed in a different order), masks identical."""
