@@ -300,6 +300,10 @@ def run_ours(args):
             extra["rollout_5v5"] = rollout_config4_share(fab, torch, dev)
         except Exception as exc:
             extra["rollout_5v5"] = {"error": repr(exc)}
+        try:
+            extra["rollout_ensemble"] = rollout_config5_share(fab, torch, dev)
+        except Exception as exc:
+            extra["rollout_ensemble"] = {"error": repr(exc)}
     del env
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -435,6 +439,35 @@ def rollout_config4_share(fab, torch, dev, E=8192, T=32):
     return {"workload": "FortAttack 5v5, %d envs (one GPU's share of BASELINE.json configs[3]), T=%d rollout with the MPNN policy" % (E, T),
             "rollout_agent_steps_per_s": E * 10 * T / (ms * 1e-3), "us_per_rollout_step": ms * 1e3 / T,
             "envs_per_tile": tr.fused[0].kernel_info()["envs_per_tile"]}
+
+
+def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5):
+    """One GPU's share of BASELINE.json configs[4] (guards-only training against an ensemble of 5 frozen attacker
+    checkpoints, 32768 envs over 8 GPUs = 4096 envs per GPU, 5v5): rollout collection with a per-env, per-episode
+    attacker draw = 1 guard forward + K masked attacker forwards + 1 env step per rollout step (random-init checkpoints:
+    there is no network for the shipped ones; the arithmetic is the same)."""
+    import importlib
+    ro = importlib.import_module("emergent-multiagent-strategies_b200.rollout")
+    mp = importlib.import_module("emergent-multiagent-strategies_b200.mpnn")
+    sds = []
+    for k in range(K):
+        torch.manual_seed(100 + k)
+        sds.append(mp.MPNN(action_space=ro._Shape(8), num_agents=5, num_opp_agents=5, input_size=6, hidden_dim=128).state_dict())
+    torch.manual_seed(0)
+    tr = ro.BatchedTrainer(E, 5, 5, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, attacker_ensemble=sds)
+    for _ in range(2):
+        tr.collect(); tr.wrap_horizon(); tr.after_update()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); tr.collect(); e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    for fz in tr.fused + tr.ensemble:
+        fz.check_status()
+    return {"workload": "FortAttack 5v5 guards vs an ensemble of %d attacker checkpoints, %d envs (one GPU's share of BASELINE.json "
+                        "configs[4]), T=%d rollout" % (K, E, T),
+            "rollout_agent_steps_per_s": E * 10 * T / (ms * 1e-3), "us_per_rollout_step": ms * 1e3 / T,
+            "policy_launches_per_step": 1 + K}
 
 
 def sweep(fab, torch, dev, peak):
