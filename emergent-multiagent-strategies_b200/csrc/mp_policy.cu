@@ -105,6 +105,8 @@ struct Params {
     uint32_t *status;
     uint64_t seed, offset, env_id0;
     const int32_t *env_sel;        // optional int32 [E]: outputs are written only for envs with env_sel[e] == sel_value
+    const int32_t *env_order;      // optional int32 [E] + env_offsets int32 [K+1] (both on the device): this launch covers only the
+    const int32_t *env_offsets;    //   envs env_order[env_offsets[sel_value] .. env_offsets[sel_value+1])  (compacted ensemble play)
     int32_t sel_value;
     unsigned long long *counter;   // optional device call counter {count, ticket}: overrides `offset`, bumped by the last CTA
     int n_own, n_opp, E, ept, n_tiles, mode;
@@ -364,6 +366,16 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     // call counter of the sampling stream: read before any CTA can have finished (the bump below happens after ALL
     // CTAs are done), so launches replayed from a CUDA graph still draw fresh numbers
     const uint64_t call_offset = p.counter != nullptr ? (uint64_t)p.counter[0] : p.offset;
+    // compacted launch: the list of environments (and with it the tile count) is read from device memory, so the host
+    // never has to know how many environments each checkpoint currently plays (no synchronisation, graph-replayable)
+    const int32_t *env_list = nullptr;
+    int n_list = p.E, n_tiles = p.n_tiles;
+    if (p.env_order != nullptr) {
+        const int lo = p.env_offsets[p.sel_value];
+        n_list = p.env_offsets[p.sel_value + 1] - lo;
+        env_list = p.env_order + lo;
+        n_tiles = (n_list + p.ept - 1) / p.ept;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -376,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             for (int i = 0; i < RES_BYTES / STAGE_BYTES; ++i)
                 bulk_g2s(smem + OFF_WRES + i * STAGE_BYTES, p.blob + BLOB_RES + i * STAGE_BYTES, STAGE_BYTES, &bar_res);
             uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < N_STREAM; ++c, ++g) {
                     const uint32_t s = g % NS, ph = (g / NS) & 1u;
                     mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 3);
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             ++g;
         };
         mbar_wait(&bar_res, 0, p.status, 2);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             stream_chunk(0);
             stream_chunk(1);
             for (int round = 0; round < 3; ++round) {      // [T | Z | Y] = h [G | Wz | U1^T]
@@ -467,10 +479,12 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
 #define WAIT_ACC(code) do { mbar_wait(&bar_acc, pc, p.status, code); pc ^= 1u; tc_fence_after(); } while (0)
 
         float o_own[6], o_opp[6];                                  // this tile's observations (prefetched one tile ahead)
-        load_obs(p.obs_own, n_own, a, p.E, blockIdx.x * ept + e, o_own);
-        load_obs(p.obs_opp, n_opp, a, p.E, blockIdx.x * ept + e, o_opp);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int eg = tile * ept + e;
+        // global env id of list entry li (p.E = "none": load_obs and the output guard treat it as out of range)
+        auto env_of = [&](int li) { return li < n_list ? (env_list != nullptr ? env_list[li] : li) : p.E; };
+        load_obs(p.obs_own, n_own, a, p.E, env_of(blockIdx.x * ept + e), o_own);
+        load_obs(p.obs_opp, n_opp, a, p.E, env_of(blockIdx.x * ept + e), o_opp);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int eg = env_of(tile * ept + e);
             TS();
             // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64); QC64 outputs per thread
             encode(C + C_ENC, o_own, bufH, r, q * QC64);
@@ -519,9 +533,9 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             }
             {   // the next tile's observations: the loads fly while the heads are computed
                 const int nt = tile + gridDim.x;
-                if (nt < p.n_tiles) {
-                    load_obs(p.obs_own, n_own, a, p.E, nt * ept + e, o_own);
-                    load_obs(p.obs_opp, n_opp, a, p.E, nt * ept + e, o_opp);
+                if (nt < n_tiles) {
+                    load_obs(p.obs_own, n_own, a, p.E, env_of(nt * ept + e), o_own);
+                    load_obs(p.obs_opp, n_opp, a, p.E, env_of(nt * ept + e), o_opp);
                 }
             }
 
@@ -679,7 +693,8 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
                           int n_envs, int mode, uint64_t seed, uint64_t offset, uint64_t *d_counter, uint64_t env_id0,
                           const int64_t *d_action_in,
                           float *d_value, int64_t *d_action, int32_t *d_action_i32, float *d_logp, float *d_entropy,
-                          float *d_logits, const int32_t *d_env_sel, int32_t sel_value, uint32_t *d_status, void *stream) {
+                          float *d_logits, const int32_t *d_env_sel, int32_t sel_value, const int32_t *d_env_order,
+                          const int32_t *d_env_offsets, uint32_t *d_status, void *stream) {
     if (!d_blob || !d_obs_own || !d_obs_opp || !d_status) return fa_internal_fail(-1, "mp_forward: NULL pointer");
     if (n_own < 1 || n_own > MP_MAX_TEAM || n_opp < 1 || n_opp > MP_MAX_TEAM || n_envs < 1)
         return fa_internal_fail(-1, "mp_forward: team sizes must be 1..%d and n_envs >= 1", MP_MAX_TEAM);
@@ -692,6 +707,9 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     p.blob = (const uint8_t *)d_blob; p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.action_in = d_action_in;
     p.value = d_value; p.logp = d_logp; p.entropy = d_entropy; p.logits = d_logits; p.action = d_action;
     p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0; p.counter = (unsigned long long *)d_counter; p.env_sel = d_env_sel; p.sel_value = sel_value;
+    p.env_order = d_env_order; p.env_offsets = d_env_offsets;
+    if ((d_env_order == nullptr) != (d_env_offsets == nullptr) || (d_env_order != nullptr && sel_value < 0))
+        return fa_internal_fail(-1, "mp_forward: d_env_order and d_env_offsets come together, with sel_value >= 0");
     p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace; p.trace_tile = g_trace_tile;
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;

@@ -80,7 +80,7 @@ def _bind(L):
     if getattr(L, "_mp_bound", False):
         return
     vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
-    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 7 + [vp, i32, vp, vp]
+    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 7 + [vp, i32, vp, vp, vp, vp]
     i32p = ctypes.POINTER(ctypes.c_int32)
     L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
     L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp]
@@ -119,11 +119,13 @@ class FusedPolicy(object):
         return None if t is None else t.data_ptr()
 
     def forward(self, own, opp, mode=MODE_SAMPLE, action_in=None, out=None, want_logits=False, want_entropy=False,
-                env_sel=None, sel_value=0):
+                env_sel=None, sel_value=0, env_order=None, env_offsets=None):
         """own float32 [n, E, 6], opp float32 [m, E, 6] (contiguous, agent-major).
         Returns dict(value [n,E], action int64 [n,E], action_i32 [n,E], logp [n,E], entropy?, logits?).
         `out` may hold preallocated tensors under the same keys (e.g. views into the rollout storage).
-        env_sel (int32 [E]) / sel_value: write outputs only for environments with env_sel[e] == sel_value."""
+        env_sel (int32 [E]) / sel_value: write outputs only for environments with env_sel[e] == sel_value.
+        env_order (int32 [E]) / env_offsets (int32 [K+1]): compacted form -- process only the environments
+        env_order[env_offsets[sel_value] : env_offsets[sel_value + 1]] (device tensors; no host synchronisation)."""
         n, m = self.n, self.m
         E = own.shape[1]
         if own.shape != (n, E, OBS_DIM) or opp.shape != (m, E, OBS_DIM):
@@ -152,7 +154,8 @@ class FusedPolicy(object):
                                          self.seed, self.calls, self.counter.data_ptr(), self.env_id0, self._ptr(action_in),
                                          out["value"].data_ptr(), out["action"].data_ptr(), out["action_i32"].data_ptr(),
                                          out["logp"].data_ptr(), self._ptr(out.get("entropy")), self._ptr(out.get("logits")),
-                                         self._ptr(env_sel), int(sel_value), self.status.data_ptr(), stream))
+                                         self._ptr(env_sel), int(sel_value), self._ptr(env_order), self._ptr(env_offsets),
+                                         self.status.data_ptr(), stream))
         self.calls += 1
         self.launches += 1
         return out

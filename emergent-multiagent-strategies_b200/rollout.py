@@ -164,8 +164,10 @@ class BatchedTrainer(object):
             if t == 1 and self.ensemble is not None:
                 out = {"value": R.value_preds[step, lo:hi], "action": R.actions[step, lo:hi],
                        "action_i32": R.actions_i32[step, lo:hi], "logp": R.action_log_probs[step, lo:hi]}
-                for k, f in enumerate(self.ensemble):
-                    f.forward(R.obs[step, lo:hi], R.obs[step, olo:ohi], MODE_SAMPLE, out=out, env_sel=self.att_id, sel_value=k)
+                order, offsets = self._ensemble_lists()
+                for k, f in enumerate(self.ensemble):          # each launch covers only the envs that play checkpoint k
+                    f.forward(R.obs[step, lo:hi], R.obs[step, olo:ohi], MODE_SAMPLE, out=out, sel_value=k,
+                              env_order=order, env_offsets=offsets)
                 continue
             if self.fused is not None:
                 # one launch: value, sampled action (int64 for the storage, int32 for the step kernel) and its
@@ -202,6 +204,16 @@ class BatchedTrainer(object):
             torch.cuda.current_stream(self.device).wait_stream(side)
         self._graph.replay()
         return self.episode_rewards
+
+    def _ensemble_lists(self):
+        """Envs grouped by the checkpoint they currently play: (order int32 [E], offsets int32 [K+1]), device-side."""
+        K = len(self.ensemble)
+        ids = self.att_id.long()
+        order = torch.argsort(ids, stable=True).to(torch.int32)
+        offsets = torch.zeros(K + 1, dtype=torch.int32, device=self.device)
+        counts = (ids[:, None] == torch.arange(K, device=self.device)[None, :]).sum(0)     # (bincount would synchronise)
+        offsets[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        return order, offsets
 
     def ensemble_table(self):
         """The reference's evaluation table (test_fortattack_v2.py:50,94-124), one row per attacker checkpoint, averaged
@@ -258,9 +270,10 @@ class BatchedTrainer(object):
                                                  (self.teams[1], self.teams[0], self.policies[1]))):
             lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
             if t == 1 and self.ensemble is not None:
+                order, offsets = self._ensemble_lists()
                 for k, f in enumerate(self.ensemble):
-                    f.forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]},
-                              env_sel=self.att_id, sel_value=k)
+                    f.forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]}, sel_value=k,
+                              env_order=order, env_offsets=offsets)
             elif self.fused is not None:
                 self.fused[t].forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]})
             else:

@@ -64,11 +64,16 @@ enum {
  * This is how an ensemble of K frozen opponent checkpoints is played with a per-environment, per-episode choice
  * (Learner.sample_attacker / select_attacker, learner.py:119-140; train_fortattack_v2.py:34-35,110-111): one launch per
  * checkpoint over all environments, each writing only the rows of the environments currently assigned to it.
+ * d_env_order (int32 [E]) / d_env_offsets (int32 [K+1]), both on the device and optional: the compacted form of the same
+ * thing -- the launch covers only the environments d_env_order[d_env_offsets[sel_value] .. d_env_offsets[sel_value+1]),
+ * e.g. argsort of the per-environment checkpoint index and the running sum of its histogram.  The kernel reads the list
+ * bounds itself, so the host needs no synchronisation and the launches can be replayed from a CUDA graph.
  * d_status: uint32 on the device, set non-zero if the kernel's internal pipeline timed out (a bug, never expected). */
 int mp_forward(const void *d_blob, const float *d_obs_own, const float *d_obs_opp, int n_own, int n_opp, int n_envs,
                int mode, uint64_t seed, uint64_t offset, uint64_t *d_counter, uint64_t env_id0, const int64_t *d_action_in, float *d_value,
                int64_t *d_action, int32_t *d_action_i32, float *d_logp, float *d_entropy, float *d_logits,
-               const int32_t *d_env_sel, int32_t sel_value, uint32_t *d_status, void *stream);
+               const int32_t *d_env_sel, int32_t sel_value, const int32_t *d_env_order, const int32_t *d_env_offsets,
+               uint32_t *d_status, void *stream);
 
 /* Static facts about the policy kernel: registers/thread, threads/block, dynamic shared memory bytes,
  * resident blocks per SM, environments per 128-row tile for this team shape. */

@@ -32,7 +32,7 @@ def test_policy_and_rollout_headers_are_exported():
         for name in declared:
             assert hasattr(L, name), name
     L.mp_forward.restype = ctypes.c_int
-    assert L.mp_forward(*([None] * 3), 3, 3, 8, 0, 0, 0, None, 0, *([None] * 7), None, 0, None, None) == -1
+    assert L.mp_forward(*([None] * 3), 3, 3, 8, 0, 0, 0, None, 0, *([None] * 7), None, 0, None, None, None, None) == -1
     assert b"NULL" in L.fa_last_error()
     L.rl_gae.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 3 + [ctypes.c_double] * 2 + [ctypes.c_void_p]
     assert L.rl_gae(None, None, None, None, None, None, 4, 2, 8, 0.99, 0.95, None) == -1
