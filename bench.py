@@ -444,7 +444,7 @@ def rollout_config4_share(fab, torch, dev, E=8192, T=32):
 def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5):
     """One GPU's share of BASELINE.json configs[4] (guards-only training against an ensemble of 5 frozen attacker
     checkpoints, 32768 envs over 8 GPUs = 4096 envs per GPU, 5v5): rollout collection with a per-env, per-episode
-    attacker draw = 1 guard forward + K masked attacker forwards + 1 env step per rollout step (random-init checkpoints:
+    attacker draw = 1 guard forward + 1 ensemble forward (all K checkpoints in one launch) + 1 env step per rollout step (random-init checkpoints:
     there is no network for the shipped ones; the arithmetic is the same)."""
     import importlib
     ro = importlib.import_module("emergent-multiagent-strategies_b200.rollout")
@@ -467,7 +467,7 @@ def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5):
     return {"workload": "FortAttack 5v5 guards vs an ensemble of %d attacker checkpoints, %d envs (one GPU's share of BASELINE.json "
                         "configs[4]), T=%d rollout" % (K, E, T),
             "rollout_agent_steps_per_s": E * 10 * T / (ms * 1e-3), "us_per_rollout_step": ms * 1e3 / T,
-            "policy_launches_per_step": 1 + K}
+            "policy_launches_per_step": 2, "note": "one mp_forward for the guards, one mp_forward_ensemble serving all %d checkpoints" % K}
 
 
 def sweep(fab, torch, dev, peak):

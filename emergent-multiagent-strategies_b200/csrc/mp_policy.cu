@@ -97,6 +97,8 @@ __constant__ Chunk c_tab[N_STREAM] = {
 
 struct Params {
     const uint8_t *blob;
+    const uint8_t *blobs[MP_MAX_ENSEMBLE];   // n_ckpt > 0: CTA c plays checkpoint c % n_ckpt with weights blobs[c % n_ckpt]
+    int n_ckpt;
     const float *obs_own, *obs_opp;     // [n][E][6]
     const int64_t *action_in;
     float *value, *logp, *entropy, *logits;
@@ -344,6 +346,12 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     uint8_t *bufH = smem + OFF_H, *bufX = smem + OFF_X;
     float *C = reinterpret_cast<float *>(smem + OFF_CONST);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ensemble launch: CTA c serves checkpoint c % n_ckpt (its weights stay resident for the whole launch) and strides
+    // over that checkpoint's tiles together with the other CTAs of the same checkpoint
+    const int ckpt = p.n_ckpt > 0 ? (int)(blockIdx.x % (unsigned)p.n_ckpt) : p.sel_value;
+    const uint8_t *blob = p.n_ckpt > 0 ? p.blobs[ckpt] : p.blob;
+    const int tile0 = p.n_ckpt > 0 ? (int)(blockIdx.x / (unsigned)p.n_ckpt) : (int)blockIdx.x;
+    const int tile_stride = p.n_ckpt > 0 ? ((int)gridDim.x - ckpt + p.n_ckpt - 1) / p.n_ckpt : (int)gridDim.x;
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     }
     if (warp == PRODUCER_WARP) tmem_alloc<TMEM_COLS>(&tmem_base_s);
     {   // fp32 constants: plain loads, once per CTA
-        const float4 *src = reinterpret_cast<const float4 *>(p.blob + MP_BLOB_F16_BYTES);
+        const float4 *src = reinterpret_cast<const float4 *>(blob + MP_BLOB_F16_BYTES);
         float4 *dst = reinterpret_cast<float4 *>(C);
         if (DW_IN_SMEM) {
             for (int i = tid; i < MP_BLOB_CONST_FLOATS / 4; i += THREADS) dst[i] = src[i];
@@ -371,8 +379,8 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     const int32_t *env_list = nullptr;
     int n_list = p.E, n_tiles = p.n_tiles;
     if (p.env_order != nullptr) {
-        const int lo = p.env_offsets[p.sel_value];
-        n_list = p.env_offsets[p.sel_value + 1] - lo;
+        const int lo = p.env_offsets[ckpt];
+        n_list = p.env_offsets[ckpt + 1] - lo;
         env_list = p.env_order + lo;
         n_tiles = (n_list + p.ept - 1) / p.ept;
     }
@@ -386,15 +394,15 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         if (lane == 0) {
             mbar_expect_tx(&bar_res, RES_BYTES);           // round weights: resident for the whole kernel
             for (int i = 0; i < RES_BYTES / STAGE_BYTES; ++i)
-                bulk_g2s(smem + OFF_WRES + i * STAGE_BYTES, p.blob + BLOB_RES + i * STAGE_BYTES, STAGE_BYTES, &bar_res);
+                bulk_g2s(smem + OFF_WRES + i * STAGE_BYTES, blob + BLOB_RES + i * STAGE_BYTES, STAGE_BYTES, &bar_res);
             uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
                 for (int c = 0; c < N_STREAM; ++c, ++g) {
                     const uint32_t s = g % NS, ph = (g / NS) & 1u;
                     mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 3);
                     if (p.trace != nullptr && blockIdx.x == 0 && tile == 0) p.trace[64 + c] = clock64();
                     mbar_expect_tx(&bar_full[s], c_tab[c].bytes);
-                    bulk_g2s(smem + OFF_RING + s * STAGE_BYTES, p.blob + c_tab[c].off, c_tab[c].bytes, &bar_full[s]);
+                    bulk_g2s(smem + OFF_RING + s * STAGE_BYTES, blob + c_tab[c].off, c_tab[c].bytes, &bar_full[s]);
                 }
             }
         }
@@ -434,7 +442,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             ++g;
         };
         mbar_wait(&bar_res, 0, p.status, 2);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
             stream_chunk(0);
             stream_chunk(1);
             for (int round = 0; round < 3; ++round) {      // [T | Z | Y] = h [G | Wz | U1^T]
@@ -471,19 +479,19 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             rowoth[b] = (uint32_t)(ro >> 3) * A_SBO + (uint32_t)(ro & 7) * 16u;
         }
         const int n_oth = n_own - 1;
-        const float *DW = DW_IN_SMEM ? C + C_DW : reinterpret_cast<const float *>(p.blob + MP_BLOB_F16_BYTES) + C_DW;   // [128][8]
+        const float *DW = DW_IN_SMEM ? C + C_DW : reinterpret_cast<const float *>(blob + MP_BLOB_F16_BYTES) + C_DW;   // [128][8]
         uint32_t pc = 0;
         int ti = 0;
 #define ARRIVE_A() do { tc_fence_before(); fence_async_smem(); mbar_arrive(&bar_a_ready); } while (0)
-#define TS() do { if (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && tile == p.trace_tile * (int)gridDim.x && ti < 96) p.trace[ti++] = clock64(); } while (0)
+#define TS() do { if (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && tile == tile0 + p.trace_tile * tile_stride && ti < 96) p.trace[ti++] = clock64(); } while (0)
 #define WAIT_ACC(code) do { mbar_wait(&bar_acc, pc, p.status, code); pc ^= 1u; tc_fence_after(); } while (0)
 
         float o_own[6], o_opp[6];                                  // this tile's observations (prefetched one tile ahead)
         // global env id of list entry li (p.E = "none": load_obs and the output guard treat it as out of range)
         auto env_of = [&](int li) { return li < n_list ? (env_list != nullptr ? env_list[li] : li) : p.E; };
-        load_obs(p.obs_own, n_own, a, p.E, env_of(blockIdx.x * ept + e), o_own);
-        load_obs(p.obs_opp, n_opp, a, p.E, env_of(blockIdx.x * ept + e), o_opp);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        load_obs(p.obs_own, n_own, a, p.E, env_of(tile0 * ept + e), o_own);
+        load_obs(p.obs_opp, n_opp, a, p.E, env_of(tile0 * ept + e), o_opp);
+        for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
             const int eg = env_of(tile * ept + e);
             TS();
             // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64); QC64 outputs per thread
@@ -532,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 TS();
             }
             {   // the next tile's observations: the loads fly while the heads are computed
-                const int nt = tile + gridDim.x;
+                const int nt = tile + tile_stride;
                 if (nt < n_tiles) {
                     load_obs(p.obs_own, n_own, a, p.E, env_of(nt * ept + e), o_own);
                     load_obs(p.obs_opp, n_opp, a, p.E, env_of(nt * ept + e), o_opp);
@@ -703,7 +711,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
         return fa_internal_fail(-4, "mp_forward: blob/logits must be 16-byte, observations 8-byte aligned");
     int sms = 0;
     if (int rc = prepare(&sms)) return rc;
-    mp::Params p;
+    mp::Params p = {};
     p.blob = (const uint8_t *)d_blob; p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.action_in = d_action_in;
     p.value = d_value; p.logp = d_logp; p.entropy = d_entropy; p.logits = d_logits; p.action = d_action;
     p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0; p.counter = (unsigned long long *)d_counter; p.env_sel = d_env_sel; p.sel_value = sel_value;
@@ -717,6 +725,41 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     mp::mp_policy_kernel<<<grid, mp::THREADS, mp::SMEM_BYTES, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "mp_forward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// One launch for an ensemble of K frozen checkpoints: CTA c serves checkpoint c % K over the environments
+// d_env_order[d_env_offsets[k] .. d_env_offsets[k+1]).
+extern "C" int mp_forward_ensemble(const void *const *d_blobs, int n_ckpt, const float *d_obs_own, const float *d_obs_opp,
+                                   int n_own, int n_opp, int n_envs, int mode, uint64_t seed, uint64_t offset,
+                                   uint64_t *d_counter, uint64_t env_id0, float *d_value, int64_t *d_action,
+                                   int32_t *d_action_i32, float *d_logp, const int32_t *d_env_order,
+                                   const int32_t *d_env_offsets, uint32_t *d_status, void *stream) {
+    if (!d_blobs || !d_obs_own || !d_obs_opp || !d_status || !d_env_order || !d_env_offsets)
+        return fa_internal_fail(-1, "mp_forward_ensemble: NULL pointer");
+    if (n_ckpt < 1 || n_ckpt > MP_MAX_ENSEMBLE) return fa_internal_fail(-1, "mp_forward_ensemble: 1 <= n_ckpt <= %d", MP_MAX_ENSEMBLE);
+    if (n_own < 1 || n_own > MP_MAX_TEAM || n_opp < 1 || n_opp > MP_MAX_TEAM || n_envs < 1 || (mode != MP_MODE_SAMPLE && mode != MP_MODE_ARGMAX))
+        return fa_internal_fail(-1, "mp_forward_ensemble: bad team sizes, n_envs or mode");
+    int sms = 0;
+    if (int rc = prepare(&sms)) return rc;
+    mp::Params p = {};
+    for (int k = 0; k < n_ckpt; ++k) {
+        if (!d_blobs[k] || ((uintptr_t)d_blobs[k] & 15)) return fa_internal_fail(-4, "mp_forward_ensemble: blob %d NULL or not 16-byte aligned", k);
+        p.blobs[k] = (const uint8_t *)d_blobs[k];
+    }
+    p.n_ckpt = n_ckpt; p.blob = p.blobs[0];
+    p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.value = d_value; p.logp = d_logp; p.action = d_action;
+    p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0;
+    p.counter = (unsigned long long *)d_counter; p.env_order = d_env_order; p.env_offsets = d_env_offsets;
+    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = nullptr;
+    p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
+    p.n_tiles = (n_envs + p.ept - 1) / p.ept;
+    // every checkpoint may own up to all tiles: one CTA per SM, at least one per checkpoint
+    int grid = p.n_tiles * n_ckpt < sms ? p.n_tiles * n_ckpt : sms;
+    if (grid < n_ckpt) grid = n_ckpt;
+    mp::mp_policy_kernel<<<grid, mp::THREADS, mp::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "mp_forward_ensemble: launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -83,6 +83,7 @@ def _bind(L):
     L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 7 + [vp, i32, vp, vp, vp, vp]
     i32p = ctypes.POINTER(ctypes.c_int32)
     L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
+    L.mp_forward_ensemble.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 8
     L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp]
     L._mp_bound = True
 
@@ -181,3 +182,31 @@ class FusedPolicy(object):
         v = [ctypes.c_int32() for _ in range(5)]
         _capi.check(self._lib.mp_kernel_info(self.n, self.m, *[ctypes.byref(x) for x in v]))
         return dict(zip(("regs", "block", "smem", "blocks_per_sm", "envs_per_tile"), [x.value for x in v]))
+
+
+def forward_ensemble(policies, own, opp, env_order, env_offsets, mode=MODE_SAMPLE, out=None):
+    """ONE launch for an ensemble of frozen checkpoints (mp_forward_ensemble): `policies` is a list of FusedPolicy of the
+    same team shape; env_order int32 [E] / env_offsets int32 [K+1] (device) group the environments by the checkpoint they
+    play.  Sampling stream, status word and seed are those of policies[0].  Returns the same dict as FusedPolicy.forward."""
+    lead = policies[0]
+    n, m, dev = lead.n, lead.m, lead.device
+    E = own.shape[1]
+    if own.shape != (n, E, OBS_DIM) or opp.shape != (m, E, OBS_DIM) or not own.is_contiguous() or not opp.is_contiguous():
+        raise ValueError("own/opp must be contiguous [%d,E,6] / [%d,E,6]" % (n, m))
+    if env_order.dtype != torch.int32 or env_offsets.dtype != torch.int32 or env_order.numel() != E or env_offsets.numel() != len(policies) + 1:
+        raise ValueError("env_order int32 [E] and env_offsets int32 [K+1] are required")
+    out = dict(out or {})
+    for key, dt in (("value", torch.float32), ("action", torch.int64), ("action_i32", torch.int32), ("logp", torch.float32)):
+        if key not in out:
+            out[key] = torch.empty((n, E), dtype=dt, device=dev)
+        if not out[key].is_contiguous() or out[key].numel() != n * E:
+            raise ValueError("output %r must be contiguous with %d rows" % (key, n * E))
+    blobs = (ctypes.c_void_p * len(policies))(*[f.blob.data_ptr() for f in policies])
+    _capi.check(lead._lib.mp_forward_ensemble(blobs, len(policies), own.data_ptr(), opp.data_ptr(), n, m, E, mode, lead.seed,
+                                              lead.calls, lead.counter.data_ptr(), lead.env_id0, out["value"].data_ptr(),
+                                              out["action"].data_ptr(), out["action_i32"].data_ptr(), out["logp"].data_ptr(),
+                                              env_order.data_ptr(), env_offsets.data_ptr(), lead.status.data_ptr(),
+                                              torch.cuda.current_stream(dev).cuda_stream))
+    lead.calls += 1
+    lead.launches += 1
+    return out

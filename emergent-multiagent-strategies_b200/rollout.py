@@ -24,7 +24,7 @@ import torch
 from . import _capi
 from .batched_env import FortAttackBatch
 from .mpnn import MPNN
-from .policy_kernel import FusedPolicy, MODE_ARGMAX, MODE_SAMPLE
+from .policy_kernel import FusedPolicy, MODE_ARGMAX, MODE_SAMPLE, forward_ensemble
 from .rlcore.algo import JointPPO
 from .rlcore.storage import RolloutStorage
 
@@ -165,9 +165,8 @@ class BatchedTrainer(object):
                 out = {"value": R.value_preds[step, lo:hi], "action": R.actions[step, lo:hi],
                        "action_i32": R.actions_i32[step, lo:hi], "logp": R.action_log_probs[step, lo:hi]}
                 order, offsets = self._ensemble_lists()
-                for k, f in enumerate(self.ensemble):          # each launch covers only the envs that play checkpoint k
-                    f.forward(R.obs[step, lo:hi], R.obs[step, olo:ohi], MODE_SAMPLE, out=out, sel_value=k,
-                              env_order=order, env_offsets=offsets)
+                # one launch: CTA c keeps checkpoint c % K resident and serves the envs that currently play it
+                forward_ensemble(self.ensemble, R.obs[step, lo:hi], R.obs[step, olo:ohi], order, offsets, MODE_SAMPLE, out=out)
                 continue
             if self.fused is not None:
                 # one launch: value, sampled action (int64 for the storage, int32 for the step kernel) and its
@@ -271,9 +270,8 @@ class BatchedTrainer(object):
             lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
             if t == 1 and self.ensemble is not None:
                 order, offsets = self._ensemble_lists()
-                for k, f in enumerate(self.ensemble):
-                    f.forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]}, sel_value=k,
-                              env_order=order, env_offsets=offsets)
+                forward_ensemble(self.ensemble, R.obs[T, lo:hi], R.obs[T, olo:ohi], order, offsets, MODE_ARGMAX,
+                                 out={"value": nv[lo:hi]})
             elif self.fused is not None:
                 self.fused[t].forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]})
             else:

@@ -34,6 +34,7 @@ extern "C" {
 #define MP_OBS_DIM 6
 #define MP_ACTIONS 8
 #define MP_MAX_TEAM 5
+#define MP_MAX_ENSEMBLE 8
 
 /* packed weight blob: MP_BLOB_F16_BYTES of fp16 GEMM operands (UMMA canonical K-major core-matrix
  * order, in the order the kernel consumes them) followed by MP_BLOB_CONST_FLOATS fp32 values
@@ -74,6 +75,15 @@ int mp_forward(const void *d_blob, const float *d_obs_own, const float *d_obs_op
                int64_t *d_action, int32_t *d_action_i32, float *d_logp, float *d_entropy, float *d_logits,
                const int32_t *d_env_sel, int32_t sel_value, const int32_t *d_env_order, const int32_t *d_env_offsets,
                uint32_t *d_status, void *stream);
+
+/* The same forward for an ENSEMBLE of n_ckpt (<= MP_MAX_ENSEMBLE) frozen checkpoints in ONE launch: CTA c keeps the weights
+ * of checkpoint c % n_ckpt resident and works through the environments d_env_order[d_env_offsets[k] .. d_env_offsets[k+1])
+ * of its checkpoint k (Learner.sample_attacker, learner.py:119-130: every environment plays the checkpoint it drew at its
+ * episode start).  d_blobs: host array of n_ckpt device pointers.  MP_MODE_SAMPLE or MP_MODE_ARGMAX. */
+int mp_forward_ensemble(const void *const *d_blobs, int n_ckpt, const float *d_obs_own, const float *d_obs_opp, int n_own,
+                        int n_opp, int n_envs, int mode, uint64_t seed, uint64_t offset, uint64_t *d_counter,
+                        uint64_t env_id0, float *d_value, int64_t *d_action, int32_t *d_action_i32, float *d_logp,
+                        const int32_t *d_env_order, const int32_t *d_env_offsets, uint32_t *d_status, void *stream);
 
 /* Static facts about the policy kernel: registers/thread, threads/block, dynamic shared memory bytes,
  * resident blocks per SM, environments per 128-row tile for this team shape. */

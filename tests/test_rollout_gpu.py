@@ -328,6 +328,17 @@ def test_attacker_ensemble_play():
         sel = ids0 == k
         assert sel.any()
         assert torch.equal(o["value"][:, sel], R.value_preds[0, 3:6, :, 0][:, sel])
+    # the one-launch ensemble forward equals K compacted single-checkpoint launches and K masked full launches
+    order, offsets = tr._ensemble_lists()
+    own, opp = R.obs[3, 3:6].contiguous(), R.obs[3, 0:3].contiguous()
+    one = pk.forward_ensemble(tr.ensemble, own, opp, order, offsets, pk.MODE_ARGMAX)
+    comp = {k: torch.zeros_like(v) for k, v in one.items()}
+    mask = {k: torch.zeros_like(v) for k, v in one.items()}
+    for k in range(3):
+        tr.ensemble[k].forward(own, opp, pk.MODE_ARGMAX, out=comp, sel_value=k, env_order=order, env_offsets=offsets)
+        tr.ensemble[k].forward(own, opp, pk.MODE_ARGMAX, out=mask, env_sel=tr.att_id, sel_value=k)
+    for key in one:
+        assert torch.equal(one[key], comp[key]) and torch.equal(one[key], mask[key]), key
     assert not torch.equal(ids0, tr.att_id)                          # episodes ended (cap 7): new draws
     n_done = int((R.done != 0).sum())
     assert int(tr.ensemble_results.sum()) == n_done and int(tr.ensemble_results[:, 0].sum()) == 0
