@@ -1,6 +1,6 @@
 """Profiling driver: a few fused policy forwards (3v3, E envs) and, with --ppo, one PPO minibatch step under torch.profiler."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from importlib import import_module
 import policy_util as pu
 from test_policy_cpu import make

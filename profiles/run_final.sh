@@ -9,7 +9,7 @@ timeout 900 python bench.py > gpurun_out/r1g_bench.json 2> gpurun_out/r1g_bench.
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r1g_launches.csv \
     python bench.py --steps 20 --warmup 3 --quick --e2e-steps 5 --reps 1 > gpurun_out/ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mp_policy_kernel -s 2 -c 1 -f -o gpurun_out/r1g_prof_policy_16384 \
-    python tests/prof_policy.py 16384 > gpurun_out/ncu_policy.log 2>&1
+    python profiles/prof_policy.py 16384 > gpurun_out/ncu_policy.log 2>&1
 ncu --set full --clock-control none -k regex:attn_ -c 2 -f -o gpurun_out/r1g_prof_attn \
     python -m pytest tests/test_rollout_gpu.py -q -k "fused_training_attention and 3-3-128" > gpurun_out/ncu_attn.log 2>&1
 ls gpurun_out | tail -12
