@@ -39,6 +39,21 @@ __global__ void __launch_bounds__(128) gae_kernel(const float *__restrict__ rew,
     }
 }
 
+// ---- per-step rollout bookkeeping: masks of slot t+1, end points, episode reward sums --------------------------------
+__global__ void __launch_bounds__(256) bookkeeping_kernel(const float *__restrict__ obs_t, const float *__restrict__ obs_t1,
+                                                          const uint8_t *__restrict__ done, const float *__restrict__ rew,
+                                                          float *__restrict__ masks_t1, uint8_t *__restrict__ ends_t1,
+                                                          float *__restrict__ ep_rew, int A, int E) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (e >= E) return;
+    const size_t k = (size_t)a * E + e;
+    const float alive_before = obs_t[k * 6];
+    const bool fin = done[e] != 0;
+    masks_t1[k] = fin ? obs_t1[k * 6] : alive_before;
+    ep_rew[k] += rew[k] * alive_before;
+    if (a == 0) ends_t1[e] = fin ? 1 : 0;
+}
+
 // ---- minibatch gather: one thread per output row (k, j); rows of one agent are consecutive threads ---------------
 struct GatherParams {
     const int64_t *idx;
@@ -332,6 +347,20 @@ extern "C" int rl_attn_backward(const RlAttnOperand *dout, const RlAttnOperand *
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_backward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rl_rollout_bookkeeping(const float *d_obs_t, const float *d_obs_t1, const uint8_t *d_done, const float *d_reward,
+                                      float *d_masks_t1, uint8_t *d_ends_t1, float *d_episode_rewards, int A, int E,
+                                      void *stream) {
+    if (!d_obs_t || !d_obs_t1 || !d_done || !d_reward || !d_masks_t1 || !d_ends_t1 || !d_episode_rewards)
+        return fa_internal_fail(-1, "rl_rollout_bookkeeping: NULL pointer");
+    if (A < 1 || E < 1 || A > 65535) return fa_internal_fail(-1, "rl_rollout_bookkeeping: bad sizes A=%d E=%d", A, E);
+    const dim3 grid((unsigned)((E + 255) / 256), (unsigned)A);
+    rl::bookkeeping_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_obs_t, d_obs_t1, d_done, d_reward, d_masks_t1, d_ends_t1,
+                                                                   d_episode_rewards, A, E);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_rollout_bookkeeping: launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

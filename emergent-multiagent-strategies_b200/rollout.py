@@ -62,6 +62,19 @@ class SharedRollouts(object):
             r.num_steps, r.step = T, 0
             self.agents.append(r)
 
+    def bookkeeping(self, step, episode_rewards):
+        """masks[step+1], ends[step+1] and episode_rewards from obs[step], obs[step+1], done[step], rewards[step]
+        (rl_rollout_bookkeeping, include/fortattack_rollout.h)."""
+        L = _capi.lib()
+        if not getattr(L, "_rl4_bound", False):
+            L.rl_rollout_bookkeeping.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+            L._rl4_bound = True
+        T, A, E = self.rewards.shape
+        _capi.check(L.rl_rollout_bookkeeping(self.obs[step].data_ptr(), self.obs[step + 1].data_ptr(), self.done[step].data_ptr(),
+                                             self.rewards[step].data_ptr(), self.masks[step + 1].data_ptr(),
+                                             self.ends[step + 1].data_ptr(), episode_rewards.data_ptr(), A, E,
+                                             torch.cuda.current_stream(self.rewards.device).cuda_stream))
+
     def compute_returns(self, next_value, gamma, tau):
         """Learner.wrap_horizon for every agent and env in ONE launch (rl_gae, include/fortattack_rollout.h):
         next_value float [A, E]; per-env episode boundaries from `ends`."""
@@ -237,15 +250,12 @@ class BatchedTrainer(object):
             actions = self.act(step)
             # obs of step+1, rewards of step, done/result are written in place by the kernel
             self.env.step(actions, auto_reset=True, out=(R.obs[step + 1], R.rewards[step], R.done[step], R.result[step]))
-            R.masks[step + 1, :, :, 0] = masks                             # RolloutStorage.insert (storage.py:41)
-            finished = R.done[step] != 0
-            R.ends[step + 1] = finished                                    # end_pts.append(step) after step += 1
-            # initialize_new_episode(step, obs, masks): the reset obs is already in place; masks become
-            # the new episode's alive flags (= 1)                         (train_fortattack.py:100-104)
-            R.masks[step + 1, :, :, 0] = torch.where(finished[None, :], R.obs[step + 1, :, :, 0], R.masks[step + 1, :, :, 0])
-            self.episode_rewards += R.rewards[step] * masks
+            # RolloutStorage.insert's masks (storage.py:41), the end point (train_fortattack.py:98), initialize_new_episode's
+            # masks for finished envs (:100-104: the reset obs is already in place) and the episode reward sums: one launch
+            R.bookkeeping(step, self.episode_rewards)
             if self.ensemble is not None:
                 K = len(self.ensemble)
+                finished = R.done[step] != 0
                 code = R.result[step].long()                                  # 0 running, 1 all dead, 2 time limit, 3 reached
                 self.ensemble_results.view(-1).index_add_(0, self.att_id.long() * 4 + code, finished.long())
                 self.ep_return += R.rewards[step] * masks

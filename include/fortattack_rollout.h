@@ -34,6 +34,15 @@ extern "C" {
 int rl_gae(const float *d_rewards, float *d_value_preds, const float *d_next_value, const float *d_masks,
            const uint8_t *d_ends, float *d_returns, int T, int A, int E, double gamma, double tau, void *stream);
 
+/* Per-step bookkeeping of the rollout loop (train_fortattack.py:53,97-104; RolloutStorage.insert, storage.py:41) for every
+ * agent and env in one launch: with alive_before = obs_t[a][e][0] and fin = done[e] != 0,
+ *   masks_t1[a][e] = fin ? obs_t1[a][e][0] (the new episode's alive flags) : alive_before
+ *   ends_t1[e]     = fin                       (the end point train_fortattack.py:98 appends)
+ *   episode_rewards[a][e] += reward[a][e] * alive_before
+ * obs_t / obs_t1 float [A][E][6]; done uint8 [E]; reward, masks_t1, episode_rewards float [A][E]; ends_t1 uint8 [E]. */
+int rl_rollout_bookkeeping(const float *d_obs_t, const float *d_obs_t1, const uint8_t *d_done, const float *d_reward,
+                           float *d_masks_t1, uint8_t *d_ends_t1, float *d_episode_rewards, int A, int E, void *stream);
+
 /* Team minibatch gather (replaces magent_feed_forward_generator's per-agent index + cat,
  * rlcore/algo/ppo.py:207-246): for mb sample indices idx[j] = t * E + e and the team's agents a0 .. a0+n-1 (opponents
  * o0 .. o0+m-1), rows are emitted agent-major (row = k * mb + j), exactly the order torch.cat([x[i][idx] ...]) gives.
