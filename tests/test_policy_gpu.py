@@ -33,7 +33,7 @@ def test_tcgen05_gemm_probe():
         assert (out.double() - ref).abs().max() < 1e-4, (K, N)
 
 
-@pytest.mark.parametrize("n,m,E", [(3, 3, 4096), (3, 3, 42), (3, 3, 43), (3, 3, 5), (5, 5, 1000), (1, 1, 300), (2, 4, 777),
+@pytest.mark.parametrize("n,m,E", [(3, 3, 4096), (3, 3, 42), (3, 3, 43), (3, 3, 5), (3, 3, 1), (5, 5, 1000), (1, 1, 300), (2, 4, 777),
                                    (4, 1, 129), (5, 3, 26), (3, 3, 16384)])
 def test_forward_matches_blob_arithmetic(n, m, E):
     net = make(n, m, seed=n * 10 + m).cuda()
@@ -91,6 +91,28 @@ def test_sampling_distribution_and_determinism():
     # evaluate mode reproduces the log-probs of given actions
     o5 = fp.forward(own, opp, pk.MODE_EVAL, action_in=o["action"], want_entropy=True)
     assert (o5["logp"] - o["logp"]).abs().max() < 1e-6
+
+
+def test_ensemble_launch_with_empty_and_tiny_lists():
+    """mp_forward_ensemble with more checkpoints than environments (some lists empty, every list shorter than a tile)
+    and with one environment: finishes (no pipeline timeout) and equals the single-checkpoint forwards."""
+    nets = [make(2, 3, seed=50 + k).cuda() for k in range(8)]
+    fps = [pk.FusedPolicy(n_, seed=4) for n_ in nets]
+    gen = torch.Generator().manual_seed(9)
+    for E in (1, 10, 300):
+        own, opp = pu.random_obs(2, E, gen, "cuda"), pu.random_obs(3, E, gen, "cuda")
+        ids = torch.randint(0, 8, (E,), generator=gen).to("cuda")
+        ids[0] = 5
+        order = torch.argsort(ids, stable=True).to(torch.int32)
+        offsets = torch.zeros(9, dtype=torch.int32, device="cuda")
+        offsets[1:] = torch.cumsum(torch.bincount(ids, minlength=8), 0).to(torch.int32)
+        one = pk.forward_ensemble(fps, own, opp, order, offsets, pk.MODE_ARGMAX)
+        fps[0].check_status()
+        for k in range(8):
+            ref = fps[k].forward(own, opp, pk.MODE_ARGMAX)
+            sel = ids == k
+            for key in ("value", "action", "logp"):
+                assert torch.equal(one[key][:, sel], ref[key][:, sel]), (E, k, key)
 
 
 def test_act_surface_matches_module_statistics():
