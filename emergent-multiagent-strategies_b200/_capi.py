@@ -17,7 +17,7 @@ FA_MAP_AUTO, FA_MAP_ENV, FA_MAP_AGENT = 0, 1, 2
 
 # every symbol include/fortattack.h declares
 SYMBOLS = ("fa_abi_version", "fa_last_error", "fa_workspace_bytes", "fa_create", "fa_destroy", "fa_reset",
-           "fa_step", "fa_step_many", "fa_step_host", "fa_host_layout", "fa_get_state", "fa_set_state", "fa_alive_counts",
+           "fa_step", "fa_step_many", "fa_step_host", "fa_step_many_host", "fa_host_stage_bytes", "fa_host_layout", "fa_get_state", "fa_set_state", "fa_alive_counts",
            "fa_set_max_steps", "fa_set_alive_end_buffer", "fa_launch_count", "fa_kernel_info")
 
 
@@ -68,6 +68,8 @@ def lib():
     L.fa_step_many.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     L.fa_step_host.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
     szp = ctypes.POINTER(ctypes.c_size_t)
+    L.fa_step_many_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    L.fa_host_stage_bytes.argtypes = [vp, ctypes.c_int, szp]
     L.fa_host_layout.argtypes = [vp, szp, szp, szp, szp]
     L.fa_get_state.argtypes = [vp, ctypes.POINTER(FaState), vp]
     L.fa_set_state.argtypes = [vp, ctypes.POINTER(FaState), vp]

@@ -127,6 +127,37 @@ class FortAttackBatch(object):
                                            self._stream()))
         return h_obs, h_rew, h_done, h_result
 
+    def make_host_streams(self, T, store_obs=True):
+        """Page-locked host streams for step_many_host: actions int32 [T,A,E] and (obs [T,A,E,6] or None,
+        reward [T,A,E], done u8 [T,E], result u8 [T,E])."""
+        pin = lambda *shape, dtype: torch.zeros(shape, dtype=dtype).pin_memory()
+        return (pin(T, self.A, self.E, dtype=torch.int32),
+                pin(T, self.A, self.E, 6, dtype=self.dtype) if store_obs else None,
+                pin(T, self.A, self.E, dtype=self.dtype), pin(T, self.E, dtype=torch.uint8),
+                pin(T, self.E, dtype=torch.uint8))
+
+    def step_many_host(self, h_actions, h_obs, h_rew, h_done, h_result, chunk_steps=None):
+        """T env.step() calls of every env with HOST streams (fa_step_many_host), synchronous.
+        chunk_steps=None: chunks of about 8 MB of results, copied by the DMA engines while the neighbouring chunks
+        compute; chunk_steps=0: no staging, one persistent launch working through mapped pinned memory."""
+        T = int(h_actions.shape[0])
+        if tuple(h_actions.shape) != (T, self.A, self.E) or h_actions.dtype != torch.int32 or h_actions.is_cuda:
+            raise ValueError("h_actions must be a host int32 tensor [T, %d, %d]" % (self.A, self.E))
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        stage, nbytes = None, 0
+        if chunk_steps is None:
+            rs = 8 if self.dtype == torch.float64 else 4
+            chunk_steps = max(1, min(T, (8 << 20) // (self.A * self.E * 7 * rs + 2 * self.E)))
+        if chunk_steps > 0:
+            need = ctypes.c_size_t()
+            _capi.check(self._lib.fa_host_stage_bytes(self._h, int(chunk_steps), ctypes.byref(need)))
+            if getattr(self, "_stage", None) is None or self._stage.numel() < need.value:
+                self._stage = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            stage, nbytes = self._stage.data_ptr(), need.value
+        _capi.check(self._lib.fa_step_many_host(self._h, T, h_actions.data_ptr(), ptr(h_obs), ptr(h_rew), ptr(h_done),
+                                                ptr(h_result), stage, nbytes, self._stream()))
+        return h_obs, h_rew, h_done, h_result
+
     # -- state exchange (canonical float64 layout, include/fortattack.h FaState) -------------------
     def get_state(self):
         st_f = self._new(self.E, self.A, 6, dtype=torch.float64)

@@ -180,7 +180,7 @@ __device__ __forceinline__ float warp_sum(float x) {
 
 template <int VEC>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(Opnd A, Opnd B, Opnd V, Opnd O, float *attn, int batch, int n, int m,
-                                                       float norm, int mask_diag) {
+                                                       float norm, int mask_diag, Opnd C = Opnd{nullptr, 0, 0}) {
     const int lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= batch) return;
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(Opnd A, Opnd B, Opnd V, O
         if (j < m) {
             VecLoad<VEC>::ld(B.p + b * B.bs + j * B.rs + c, bb[j]);
             VecLoad<VEC>::ld(V.p + b * V.bs + j * V.rs + c, vv[j]);
+            if (C.p) VecLoad<VEC>::st(C.p + b * C.bs + j * C.rs + c, vv[j]);     // the value rows, re-emitted (rl_attn_mix_forward)
         }
 #pragma unroll
     for (int i = 0; i < ATT_MAX; ++i) {
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(Opnd A, Opnd B, Opnd V, O
 
 template <int VEC>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(Opnd G, Opnd A, Opnd B, Opnd V, const float *attn, Opnd dA, Opnd dB,
-                                                       Opnd dV, int batch, int n, int m, float norm) {
+                                                       Opnd dV, int batch, int n, int m, float norm, int sum_bv = 0,
+                                                       Opnd Cin = Opnd{nullptr, 0, 0}) {
     const int lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= batch) return;
@@ -290,9 +292,47 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(Opnd G, Opnd A, Opnd B, O
 #pragma unroll
     for (int j = 0; j < ATT_MAX; ++j)
         if (j < m) {
-            VecLoad<VEC>::st(dB.p + b * dB.bs + j * dB.rs + c, db[j]);
-            VecLoad<VEC>::st(dV.p + b * dV.bs + j * dV.rs + c, dv[j]);
+            if (sum_bv) {       // keys and values are the same rows (rl_attn_mix_backward): one gradient, plus an optional addend
+                float t[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) t[q] = 0.0f;
+                if (Cin.p) VecLoad<VEC>::ld(Cin.p + b * Cin.bs + j * Cin.rs + c, t);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) t[q] += db[j][q] + dv[j][q];
+                VecLoad<VEC>::st(dB.p + b * dB.bs + j * dB.rs + c, t);
+            } else {
+                VecLoad<VEC>::st(dB.p + b * dB.bs + j * dB.rs + c, db[j]);
+                VecLoad<VEC>::st(dV.p + b * dV.bs + j * dV.rs + c, dv[j]);
+            }
         }
+}
+
+// ---- ReLU backward fused with the bias gradient: dpre = dout * [out > 0], partial[block][c] = sum over the block's rows
+// of dpre[., c].  Row-major [rows, cols], cols = 4 * c4 with c4 in {8, 16, 32, 64}: c4 lanes cover one row with 16-byte
+// accesses, 256 / c4 rows per block iteration, a fixed block -> rows assignment and a fixed summation order (the
+// caller adds the [blocks, cols] partials), so the result is reproducible run to run.
+__global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(const float4 *__restrict__ dout, const float4 *__restrict__ out,
+                                                              float4 *__restrict__ dpre, float4 *__restrict__ partial,
+                                                              long long rows, int c4) {
+    __shared__ float4 sm[256];
+    const int lane = threadIdx.x % c4, rsub = threadIdx.x / c4, rpi = 256 / c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = (long long)blockIdx.x * rpi + rsub; r < rows; r += (long long)gridDim.x * rpi) {
+        float4 g = dout[r * c4 + lane];
+        const float4 o = out[r * c4 + lane];
+        g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        dpre[r * c4 + lane] = g;
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (rsub == 0) {
+        for (int q = 1; q < rpi; ++q) {
+            const float4 t = sm[q * c4 + lane];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        partial[(long long)blockIdx.x * c4 + lane] = acc;
+    }
 }
 
 }  // namespace rl
@@ -347,6 +387,67 @@ extern "C" int rl_attn_backward(const RlAttnOperand *dout, const RlAttnOperand *
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_backward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rl_attn_mix_forward(const RlAttnOperand *A, const RlAttnOperand *X, const RlAttnOperand *out,
+                                   const RlAttnOperand *x_copy, float *d_attn, int batch, int n, int m, int k, float norm,
+                                   int mask_diag, void *stream) {
+    const RlAttnOperand *ops[4] = {A, X, out, x_copy ? x_copy : X};
+    if (int rc = attn_check("rl_attn_mix_forward", batch, n, m, k, ops, 4)) return rc;
+    if (!d_attn) return fa_internal_fail(-1, "rl_attn_mix_forward: NULL attention output");
+    const int grid = (batch + 3) / 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    const rl::Opnd C = x_copy ? opnd(x_copy) : rl::Opnd{nullptr, 0, 0};
+    switch (k / 32) {
+        case 1: rl::attn_fwd_kernel<1><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+        case 2: rl::attn_fwd_kernel<2><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+        case 3: rl::attn_fwd_kernel<3><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+        default: rl::attn_fwd_kernel<4><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_mix_forward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rl_attn_mix_backward(const RlAttnOperand *dout, const RlAttnOperand *A, const RlAttnOperand *X, const float *d_attn,
+                                    const RlAttnOperand *dA, const RlAttnOperand *dX, const RlAttnOperand *dx_add, int batch,
+                                    int n, int m, int k, float norm, void *stream) {
+    const RlAttnOperand *ops[6] = {dout, A, X, dA, dX, dx_add ? dx_add : dX};
+    if (int rc = attn_check("rl_attn_mix_backward", batch, n, m, k, ops, 6)) return rc;
+    if (!d_attn) return fa_internal_fail(-1, "rl_attn_mix_backward: NULL attention input");
+    const int grid = (batch + 3) / 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    const rl::Opnd C = dx_add ? opnd(dx_add) : rl::Opnd{nullptr, 0, 0};
+    switch (k / 32) {
+        case 1: rl::attn_bwd_kernel<1><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
+        case 2: rl::attn_bwd_kernel<2><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
+        case 3: rl::attn_bwd_kernel<3><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
+        default: rl::attn_bwd_kernel<4><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_mix_backward: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rl_relu_bwd_colsum_blocks(long long rows, int cols) {
+    if (rows < 1 || (cols != 32 && cols != 64 && cols != 128 && cols != 256)) return -1;
+    const long long rpi = 256 / (cols / 4), need = (rows + rpi - 1) / rpi;
+    return (int)(need < 148 * 8 ? need : 148 * 8);
+}
+
+extern "C" int rl_relu_bwd_colsum(const float *d_dout, const float *d_out, float *d_dpre, float *d_partial, long long rows,
+                                  int cols, void *stream) {
+    if (!d_dout || !d_out || !d_dpre || !d_partial) return fa_internal_fail(-1, "rl_relu_bwd_colsum: NULL pointer");
+    const int blocks = rl_relu_bwd_colsum_blocks(rows, cols);
+    if (blocks < 1) return fa_internal_fail(-1, "rl_relu_bwd_colsum: need rows >= 1 and cols in {32, 64, 128, 256} (got %lld x %d)", rows, cols);
+    if (((uintptr_t)d_dout | (uintptr_t)d_out | (uintptr_t)d_dpre | (uintptr_t)d_partial) % 16)
+        return fa_internal_fail(-4, "rl_relu_bwd_colsum: pointers must be 16-byte aligned");
+    rl::relu_bwd_colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(d_dout), reinterpret_cast<const float4 *>(d_out), reinterpret_cast<float4 *>(d_dpre),
+        reinterpret_cast<float4 *>(d_partial), rows, cols / 4);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_relu_bwd_colsum: launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -149,6 +149,7 @@ class MPNN(nn.Module):
     # the [batch, n, n] bmm -> mask -> softmax -> bmm chains (42 % of the TF32 update, profiles/) are one kernel each way,
     # and update(cat(h, msg)) is two accumulating GEMMs instead of cat + GEMM.  Opt-in: `fused_attention = True`.
     fused_attention = False
+    fold_projections = True     # within the fused path: message rounds with the attention projections folded (see _fwd_fused)
 
     def _fwd_fused(self, inp, oppInp):
         try:
@@ -157,15 +158,24 @@ class MPNN(nn.Module):
             from rlcore import fused
         n, m = self.num_agents, self.num_opp_agents
         oa, ms = self.oppAttn, self.messages
-        h0 = self.encoder(inp)                                                     # [n*B, 64] agent-major rows
-        hO = self.oppEncoder(oppInp)                                               # [m*B, 64]
-        e, oattn = fused.cross_attention(h0 @ oa.W_key[0], hO @ torch.cat((oa.W_query[0], oa.W_val[0]), dim=1),
-                                         n, m, oa.norm_factor)
-        h = torch.cat((h0, e @ oa.W_out[0]), dim=1)                                # [n*B, 128]
-        wqkv = torch.cat((ms.W_query[0], ms.W_key[0], ms.W_val[0]), dim=1)
+        h0 = fused.linear(inp, self.encoder[0].weight, self.encoder[0].bias, True)  # [n*B, 64] agent-major rows
+        hO = fused.linear(oppInp, self.oppEncoder[0].weight, self.oppEncoder[0].bias, True)   # [m*B, 64]
+        e, oattn = fused.cross_attention(fused.matmul(h0, oa.W_key[0]),
+                                         fused.matmul(hO, torch.cat((oa.W_query[0], oa.W_val[0]), dim=1)), n, m, oa.norm_factor)
+        h = torch.cat((h0, fused.matmul(e, oa.W_out[0])), dim=1)                   # [n*B, 128]
         W, bias = self.update[0].weight, self.update[0].bias
         U1t, U2t = W[:, :self.h_dim].t(), W[:, self.h_dim:].t()
         attn = None
+        if self.fold_projections and n > 1 and self.h_dim <= 128:
+            # Q/K/V/out projections folded into [d, d] products of the weights (rlcore/fused.py _MessageRound)
+            Mqk = ms.W_query[0] @ ms.W_key[0].t()
+            Wc = torch.cat((U1t, ms.W_val[0] @ ms.W_out[0] @ U2t), dim=0)
+            for _ in range(self.K):
+                h, attn = fused.message_round(h, Mqk, Wc, bias, n, ms.norm_factor)
+            self._opp_attn = oattn
+            self._attn = attn.unsqueeze(0)
+            return h
+        wqkv = torch.cat((ms.W_query[0], ms.W_key[0], ms.W_val[0]), dim=1)
         for _ in range(self.K):
             if n > 1:
                 msg, attn = fused.self_attention(h @ wqkv, n, ms.norm_factor)
@@ -179,7 +189,7 @@ class MPNN(nn.Module):
 
     def _fwd(self, inp, oppInp, masks=None):
         if (self.fused_attention and inp.is_cuda and inp.dtype == torch.float32 and self.h_dim % 64 == 0
-                and self.h_dim <= 256 and self.num_agents <= 5 and self.num_opp_agents <= 5):
+                and self.nonlin is nn.ReLU and self.h_dim <= 256 and self.num_agents <= 5 and self.num_opp_agents <= 5):
             return self._fwd_fused(inp, oppInp)
         n, m, half = self.num_agents, self.num_opp_agents, self.h_dim // 2
         h = self.encoder(inp).view(n, -1, half).transpose(0, 1)                    # [B, n, 64]
@@ -196,10 +206,39 @@ class MPNN(nn.Module):
     def forward(self, inp, state, mask=None):
         raise NotImplementedError
 
+    def _use_fused(self, x):
+        return (self.fused_attention and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
+                and self.nonlin is nn.ReLU)
+
+    def _dist(self, p):
+        if self._use_fused(p):
+            try:
+                from .rlcore import fused
+                from .rlcore.distributions import FixedCategorical
+            except ImportError:
+                from rlcore import fused
+                from rlcore.distributions import FixedCategorical
+            logits = fused.linear(p, self.dist.linear.weight, self.dist.linear.bias)
+            return FixedCategorical(logits=logits, validate_args=False if torch.cuda.is_current_stream_capturing() else None)
+        return self.dist(p)
+
     def _value(self, x):
+        if self._use_fused(x):               # the same layers through rlcore/fused.py's dense functions (training backward)
+            try:
+                from .rlcore import fused
+            except ImportError:
+                from rlcore import fused
+            v0, v2 = self.value_head[0], self.value_head[2]
+            return fused.linear(fused.linear(x, v0.weight, v0.bias, True), v2.weight, v2.bias)
         return self.value_head(x)
 
     def _policy(self, x):
+        if self._use_fused(x) and self.policy_layers == 1:
+            try:
+                from .rlcore import fused
+            except ImportError:
+                from rlcore import fused
+            return fused.linear(x, self.policy_head[0].weight, self.policy_head[0].bias, True)
         return self.policy_head(x)
 
     def act(self, inp, state, oppInp, mask=None, deterministic=False):
@@ -212,7 +251,7 @@ class MPNN(nn.Module):
     def evaluate_actions(self, inp, state, oppInp, mask, action):
         x = self._fwd(inp, oppInp, mask)
         value = self._value(x)
-        dist = self.dist(self._policy(x))
+        dist = self._dist(self._policy(x))
         return value, dist.log_probs(action), dist.entropy(), state
 
     def get_value(self, inp, state, oppInp, mask):

@@ -83,6 +83,8 @@ def _attn_lib():
         P, vp, i32, f32 = ctypes.POINTER(_Opnd), ctypes.c_void_p, ctypes.c_int, ctypes.c_float
         L.rl_attn_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
         L.rl_attn_backward.argtypes = [P, P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
+        L.rl_attn_mix_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
+        L.rl_attn_mix_backward.argtypes = [P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
         L._rl3_bound = True
     return L
 
@@ -162,3 +164,172 @@ def self_attention(qkv, n, norm):
 
 def cross_attention(a, bv, n, m, norm):
     return _CrossAttention.apply(a, bv, n, m, norm)
+
+
+# ---- dense layers of the training forward with a hand-written backward ------------------------------------------------
+def _relu_bwd_colsum_cuda(dout, out):
+    """(dpre = dout * [out > 0], column sums of dpre) in one pass over [rows, cols] (rl_relu_bwd_colsum)."""
+    L = _lib()
+    if not getattr(L, "_rl4_bound", False):
+        vp, i64, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+        L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
+        L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+        L._rl4_bound = True
+    rows, cols = out.shape
+    blocks = L.rl_relu_bwd_colsum_blocks(rows, cols)
+    if blocks < 1:                                   # widths the kernel does not cover
+        dpre = torch.ops.aten.threshold_backward(dout, out, 0)
+        return dpre, dpre.sum(0)
+    dout = dout.contiguous()
+    dpre = torch.empty_like(out)
+    partial = torch.empty(blocks, cols, device=out.device)
+    _capi.check(L.rl_relu_bwd_colsum(dout.data_ptr(), out.data_ptr(), dpre.data_ptr(), partial.data_ptr(), rows, cols,
+                                     torch.cuda.current_stream(out.device).cuda_stream))
+    return dpre, partial.sum(0)
+
+
+relu_bwd_colsum = _relu_bwd_colsum_cuda               # tests substitute a torch restatement on the CPU
+
+_SPLITS = {}
+
+
+def _split(rows):
+    """Number of row chunks for xt_dy: the largest divisor of `rows` that is <= 192 and leaves chunks of >= 512 rows."""
+    if rows not in _SPLITS:
+        s = 1
+        for c in range(min(192, rows // 512), 1, -1):
+            if rows % c == 0:
+                s = c
+                break
+        _SPLITS[rows] = s
+    return _SPLITS[rows]
+
+
+def xt_dy(x, dy):
+    """x^T @ dy for tall operands ([rows, a]^T [rows, b] -> [a, b], rows ~ 2e5): the weight-gradient product of every
+    dense layer.  As a plain GEMM its whole reduction dimension lands on a handful of CTAs (measured 90-170 us for
+    200 MB of operands); as a batched GEMM over row chunks plus a sum of the [chunks, a, b] partials every SM works."""
+    rows = x.shape[0]
+    S = _split(rows)
+    if S == 1:
+        return x.t() @ dy
+    r = rows // S
+    return torch.bmm(x.unflatten(0, (S, r)).transpose(1, 2), dy.unflatten(0, (S, r))).sum(0)
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b, optionally followed by ReLU (bias and activation in the GEMM epilogue); backward = fused ReLU-backward
+    + bias gradient, split-K weight gradient, one GEMM for dx (skipped for network inputs)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        if relu:
+            y = torch._addmm_activation(b, x, W.t()) if x.is_cuda else torch.relu(torch.addmm(b, x, W.t()))
+        else:
+            y = torch.addmm(b, x, W.t())
+        ctx.relu = relu
+        ctx.save_for_backward(x, W, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        if ctx.relu:
+            dpre, db = relu_bwd_colsum(dy, y)
+        else:
+            dpre = dy.contiguous()
+            db = dpre.sum(0)
+        dW = xt_dy(dpre, x)
+        dx = dpre @ W if ctx.needs_input_grad[0] else None
+        return dx, dW, db, None
+
+
+class _Matmul(torch.autograd.Function):
+    """y = x M with the split-K weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, M):
+        ctx.save_for_backward(x, M)
+        return x @ M
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, M = ctx.saved_tensors
+        dy = dy.contiguous()
+        return (dy @ M.t() if ctx.needs_input_grad[0] else None), xt_dy(x, dy)
+
+
+def linear(x, W, b, relu=False):
+    return _Linear.apply(x, W, b, relu)
+
+
+def matmul(x, M):
+    return _Matmul.apply(x, M)
+
+
+# ---- one message-passing round with the projections folded into the weights --------------------------------------------
+def _col(t, col, batch):
+    """Columns `col`... of a row-major [agents * batch, width] tensor as an attention operand (agent-major rows)."""
+    assert t.stride(1) == 1
+    return _Opnd(t.data_ptr() + 4 * col, t.stride(0), batch * t.stride(0))
+
+
+def _mix_forward_cuda(g, h, n, norm):
+    B, k = h.shape[0] // n, h.shape[1]
+    hm = torch.empty(n * B, 2 * k, device=h.device)
+    attn = torch.empty(B, n, n, device=h.device)
+    _capi.check(_attn_lib().rl_attn_mix_forward(_col(g, 0, B), _col(h, 0, B), _col(hm, k, B), _col(hm, 0, B), attn.data_ptr(),
+                                                B, n, n, k, float(norm), 1, torch.cuda.current_stream(h.device).cuda_stream))
+    return hm, attn
+
+
+def _mix_backward_cuda(dhm, g, hm, attn, n, norm):
+    """dhm [n*B, 2k] = [dh_direct | dmixed] -> (dg [n*B, k], dh [n*B, k] = dh_direct + attention gradient)."""
+    B, k = g.shape[0] // n, g.shape[1]
+    dg, dh = torch.empty_like(g), torch.empty_like(g)
+    _capi.check(_attn_lib().rl_attn_mix_backward(_col(dhm, k, B), _col(g, 0, B), _col(hm, 0, B), attn.data_ptr(), _col(dg, 0, B),
+                                                 _col(dh, 0, B), _col(dhm, 0, B), B, n, n, k, float(norm),
+                                                 torch.cuda.current_stream(g.device).cuda_stream))
+    return dg, dh
+
+
+# the two device steps of a round; tests substitute torch restatements to check the hand-written backward on the CPU
+mix_forward, mix_backward = _mix_forward_cuda, _mix_backward_cuda
+
+
+class _MessageRound(torch.autograd.Function):
+    """h' = relu(cat(h, mixed) @ Wc + bias),  mixed_i = sum_{j != i} softmax_j(norm <(h Mqk)_i, h_j>) h_j.
+
+    With Mqk = W_query W_key^T and Wc = [U1^T ; W_val W_out U2^T] this is one round of mpnn.py:157-159
+    (h = update(cat(h, messages(h)))) with every [rows, d] x [d, d] projection of the attention folded into [d, d] products
+    of the weights: three row-sized GEMMs per round (G, the update, and none for Q/K/V/out) instead of six, and half
+    the activation traffic.  Forward and backward are written out by hand so that nothing but hm, G, the attention
+    matrix and the output is kept."""
+
+    @staticmethod
+    def forward(ctx, h, Mqk, Wc, bias, n, norm):
+        h = h.contiguous()
+        g = h @ Mqk
+        hm, attn = mix_forward(g, h, n, norm)
+        out = torch._addmm_activation(bias, hm, Wc) if h.is_cuda else torch.relu(torch.addmm(bias, hm, Wc))
+        ctx.save_for_backward(g, hm, attn, out, Mqk, Wc)
+        ctx.meta = (n, float(norm))
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, dout, _dattn):
+        g, hm, attn, out, Mqk, Wc = ctx.saved_tensors
+        n, norm = ctx.meta
+        k = g.shape[1]
+        dpre, dbias = relu_bwd_colsum(dout, out)
+        dWc = xt_dy(hm, dpre)
+        dhm = dpre @ Wc.t()                                  # [dh through U1 | dmixed]
+        dg, dh = mix_backward(dhm, g, hm, attn, n, norm)
+        dMqk = xt_dy(hm[:, :k], dg)
+        dh.addmm_(dg, Mqk.t())
+        return dh, dMqk, dWc, dbias, None, None
+
+
+def message_round(h, Mqk, Wc, bias, n, norm):
+    return _MessageRound.apply(h, Mqk, Wc, bias, n, norm)

@@ -145,6 +145,25 @@ int fa_step_host(FaHandle *h, const int32_t *h_actions, void *h_obs, void *h_rew
  * block that fa_step_host's staged path returns in one copy. */
 int fa_host_layout(const FaHandle *h, size_t *off_reward, size_t *off_done, size_t *off_result, size_t *total);
 
+/* T consecutive steps with HOST streams: h_actions int32 [T][A][E] in, h_obs Real [T][A][E][6], h_reward Real [T][A][E],
+ * h_done / h_result uint8 [T][E] out (any output may be NULL); auto-reset always on; returns when the results are in
+ * host memory.  This is the reference's `for step in range(T): obs, reward, done, info = env.step(actions[step])`
+ * (train_fortattack.py:51-104 with a pre-drawn action stream, the synthetic-action workload of BASELINE configs[1])
+ * for all E envs, with the host<->device traffic of step t overlapped with the arithmetic of its neighbours:
+ *  - d_stage != NULL: a device staging buffer of stage_bytes (256-byte aligned, caller-owned; size it with
+ *    fa_host_stage_bytes for the chunk length you want, any size >= one-step chunks works and the chunk length is
+ *    derived from it).  Chunks of c steps run as a three-stage pipeline on two internal copy streams and `stream`:
+ *    actions of chunk k+1 host->device | one persistent fa_step_many launch for chunk k | results of chunk k-1
+ *    device->host.  Page-locked host buffers make the copies asynchronous; pageable ones still give correct results.
+ *  - d_stage == NULL: all host buffers must be page-locked; ONE persistent launch reads the action stream and writes
+ *    the result streams through the mapped host addresses (no copy calls).
+ * Results are bit-identical to T calls of fa_step_host (and to fa_step_many on device buffers). */
+int fa_step_many_host(FaHandle *h, int T, const int32_t *h_actions, void *h_obs, void *h_reward, uint8_t *h_done,
+                      uint8_t *h_result, void *d_stage, size_t stage_bytes, void *stream);
+
+/* Bytes of staging buffer for fa_step_many_host chunks of chunk_steps steps (two chunk buffers). */
+int fa_host_stage_bytes(const FaHandle *h, int chunk_steps, size_t *out_bytes);
+
 /* Full state exchange in the canonical layout (device pointers).  fa_set_state accepts any state
  * the reference can be in; FA_F32 handles store ang as (ang mod 2pi, turn count < 65536). */
 int fa_get_state(FaHandle *h, const FaState *out, void *stream);

@@ -94,6 +94,28 @@ int rl_attn_backward(const RlAttnOperand *dout, const RlAttnOperand *A, const Rl
                      const float *d_attn, const RlAttnOperand *dA, const RlAttnOperand *dB, const RlAttnOperand *dV,
                      int batch, int n, int m, int k, float norm, void *stream);
 
+/* The same attention with keys == values == X (the "folded" training forward: with G = H (W_query W_key^T) the
+ * scores of mpnn.py:289-295 are <G_i, H_j>, and sum_j p_ij (H_j W_val) W_out = (sum_j p_ij H_j) (W_val W_out), so the
+ * kernel mixes the hidden rows themselves and the projections collapse into two [d, d] products on the weights).
+ *   out_i = sum_j softmax_j(norm <A_i, X_j>) X_j;  x_copy (may be NULL) receives a copy of the X rows -- with `out`
+ *   pointing at the other half of the same [rows, 2d] buffer this builds the input cat(h, m) of update (mpnn.py:159)
+ *   without a cat kernel.
+ * Backward: dA as rl_attn_backward; dX = dB + dV (+ dx_add, may be NULL: a gradient that reaches X by another path). */
+int rl_attn_mix_forward(const RlAttnOperand *A, const RlAttnOperand *X, const RlAttnOperand *out, const RlAttnOperand *x_copy,
+                        float *d_attn, int batch, int n, int m, int k, float norm, int mask_diag, void *stream);
+int rl_attn_mix_backward(const RlAttnOperand *dout, const RlAttnOperand *A, const RlAttnOperand *X, const float *d_attn,
+                         const RlAttnOperand *dA, const RlAttnOperand *dX, const RlAttnOperand *dx_add, int batch, int n,
+                         int m, int k, float norm, void *stream);
+
+/* Backward of y = relu(x W^T + b) up to the GEMMs (every Linear + ReLU of mpnn.py:37-58 in JointPPO.update's backward,
+ * ppo.py:189-190): d_dpre = d_dout * [d_out > 0] and the bias gradient in the same pass.  Row-major [rows, cols] floats,
+ * cols in {32, 64, 128, 256}; d_partial float [rl_relu_bwd_colsum_blocks(rows, cols)][cols] receives one partial column
+ * sum per block in a fixed order (the bias gradient is their sum over dim 0 -- reproducible, no atomics).  Replaces
+ * threshold_backward + a column reduction that ran at 12 % of the HBM bandwidth. */
+int rl_relu_bwd_colsum_blocks(long long rows, int cols);     /* number of partial rows, or -1 for unsupported sizes */
+int rl_relu_bwd_colsum(const float *d_dout, const float *d_out, float *d_dpre, float *d_partial, long long rows, int cols,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,11 +8,18 @@ pk = import_module("emergent-multiagent-strategies_b200.policy_kernel")
 E = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 16384
 if "--ppo" in sys.argv:
     ro = import_module("emergent-multiagent-strategies_b200.rollout")
+    if "--nofold" in sys.argv:       # message rounds with explicit Q/K/V/out projections (the pre-r1i training forward)
+        import_module("emergent-multiagent-strategies_b200.mpnn").MPNN.fold_projections = False
     tr = ro.BatchedTrainer(E, 3, 3, num_steps=32, max_episode_steps=100, seed=0, ppo_epoch=1, num_mini_batch=8,
                            allow_tf32="--tf32" in sys.argv)
     tr.collect(); tr.wrap_horizon()
     tr.update()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); tr.update(); e1.record()
+    torch.cuda.synchronize()
+    print("update: %.2f ms for 16 optimizer steps (8 minibatches x 2 teams, %d rows per team minibatch) = %.2f ms per step"
+          % (e0.elapsed_time(e1), 3 * E * 32 // 8, e0.elapsed_time(e1) / 16))
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         tr.update()

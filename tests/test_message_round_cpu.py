@@ -1,0 +1,103 @@
+"""CPU: the hand-written forward/backward of one folded message-passing round (rlcore/fused.py _MessageRound) against
+autograd on the mirror of mpnn.py:157-159,249-331.  The two device steps (rl_attn_mix_forward / rl_attn_mix_backward)
+are replaced by torch restatements here, so what is checked is the folding algebra and the manual gradient chain; the
+kernels themselves are compared with the bmm path on the GPU (tests/test_rollout_gpu.py)."""
+from importlib import import_module
+
+import pytest
+import torch
+
+PKG = "emergent-multiagent-strategies_b200"
+mp = import_module(PKG + ".mpnn")
+fused = import_module(PKG + ".rlcore.fused")
+
+
+class Shape(object):
+    def __init__(self, *shape):
+        self.shape = shape
+
+
+def _mix(g, h, n, norm):
+    B, k = h.shape[0] // n, h.shape[1]
+    G, H = g.view(n, B, k).transpose(0, 1), h.view(n, B, k).transpose(0, 1)
+    s = norm * G @ H.transpose(1, 2)
+    s = s.masked_fill(torch.eye(n, dtype=torch.bool), float("-inf"))
+    attn = torch.softmax(s, dim=-1)
+    return (attn @ H).transpose(0, 1).reshape(n * B, k), attn
+
+
+def mix_forward(g, h, n, norm):
+    mixed, attn = _mix(g, h, n, norm)
+    return torch.cat((h, mixed), dim=1), attn
+
+
+def mix_backward(dhm, g, hm, attn, n, norm):
+    k = g.shape[1]
+    with torch.enable_grad():
+        g2, h2 = g.detach().clone().requires_grad_(), hm[:, :k].detach().clone().requires_grad_()
+        mixed, _ = _mix(g2, h2, n, norm)
+        dg, dh = torch.autograd.grad(mixed, (g2, h2), dhm[:, k:])
+    return dg, dh + dhm[:, :k]
+
+
+def relu_bwd_colsum(dout, out):
+    dpre = dout * (out > 0)
+    return dpre, dpre.sum(0)
+
+
+def test_dense_functions_match_autograd(monkeypatch):
+    """fused.linear / fused.matmul (manual backward: ReLU-backward + bias gradient, split weight gradient) == F.linear."""
+    monkeypatch.setattr(fused, "relu_bwd_colsum", relu_bwd_colsum)
+    torch.manual_seed(0)
+    for rows in (7, 1024 * 3, 5120):                    # 3072 -> 6 chunks, 5120 -> 10 chunks, 7 -> plain product
+        x = torch.randn(rows, 24, dtype=torch.float64, requires_grad=True)
+        W = torch.randn(16, 24, dtype=torch.float64, requires_grad=True)
+        b = torch.randn(16, dtype=torch.float64, requires_grad=True)
+        M = torch.randn(16, 8, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(rows, 8, dtype=torch.float64)
+        for relu in (True, False):
+            ref = torch.nn.functional.linear(x, W, b)
+            ref = (torch.relu(ref) if relu else ref) @ M
+            got = fused.matmul(fused.linear(x, W, b, relu), M)
+            assert torch.allclose(ref, got, rtol=1e-12, atol=1e-12)
+            for a, c in zip(torch.autograd.grad((ref * w).sum(), (x, W, b, M)), torch.autograd.grad((got * w).sum(), (x, W, b, M))):
+                assert torch.allclose(a, c, rtol=1e-10, atol=1e-10)
+    assert fused._split(5120) == 10 and fused._split(196608) == 192 and fused._split(7) == 1 and fused._split(40960 * 5) == 160
+
+
+@pytest.mark.parametrize("n,hid", [(3, 128), (5, 128), (2, 64)])
+def test_folded_rounds_match_the_mirror(n, hid, monkeypatch):
+    monkeypatch.setattr(fused, "mix_forward", mix_forward)
+    monkeypatch.setattr(fused, "mix_backward", mix_backward)
+    monkeypatch.setattr(fused, "relu_bwd_colsum", relu_bwd_colsum)
+    torch.manual_seed(n + hid)
+    net = mp.MPNN(action_space=Shape(8), num_agents=n, num_opp_agents=3, input_size=6, hidden_dim=hid).double()
+    with torch.no_grad():
+        net.update[0].bias.uniform_(-0.3, 0.3)
+    ms, B = net.messages, 37
+    h_in = torch.randn(n * B, hid, dtype=torch.float64)
+    w = torch.randn(n * B, hid, dtype=torch.float64)
+    params = [ms.W_query, ms.W_key, ms.W_val, ms.W_out, net.update[0].weight, net.update[0].bias]
+    res = []
+    for folded in (False, True):
+        h = h_in.clone().requires_grad_()
+        x = h
+        if folded:
+            W, bias = net.update[0].weight, net.update[0].bias
+            Mqk = ms.W_query[0] @ ms.W_key[0].t()
+            Wc = torch.cat((W[:, :hid].t(), ms.W_val[0] @ ms.W_out[0] @ W[:, hid:].t()), dim=0)
+            for _ in range(3):
+                x, attn = fused.message_round(x, Mqk, Wc, bias, n, ms.norm_factor)
+        else:
+            x3 = x.view(n, B, hid).transpose(0, 1)
+            for _ in range(3):
+                msg, attn = ms(x3, return_attn=True)
+                x3 = net.update(torch.cat((x3, msg), dim=2))
+            x = x3.transpose(0, 1).reshape(n * B, hid)
+            attn = attn.squeeze(0)
+        grads = torch.autograd.grad((x * w).sum(), [h] + params)
+        res.append((x.detach(), attn.detach(), grads))
+    (xa, aa, ga), (xb, ab, gb) = res
+    assert torch.allclose(xa, xb, rtol=1e-10, atol=1e-12) and torch.allclose(aa.reshape(ab.shape), ab, atol=1e-12)
+    for a, b in zip(ga, gb):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-11), float((a - b).abs().max())

@@ -265,21 +265,22 @@ def test_fused_training_attention_matches_bmm_path(n, m, hid):
     act = torch.randint(0, 8, (n * B, 1), device="cuda")
     w = torch.randn(n * B, 1, device="cuda")
     res = []
-    for fused_on in (False, True):
-        net.fused_attention = fused_on
+    for fused_on, fold in ((False, False), (True, False), (True, True)):
+        net.fused_attention, net.fold_projections = fused_on, fold
         net.zero_grad()
         v, lp, ent, _ = net.evaluate_actions(own, None, opp, None, act)
         ((v * w).sum() + (lp * w).sum() * 0.7 + ent.sum() * 0.3).backward()
         grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
         res.append((v.detach(), lp.detach(), ent.detach(), net.attn_mat, net.opp_attn_mat, grads))
-    a, b = res
-    for x, y in zip(a[:3], b[:3]):
-        assert torch.allclose(x, y, rtol=1e-4, atol=2e-5)
-    assert np.allclose(a[3], b[3], atol=1e-5) and np.allclose(a[4], b[4], atol=1e-5)
-    assert set(a[5]) == set(b[5])
-    for k in a[5]:
-        scale = float(a[5][k].abs().max()) + 1e-6
-        assert float((a[5][k] - b[5][k]).abs().max()) < 2e-4 * scale, (k, float((a[5][k] - b[5][k]).abs().max()), scale)
+    a = res[0]
+    for b in res[1:]:        # attention kernels with explicit projections, then with the projections folded into the weights
+        for x, y in zip(a[:3], b[:3]):
+            assert torch.allclose(x, y, rtol=1e-4, atol=2e-5)
+        assert np.allclose(a[3], b[3], atol=1e-5) and np.allclose(a[4], b[4], atol=1e-5)
+        assert set(a[5]) == set(b[5])
+        for k in a[5]:
+            scale = float(a[5][k].abs().max()) + 1e-6
+            assert float((a[5][k] - b[5][k]).abs().max()) < 2e-4 * scale, (k, float((a[5][k] - b[5][k]).abs().max()), scale)
 
 
 def test_graph_captured_update_tracks_eager_update():

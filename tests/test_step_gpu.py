@@ -206,6 +206,39 @@ def test_step_host_matches_device_step(path, pinned, monkeypatch):
         assert torch.equal(o.cpu(), ho) and torch.equal(r.cpu(), hr) and torch.equal(d.cpu(), hd) and torch.equal(rs.cpu(), hrs)
 
 
+@pytest.mark.parametrize("chunk,pinned", [(None, True), (7, True), (1, True), (0, True), (5, False)])
+@pytest.mark.parametrize("ng,na,E,dtype", [(3, 3, 1000, torch.float32), (5, 5, 333, torch.float64)])
+def test_step_many_host_matches_device_steps(ng, na, E, dtype, chunk, pinned):
+    """fa_step_many_host: chunk pipeline (default chunk, ragged last chunk, one-step chunks, pageable buffers) and the
+    mapped single-launch form (chunk 0) are bit-equal to T device-side steps, alive-end output included; the
+    state left behind is the same (a following step agrees)."""
+    T, A = 45, ng + na
+    e1, e2 = make(E, ng, na, dtype, seed=5, max_steps=30), make(E, ng, na, dtype, seed=5, max_steps=30)
+    e1.reset(); e2.reset()
+    hs = e2.make_host_streams(T)
+    if not pinned:
+        hs = tuple(torch.empty_like(b, pin_memory=False) for b in hs)
+    ae = torch.zeros(T, E, dtype=torch.uint8, device="cuda")
+    e2.set_alive_end_buffer(ae)
+    rng = np.random.RandomState(1)
+    acts = torch.from_numpy(rng.choice(8, size=(T + 1, A, E), p=[.1] * 7 + [.3]).astype(np.int32))
+    hs[0].copy_(acts[:T])
+    ho, hr, hd, hrs = e2.step_many_host(*hs, chunk_steps=chunk)
+    ae1 = torch.zeros(E, dtype=torch.uint8, device="cuda")
+    e1.set_alive_end_buffer(ae1)
+    for t in range(T):
+        o, r, d, rs = e1.step(acts[t].cuda())
+        assert torch.equal(o.cpu(), ho[t]) and torch.equal(r.cpu(), hr[t]), t
+        assert torch.equal(d.cpu(), hd[t]) and torch.equal(rs.cpu(), hrs[t]) and torch.equal(ae1, ae[t]), t
+    assert hd.sum() > 0
+    e1.set_alive_end_buffer(None); e2.set_alive_end_buffer(None)
+    for x, y in zip(e1.step(acts[T].cuda()), e2.step(acts[T].cuda())):
+        assert torch.equal(x, y)
+    # outputs may be skipped
+    hs2 = e2.make_host_streams(3, store_obs=False)
+    e2.step_many_host(*hs2, chunk_steps=chunk if pinned else 2)
+
+
 def test_full_size_properties():
     """BASELINE config 2 size (3v3 x 4096 envs x 1000 steps, cap 100) and a >L2 batch: size-independent
     properties of the reference semantics."""
@@ -329,6 +362,25 @@ def test_both_mappings_agree_and_auto_picks_by_batch_size():
     assert (oa - ob).abs().max() < 1e-9 and (ra - rb).abs().max() < 1e-9
     assert make(4096, 3, 3, torch.float32).kernel_info()["mapping"] == "agent"
     assert make(1 << 17, 3, 3, torch.float32).kernel_info()["mapping"] == "env"
+
+
+def test_step_many_host_errors_are_loud():
+    import fortattack_b200 as fab
+    env = make(64, 3, 3, torch.float32)
+    env.reset()
+    hs = env.make_host_streams(4)
+    lib, h = fab._capi.lib(), env._h
+    small = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    assert lib.fa_step_many_host(h, 4, hs[0].data_ptr(), hs[1].data_ptr(), hs[2].data_ptr(), hs[3].data_ptr(),
+                                 hs[4].data_ptr(), small.data_ptr(), 1024, None) == -1
+    assert b"staging buffer" in lib.fa_last_error()
+    pageable = torch.zeros(4, 6, 64, dtype=torch.int32)
+    assert lib.fa_step_many_host(h, 4, pageable.data_ptr(), hs[1].data_ptr(), hs[2].data_ptr(), hs[3].data_ptr(),
+                                 hs[4].data_ptr(), None, 0, None) == -1
+    assert b"page-locked" in lib.fa_last_error()
+    assert lib.fa_step_many_host(h, 0, hs[0].data_ptr(), None, None, None, None, None, 0, None) == -1
+    with pytest.raises(ValueError):
+        env.step_many_host(hs[0][:, :5], *hs[1:])
 
 
 def test_errors_are_loud():
