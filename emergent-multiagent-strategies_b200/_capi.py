@@ -32,6 +32,11 @@ class FaState(ctypes.Structure):
                 ("d_episode", ctypes.c_void_p)]
 
 
+class RlAttnOperand(ctypes.Structure):
+    """include/fortattack_rollout.h RlAttnOperand."""
+    _fields_ = [("ptr", ctypes.c_void_p), ("batch_stride", ctypes.c_int64), ("row_stride", ctypes.c_int64)]
+
+
 class FaError(RuntimeError):
     pass
 
@@ -78,6 +83,27 @@ def lib():
     L.fa_set_alive_end_buffer.argtypes = [vp, vp]
     L.fa_launch_count.argtypes = [vp, u64p]
     L.fa_kernel_info.argtypes = [vp, i32p, i32p, i32p, i32p, i32p]
+    # every other entry point of the library (include/fortattack_policy.h, fortattack_rollout.h, mape_world.h).  ALL
+    # prototypes are declared here, once: a function called without argtypes gets its pointers truncated to C ints.
+    i64, u32, u64, f32, f64 = ctypes.c_longlong, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_float, ctypes.c_double
+    P = ctypes.POINTER(RlAttnOperand)
+    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 7 + [vp, i32, vp, vp, vp, vp]
+    L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
+    L.mp_forward_ensemble.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 8
+    L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, u32, u32, u32, vp, vp]
+    L.mp_set_trace.argtypes = [vp]
+    L.mp_probe_timing.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.rl_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, vp]
+    L.rl_rollout_bookkeeping.argtypes = [vp] * 7 + [i32, i32, vp]
+    L.rl_gather_minibatch.argtypes = [vp] + [i32] * 8 + [vp] * 18
+    L.rl_ppo_loss.argtypes = [vp] * 9 + [i32, f32, f32, f32] + [vp] * 5
+    L.rl_attn_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
+    L.rl_attn_backward.argtypes = [P, P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
+    L.rl_attn_mix_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
+    L.rl_attn_mix_backward.argtypes = [P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
+    L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
+    L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    L.mw_step.argtypes = [vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)   # AttributeError here = the library does not match the header
     if L.fa_abi_version() != FA_ABI_VERSION:

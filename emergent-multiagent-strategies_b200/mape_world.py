@@ -49,7 +49,6 @@ class MapeWorldBatch(object):
         self.pos = torch.zeros(self.n_entities, self.E, 2, device=dev, dtype=dtype)
         self.vel = torch.zeros(self.n_entities, self.E, 2, device=dev, dtype=dtype)
         self._lib = _capi.lib()
-        self._lib.mw_step.argtypes = [ctypes.POINTER(MwConfig)] + [ctypes.c_void_p] * 4
         self.launches = 0
 
     def step(self, u):

@@ -76,18 +76,6 @@ def pack_mpnn(m, device=None):
     return blob.contiguous()
 
 
-def _bind(L):
-    if getattr(L, "_mp_bound", False):
-        return
-    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
-    L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 7 + [vp, i32, vp, vp, vp, vp]
-    i32p = ctypes.POINTER(ctypes.c_int32)
-    L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
-    L.mp_forward_ensemble.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 8
-    L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp, vp]
-    L._mp_bound = True
-
-
 class FusedPolicy(object):
     """Rollout-time forward of one team's MPNN in a single kernel launch."""
 
@@ -98,7 +86,6 @@ class FusedPolicy(object):
         if self.device.type != "cuda":
             raise _capi.FaError("FusedPolicy needs the module on a CUDA device; there is no CPU path")
         self._lib = _capi.lib()
-        _bind(self._lib)
         self.n, self.m = module.num_agents, module.num_opp_agents
         self.seed, self.env_id0, self.calls = int(seed), int(env_id0), 0
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)

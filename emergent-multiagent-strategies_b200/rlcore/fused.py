@@ -13,13 +13,7 @@ except ImportError:          # drop-in mode (this directory's parent is on sys.p
 
 
 def _lib():
-    L = _capi.lib()
-    if not getattr(L, "_rl2_bound", False):
-        vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
-        L.rl_gather_minibatch.argtypes = [vp] + [i32] * 8 + [vp] * 18
-        L.rl_ppo_loss.argtypes = [vp] * 9 + [i32, f32, f32, f32] + [vp] * 5
-        L._rl2_bound = True
-    return L
+    return _capi.lib()           # every prototype is declared there
 
 
 def gather_minibatch(shared, idx, a0, n, o0, m, adv):
@@ -73,20 +67,11 @@ def ppo_loss(values, logp, entropy, old_values, returns, old_logp, adv, mask, no
 
 
 # ---- attention over a handful of agents: forward + backward kernels behind autograd ---------------------------------
-class _Opnd(ctypes.Structure):
-    _fields_ = [("ptr", ctypes.c_void_p), ("batch_stride", ctypes.c_int64), ("row_stride", ctypes.c_int64)]
+_Opnd = _capi.RlAttnOperand
 
 
 def _attn_lib():
-    L = _lib()
-    if not getattr(L, "_rl3_bound", False):
-        P, vp, i32, f32 = ctypes.POINTER(_Opnd), ctypes.c_void_p, ctypes.c_int, ctypes.c_float
-        L.rl_attn_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
-        L.rl_attn_backward.argtypes = [P, P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
-        L.rl_attn_mix_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
-        L.rl_attn_mix_backward.argtypes = [P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
-        L._rl3_bound = True
-    return L
+    return _capi.lib()
 
 
 def _op(t, col, width, batch):
@@ -170,11 +155,6 @@ def cross_attention(a, bv, n, m, norm):
 def _relu_bwd_colsum_cuda(dout, out):
     """(dpre = dout * [out > 0], column sums of dpre) in one pass over [rows, cols] (rl_relu_bwd_colsum)."""
     L = _lib()
-    if not getattr(L, "_rl4_bound", False):
-        vp, i64, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
-        L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
-        L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
-        L._rl4_bound = True
     rows, cols = out.shape
     blocks = L.rl_relu_bwd_colsum_blocks(rows, cols)
     if blocks < 1:                                   # widths the kernel does not cover

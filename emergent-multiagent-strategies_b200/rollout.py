@@ -66,9 +66,6 @@ class SharedRollouts(object):
         """masks[step+1], ends[step+1] and episode_rewards from obs[step], obs[step+1], done[step], rewards[step]
         (rl_rollout_bookkeeping, include/fortattack_rollout.h)."""
         L = _capi.lib()
-        if not getattr(L, "_rl4_bound", False):
-            L.rl_rollout_bookkeeping.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
-            L._rl4_bound = True
         T, A, E = self.rewards.shape
         _capi.check(L.rl_rollout_bookkeeping(self.obs[step].data_ptr(), self.obs[step + 1].data_ptr(), self.done[step].data_ptr(),
                                              self.rewards[step].data_ptr(), self.masks[step + 1].data_ptr(),
@@ -79,10 +76,6 @@ class SharedRollouts(object):
         """Learner.wrap_horizon for every agent and env in ONE launch (rl_gae, include/fortattack_rollout.h):
         next_value float [A, E]; per-env episode boundaries from `ends`."""
         L = _capi.lib()
-        if not getattr(L, "_rl_bound", False):
-            vp, i32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
-            L.rl_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, vp]
-            L._rl_bound = True
         T, A, E = self.rewards.shape
         nv = next_value.to(torch.float32).contiguous()
         assert nv.shape == (A, E) and self.ends.dtype == torch.bool

@@ -23,7 +23,6 @@ net = make(n, m, seed=33).cuda()
 fp = pk.FusedPolicy(net, seed=3)
 print(fp.kernel_info())
 L = fp._lib
-L.mp_set_trace.argtypes = [ctypes.c_void_p]
 head = ["start", "enc+arrive", "wait(T')", "scores', wait z', drain, combine", "opp msg+arrive"]
 rnd = ["wait(T)", "scores", "wait(ZY)+drain+combine+softmax", "update+arrive"]
 labels = head + rnd * 3 + ["wait(heads)", "heads math"]

@@ -31,10 +31,11 @@ def test_policy_and_rollout_headers_are_exported():
         assert declared, hdr_name
         for name in declared:
             assert hasattr(L, name), name
+            # prototypes live in ONE place (_capi.lib): an unbound function would get its pointers truncated to C ints
+            assert getattr(L, name).argtypes is not None, name + " has no ctypes prototype in _capi.lib()"
     L.mp_forward.restype = ctypes.c_int
     assert L.mp_forward(*([None] * 3), 3, 3, 8, 0, 0, 0, None, 0, *([None] * 7), None, 0, None, None, None, None) == -1
     assert b"NULL" in L.fa_last_error()
-    L.rl_gae.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 3 + [ctypes.c_double] * 2 + [ctypes.c_void_p]
     assert L.rl_gae(None, None, None, None, None, None, 4, 2, 8, 0.99, 0.95, None) == -1
     blob_bytes = int(re.search(r"#define MP_BLOB_F16_BYTES (\d+)", open(os.path.join(ROOT, "include", "fortattack_policy.h")).read()).group(1))
     from importlib import import_module
