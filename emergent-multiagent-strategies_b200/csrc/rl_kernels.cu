@@ -178,20 +178,22 @@ __device__ __forceinline__ float warp_sum(float x) {
     return x;
 }
 
-template <int VEC>
+// MIX = keys and values are the same rows X (rl_attn_mix_*): X is loaded once, the backward accumulates ONE gradient for it.
+template <int VEC, bool MIX>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(Opnd A, Opnd B, Opnd V, Opnd O, float *attn, int batch, int n, int m,
-                                                       float norm, int mask_diag, Opnd C = Opnd{nullptr, 0, 0}) {
+                                                       float norm, int mask_diag, Opnd C) {
     const int lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= batch) return;
     const int c = lane * VEC;
-    float bb[ATT_MAX][VEC], vv[ATT_MAX][VEC];
+    float bb[ATT_MAX][VEC], vvs[MIX ? 1 : ATT_MAX][VEC];
+    float (&vv)[ATT_MAX][VEC] = *reinterpret_cast<float (*)[ATT_MAX][VEC]>(MIX ? &bb[0][0] : &vvs[0][0]);
 #pragma unroll
     for (int j = 0; j < ATT_MAX; ++j)
         if (j < m) {
             VecLoad<VEC>::ld(B.p + b * B.bs + j * B.rs + c, bb[j]);
-            VecLoad<VEC>::ld(V.p + b * V.bs + j * V.rs + c, vv[j]);
-            if (C.p) VecLoad<VEC>::st(C.p + b * C.bs + j * C.rs + c, vv[j]);     // the value rows, re-emitted (rl_attn_mix_forward)
+            if (!MIX) VecLoad<VEC>::ld(V.p + b * V.bs + j * V.rs + c, vv[j]);
+            if (MIX && C.p) VecLoad<VEC>::st(C.p + b * C.bs + j * C.rs + c, bb[j]);     // the X rows, re-emitted
         }
 #pragma unroll
     for (int i = 0; i < ATT_MAX; ++i) {
@@ -234,22 +236,25 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(Opnd A, Opnd B, Opnd V, O
     }
 }
 
-template <int VEC>
+// MIX: dB receives dB + dV (+ Cin, a gradient that reaches X by another path; may be null); dV is not written.
+template <int VEC, bool MIX>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(Opnd G, Opnd A, Opnd B, Opnd V, const float *attn, Opnd dA, Opnd dB,
-                                                       Opnd dV, int batch, int n, int m, float norm, int sum_bv = 0,
-                                                       Opnd Cin = Opnd{nullptr, 0, 0}) {
+                                                       Opnd dV, int batch, int n, int m, float norm, Opnd Cin) {
     const int lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= batch) return;
     const int c = lane * VEC;
-    float bb[ATT_MAX][VEC], vv[ATT_MAX][VEC], db[ATT_MAX][VEC], dv[ATT_MAX][VEC];
+    float bb[ATT_MAX][VEC], db[ATT_MAX][VEC], vvs[MIX ? 1 : ATT_MAX][VEC], dvs[MIX ? 1 : ATT_MAX][VEC];
+    float (&vv)[ATT_MAX][VEC] = *reinterpret_cast<float (*)[ATT_MAX][VEC]>(MIX ? &bb[0][0] : &vvs[0][0]);
+    float (&dv)[ATT_MAX][VEC] = *reinterpret_cast<float (*)[ATT_MAX][VEC]>(MIX ? &db[0][0] : &dvs[0][0]);
 #pragma unroll
     for (int j = 0; j < ATT_MAX; ++j)
         if (j < m) {
             VecLoad<VEC>::ld(B.p + b * B.bs + j * B.rs + c, bb[j]);
-            VecLoad<VEC>::ld(V.p + b * V.bs + j * V.rs + c, vv[j]);
+            if (!MIX) VecLoad<VEC>::ld(V.p + b * V.bs + j * V.rs + c, vv[j]);
 #pragma unroll
             for (int q = 0; q < VEC; ++q) { db[j][q] = 0.0f; dv[j][q] = 0.0f; }
+            if (MIX && Cin.p) VecLoad<VEC>::ld(Cin.p + b * Cin.bs + j * Cin.rs + c, db[j]);
         }
 #pragma unroll
     for (int i = 0; i < ATT_MAX; ++i) {
@@ -292,18 +297,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(Opnd G, Opnd A, Opnd B, O
 #pragma unroll
     for (int j = 0; j < ATT_MAX; ++j)
         if (j < m) {
-            if (sum_bv) {       // keys and values are the same rows (rl_attn_mix_backward): one gradient, plus an optional addend
-                float t[VEC];
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) t[q] = 0.0f;
-                if (Cin.p) VecLoad<VEC>::ld(Cin.p + b * Cin.bs + j * Cin.rs + c, t);
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) t[q] += db[j][q] + dv[j][q];
-                VecLoad<VEC>::st(dB.p + b * dB.bs + j * dB.rs + c, t);
-            } else {
-                VecLoad<VEC>::st(dB.p + b * dB.bs + j * dB.rs + c, db[j]);
-                VecLoad<VEC>::st(dV.p + b * dV.bs + j * dV.rs + c, dv[j]);
-            }
+            VecLoad<VEC>::st(dB.p + b * dB.bs + j * dB.rs + c, db[j]);
+            if (!MIX) VecLoad<VEC>::st(dV.p + b * dV.bs + j * dV.rs + c, dv[j]);
         }
 }
 
@@ -351,6 +346,7 @@ static int attn_check(const char *who, int batch, int n, int m, int k, const RlA
     }
     return 0;
 }
+static const rl::Opnd NOOP{nullptr, 0, 0};
 static rl::Opnd opnd(const RlAttnOperand *o) { return rl::Opnd{o->ptr, (long long)o->batch_stride, (long long)o->row_stride}; }
 
 extern "C" int rl_attn_forward(const RlAttnOperand *A, const RlAttnOperand *B, const RlAttnOperand *V, const RlAttnOperand *out,
@@ -361,10 +357,10 @@ extern "C" int rl_attn_forward(const RlAttnOperand *A, const RlAttnOperand *B, c
     const int grid = (batch + 3) / 4;
     cudaStream_t st = (cudaStream_t)stream;
     switch (k / 32) {
-        case 1: rl::attn_fwd_kernel<1><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
-        case 2: rl::attn_fwd_kernel<2><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
-        case 3: rl::attn_fwd_kernel<3><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
-        default: rl::attn_fwd_kernel<4><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag); break;
+        case 1: rl::attn_fwd_kernel<1, false><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag, NOOP); break;
+        case 2: rl::attn_fwd_kernel<2, false><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag, NOOP); break;
+        case 3: rl::attn_fwd_kernel<3, false><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag, NOOP); break;
+        default: rl::attn_fwd_kernel<4, false><<<grid, 128, 0, st>>>(opnd(A), opnd(B), opnd(V), opnd(out), d_attn, batch, n, m, norm, mask_diag, NOOP); break;
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_forward: launch: %s", cudaGetErrorString(e));
@@ -380,10 +376,10 @@ extern "C" int rl_attn_backward(const RlAttnOperand *dout, const RlAttnOperand *
     const int grid = (batch + 3) / 4;
     cudaStream_t st = (cudaStream_t)stream;
     switch (k / 32) {
-        case 1: rl::attn_bwd_kernel<1><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
-        case 2: rl::attn_bwd_kernel<2><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
-        case 3: rl::attn_bwd_kernel<3><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
-        default: rl::attn_bwd_kernel<4><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm); break;
+        case 1: rl::attn_bwd_kernel<1, false><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm, NOOP); break;
+        case 2: rl::attn_bwd_kernel<2, false><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm, NOOP); break;
+        case 3: rl::attn_bwd_kernel<3, false><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm, NOOP); break;
+        default: rl::attn_bwd_kernel<4, false><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(B), opnd(V), d_attn, opnd(dA), opnd(dB), opnd(dV), batch, n, m, norm, NOOP); break;
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_backward: launch: %s", cudaGetErrorString(e));
@@ -400,10 +396,10 @@ extern "C" int rl_attn_mix_forward(const RlAttnOperand *A, const RlAttnOperand *
     cudaStream_t st = (cudaStream_t)stream;
     const rl::Opnd C = x_copy ? opnd(x_copy) : rl::Opnd{nullptr, 0, 0};
     switch (k / 32) {
-        case 1: rl::attn_fwd_kernel<1><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
-        case 2: rl::attn_fwd_kernel<2><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
-        case 3: rl::attn_fwd_kernel<3><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
-        default: rl::attn_fwd_kernel<4><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+        case 1: rl::attn_fwd_kernel<1, true><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+        case 2: rl::attn_fwd_kernel<2, true><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+        case 3: rl::attn_fwd_kernel<3, true><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
+        default: rl::attn_fwd_kernel<4, true><<<grid, 128, 0, st>>>(opnd(A), opnd(X), opnd(X), opnd(out), d_attn, batch, n, m, norm, mask_diag, C); break;
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_mix_forward: launch: %s", cudaGetErrorString(e));
@@ -420,10 +416,10 @@ extern "C" int rl_attn_mix_backward(const RlAttnOperand *dout, const RlAttnOpera
     cudaStream_t st = (cudaStream_t)stream;
     const rl::Opnd C = dx_add ? opnd(dx_add) : rl::Opnd{nullptr, 0, 0};
     switch (k / 32) {
-        case 1: rl::attn_bwd_kernel<1><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
-        case 2: rl::attn_bwd_kernel<2><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
-        case 3: rl::attn_bwd_kernel<3><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
-        default: rl::attn_bwd_kernel<4><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, 1, C); break;
+        case 1: rl::attn_bwd_kernel<1, true><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, C); break;
+        case 2: rl::attn_bwd_kernel<2, true><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, C); break;
+        case 3: rl::attn_bwd_kernel<3, true><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, C); break;
+        default: rl::attn_bwd_kernel<4, true><<<grid, 128, 0, st>>>(opnd(dout), opnd(A), opnd(X), opnd(X), d_attn, opnd(dA), opnd(dX), opnd(dX), batch, n, m, norm, C); break;
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_attn_mix_backward: launch: %s", cudaGetErrorString(e));

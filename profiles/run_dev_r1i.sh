@@ -1,4 +1,6 @@
+# Dev pass r1i on the GPU box: all GPU tests, then the PPO update under torch.profiler (TF32 and fp32, folded rounds + dense functions).
 set -x
 mkdir -p gpurun_out
-export CUDA_LAUNCH_BLOCKING=1 FA_DBG_COLSUM=1
-timeout 200 python profiles/dbg_dense.py update > gpurun_out/r1i_dbg_update.log 2>&1; grep -n "colsum\|Error" gpurun_out/r1i_dbg_update.log | head -40
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r1i_pytest_gpu.log 2>&1; tail -5 gpurun_out/r1i_pytest_gpu.log
+timeout 300 python profiles/prof_policy.py 16384 --ppo --tf32 > gpurun_out/r1i_ppo_update_tf32_torch_profile.txt 2>&1; head -1 gpurun_out/r1i_ppo_update_tf32_torch_profile.txt
+timeout 300 python profiles/prof_policy.py 16384 --ppo > gpurun_out/r1i_ppo_update_fp32_torch_profile.txt 2>&1; head -1 gpurun_out/r1i_ppo_update_fp32_torch_profile.txt
