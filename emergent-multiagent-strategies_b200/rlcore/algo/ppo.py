@@ -71,7 +71,10 @@ class JointPPO(object):
         self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
         on_cuda = next(actor_critic.parameters()).is_cuda
         # eps is ignored by the reference too (:114); capturable keeps Adam's step counters on the device (graph capture)
-        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, capturable=bool(graph_update) and on_cuda)
+        # on CUDA the whole Adam step is ONE fused kernel (24 parameter tensors; the foreach form cost 240 us of GPU time per
+        # optimizer step, 7 % of it)
+        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, capturable=bool(graph_update) and on_cuda,
+                                    fused=True if on_cuda else None)
         self.process_group = process_group
 
     # -- distributed helpers (identity on one rank) ------------------------------------------------

@@ -174,10 +174,10 @@ _SPLITS = {}
 
 
 def _split(rows):
-    """Number of row chunks for xt_dy: the largest divisor of `rows` that is <= 192 and leaves chunks of >= 512 rows."""
+    """Number of row chunks for xt_dy: the largest divisor of `rows` that is <= 96 and leaves chunks of >= 512 rows."""
     if rows not in _SPLITS:
         s = 1
-        for c in range(min(192, rows // 512), 1, -1):
+        for c in range(min(96, rows // 512), 1, -1):
             if rows % c == 0:
                 s = c
                 break

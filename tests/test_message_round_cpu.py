@@ -62,7 +62,7 @@ def test_dense_functions_match_autograd(monkeypatch):
             assert torch.allclose(ref, got, rtol=1e-12, atol=1e-12)
             for a, c in zip(torch.autograd.grad((ref * w).sum(), (x, W, b, M)), torch.autograd.grad((got * w).sum(), (x, W, b, M))):
                 assert torch.allclose(a, c, rtol=1e-10, atol=1e-10)
-    assert fused._split(5120) == 10 and fused._split(196608) == 192 and fused._split(7) == 1 and fused._split(40960 * 5) == 160
+    assert fused._split(5120) == 10 and fused._split(196608) == 96 and fused._split(7) == 1 and fused._split(40960 * 4) == 80
 
 
 @pytest.mark.parametrize("n,hid", [(3, 128), (5, 128), (2, 64)])
