@@ -450,8 +450,10 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     return {"workload": "FortAttack 3v3 (BASELINE.json configs[2]), %d envs, T=%d rollout with the MPNN policy + one JointPPO update" % (E, T),
             "rollout_agent_steps_per_s": E * A * T / (collect_ms * 1e-3), "collect_ms": collect_ms,
             "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_tf32_ms": update_tf32_ms, "ppo_update_tf32_graph_ms": update_tf32_graph_ms,
-            "ppo_update": "4 epochs x 32 minibatches x 2 teams: torch autograd for the dense layers; attention forward/backward, "
-                          "minibatch gather and clipped-PPO loss are this repo's kernels (rl_attn_*, rl_gather_minibatch, rl_ppo_loss)",
+            "ppo_update": "4 epochs x 32 minibatches x 2 teams = 256 optimizer steps: message rounds with folded projections and "
+                          "hand-written forward/backward (rlcore/fused.py) over cuBLAS GEMMs (split-K weight gradients); attention "
+                          "forward/backward, ReLU-backward + bias gradient, minibatch gather and clipped-PPO loss are this repo's "
+                          "kernels (rl_attn_*, rl_attn_mix_*, rl_relu_bwd_colsum, rl_gather_minibatch, rl_ppo_loss)",
             "losses": vals,
             "policy_kernel": {"kernel": "mp::mp_policy_kernel", "us_per_team_forward": pol_us, "rows": NG * E,
                               "torch_module_act_us": torch_us, "speedup_vs_torch_module": torch_us / pol_us,
