@@ -144,10 +144,12 @@ class MPNN(nn.Module):
     def opp_attn_mat(self):
         return None if self._opp_attn is None else self._opp_attn.squeeze(0).squeeze(0).detach().cpu().numpy()
 
-    # Training-time forward on CUDA with the two attentions as fused kernels (rlcore/fused.py, csrc/rl_kernels.cu): same
-    # function as _fwd, but everything stays in the agent-major row layout (no transposes), Q|K|V come from one product,
-    # the [batch, n, n] bmm -> mask -> softmax -> bmm chains (42 % of the TF32 update, profiles/) are one kernel each way,
-    # and update(cat(h, msg)) is two accumulating GEMMs instead of cat + GEMM.  Opt-in: `fused_attention = True`.
+    # Training-time forward on CUDA (rlcore/fused.py, csrc/rl_kernels.cu): same function as _fwd, but everything stays in the
+    # agent-major row layout (no transposes), the [batch, n, n] bmm -> mask -> softmax -> bmm chains are one kernel each
+    # way, every dense layer has a hand-written backward (ReLU-backward + bias gradient in one kernel, split-K weight
+    # gradients), and -- with fold_projections -- the Q/K/V/out projections of the message rounds are folded into
+    # [d, d] products of the weights, so a round is G = h Mqk -> rl_attn_mix -> ONE K = 2d GEMM with bias + ReLU in its
+    # epilogue.  Opt-in: `fused_attention = True` (BatchedTrainer(fused_update=True) sets it).
     fused_attention = False
     fold_projections = True     # within the fused path: message rounds with the attention projections folded (see _fwd_fused)
 

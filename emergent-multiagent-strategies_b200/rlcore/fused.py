@@ -2,7 +2,6 @@
 `gather_minibatch` replaces magent_feed_forward_generator's ~10 x n index + cat launches per minibatch
 (rlcore/algo/ppo.py:207-246) by one kernel, `ppo_loss` evaluates the masked clipped-PPO loss of
 ppo.py:150-187 and its gradient with respect to (values, log-probs, entropy) in one pass."""
-import ctypes
 
 import torch
 

@@ -17,7 +17,6 @@ Checkpoints use the reference's file format ({'models': [state_dict per agent], 
 train_fortattack.py:121-128) and its loading rule (models[0] -> guards, models[-1] -> attackers,
 learner.py:245-249).
 """
-import ctypes
 
 import torch
 

@@ -1,4 +1,4 @@
-import sys, os, ctypes, torch
+import sys, os, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from importlib import import_module
 import policy_util as pu

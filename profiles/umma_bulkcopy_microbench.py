@@ -1,4 +1,4 @@
-import sys, ctypes, torch
+import sys, torch
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fortattack_b200 as fab
 L = fab._capi.lib()

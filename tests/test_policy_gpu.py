@@ -1,7 +1,6 @@
 """GPU: the fused MPNN rollout forward (csrc/mp_policy.cu) against (a) a torch evaluation of the same
 blob with fp16 rounding at the kernel's rounding points (tight) and (b) the fp32 module (the
 reference's arithmetic, mpnn.py:117-205; loose: fp16 tensor-core operands), plus the sampling contract."""
-import ctypes
 from importlib import import_module
 
 import pytest
