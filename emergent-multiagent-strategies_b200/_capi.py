@@ -37,6 +37,13 @@ class RlAttnOperand(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("batch_stride", ctypes.c_int64), ("row_stride", ctypes.c_int64)]
 
 
+class FrConfig(ctypes.Structure):
+    """include/fortattack_render.h FrConfig."""
+    _fields_ = [("n_envs", ctypes.c_int32), ("n_guards", ctypes.c_int32), ("n_attackers", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("draw_dead", ctypes.c_int32),
+                ("reserved0", ctypes.c_int32), ("reserved1", ctypes.c_int32)]
+
+
 class FaError(RuntimeError):
     pass
 
@@ -104,6 +111,7 @@ def lib():
     L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
     L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     L.mw_step.argtypes = [vp, vp, vp, vp, vp]
+    L.fr_render.argtypes = [ctypes.POINTER(FrConfig), vp, vp, vp, vp, i32, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)   # AttributeError here = the library does not match the header
     if L.fa_abi_version() != FA_ABI_VERSION:

@@ -70,6 +70,7 @@ class _World(object):
         self.gameResult = np.array([0, 0, 0])        # [all attackers dead, time up, attacker reached] fortattack.py:205-222
         self.fortDim, self.doorLoc = 0.15, np.array([0, 0.8])
         self.wall_pos = [-1, 1, -0.8, 0.8]
+        self.vizDead, self.vizAttn = False, True     # fortattack_env_v1.py:42-43 (read by render)
 
     @property
     def policy_agents(self):
@@ -116,6 +117,7 @@ class FortAttackGlobalEnv(object):
         self.observation_spaces = tuple(Box(-np.inf, np.inf, (6,)) for _ in range(self.n))
         self.action_range = [0., 1.]
         self._last_obs = np.zeros((self.n, 6))
+        self._last_actions = np.zeros(self.n, np.int32)            # agent.action.shoot of the last step (for render)
         self.reset()                                               # the reference's constructor resets once (v1:45)
 
     def _make_batch(self):
@@ -138,6 +140,7 @@ class FortAttackGlobalEnv(object):
         obs = self._batch.reset()                                  # [A,1,6] on device
         self.world.gameResult[:] = 0                               # v1:57
         self._last_obs = obs[:, 0].double().cpu().numpy()
+        self._last_actions = np.zeros(self.n, np.int32)
         return self._last_obs.copy()
 
     def step(self, action_n):
@@ -146,6 +149,7 @@ class FortAttackGlobalEnv(object):
             raise ValueError("expected %d actions, got %d" % (self.n, act.shape[0]))
         h_act, h_obs, h_rew, h_done, h_res = self._bufs
         h_act[:, 0] = torch.from_numpy(act.astype(np.int32))
+        self._last_actions = act.astype(np.int32)
         self._batch.step_host(h_act, h_obs, h_rew, h_done, h_res, auto_reset=False)
         self._last_obs = h_obs[:, 0].double().numpy()
         done = bool(h_done[0])
@@ -154,9 +158,23 @@ class FortAttackGlobalEnv(object):
             self.world.gameResult[{1: 0, 2: 1, 3: 2}[res]] = 1
         return self._last_obs.copy(), [float(r) for r in h_rew[:, 0].tolist()], done, {"n": [{} for _ in range(self.n)]}
 
-    def render(self, *args, **kwargs):
-        """Rendering (pyglet viewer, fortattack.py:368-596) is outside the accelerated path."""
-        return None
+    def render(self, attn_list=None, mode="human", close=False):
+        """The scene of the reference's render (fortattack.py:368-596) rasterised on the device from the current state
+        (render.render_batch / fr_render): no window is opened.  mode='rgb_array' returns [uint8 array 700 x 700 x 3] (the
+        reference returns one entry per viewer, :583-591); any other mode returns [True] after drawing into
+        `self.last_frame`.  attn_list = [[team_attn, opp_attn], ...] as the reference's callers pass it
+        (train_fortattack_v2.py:69): the guards' matrices become the yellow attention halos (:441-466)."""
+        from ..render import attention_halos, render_batch
+        obs = torch.from_numpy(self._last_obs).to(device=self._batch.device, dtype=torch.float32).view(self.n, 1, 6).contiguous()
+        act = torch.as_tensor(self._last_actions, dtype=torch.int32, device=obs.device).view(self.n, 1).contiguous()
+        halo = None
+        ng = self.world.numGuards
+        if attn_list is not None and self.world.vizAttn:
+            team = torch.as_tensor(np.asarray(attn_list[0][0]), dtype=torch.float32, device=obs.device).reshape(1, ng, ng)
+            opp = torch.as_tensor(np.asarray(attn_list[0][1]), dtype=torch.float32, device=obs.device).reshape(1, ng, self.n - ng)
+            halo = attention_halos(obs, ng, team, opp)
+        self.last_frame = render_batch(obs, ng, actions=act, halo=halo, draw_dead=bool(self.world.vizDead))[0].cpu().numpy()
+        return [self.last_frame] if mode == "rgb_array" else [True]
 
     def terminate(self):
         pass

@@ -25,7 +25,8 @@ def test_policy_and_rollout_headers_are_exported():
     """Every entry point of include/fortattack_policy.h and include/fortattack_rollout.h is in the library, and
     they reject bad arguments without a GPU."""
     L = _capi.lib()
-    for hdr_name, prefix in (("fortattack_policy.h", "mp_"), ("fortattack_rollout.h", "rl_"), ("mape_world.h", "mw_")):
+    for hdr_name, prefix in (("fortattack_policy.h", "mp_"), ("fortattack_rollout.h", "rl_"), ("mape_world.h", "mw_"),
+                             ("fortattack_render.h", "fr_")):
         hdr = open(os.path.join(ROOT, "include", hdr_name)).read()
         declared = set(re.findall(r"^int\s+(%s\w+)\(" % prefix, hdr, re.M))
         assert declared, hdr_name
@@ -79,4 +80,4 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(d, f)).read()
-                assert "fa_oracle" not in src and "oracle/" not in src, os.path.join(d, f)
+                assert not any(w in src for w in ("fa_oracle", "mw_oracle", "render_oracle", "oracle/")), os.path.join(d, f)

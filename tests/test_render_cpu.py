@@ -1,0 +1,70 @@
+"""CPU: known answers of the rasteriser's numpy restatement (oracle/render_oracle.py) derived from the reference's scene
+description (gym_fortattack/fortattack.py:368-596) and from its recorded out_files/1.gif."""
+import math
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import render_oracle as ro
+
+GREEN, RED, BLACK, GREY, CYAN = (0, 255, 0), (255, 0, 0), (0, 0, 0), (128, 128, 128), (0, 255, 255)
+
+
+def count(img, rgb):
+    return int((img == np.array(rgb, np.uint8)).all(-1).sum())
+
+
+def one_guard(x=0.3, y=0.1, ang=1.0, alive=1.0):
+    obs = np.zeros((2, 6), np.float32)
+    obs[0] = [alive, x, y, ang, 0, 0]
+    obs[1] = [0.0, -0.5, -0.5, 0, 0, 0]          # a dead attacker: not drawn unless draw_dead
+    return obs
+
+
+def test_static_scene():
+    img = ro.render(one_guard(alive=0.0), 1)
+    assert img.shape == (700, 700, 3)
+    # grey strips |y| > 0.8 <-> rows 0..69 and 630..699 (fortattack.py:549-563); black world in between
+    assert (img[:70] == GREY).all() and (img[630:] == GREY).all() and count(img[70:630], GREY) == 0
+    # lower half of the fort disc (radius 0.15 = 52.5 px at doorLoc (0, 0.8)) shows below the strip: pi r^2 / 2
+    assert abs(count(img, CYAN) - math.pi * 52.5 ** 2 / 2) < 60
+    assert count(img, CYAN) + count(img, BLACK) == 560 * 700 and count(img, GREEN) == 0 == count(img, RED)
+
+
+def test_agent_blob_area_matches_the_reference_recording():
+    """Body disc radius 0.05 = 17.5 px, head disc 8.75 px centred 14 px ahead.  Isolated agent blobs in the reference's own
+    recording out_files/1.gif (frames 1, 7, 14; green, colour-thresholded on its dithered palette) measure 945..981 px;
+    the reference draws 30-gons (rendering.py:260-270), whose body area is 955 px."""
+    img = ro.render(one_guard(), 1)
+    R, r, d = 17.5, 8.75, 14.0
+    lens = (r * r * math.acos((d * d + r * r - R * R) / (2 * d * r)) + R * R * math.acos((d * d + R * R - r * r) / (2 * d * R))
+            - 0.5 * math.sqrt((-d + r + R) * (d + r - R) * (d - r + R) * (d + r + R)))
+    union = math.pi * (R * R + r * r) - lens
+    assert abs(count(img, GREEN) - union) < 0.015 * union
+    for gif_blob in (964, 971, 974, 981):                       # measured from out_files/1.gif
+        assert 0.90 < gif_blob / count(img, GREEN) < 1.0        # the threshold drops the dithered rim and part of the head
+
+
+def test_dead_laser_halo_and_order():
+    obs = one_guard(x=-0.5, y=0.0, ang=0.0)
+    base = ro.render(obs, 1)
+    # dead agents appear only with draw_dead, in half colour (core.py:297)
+    dead = ro.render(obs, 1, draw_dead=True)
+    assert count(base, (128, 0, 0)) == 0 and count(dead, (128, 0, 0)) > 900
+    # laser triangle: area 0.5 * 0.8^2 * sin(pi/4) world units = 0.2263 * 350^2 px, blended 0.3 * green over black = (0, 77, 0)
+    shot = ro.render(obs, 1, actions=[7, 7])                    # the dead attacker's action is ignored (core.py:268)
+    tri = 0.5 * 0.8 * 0.8 * math.sin(math.pi / 4) * 350 * 350
+    assert abs(count(shot, (0, 77, 0)) - tri) < 0.04 * tri and count(shot, (77, 0, 0)) == 0
+    assert count(shot, GREEN) == count(base, GREEN)             # body and head cover the laser (paint order)
+    # halo: yellow disc of radius size * (1 + w) under the agent, alpha 0.9
+    halo = ro.render(obs, 1, halo=[1.0, -1.0])
+    ring = math.pi * (35.0 ** 2) - count(base, GREEN)
+    assert abs(count(halo, (230, 230, 0)) - ring) < 0.06 * ring
+    # a later agent covers an earlier one
+    two = np.zeros((2, 6), np.float32)
+    two[0] = [1, 0.0, 0.0, 0.0, 0, 0]
+    two[1] = [1, 0.02, 0.0, 0.0, 0, 0]
+    img = ro.render(two, 1)
+    assert count(img, RED) > count(img, GREEN) > 0
