@@ -57,7 +57,7 @@ class JointPPO(object):
                  lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=False, process_group=None,
                  allow_tf32=False, graph_update=False):
         self.actor_critic = actor_critic
-        # graph_update (new, fused path on one rank only): after three eager minibatch steps the whole optimizer step
+        # graph_update (new, fused path): after three eager minibatch steps the whole optimizer step
         # (gather -> forward -> loss -> backward -> clip -> Adam) is captured in a CUDA graph and replayed; with TF32
         # GEMMs the eager step is CPU-launch-bound (~9 ms of Python/autograd dispatch vs ~7 ms of GPU work at config 3)
         self.graph_update = bool(graph_update)
@@ -187,8 +187,11 @@ class JointPPO(object):
 
     def _graphed_step(self, fused, R, team, idx, advantages, totals, mini_batch_size, world):
         """Replay (or, on its fourth call, capture) the optimizer step as one CUDA graph.  Returns False when the step
-        has to run eagerly (option off, several ranks, a ragged last minibatch, or still warming up)."""
-        if not self.graph_update or world != 1 or idx.numel() != mini_batch_size or not idx.is_cuda:
+        has to run eagerly (option off, a ragged last minibatch, or still warming up).  With several ranks the two
+        all-reduces of the step (loss normaliser, flat gradient) are captured with it -- NCCL collectives are graph nodes --
+        so the replicas replay in lockstep and the multi-rank step costs no host work either; every rank takes the same
+        eager / capture / replay decisions because they depend only on call counts and sizes."""
+        if not self.graph_update or idx.numel() != mini_batch_size or not idx.is_cuda:
             return False
         g = self._g
         if g is None or g["key"] != (id(R), team, mini_batch_size, tuple(advantages.shape)):
@@ -207,8 +210,9 @@ class JointPPO(object):
             side.wait_stream(torch.cuda.current_stream(idx.device))
             self.optimizer.zero_grad(set_to_none=True)
             with torch.cuda.stream(side):
-                with torch.cuda.graph(graph, stream=side):
-                    self._minibatch_step(fused, R, team, g["idx"], g["adv"], g["totals"], params, 1)
+                # several ranks: the process group's watchdog thread polls its events while we capture -> thread-local mode
+                with torch.cuda.graph(graph, stream=side, capture_error_mode="global" if world == 1 else "thread_local"):
+                    self._minibatch_step(fused, R, team, g["idx"], g["adv"], g["totals"], params, world)
             torch.cuda.current_stream(idx.device).wait_stream(side)
             g["graph"] = graph
         g["idx"].copy_(idx)
