@@ -68,3 +68,22 @@ def test_dead_laser_halo_and_order():
     two[1] = [1, 0.02, 0.0, 0.0, 0, 0]
     img = ro.render(two, 1)
     assert count(img, RED) > count(img, GREEN) > 0
+
+
+def test_attention_halos_pick_the_reference_agent_like_the_reference():
+    """render.attention_halos (pure tensor code) against the selection loop of fortattack.py:441-466, per env."""
+    import torch
+    from importlib import import_module
+    rd = import_module("emergent-multiagent-strategies_b200.render")
+    g = torch.Generator().manual_seed(0)
+    ng, na, E = 3, 4, 64
+    obs = torch.zeros(ng + na, E, 6)
+    obs[:, :, 0] = (torch.rand(ng + na, E, generator=g) > 0.4).float()
+    team, opp = torch.rand(E, ng, ng, generator=g), torch.rand(E, ng, na, generator=g)
+    halo = rd.attention_halos(obs, ng, team, opp)
+    for e in range(E):
+        k = next(i for i in range(ng + na) if obs[i, e, 0] != 0 or i == ng - 1)       # :441-446
+        assert k < ng
+        for i in range(ng + na):
+            want = -1.0 if i == k else float(team[e, k, i] if i < ng else opp[e, k, i - ng])     # :452-458
+            assert float(halo[i, e]) == want
