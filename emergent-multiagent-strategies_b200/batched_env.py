@@ -140,9 +140,7 @@ class FortAttackBatch(object):
         """T env.step() calls of every env with HOST streams (fa_step_many_host), synchronous.
         chunk_steps=None: chunks of about 8 MB of results, copied by the DMA engines while the neighbouring chunks
         compute; chunk_steps=0: no staging, one persistent launch working through mapped pinned memory."""
-        T = int(h_actions.shape[0])
-        if tuple(h_actions.shape) != (T, self.A, self.E) or h_actions.dtype != torch.int32 or h_actions.is_cuda:
-            raise ValueError("h_actions must be a host int32 tensor [T, %d, %d]" % (self.A, self.E))
+        T = self._check_host_streams(h_actions, h_obs, h_rew, h_done, h_result)
         ptr = lambda t: t.data_ptr() if t is not None else None
         stage, nbytes = None, 0
         if chunk_steps is None:
@@ -157,6 +155,22 @@ class FortAttackBatch(object):
         _capi.check(self._lib.fa_step_many_host(self._h, T, h_actions.data_ptr(), ptr(h_obs), ptr(h_rew), ptr(h_done),
                                                 ptr(h_result), stage, nbytes, self._stream()))
         return h_obs, h_rew, h_done, h_result
+
+    def _check_host_streams(self, h_actions, h_obs, h_rew, h_done, h_result):
+        """The library writes T steps through these raw pointers: refuse anything that is not a contiguous host tensor of
+        exactly the documented shape and type.  Returns T."""
+        T = int(h_actions.shape[0]) if h_actions.dim() == 3 else -1
+        want = (("h_actions", h_actions, (T, self.A, self.E), torch.int32, False),
+                ("h_obs", h_obs, (T, self.A, self.E, 6), self.dtype, True),
+                ("h_rew", h_rew, (T, self.A, self.E), self.dtype, True),
+                ("h_done", h_done, (T, self.E), torch.uint8, True),
+                ("h_result", h_result, (T, self.E), torch.uint8, True))
+        for name, t, shape, dtype, optional in want:
+            if t is None and optional:
+                continue
+            if (t is None or T < 1 or tuple(t.shape) != shape or t.dtype != dtype or t.is_cuda or not t.is_contiguous()):
+                raise ValueError("%s must be a contiguous host %s tensor of shape %r" % (name, dtype, shape))
+        return T
 
     # -- state exchange (canonical float64 layout, include/fortattack.h FaState) -------------------
     def get_state(self):
