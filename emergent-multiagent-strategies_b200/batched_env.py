@@ -122,6 +122,11 @@ class FortAttackBatch(object):
 
     def step_host(self, h_actions, h_obs, h_rew, h_done, h_result, auto_reset=True):
         """One env.step() with HOST tensors: H2D actions, fused step, D2H results, synchronous."""
+        for name, t, shape, dtype in (("h_actions", h_actions, (self.A, self.E), torch.int32),
+                                      ("h_obs", h_obs, (self.A, self.E, 6), self.dtype), ("h_rew", h_rew, (self.A, self.E), self.dtype),
+                                      ("h_done", h_done, (self.E,), torch.uint8), ("h_result", h_result, (self.E,), torch.uint8)):
+            if tuple(t.shape) != shape or t.dtype != dtype or t.is_cuda or not t.is_contiguous():
+                raise ValueError("%s must be a contiguous host %s tensor of shape %r" % (name, dtype, shape))
         _capi.check(self._lib.fa_step_host(self._h, h_actions.data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
                                            h_done.data_ptr(), h_result.data_ptr(), int(bool(auto_reset)),
                                            self._stream()))

@@ -42,3 +42,15 @@ def test_rejects_wrong_streams(which, bad):
     s[0] = None
     with pytest.raises((ValueError, AttributeError)):
         _fake()._check_host_streams(*s)
+
+
+def test_step_host_rejects_wrong_buffers_before_touching_the_library():
+    b = _fake()
+    ok = [torch.zeros(6, 10, dtype=torch.int32), torch.zeros(6, 10, 6), torch.zeros(6, 10), torch.zeros(10, dtype=torch.uint8),
+          torch.zeros(10, dtype=torch.uint8)]
+    for which, bad in ((0, torch.zeros(6, 10)), (1, torch.zeros(6, 10, 5)), (2, torch.zeros(10, 6).t()), (3, torch.zeros(10)),
+                       (4, torch.zeros(11, dtype=torch.uint8))):
+        args = list(ok)
+        args[which] = bad
+        with pytest.raises(ValueError):
+            b.step_host(*args)          # raises in the argument check: the fake object has no library handle at all
