@@ -130,24 +130,96 @@ def cpu_oracle_rate(n_steps, warm, threads, rank_seed=0):
     return E_PER_GPU * A * n_steps / dt, dt
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _pyref_worker(rank, n_env_steps, warm, barrier, q):
+    """One process = one core stepping the UNMODIFIED reference env (baseline/_ref/reference, imported through the stub
+    modules of ref_shim.py) with uniform random actions; resets on done as train_fortattack.py:97-100 does."""
+    try:
+        sys.stdout = open(os.devnull, "w")                  # the env prints on every episode end (fortattack.py:208-220)
+        os.environ["FA_REFERENCE_DIR"] = os.path.join(REF_DIR, "reference")
+        sys.path.insert(0, REF_DIR)
+        import numpy as np
+        import ref_shim
+        env, _ = ref_shim.make_ref_env(NG, NA, CAP)
+        np.random.seed(1000 + rank)
+        env.reset()
+        acts = np.random.randint(0, 8, size=(n_env_steps + warm, A))
+        for t in range(warm):
+            if env.step(acts[t])[2]:
+                env.reset()
+        barrier.wait()
+        t0 = time.perf_counter()
+        for t in range(warm, warm + n_env_steps):
+            if env.step(acts[t])[2]:
+                env.reset()
+        q.put((rank, n_env_steps, time.perf_counter() - t0, None))
+    except Exception as exc:                                 # pragma: no cover
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        q.put((rank, 0, 0.0, repr(exc)))
+
+
+def python_reference_rate(env_steps_total, cores, warm=100):
+    """agent-steps/s of the reference's own Python env.step, one process per host core.
+    Returns (rate, seconds, env_steps_done) or None when baseline/_ref is not installed."""
+    if not os.path.isdir(os.path.join(REF_DIR, "reference")):
+        return None
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    per = max(1, (env_steps_total + cores - 1) // cores)
+    barrier, q = ctx.Barrier(cores), ctx.Queue()
+    procs = [ctx.Process(target=_pyref_worker, args=(r, per, warm, barrier, q), daemon=True) for r in range(cores)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=30)
+    bad = [r for r in res if r[3]]
+    if bad:
+        raise RuntimeError("python reference worker failed: %s" % bad[0][3])
+    dt = max(r[2] for r in res)
+    n = sum(r[1] for r in res)
+    return n * A / dt, dt, n
+
+
 def run_reference(args):
+    """The reference arm: the UNMODIFIED Python reference (baseline/_ref) on all host cores, K steps of the bench's
+    E_PER_GPU-env batch split over one process per core (bounded to ~25 s); the C port of the same arithmetic
+    (oracle/fa_oracle.c) is timed beside it and reported under cpu_baseline.port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    # bounded: at most ~60 s of CPU work whatever K is
     probe, _ = cpu_oracle_rate(20, 5, cores)
-    k = max(1, min(args.steps, int(60.0 * probe / (E_PER_GPU * A))))
-    rate, dt = cpu_oracle_rate(k, args.warmup, cores)
-    sample = "%d env.step() calls of %d envs (oracle/fa_oracle.c float64, %d pthreads), %.1f s" % (k, E_PER_GPU, cores, dt)
+    kp = max(1, min(args.steps, int(30.0 * probe / (E_PER_GPU * A))))
+    port_rate, port_dt = cpu_oracle_rate(kp, args.warmup, cores)
+    port = {"value": port_rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d env.step() calls of %d envs (oracle/fa_oracle.c float64, %d pthreads), %.3f s" % (kp, E_PER_GPU, cores, port_dt)}
+    # K steps of the 4096-env batch = K*4096 env-steps; bounded to ~25 s at ~1.4e3 env-steps/s per core
+    budget = int(25.0 * 1400 * cores)
+    k = max(1, min(args.steps, budget // E_PER_GPU))
+    ref = python_reference_rate(k * E_PER_GPU, cores)
+    if ref is not None:
+        rate, dt, n = ref
+        kind = "reference"
+        sample = ("%d steps of the %d-env batch = %d env.step() calls of the unmodified Python reference "
+                  "(baseline/_ref/reference/gym_fortattack, numpy float64), one process per core x %d, %.1f s"
+                  % (k, E_PER_GPU, n, cores, dt))
+        what = ("the reference's own gym_fortattack env.step (byte copy of /root/reference under baseline/_ref, imported through "
+                "stub modules for gym/pygame/pyglet), one Python process per host core, each stepping its own env")
+    else:
+        rate, dt, k, kind, sample = port_rate, port_dt, kp, "port", port["sample"]
+        what = "oracle/fa_oracle.c (baseline/_ref not installed: python baseline/install_ref.py needs /root/reference)"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm runs one shard of %d envs on the host cores whatever N is" % E_PER_GPU,
-                       "what_runs": "oracle/fa_oracle.c: the reference's float64 arithmetic restated in C with one pthread per core "
-                                    "(the reference itself is Python and cannot travel to the GPU box; through the import shim it "
-                                    "steps ~1 450 envs/s per core at 3v3 = ~8.7e3 agent-steps/s per core, SURVEY.md section 6)"},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                       "what_runs": what},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "port": port},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -367,11 +439,24 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.quick:
         cores = len(os.sched_getaffinity(0))
         probe, _ = cpu_oracle_rate(20, 5, cores)
-        n = max(20, int(12.0 * probe / (E_PER_GPU * A)))
+        n = max(20, int(8.0 * probe / (E_PER_GPU * A)))
         rate, dt = cpu_oracle_rate(n, 5, cores)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d env.step() calls of %d envs, oracle/fa_oracle.c (float64, %d pthreads), %.1f s"
-                                          % (n, E_PER_GPU, cores, dt)}
+        port = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d env.step() calls of %d envs, oracle/fa_oracle.c (float64, %d pthreads), %.1f s"
+                          % (n, E_PER_GPU, cores, dt)}
+        ref = None
+        try:
+            ref = python_reference_rate(int(12.0 * 1400 * cores), cores)      # ~12 s of the unmodified Python reference
+        except Exception as exc:
+            port["python_reference_error"] = repr(exc)
+        if ref is not None:
+            line["cpu_baseline"] = {"value": ref[0], "unit": UNIT, "cores": cores, "kind": "reference",
+                                    "sample": "%d env.step() calls (3v3, uniform random actions, cap %d) of the unmodified Python "
+                                              "reference from baseline/_ref, one process per core x %d, %.1f s"
+                                              % (ref[2], CAP, cores, ref[1]),
+                                    "per_core": ref[0] / cores, "port": port}
+        else:
+            line["cpu_baseline"] = port
     if rank == 0:
         emit(line)
     if world > 1:

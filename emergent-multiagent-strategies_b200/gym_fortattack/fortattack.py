@@ -12,19 +12,22 @@ train_fortattack.py:25-29,60,100,124).  One env = a batch of E=1 on the GPU: eve
 fa_step_host call (kernel reads the actions from, and writes obs/reward/done into, pinned host memory).
 The reference hard-codes 5 guards v 5 attackers (fortattack_env_v1.py:18-19); here they are arguments.
 """
+import os
+
 import numpy as np
 import torch
 
 try:
     from ..batched_env import FortAttackBatch
+    from .. import render as _render
 except ImportError:      # drop-in mode: this package was imported top-level as `gym_fortattack`
     import importlib
-    import os
     import sys
     _root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     if _root not in sys.path:
         sys.path.insert(0, _root)
     FortAttackBatch = importlib.import_module("emergent-multiagent-strategies_b200").FortAttackBatch
+    _render = importlib.import_module("emergent-multiagent-strategies_b200.render")
 
 
 class Discrete(object):
@@ -84,17 +87,19 @@ class _World(object):
     def max_time_steps(self, v):
         self._env._batch.set_max_steps(v)
 
+    # world.time_step / numAliveGuards / numAliveAttackers (core.py:123-126, fortattack.py:171): host-side mirrors of what
+    # the last step returned -- no launch, no device->host copy per read (test_fortattack_v2.py:94-99 reads them per episode)
     @property
     def time_step(self):
-        return int(self._env._batch.get_state()[2][0].item())
+        return self._env._time_step
 
     @property
     def numAliveGuards(self):
-        return int(self._env._batch.alive_counts()[0][0].item())
+        return int((self._env._last_obs[:self.numGuards, 0] > 0).sum())
 
     @property
     def numAliveAttackers(self):
-        return int(self._env._batch.alive_counts()[1][0].item())
+        return int((self._env._last_obs[self.numGuards:, 0] > 0).sum())
 
 
 class FortAttackGlobalEnv(object):
@@ -117,6 +122,7 @@ class FortAttackGlobalEnv(object):
         self.observation_spaces = tuple(Box(-np.inf, np.inf, (6,)) for _ in range(self.n))
         self.action_range = [0., 1.]
         self._last_obs = np.zeros((self.n, 6))
+        self._time_step = 0
         self._last_actions = np.zeros(self.n, np.int32)            # agent.action.shoot of the last step (for render)
         self.reset()                                               # the reference's constructor resets once (v1:45)
 
@@ -141,6 +147,7 @@ class FortAttackGlobalEnv(object):
         self.world.gameResult[:] = 0                               # v1:57
         self._last_obs = obs[:, 0].double().cpu().numpy()
         self._last_actions = np.zeros(self.n, np.int32)
+        self._time_step = 0                                        # v1:51
         return self._last_obs.copy()
 
     def step(self, action_n):
@@ -152,6 +159,7 @@ class FortAttackGlobalEnv(object):
         self._last_actions = act.astype(np.int32)
         self._batch.step_host(h_act, h_obs, h_rew, h_done, h_res, auto_reset=False)
         self._last_obs = h_obs[:, 0].double().numpy()
+        self._time_step += 1                                       # fortattack.py:171
         done = bool(h_done[0])
         res = int(h_res[0])
         if res:                                                    # fortattack.py:205-222
@@ -164,7 +172,7 @@ class FortAttackGlobalEnv(object):
         reference returns one entry per viewer, :583-591); any other mode returns [True] after drawing into
         `self.last_frame`.  attn_list = [[team_attn, opp_attn], ...] as the reference's callers pass it
         (train_fortattack_v2.py:69): the guards' matrices become the yellow attention halos (:441-466)."""
-        from ..render import attention_halos, render_batch
+        attention_halos, render_batch = _render.attention_halos, _render.render_batch
         obs = torch.from_numpy(self._last_obs).to(device=self._batch.device, dtype=torch.float32).view(self.n, 1, 6).contiguous()
         act = torch.as_tensor(self._last_actions, dtype=torch.int32, device=obs.device).view(self.n, 1).contiguous()
         halo = None
@@ -183,6 +191,12 @@ class FortAttackGlobalEnv(object):
         self._batch.close()
 
 
-def make_fortattack_env(num_steps, benchmark=False, n_guards=5, n_attackers=5, seed=0, device="cuda:0"):
-    """make_fortattack_env(num_steps) of the reference (fortattack.py:17-27): world.max_time_steps = num_steps."""
+def make_fortattack_env(num_steps, benchmark=False, n_guards=None, n_attackers=None, seed=0, device="cuda:0"):
+    """make_fortattack_env(num_steps) of the reference (fortattack.py:17-27): world.max_time_steps = num_steps.
+    Team sizes default to the reference's hard-coded 5v5 (fortattack_env_v1.py:18-19); callers that cannot pass
+    arguments (the reference's own scripts call make_fortattack_env(num_steps), utils.py:24) set FORTATTACK_TEAMS=3v3."""
+    if n_guards is None or n_attackers is None:
+        g, a = (int(x) for x in os.environ.get("FORTATTACK_TEAMS", "5v5").lower().split("v"))
+        n_guards = g if n_guards is None else n_guards
+        n_attackers = a if n_attackers is None else n_attackers
     return FortAttackGlobalEnv(num_steps, n_guards=n_guards, n_attackers=n_attackers, seed=seed, device=device)
