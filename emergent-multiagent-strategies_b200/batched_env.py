@@ -49,6 +49,20 @@ class FortAttackBatch(object):
     def _new(self, *shape, dtype=None):
         return torch.empty(shape, dtype=dtype or self.dtype, device=self.device)
 
+    def _dev(self, name, t, shape, dtype, optional=False):
+        """The library reads / writes through raw pointers: refuse anything that is not a contiguous tensor of exactly
+        the documented shape and type on this handle's device."""
+        if t is None and optional:
+            return None
+        if (t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.workspace.device
+                or not t.is_contiguous()):
+            raise ValueError("%s must be a contiguous %s tensor of shape %r on %s" % (name, dtype, tuple(shape), self.device))
+        return t
+
+    def _guard(self):
+        """Launches, streams and events of this handle belong to its device whatever device is current."""
+        return torch.cuda.device(self.device)
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.fa_destroy(self._h)
@@ -63,12 +77,15 @@ class FortAttackBatch(object):
     # -- the env seam -----------------------------------------------------------------------------
     def reset(self, mask=None, out=None):
         """Reset every env (or those with mask != 0); returns obs [A, E, 6] of all envs."""
-        obs = out if out is not None else self._new(self.A, self.E, 6)
+        obs = self._dev("out", out, (self.A, self.E, 6), self.dtype) if out is not None else self._new(self.A, self.E, 6)
         m = None
         if mask is not None:
-            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        _capi.check(self._lib.fa_reset(self._h, m.data_ptr() if m is not None else None, obs.data_ptr(),
-                                       self._stream()))
+            if mask.numel() != self.E:
+                raise ValueError("mask must have one entry per env (%d), got %d" % (self.E, mask.numel()))
+            m = mask.reshape(self.E).to(device=self.device, dtype=torch.uint8).contiguous()
+        with self._guard():
+            _capi.check(self._lib.fa_reset(self._h, m.data_ptr() if m is not None else None, obs.data_ptr(),
+                                           self._stream()))
         return obs
 
     def step(self, actions, auto_reset=True, out=None):
@@ -77,9 +94,18 @@ class FortAttackBatch(object):
         if out is None:
             out = (self._new(self.A, self.E, 6), self._new(self.A, self.E),
                    self._new(self.E, dtype=torch.uint8), self._new(self.E, dtype=torch.uint8))
+        else:
+            if len(out) != 4:
+                raise ValueError("out = (obs, reward, done, result)")
+            self._dev("out[0] (obs)", out[0], (self.A, self.E, 6), self.dtype)
+            self._dev("out[1] (reward)", out[1], (self.A, self.E), self.dtype)
+            self._dev("out[2] (done)", out[2], (self.E,), torch.uint8)
+            self._dev("out[3] (result)", out[3], (self.E,), torch.uint8)
+        self._check_alive_end(1)
         obs, rew, done, result = out
-        _capi.check(self._lib.fa_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                                      result.data_ptr(), int(bool(auto_reset)), self._stream()))
+        with self._guard():
+            _capi.check(self._lib.fa_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                          result.data_ptr(), int(bool(auto_reset)), self._stream()))
         return obs, rew, done, result
 
     def step_many(self, actions, out=None, store_obs=True):
@@ -89,11 +115,26 @@ class FortAttackBatch(object):
         if out is None:
             out = (self._new(T, self.A, self.E, 6) if store_obs else None, self._new(T, self.A, self.E),
                    self._new(T, self.E, dtype=torch.uint8), self._new(T, self.E, dtype=torch.uint8))
+        else:
+            if len(out) != 4:
+                raise ValueError("out = (obs or None, reward, done, result)")
+            self._dev("out[0] (obs)", out[0], (T, self.A, self.E, 6), self.dtype, optional=True)
+            self._dev("out[1] (reward)", out[1], (T, self.A, self.E), self.dtype, optional=True)
+            self._dev("out[2] (done)", out[2], (T, self.E), torch.uint8, optional=True)
+            self._dev("out[3] (result)", out[3], (T, self.E), torch.uint8, optional=True)
+        self._check_alive_end(T)
         obs, rew, done, result = out
         ptr = lambda t: t.data_ptr() if t is not None else None
-        _capi.check(self._lib.fa_step_many(self._h, T, a.data_ptr(), ptr(obs), ptr(rew), ptr(done), ptr(result),
-                                           self._stream()))
+        with self._guard():
+            _capi.check(self._lib.fa_step_many(self._h, T, a.data_ptr(), ptr(obs), ptr(rew), ptr(done), ptr(result),
+                                               self._stream()))
         return obs, rew, done, result
+
+    def _check_alive_end(self, T):
+        buf = getattr(self, "_alive_end", None)
+        if buf is not None and buf.numel() < T * self.E:
+            raise ValueError("the alive-end buffer holds %d entries; %d step(s) of %d envs write %d (set_alive_end_buffer "
+                             "with a [T, E] tensor, or None)" % (buf.numel(), T, self.E, T * self.E))
 
     def _actions(self, actions, shape):
         a = actions
@@ -127,9 +168,11 @@ class FortAttackBatch(object):
                                       ("h_done", h_done, (self.E,), torch.uint8), ("h_result", h_result, (self.E,), torch.uint8)):
             if tuple(t.shape) != shape or t.dtype != dtype or t.is_cuda or not t.is_contiguous():
                 raise ValueError("%s must be a contiguous host %s tensor of shape %r" % (name, dtype, shape))
-        _capi.check(self._lib.fa_step_host(self._h, h_actions.data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
-                                           h_done.data_ptr(), h_result.data_ptr(), int(bool(auto_reset)),
-                                           self._stream()))
+        self._check_alive_end(1)
+        with self._guard():
+            _capi.check(self._lib.fa_step_host(self._h, h_actions.data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
+                                               h_done.data_ptr(), h_result.data_ptr(), int(bool(auto_reset)),
+                                               self._stream()))
         return h_obs, h_rew, h_done, h_result
 
     def make_host_streams(self, T, store_obs=True):
@@ -146,6 +189,7 @@ class FortAttackBatch(object):
         chunk_steps=None: chunks of about 8 MB of results, copied by the DMA engines while the neighbouring chunks
         compute; chunk_steps=0: no staging, one persistent launch working through mapped pinned memory."""
         T = self._check_host_streams(h_actions, h_obs, h_rew, h_done, h_result)
+        self._check_alive_end(T)
         ptr = lambda t: t.data_ptr() if t is not None else None
         stage, nbytes = None, 0
         if chunk_steps is None:
@@ -157,8 +201,9 @@ class FortAttackBatch(object):
             if getattr(self, "_stage", None) is None or self._stage.numel() < need.value:
                 self._stage = torch.empty(need.value, dtype=torch.uint8, device=self.device)
             stage, nbytes = self._stage.data_ptr(), need.value
-        _capi.check(self._lib.fa_step_many_host(self._h, T, h_actions.data_ptr(), ptr(h_obs), ptr(h_rew), ptr(h_done),
-                                                ptr(h_result), stage, nbytes, self._stream()))
+        with self._guard():
+            _capi.check(self._lib.fa_step_many_host(self._h, T, h_actions.data_ptr(), ptr(h_obs), ptr(h_rew), ptr(h_done),
+                                                    ptr(h_result), stage, nbytes, self._stream()))
         return h_obs, h_rew, h_done, h_result
 
     def _check_host_streams(self, h_actions, h_obs, h_rew, h_done, h_result):
@@ -184,7 +229,8 @@ class FortAttackBatch(object):
         t = self._new(self.E, dtype=torch.int32)
         ep = self._new(self.E, dtype=torch.int32)       # bit pattern of uint32
         s = _capi.FaState(st_f.data_ptr(), st_i.data_ptr(), t.data_ptr(), ep.data_ptr())
-        _capi.check(self._lib.fa_get_state(self._h, ctypes.byref(s), self._stream()))
+        with self._guard():
+            _capi.check(self._lib.fa_get_state(self._h, ctypes.byref(s), self._stream()))
         return st_f, st_i, t, ep
 
     def set_state(self, st_f, st_i, time_step, episode):
@@ -196,13 +242,15 @@ class FortAttackBatch(object):
         assert tuple(st_f.shape) == (self.E, self.A, 6) and tuple(st_i.shape) == (self.E, self.A, 6)
         assert tuple(t.shape) == (self.E,) and tuple(ep.shape) == (self.E,)
         s = _capi.FaState(st_f.data_ptr(), st_i.data_ptr(), t.data_ptr(), ep.data_ptr())
-        _capi.check(self._lib.fa_set_state(self._h, ctypes.byref(s), self._stream()))
+        with self._guard():
+            _capi.check(self._lib.fa_set_state(self._h, ctypes.byref(s), self._stream()))
         torch.cuda.current_stream(dev).synchronize()    # the temporaries above may be freed on return
 
     def alive_counts(self):
         """(numAliveGuards [E], numAliveAttackers [E]) int32 (core.py:113-114)."""
         c = self._new(2, self.E, dtype=torch.int32)
-        _capi.check(self._lib.fa_alive_counts(self._h, c.data_ptr(), self._stream()))
+        with self._guard():
+            _capi.check(self._lib.fa_alive_counts(self._h, c.data_ptr(), self._stream()))
         return c[0], c[1]
 
     def set_max_steps(self, max_steps):

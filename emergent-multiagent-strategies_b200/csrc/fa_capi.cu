@@ -116,6 +116,19 @@ struct FaHandle {
     bool pipe_ready;
 };
 
+// Every entry point that launches, copies or touches the handle's streams/events runs on the handle's device whatever
+// device the calling thread has current (a FortAttackBatch(device="cuda:1") used while cuda:0 is current), and restores it.
+struct DevGuard {
+    int prev = -1, dev;
+    explicit DevGuard(const FaHandle *h) : dev(h->cfg.device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
 struct Carve {
     size_t off = 0;
     size_t take(size_t bytes) {
@@ -220,6 +233,7 @@ static cudaError_t do_step(FaHandle *h, bool many, int T, const int32_t *act, vo
 static int step_common(FaHandle *h, bool many, int T, const int32_t *d_actions, void *d_obs, void *d_reward,
                        uint8_t *d_done, uint8_t *d_result, int auto_reset, void *stream) {
     NEED_HANDLE(h);
+    DevGuard dev_guard(h);
     if (!d_actions) return fail(FA_EINVAL, "actions is NULL");
     if (T < 1) return fail(FA_EINVAL, "T must be >= 1 (got %d)", T);
     if (d_obs && (uintptr_t)d_obs % (2 * h->rs)) return fail(FA_EALIGN, "obs must be aligned to %zu bytes", 2 * h->rs);
@@ -308,6 +322,7 @@ int fa_create(const FaConfig *cfg, void *d_workspace, FaHandle **out) {
 
 int fa_destroy(FaHandle *h) {
     if (h && h->pipe_ready) {
+        DevGuard dev_guard(h);
         cudaStreamDestroy(h->st_in);
         cudaStreamDestroy(h->st_out);
         for (int b = 0; b < 2; ++b) {
@@ -322,6 +337,7 @@ int fa_destroy(FaHandle *h) {
 
 int fa_reset(FaHandle *h, const uint8_t *d_env_mask, void *d_obs, void *stream) {
     NEED_HANDLE(h);
+    DevGuard dev_guard(h);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const FaConfig &c = h->cfg;
     // fa_reset_kernel is always one thread per env
@@ -365,6 +381,7 @@ static void *mapped_alias(const void *p) {
 int fa_step_host(FaHandle *h, const int32_t *h_actions, void *h_obs, void *h_reward, uint8_t *h_done,
                  uint8_t *h_result, int auto_reset, void *stream) {
     NEED_HANDLE(h);
+    DevGuard dev_guard(h);
     if (!h_actions) return fail(FA_EINVAL, "actions is NULL");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t E = (size_t)h->cfg.n_envs, A = (size_t)h->A;
@@ -457,6 +474,7 @@ static int pipe_init(FaHandle *h) {
 int fa_step_many_host(FaHandle *h, int T, const int32_t *h_actions, void *h_obs, void *h_reward, uint8_t *h_done,
                       uint8_t *h_result, void *d_stage, size_t stage_bytes, void *stream) {
     NEED_HANDLE(h);
+    DevGuard dev_guard(h);
     if (!h_actions) return fail(FA_EINVAL, "actions is NULL");
     if (T < 1) return fail(FA_EINVAL, "T must be >= 1 (got %d)", T);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -539,6 +557,7 @@ int fa_host_layout(const FaHandle *h, size_t *off_reward, size_t *off_done, size
 
 int fa_get_state(FaHandle *h, const FaState *out, void *stream) {
     NEED_HANDLE(h);
+    DevGuard dev_guard(h);
     if (!out || !out->d_st_f || !out->d_st_i || !out->d_time_step || !out->d_episode)
         return fail(FA_EINVAL, "FaState has a NULL member");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -556,6 +575,7 @@ int fa_get_state(FaHandle *h, const FaState *out, void *stream) {
 
 int fa_set_state(FaHandle *h, const FaState *in, void *stream) {
     NEED_HANDLE(h);
+    DevGuard dev_guard(h);
     if (!in || !in->d_st_f || !in->d_st_i || !in->d_time_step || !in->d_episode)
         return fail(FA_EINVAL, "FaState has a NULL member");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -573,6 +593,7 @@ int fa_set_state(FaHandle *h, const FaState *in, void *stream) {
 
 int fa_alive_counts(FaHandle *h, int32_t *d_counts, void *stream) {
     NEED_HANDLE(h);
+    DevGuard dev_guard(h);
     if (!d_counts) return fail(FA_EINVAL, "counts is NULL");
     const int E = h->cfg.n_envs, b = 128, g = (E + b - 1) / b;
     fa::fa_alive_counts_kernel<<<g, b, 0, static_cast<cudaStream_t>(stream)>>>(h->fl, d_counts, E, h->cfg.n_guards, h->A);

@@ -25,8 +25,16 @@ template <typename R> struct Par {
     uint32_t collide, movable;      // bit masks
 };
 
-// penetration = k * log(1 + exp(-x / k))  (core.py:205,221); float: max(0, -x), which differs by <= k ln 2 = 7e-11
-__device__ __forceinline__ float pen(float x, float) { return fmaxf(0.0f, -x); }
+// penetration = k * log(1 + exp(-x / k))  (core.py:205,221).  float: with the reference's k = 1e-10 it is max(0, -x) to
+// within k ln 2 = 7e-11 (below float resolution); for a margin that float can resolve (the stock MPE 1e-3 commented beside
+// it in the reference) the softplus itself is evaluated, so float mode follows the double path / the oracle for any k
+__device__ __forceinline__ float pen(float x, float k) {
+    if (k <= 1e-6f) return fmaxf(0.0f, -x);
+    const float t = -x / k;
+    if (t > 30.0f) return -x;
+    if (t < -80.0f) return 0.0f;
+    return (t > 0.0f ? t + log1pf(expf(-t)) : log1pf(expf(t))) * k;
+}
 __device__ __forceinline__ double pen(double x, double k) {
     const double t = -x / k;
     if (t > 40.0) return (t + log1p(exp(-t))) * k;

@@ -151,6 +151,7 @@ class MPNN(nn.Module):
     # [d, d] products of the weights, so a round is G = h Mqk -> rl_attn_mix -> ONE K = 2d GEMM with bias + ReLU in its
     # epilogue.  Opt-in: `fused_attention = True` (BatchedTrainer(fused_update=True) sets it).
     fused_attention = False
+    fused_no_grad = False       # also take the fused path under torch.no_grad() (BatchedTrainer.recompute_old: same arithmetic as the update)
     fold_projections = True     # within the fused path: message rounds with the attention projections folded (see _fwd_fused)
 
     def _fwd_fused(self, inp, oppInp):
@@ -209,8 +210,8 @@ class MPNN(nn.Module):
         raise NotImplementedError
 
     def _use_fused(self, x):
-        return (self.fused_attention and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
-                and self.nonlin is nn.ReLU)
+        return (self.fused_attention and x.is_cuda and x.dtype == torch.float32
+                and (torch.is_grad_enabled() or self.fused_no_grad) and self.nonlin is nn.ReLU)
 
     def _dist(self, p):
         if self._use_fused(p):

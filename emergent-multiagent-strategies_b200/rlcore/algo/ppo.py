@@ -153,7 +153,9 @@ class JointPPO(object):
                 n_updates += 1
         if world > 1:
             totals = self._allreduce(totals) / world
-        v, a, e = (totals / max(n_updates, 1)).tolist()
+        # the reference divides the summed losses by ppo_epoch * num_mini_batch whatever the number of minibatches the
+        # sampler produced (ppo.py:198-202: a ragged tail adds one more term to the sums)
+        v, a, e = (totals / (self.ppo_epoch * self.num_mini_batch)).tolist()
         return v, a, e
 
     def _minibatch_step(self, fused, R, team, idx, advantages, totals, params, world):
@@ -289,7 +291,7 @@ class JointPPO(object):
                 n_updates += 1
         if world > 1:
             totals = self._allreduce(totals) / world
-        v, a, e = (totals / max(n_updates, 1)).tolist()          # the only host sync of the update
+        v, a, e = (totals / (self.ppo_epoch * self.num_mini_batch)).tolist()          # the only host sync of the update (ppo.py:198-202)
         return v, a, e
 
 

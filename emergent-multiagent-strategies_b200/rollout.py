@@ -95,7 +95,7 @@ class BatchedTrainer(object):
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
                  use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False,
-                 graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=False):
+                 graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=False, exact_old="auto"):
         self.device = torch.device(device)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
@@ -124,6 +124,12 @@ class BatchedTrainer(object):
             fused_policy = hidden_dim == 128
         self.fused = [FusedPolicy(p, seed=seed * 2 + t, env_id0=env_id0) for t, p in enumerate(self.policies)] \
             if fused_policy else None
+        # exact_old: the rollout kernel computes with fp16 tensor-core operands; with trained weights its stored
+        # log-probs / values differ from the update's fp32-grade forward by up to ~1e-2, so the PPO ratio would start at
+        # 1 +- 1e-2 instead of exactly 1 (rlcore/algo/ppo.py:163-173).  When on (default whenever the fused rollout
+        # kernel is used) train_once() re-evaluates the stored (obs, action) rows with the update's own forward before
+        # GAE, the way RL stacks with a separate inference engine recompute the behaviour log-probs in the trainer.
+        self.exact_old = (self.fused is not None) if exact_old == "auto" else bool(exact_old)
         # Ensemble play (train_fortattack_v2.py:34-35,110-111; Learner.sample_attacker / select_attacker,
         # learner.py:119-140): K frozen attacker checkpoints; every env draws one uniformly at each of its episode
         # starts.  One forward per checkpoint over all envs, each writing only the envs assigned to it.
@@ -262,6 +268,33 @@ class BatchedTrainer(object):
         R.ends[self.T] = True                                              # (:108-109)
         return self.episode_rewards
 
+    # -- old log-probs / values in the update's arithmetic ----------------------------------------------
+    @torch.no_grad()
+    def recompute_old(self, chunk_rows=1 << 18):
+        """Overwrite action_log_probs[0:T] and value_preds[0:T] of the TRAINED teams with MPNN.evaluate_actions of the
+        stored observations and actions, computed by the same forward the update uses (mpnn.py:194-200 through
+        rlcore/fused.py), so that ratio = exp(new - old) is 1 at the first minibatch of the update (ppo.py:163).
+        Rows are agent-major per chunk of time steps, exactly the minibatch layout (ppo.py:222-234)."""
+        R, T, E = self.roll, self.T, self.E
+        for t, policy in enumerate(self.policies):
+            if t == 1 and self.ensemble is not None:       # frozen attackers are not trained
+                continue
+            team, opp = self.teams[t], self.teams[1 - t]
+            lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
+            n = hi - lo
+            steps = max(1, chunk_rows // (max(n, ohi - olo) * E))
+            policy.fused_no_grad = True
+            try:
+                for s0 in range(0, T, steps):
+                    s1 = min(T, s0 + steps)
+                    rows = lambda x, a, b: x[s0:s1, a:b].transpose(0, 1).reshape(-1, x.shape[-1])
+                    v, lp, _, _ = policy.evaluate_actions(rows(R.obs, lo, hi), None, rows(R.obs, olo, ohi), None,
+                                                          rows(R.actions, lo, hi))
+                    R.value_preds[s0:s1, lo:hi] = v.view(n, s1 - s0, E, 1).transpose(0, 1)
+                    R.action_log_probs[s0:s1, lo:hi] = lp.view(n, s1 - s0, E, 1).transpose(0, 1)
+            finally:
+                policy.fused_no_grad = False
+
     # -- Learner.wrap_horizon (learner.py:191-211) ---------------------------------------------------
     @torch.no_grad()
     def wrap_horizon(self):
@@ -274,6 +307,14 @@ class BatchedTrainer(object):
                 order, offsets = self._ensemble_lists()
                 forward_ensemble(self.ensemble, R.obs[T, lo:hi], R.obs[T, olo:ohi], order, offsets, MODE_ARGMAX,
                                  out={"value": nv[lo:hi]})
+            elif self.fused is not None and self.exact_old:
+                # bootstrap values in the same arithmetic as the recomputed value_preds (recompute_old)
+                policy.fused_no_grad = True
+                try:
+                    nv[lo:hi] = policy.get_value(R.obs[T, lo:hi].reshape(-1, 6), None, R.obs[T, olo:ohi].reshape(-1, 6),
+                                                 None).view(len(team), self.E)
+                finally:
+                    policy.fused_no_grad = False
             elif self.fused is not None:
                 self.fused[t].forward(R.obs[T, lo:hi], R.obs[T, olo:ohi], MODE_ARGMAX, out={"value": nv[lo:hi]})
             else:
@@ -306,6 +347,8 @@ class BatchedTrainer(object):
 
     def train_once(self, train_guards_only=None):
         rewards = self.collect()
+        if self.exact_old:
+            self.recompute_old()
         self.wrap_horizon()
         vals = self.update(train_guards_only)
         self.after_update()

@@ -79,3 +79,23 @@ def random_obs(n, E, gen, device="cpu"):
     o[..., 3] = torch.rand(n, E, generator=gen) * 40
     o[..., 4:] = torch.randn(n, E, 2, generator=gen)
     return o.to(device)
+
+
+def trained_state_dict():
+    """The guards' policy of the reference's shipped checkpoint marlsave/tmp_1/ep2520.pt (5v5), as stored in
+    tests/golden/rl_mpnn.npz by tests/golden/make_rl_golden.py (ckpt/param/*)."""
+    import os
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rl_mpnn.npz"))
+    return {k[len("ckpt/param/"):]: torch.from_numpy(d[k]) for k in d.files if k.startswith("ckpt/param/")}, d
+
+
+def trained_net(n=5, m=5, device="cpu"):
+    """MPNN with the shipped ep2520 guard weights (no parameter depends on the team sizes: SURVEY 3.5)."""
+    mp = importlib.import_module("emergent-multiagent-strategies_b200.mpnn")
+
+    class Shape(object):
+        shape = (8,)
+    net = mp.MPNN(action_space=Shape(), num_agents=n, num_opp_agents=m, num_entities=0, input_size=6, hidden_dim=128, pos_index=2)
+    net.load_state_dict(trained_state_dict()[0])
+    return net.to(device)

@@ -60,6 +60,65 @@ def test_forward_matches_blob_arithmetic(n, m, E):
     assert torch.equal(o["action_i32"].cpu().long(), act)
 
 
+# Tolerances of the fp16-operand rollout kernel with TRAINED weights (logits O(10), values O(20)).  They are
+# what the kernel's arithmetic gives, stated as gates: 2.5e-2 on log-probs / logits, 6e-2 on values, against both the
+# reference's own outputs (golden rows) and the fp32 module on realistic observations.
+TRAINED_TOL_LOGP, TRAINED_TOL_VALUE = 2.5e-2, 6e-2
+
+
+def test_trained_checkpoint_against_reference_outputs():
+    """Kernel with the shipped ep2520 guard policy vs what the UNCHANGED reference computed for the same rows
+    (tests/golden/rl_mpnn.npz ckpt/*: MPNN.evaluate_actions of /root/reference on 6 envs x 5 agents)."""
+    sd, d = pu.trained_state_dict()
+    net = pu.trained_net(5, 5, "cuda")
+    fp = pk.FusedPolicy(net, seed=0)
+    own = torch.from_numpy(d["ckpt/own"]).cuda().view(5, 6, 6).contiguous()      # agent-major rows [n*B, 6]
+    opp = torch.from_numpy(d["ckpt/opp"]).cuda().view(5, 6, 6).contiguous()
+    act = torch.from_numpy(d["ckpt/act"]).cuda().view(5, 6)
+    o = fp.forward(own, opp, pk.MODE_EVAL, action_in=act, want_entropy=True)
+    fp.check_status()
+    ref_v = torch.from_numpy(d["ckpt/value"]).view(5, 6)
+    ref_lp = torch.from_numpy(d["ckpt/logp"]).view(5, 6)
+    ref_en = torch.from_numpy(d["ckpt/entropy"]).view(5, 6)
+    ev, elp, een = [float((a.cpu() - b).abs().max()) for a, b in ((o["value"], ref_v), (o["logp"], ref_lp), (o["entropy"], ref_en))]
+    print("trained ep2520, kernel vs reference rows: |dvalue| %.2e (scale %.1f)  |dlogp| %.2e  |dentropy| %.2e"
+          % (ev, float(ref_v.abs().max()), elp, een))
+    assert elp < TRAINED_TOL_LOGP and een < TRAINED_TOL_LOGP and ev < TRAINED_TOL_VALUE * max(1.0, float(ref_v.abs().max()) / 10)
+    # the fp32 module itself reproduces the reference rows (state_dict + arithmetic parity, tight)
+    with torch.no_grad():
+        v, lp, en, _ = net.evaluate_actions(own.view(-1, 6), None, opp.view(-1, 6), None, act.view(-1, 1))
+    assert (v.cpu().view(5, 6) - ref_v).abs().max() < 2e-4 and (lp.cpu().view(5, 6) - ref_lp).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("n,m", [(5, 5), (3, 3)])
+def test_trained_checkpoint_on_rollout_observations(n, m):
+    """Same policy on observations of real rollouts driven by it (E = 2048, 60 steps in): kernel vs fp32 module."""
+    fab = import_module("fortattack_b200")
+    net = pu.trained_net(n, m, "cuda")
+    onet = pu.trained_net(m, n, "cuda")
+    fp, fo = pk.FusedPolicy(net, seed=1), pk.FusedPolicy(onet, seed=2)
+    E = 2048
+    env = fab.FortAttackBatch(E, n, m, max_steps=100, seed=5, device="cuda:0")
+    obs = env.reset()
+    acts = torch.empty(n + m, E, dtype=torch.int32, device="cuda")
+    for t in range(60):
+        a = fp.forward(obs[:n].contiguous(), obs[n:].contiguous(), pk.MODE_SAMPLE)["action_i32"]
+        b = fo.forward(obs[n:].contiguous(), obs[:n].contiguous(), pk.MODE_SAMPLE)["action_i32"]
+        acts[:n], acts[n:] = a, b
+        obs = env.step(acts, auto_reset=True)[0]
+    own, opp = obs[:n].contiguous(), obs[n:].contiguous()
+    o = fp.forward(own, opp, pk.MODE_SAMPLE, want_logits=True)
+    fp.check_status()
+    lgr, vr = pu.module_forward(net, own, opp)
+    lp_ref = torch.log_softmax(lgr, -1).gather(-1, o["action"].unsqueeze(-1)).squeeze(-1)
+    e_lg, e_lp, e_v = [float(x) for x in ((o["logits"] - lgr).abs().max(), (o["logp"] - lp_ref).abs().max(), (o["value"] - vr).abs().max())]
+    m_lp = float((o["logp"] - lp_ref).abs().mean())
+    print("trained ep2520 %dv%d on rollout obs: logits scale %.1f  |dlogits| %.2e  |dlogp| max %.2e mean %.2e  |dvalue| %.2e (scale %.1f)"
+          % (n, m, float(lgr.abs().max()), e_lg, e_lp, m_lp, e_v, float(vr.abs().max())))
+    assert e_lp < TRAINED_TOL_LOGP and m_lp < 3e-3 and e_lg < 2 * TRAINED_TOL_LOGP
+    assert e_v < TRAINED_TOL_VALUE * max(1.0, float(vr.abs().max()) / 10)
+
+
 def test_sampling_distribution_and_determinism():
     n = m = 3
     E = 60000

@@ -59,9 +59,10 @@ def test_drop_in_import_paths():
             "from gym_fortattack.fortattack import make_fortattack_env\n"
             "from rlcore.algo import JointPPO, PPO\nfrom rlcore.storage import RolloutStorage\nfrom mpnn import MPNN\n"
             "env = make_fortattack_env(20, n_guards=2, n_attackers=2)\n"
-            "o = env.reset(); o, r, d, i = env.step([0, 1, 2, 7])\nprint('ok', o.shape)\n") % os.path.join(ROOT, PKG)
+            "o = env.reset(); o, r, d, i = env.step([0, 1, 2, 7])\nprint('ok', o.shape)\n"
+            "f = env.render(mode='rgb_array')\nprint('frame', f[0].shape, f[0].dtype)\n") % os.path.join(ROOT, PKG)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "ok (4, 6)" in out.stdout, out.stderr[-2000:]
+    assert out.returncode == 0 and "ok (4, 6)" in out.stdout and "frame (700, 700, 3) uint8" in out.stdout, out.stderr[-2000:]
 
 
 def test_batched_collect_matches_per_env_protocol():
@@ -161,6 +162,43 @@ def test_fused_policy_rollout_statistics():
     assert int(R.actions.min()) >= 0 and int(R.actions.max()) <= 7
     assert len(torch.unique(R.actions)) == 8
     assert torch.isfinite(R.returns).all()
+
+
+def test_ppo_ratio_starts_at_one_with_trained_weights():
+    """Rollout log-probs come from the fp16-operand kernel, the update re-evaluates in fp32: with the shipped trained
+    policy the PPO ratio of the first minibatch (ppo.py:163) is 1 +- ~1e-2 as collected, and 1 +- 1e-5 after
+    BatchedTrainer.recompute_old() (default in train_once)."""
+    import policy_util as pu
+    ro = import_module(PKG + ".rollout")
+    fused = import_module(PKG + ".rlcore.fused")
+    torch.manual_seed(0)
+    tr = ro.BatchedTrainer(512, 5, 5, num_steps=16, max_episode_steps=100, seed=4)
+    sd = pu.trained_state_dict()[0]
+    tr.load_models([sd] * 10)
+    assert tr.exact_old
+    tr.collect()
+    R = tr.roll
+
+    def first_minibatch_ratio():
+        trainer, pol = tr.trainers[0], tr.policies[0]
+        adv = torch.zeros(5, tr.T, tr.E, device=R.obs.device)
+        idx = torch.arange(0, tr.T * tr.E, 3, device=R.obs.device)
+        ob, mask, oo, act, vp, ret, msk, olp, ad, alive = fused.gather_minibatch(R, idx, 0, 5, 5, 5, adv)
+        with torch.no_grad():
+            pol.fused_no_grad = True
+            v, lp, ent, _ = pol.evaluate_actions(ob, None, oo, msk, act)
+            pol.fused_no_grad = False
+        return (torch.exp(lp - olp) - 1).abs(), (v - vp).abs()
+    r0, v0 = first_minibatch_ratio()
+    tr.recompute_old()
+    r1, v1 = first_minibatch_ratio()
+    print("|ratio - 1| as collected: max %.2e mean %.2e; after recompute_old: max %.2e;  |value - value_pred|: %.2e -> %.2e"
+          % (float(r0.max()), float(r0.mean()), float(r1.max()), float(v0.max()), float(v1.max())))
+    assert float(r0.max()) < 4e-2 and float(r0.mean()) < 3e-3
+    assert float(r1.max()) < 1e-5 and float(v1.max()) < 1e-4
+    tr.wrap_horizon()
+    vals = tr.update()
+    assert all(np.isfinite(v).all() for v in vals)
 
 
 def test_graph_replayed_rollouts_equal_eager():

@@ -394,3 +394,38 @@ def test_errors_are_loud():
         env.step(torch.zeros(6, 9, dtype=torch.int32, device="cuda"))
     info = env.kernel_info()
     assert info["regs"] > 0 and info["block"] in (32, 64, 128, 192) and env.launch_count() >= 1
+
+
+def test_raw_pointer_arguments_are_validated():
+    """Every tensor handed to the library as a raw pointer is checked for shape / dtype / device / contiguity first
+    (a short mask, a wrong `out`, or an [E] alive-end buffer under a T-step call would be silent out-of-bounds access)."""
+    import fortattack_b200 as fab
+    E = 64
+    env = fab.FortAttackBatch(E, 3, 3, max_steps=20, seed=1, device="cuda:0")
+    env.reset()
+    acts = torch.zeros(6, E, dtype=torch.int32, device="cuda")
+    with pytest.raises(ValueError):
+        env.reset(mask=torch.ones(E - 1, dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        env.reset(out=torch.empty(6, E, 5, device="cuda"))
+    good = (torch.empty(6, E, 6, device="cuda"), torch.empty(6, E, device="cuda"),
+            torch.empty(E, dtype=torch.uint8, device="cuda"), torch.empty(E, dtype=torch.uint8, device="cuda"))
+    env.step(acts, out=good)
+    for k, bad in ((0, torch.empty(6, E, 6, device="cuda", dtype=torch.float64)), (1, torch.empty(E, 6, device="cuda").t()),
+                   (2, torch.empty(E, dtype=torch.int32, device="cuda")), (3, torch.empty(E, dtype=torch.uint8))):
+        out = list(good)
+        out[k] = bad
+        with pytest.raises(ValueError):
+            env.step(acts, out=tuple(out))
+    with pytest.raises(ValueError):
+        env.step_many(acts.expand(4, 6, E).contiguous(), out=(None, torch.empty(3, 6, E, device="cuda"), None, None))
+    env.set_alive_end_buffer(torch.zeros(E, dtype=torch.uint8, device="cuda"))
+    env.step(acts, out=good)
+    with pytest.raises(ValueError):
+        env.step_many(acts.expand(4, 6, E).contiguous())
+    env.set_alive_end_buffer(torch.zeros(4, E, dtype=torch.uint8, device="cuda"))
+    env.step_many(acts.expand(4, 6, E).contiguous())
+    env.set_alive_end_buffer(None)
+    # a mask given as [E, 1] / bool is accepted (reshaped, converted)
+    o = env.reset(mask=torch.ones(E, 1, dtype=torch.bool, device="cuda"))
+    assert (o[:, :, 0] == 1).all()
