@@ -38,7 +38,9 @@ def _check(res, n_agents, updates, env_mod, rl_mod):
     assert res["ckpt"] == {"keys": 24, "params": 158153}
     for tag in ("all/value_loss", "all/action_loss", "all/dist_entropy"):
         assert len(res["scalars"][tag]) == updates and all(math.isfinite(v) for v in res["scalars"][tag]), res["scalars"]
-    assert 0.5 < res["scalars"]["all/dist_entropy"][0] <= math.log(8) + 1e-3          # a fresh policy is near uniform
+    # a fresh policy is near uniform; the reference divides the per-minibatch sum by ppo_epoch * 32 even when T is not a
+    # multiple of 32 and the sampler yields more minibatches (ppo.py:198-202), hence the slack above ln 8
+    assert 0.5 < res["scalars"]["all/dist_entropy"][0] <= math.log(8) * 1.25
     for i in range(n_agents):
         assert len(res["scalars"]["agent%d/training_reward" % i]) == updates
 
