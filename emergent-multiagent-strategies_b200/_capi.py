@@ -37,6 +37,12 @@ class RlAttnOperand(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("batch_stride", ctypes.c_int64), ("row_stride", ctypes.c_int64)]
 
 
+class TgTensor(ctypes.Structure):
+    """include/fortattack_train.h TgTensor."""
+    _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("numel", ctypes.c_longlong)]
+
+
 class FrConfig(ctypes.Structure):
     """include/fortattack_render.h FrConfig."""
     _fields_ = [("n_envs", ctypes.c_int32), ("n_guards", ctypes.c_int32), ("n_attackers", ctypes.c_int32),
@@ -110,6 +116,16 @@ def lib():
     L.rl_attn_mix_backward.argtypes = [P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
     L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
     L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    L.tg_packed_bytes.argtypes = [i32, i32]
+    L.tg_packed_bytes.restype = ctypes.c_size_t
+    L.tg_pack_weight.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.tg_linear.argtypes = [vp, i32, i64, i32, vp, i32, vp, i32, i32, vp, i32, vp, vp]
+    L.tg_wgrad_scratch_bytes.argtypes = [i32, i32]
+    L.tg_wgrad_scratch_bytes.restype = ctypes.c_size_t
+    L.tg_wgrad.argtypes = [vp, i32, i32, vp, i32, i32, i64, vp, i32, i32, vp, vp, vp]
+    L.tg_adam_step.argtypes = [ctypes.POINTER(TgTensor), i32, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp]
+    L.tg_kernel_info.argtypes = [i32, i32p, i32p, i32p]
+    L.tg_debug_wgrad_desc.argtypes = [u32, u32]
     L.mw_step.argtypes = [vp, vp, vp, vp, vp]
     L.fr_render.argtypes = [ctypes.POINTER(FrConfig), vp, vp, vp, vp, i32, vp, vp]
     for name in SYMBOLS:

@@ -1,0 +1,702 @@
+// tg_gemm.cu -- the dense products of the PPO update (MPNN.evaluate_actions forward / backward, mpnn.py:117-205,
+// rlcore/algo/ppo.py:146-192) and its optimizer step as hand-written sm_100a kernels.  C ABI: include/fortattack_train.h.
+//
+//   tg_linear   out = act(x B^T + bias)     rows ~ 2e5, K, N <= 256: HBM-bound (512 B in + 512 B out per row and 128
+//               columns); fp32 operands are split into fp16 hi/lo terms on the fly, three tcgen05.mma per product
+//   tg_wgrad    dW = x^T y  (reduction over the rows): bf16 three-term split, six MMAs per product, operands consumed
+//               straight from their row-major tiles through MN-major shared-memory descriptors
+//   tg_adam_step  gradient-norm clip + Adam for all parameter tensors in two launches
+//
+// tg_linear_kernel, persistent, one CTA per SM, 416 threads:
+//   warps 0-3   epilogue: thread = accumulator row (tensor-memory lane); scales by the row's and the weight's inverse
+//               power-of-two scale, transposes 32x32 blocks through shared memory so that global stores are full lines,
+//               adds bias / ReLU / the previous output (accumulate)
+//   warps 4-11  loaders: coalesced float4 reads of a 128-row x 128-column group of x, per-row amax -> power-of-two scale,
+//               hi = fp16(x s), lo = fp16(x s - hi), 16-byte stores into the canonical no-swizzle K-major layout
+//               (8-row core matrices contiguous: SBO = 128; k-chunk stride LBO = 2048 + 16: the pad makes the stores of
+//               a warp whose lanes run along k bank-conflict free)
+//   warp 12     MMA issuer (converged warp, one elected lane): per 64-column stage 4 k-steps x {hi.hi, hi.lo, lo.hi}
+//   ring of NST stages (full/empty mbarriers), two accumulator buffers in tensor memory (acc_full/acc_empty), weights
+//   (fp16 hi/lo planes, packed by tg_pack_weight) resident in shared memory for the whole launch.
+// K = 256 is handled as two 128-column groups with their own row scales and their own accumulators (summed in the
+// epilogue), so the per-row scale never has to wait for more than 128 columns.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fortattack_train.h"
+#include "mp_umma.cuh"
+
+int fa_internal_fail(int code, const char *fmt, ...);
+
+namespace tg {
+using namespace mp;
+
+constexpr int ROWS = 128, KC = 64;
+constexpr uint32_t A_SBO = 128, A_LBO = ROWS * 16 + 16;           // bytes
+constexpr uint32_t HALF = (KC / 8) * A_LBO, STAGE = 2 * HALF;     // 16512, 33024
+constexpr int EPI_WARPS = 4, LOAD_WARPS = 8, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS;
+constexpr int THREADS = (MMA_WARP + 1) * 32, LOAD_THREADS = LOAD_WARPS * 32;
+constexpr int MAX_NST = 6, SCALE_SLOTS = 2;
+constexpr int TB_BYTES = EPI_WARPS * 32 * 33 * 4, RS_BYTES = SCALE_SLOTS * 2 * ROWS * 4, BIAS_BYTES = 256 * 4;
+constexpr int FIXED_BYTES = TB_BYTES + RS_BYTES + BIAS_BYTES;
+constexpr int SMEM_LIMIT = 232448 - 1024;                         // 227 KB minus the static barriers
+
+struct LinParams {
+    const float *x;
+    const uint8_t *packed;
+    const float *bias;
+    float *out;
+    uint32_t *status;
+    long long rows;
+    int ldx, ldo, K, Kp, N, Np, relu, acc, n_tiles, nst, groups, gw, vec_ok, wbytes;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2 *>(&u)); }
+
+// 8 consecutive fp32 (already scaled) -> 16 bytes of fp16 hi and 16 bytes of fp16 lo
+__device__ __forceinline__ void split8_f16(const float4 &a, const float4 &b, uint4 &hi, uint4 &lo) {
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = pack_h2(v[2 * j], v[2 * j + 1]);
+        const float2 f = unpack_h2(h[j]);
+        l[j] = pack_h2(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ float amax4(const float4 &a) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))); }
+__device__ __forceinline__ void scale4(float4 &a, float s) { a.x *= s; a.y *= s; a.z *= s; a.w *= s; }
+
+// power-of-two scale s with amax * s in [2^14, 2^15) (s = 1 for an all-zero row); returns s, *inv = 1 / s
+__device__ __forceinline__ float pow2_scale(float amax, float *inv) {
+    int e = (int)(__float_as_uint(amax) >> 23) - 127;
+    e = amax > 0.0f ? max(-100, min(100, e)) : 14;
+    *inv = __uint_as_float((uint32_t)(127 + e - 14) << 23);
+    return __uint_as_float((uint32_t)(127 + 14 - e) << 23);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_acc_full[2], bar_acc_empty[2], bar_w;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *ring = smem + p.wbytes;
+    float *tb = reinterpret_cast<float *>(ring + (size_t)p.nst * STAGE);
+    float *rowscale = tb + EPI_WARPS * 32 * 33;                  // [SCALE_SLOTS][2][ROWS]
+    float *bias_s = rowscale + SCALE_SLOTS * 2 * ROWS;            // [256]
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nst; ++s) { mbar_init(&bar_full[s], LOAD_THREADS); mbar_init(&bar_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_WARPS * 32); }
+        mbar_init(&bar_w, 1);
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
+    for (int i = tid; i < 256; i += THREADS) bias_s[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int spt = p.Kp / KC;                                    // stages per tile
+    const int spg = p.gw / KC;                                    // stages per group
+    const int acc_cols = p.groups * p.Np;                         // tensor-memory columns of one accumulator buffer
+
+    if (warp == MMA_WARP) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            mbar_expect_tx(&bar_w, (uint32_t)p.wbytes);
+            for (int off = 0; off < p.wbytes; off += 16384) {
+                const int n = p.wbytes - off < 16384 ? p.wbytes - off : 16384;
+                bulk_g2s(smem + off, p.packed + off, (uint32_t)n, &bar_w);
+            }
+        }
+        __syncwarp();
+        const uint32_t idesc = idesc_f16(128, p.Np);
+        const uint32_t sbase = smem_u32(smem), rbase = smem_u32(ring);
+        const uint32_t w_sbo = (uint32_t)p.Kp * 16u, w_half = (uint32_t)p.Np * (uint32_t)p.Kp * 2u;
+        mbar_wait(&bar_w, 0, p.status, 1);
+        uint32_t sc = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            mbar_wait(&bar_acc_empty[b], (uint32_t)(((it >> 1) & 1) ^ 1), p.status, 2);
+            tc_fence_after();
+            for (int j = 0; j < spt; ++j, ++sc) {
+                const uint32_t s = sc % (uint32_t)p.nst, ph = (sc / (uint32_t)p.nst) & 1u;
+                mbar_wait(&bar_full[s], ph, p.status, 3);
+                tc_fence_after();
+                const int g = j / spg;
+                const uint32_t dcol = tmem + (uint32_t)(b * acc_cols + g * p.Np);
+                const uint32_t a_hi = rbase + s * STAGE, a_lo = a_hi + HALF;
+                const uint32_t w_hi = sbase + (uint32_t)j * (KC / 8) * 128u, w_lo = w_hi + w_half;
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t kk = 0; kk < KC / 16; ++kk) {
+                        const uint64_t ah = smem_desc(a_hi + kk * 2u * A_LBO, A_LBO, A_SBO);
+                        const uint64_t al = smem_desc(a_lo + kk * 2u * A_LBO, A_LBO, A_SBO);
+                        const uint64_t bh = smem_desc(w_hi + kk * 256u, 128u, w_sbo);
+                        const uint64_t bl = smem_desc(w_lo + kk * 256u, 128u, w_sbo);
+                        umma_f16(dcol, ah, bh, idesc, (j % spg) != 0 || kk != 0);
+                        umma_f16(dcol, ah, bl, idesc, true);
+                        umma_f16(dcol, al, bh, idesc, true);
+                    }
+                    umma_commit(&bar_empty[s]);
+                    if (j == spt - 1) umma_commit(&bar_acc_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= LOAD_WARP0) {
+        // ================= loaders =================
+        const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
+        const int halves = p.gw / KC;                             // 64-column halves of a group: 1 or 2
+        uint32_t sc = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            for (int g = 0; g < p.groups; ++g) {
+                float4 v[4][2][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const long long row = (long long)tile * ROWS + lw * 16 + q * 4 + sub;
+                    const float *src = p.x + row * p.ldx;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = g * p.gw + h * KC + kc * 8;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+                        if (h < halves && row < p.rows) {
+                            if (p.vec_ok && col + 8 <= p.K) {
+                                a = __ldg(reinterpret_cast<const float4 *>(src + col));
+                                c = __ldg(reinterpret_cast<const float4 *>(src + col + 4));
+                            } else if (col < p.K) {
+                                float t[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) t[e] = col + e < p.K ? __ldg(src + col + e) : 0.0f;
+                                a = make_float4(t[0], t[1], t[2], t[3]);
+                                c = make_float4(t[4], t[5], t[6], t[7]);
+                            }
+                        }
+                        v[q][h][0] = a; v[q][h][1] = c;
+                    }
+                }
+                // the row scales of tile `it` live in slot it & 1, which the epilogue of tile it - 2 may still be reading: wait
+                // for it exactly as the MMA issuer does (the loads above are already in flight)
+                if (g == 0) mbar_wait(&bar_acc_empty[it & 1], (uint32_t)(((it >> 1) & 1) ^ 1), p.status, 6);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float m = fmaxf(fmaxf(amax4(v[q][0][0]), amax4(v[q][0][1])), fmaxf(amax4(v[q][1][0]), amax4(v[q][1][1])));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    float inv;
+                    const float s = pow2_scale(m, &inv);
+                    if (kc == 0) rowscale[((it & (SCALE_SLOTS - 1)) * 2 + g) * ROWS + lw * 16 + q * 4 + sub] = inv;
+                    scale4(v[q][0][0], s); scale4(v[q][0][1], s); scale4(v[q][1][0], s); scale4(v[q][1][1], s);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h < halves) {
+                        const uint32_t s = sc % (uint32_t)p.nst, ph = (sc / (uint32_t)p.nst) & 1u;
+                        mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 4);
+                        uint8_t *st = ring + (size_t)s * STAGE + (uint32_t)kc * A_LBO;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 hi, lo;
+                            split8_f16(v[q][h][0], v[q][h][1], hi, lo);
+                            const uint32_t off = (uint32_t)(lw * 16 + q * 4 + sub) * 16u;
+                            *reinterpret_cast<uint4 *>(st + off) = hi;
+                            *reinterpret_cast<uint4 *>(st + HALF + off) = lo;
+                        }
+                        fence_async_smem();
+                        mbar_arrive(&bar_full[s]);
+                        ++sc;
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: thread = accumulator row =================
+        const int r = warp * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        float *tbw = tb + warp * 32 * 33;
+        const float w_inv = *reinterpret_cast<const float *>(p.packed + p.wbytes);
+        const int chunks = (p.N + 31) / 32;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            mbar_wait(&bar_acc_full[b], (uint32_t)((it >> 1) & 1), p.status, 5);
+            tc_fence_after();
+            const float *rs = rowscale + (it & (SCALE_SLOTS - 1)) * 2 * ROWS;
+            const float inv0 = rs[r] * w_inv, inv1 = p.groups > 1 ? rs[ROWS + r] * w_inv : 0.0f;
+            const long long row0 = (long long)tile * ROWS + warp * 32;
+            for (int c = 0; c < chunks; ++c) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(trow + (uint32_t)(b * acc_cols + c * 32), v0);
+                if (p.groups > 1) tmem_ld32(trow + (uint32_t)(b * acc_cols + p.Np + c * 32), v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float f = __uint_as_float(v0[j]) * inv0;
+                    if (p.groups > 1) f = fmaf(__uint_as_float(v1[j]), inv1, f);
+                    tbw[lane * 33 + j] = f;
+                }
+                __syncwarp();
+                const int col = c * 32 + lane;
+                if (col < p.N) {
+                    const float bias = bias_s[col];
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const long long row = row0 + rr;
+                        if (row < p.rows) {
+                            float f = tbw[rr * 33 + lane] + bias;
+                            if (p.relu) f = fmaxf(f, 0.0f);
+                            float *dst = p.out + row * p.ldo + col;
+                            if (p.acc) f += *dst;
+                            *dst = f;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_acc_empty[b]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc<512>(tmem);
+}
+
+// ---- weight packing ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tg_pack_kernel(const float *w, int N, int K, int Np, int Kp, int ld, int transposed,
+                                                      uint8_t *out) {
+    __shared__ float red[8];
+    __shared__ float s_scale;
+    const int tid = threadIdx.x;
+    float m = 0.0f;
+    for (int i = tid; i < N * K; i += 256) {
+        const int n = transposed ? i % N : i / K, k = transposed ? i / N : i % K;      // coalesced in either orientation
+        m = fmaxf(m, fabsf(w[transposed ? (size_t)k * ld + n : (size_t)n * ld + k]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float t = red[0];
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+        float inv;
+        s_scale = pow2_scale(t, &inv);
+        *reinterpret_cast<float *>(out + (size_t)4 * Np * Kp) = inv;
+    }
+    __syncthreads();
+    const float s = s_scale;
+    __half *hi = reinterpret_cast<__half *>(out), *lo = hi + (size_t)Np * Kp;
+    for (int i = tid; i < Np * Kp; i += 256) {
+        // i runs over the canonical order: ((n/8) * (Kp/8) + k/8) * 64 + (n%8) * 8 + k%8
+        const int k8 = i & 7, n8 = (i >> 3) & 7, blk = i >> 6, kb = blk % (Kp / 8), nb = blk / (Kp / 8);
+        const int n = nb * 8 + n8, k = kb * 8 + k8;
+        float x = 0.0f;
+        if (n < N && k < K) x = w[transposed ? (size_t)k * ld + n : (size_t)n * ld + k] * s;
+        const __half h = __float2half_rn(x);
+        hi[i] = h;
+        lo[i] = __float2half_rn(x - __half2float(h));
+    }
+}
+
+// ---- weight gradient: dW = x^T y ----------------------------------------------------------------------------------
+// Row step = 64 rows.  An operand block = 64 rows x 128 features of x or y as three bf16 planes (h, m, l), laid out like
+// the tiles above (feature chunk kc at kc * FB_LBO, row r at + r * 16).  Read as an MN-major operand: mn = feature
+// (M = N = 128), k = row: 8 features of one row are the 16 contiguous bytes, 8 rows the 128-byte core matrix,
+// SBO = FB_LBO (next 8 features), LBO = 128 (next 8 rows); one MMA consumes 16 rows (+256 bytes).
+constexpr int WROWS = 64;
+constexpr uint32_t FB_LBO = WROWS * 16 + 16, PLANE = 16 * FB_LBO, BLOCK = 3 * PLANE;      // 1040, 16640, 49920
+constexpr int NB = 4;                                                                       // ring of operand blocks
+constexpr int W_SMEM = NB * BLOCK;
+__device__ uint32_t g_dbg_lbo = 0, g_dbg_sbo = 0;
+
+struct WgParams {
+    const float *x, *y;
+    float *partial;
+    uint32_t *status;
+    long long rows;
+    int ldx, ldy, a, b, ab, bb, n_steps, vx, vy;
+    uint32_t lbo, sbo;
+};
+
+__host__ __device__ constexpr uint32_t idesc_bf16_mn(int M, int N) {
+    return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ | (1u << 15) /* A MN-major */ |
+           (1u << 16) /* B MN-major */ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
+__device__ __forceinline__ void split8_bf16(const float4 &a, const float4 &b, uint4 &h, uint4 &m, uint4 &l) {
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hh[4], mm[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hh[j] = pack_bf2(v[2 * j], v[2 * j + 1]);
+        const float2 f = unpack_bf2(hh[j]);
+        const float r0 = v[2 * j] - f.x, r1 = v[2 * j + 1] - f.y;
+        mm[j] = pack_bf2(r0, r1);
+        const float2 g = unpack_bf2(mm[j]);
+        ll[j] = pack_bf2(r0 - g.x, r1 - g.y);
+    }
+    h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    m = make_uint4(mm[0], mm[1], mm[2], mm[3]);
+    l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[NB], bar_empty[NB], bar_done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < NB; ++s) { mbar_init(&bar_full[s], LOAD_THREADS); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int nblk = p.ab + p.bb;                                 // operand blocks per row step
+
+    if (warp == MMA_WARP) {
+        const uint32_t idesc = idesc_bf16_mn(128, 128);
+        const uint32_t sbase = smem_u32(smem);
+        uint32_t bc = 0;
+        bool first = true;
+        for (int step = blockIdx.x; step < p.n_steps; step += gridDim.x) {
+            uint32_t slot[4];
+            for (int k = 0; k < nblk; ++k, ++bc) {
+                slot[k] = bc % NB;
+                mbar_wait(&bar_full[slot[k]], (bc / NB) & 1u, p.status, 11);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+                for (int i = 0; i < p.ab; ++i)
+                    for (int j = 0; j < p.bb; ++j) {
+                        const uint32_t dcol = tmem + (uint32_t)(i * p.bb + j) * 128u;
+                        const uint32_t xa = sbase + slot[i] * BLOCK, ya = sbase + slot[p.ab + j] * BLOCK;
+#pragma unroll
+                        for (uint32_t kk = 0; kk < WROWS / 16; ++kk) {
+                            uint64_t xd[3], yd[3];
+#pragma unroll
+                            for (uint32_t c = 0; c < 3; ++c) {
+                                xd[c] = smem_desc(xa + c * PLANE + kk * 256u, p.lbo, p.sbo);
+                                yd[c] = smem_desc(ya + c * PLANE + kk * 256u, p.lbo, p.sbo);
+                            }
+                            umma_f16(dcol, xd[0], yd[0], idesc, !first || kk != 0);
+                            umma_f16(dcol, xd[0], yd[1], idesc, true);
+                            umma_f16(dcol, xd[1], yd[0], idesc, true);
+                            umma_f16(dcol, xd[0], yd[2], idesc, true);
+                            umma_f16(dcol, xd[2], yd[0], idesc, true);
+                            umma_f16(dcol, xd[1], yd[1], idesc, true);
+                        }
+                    }
+                for (int k = 0; k < nblk; ++k) umma_commit(&bar_empty[slot[k]]);
+            }
+            __syncwarp();
+            first = false;
+        }
+        if (elect_one()) umma_commit(&bar_done);
+        __syncwarp();
+    } else if (warp >= LOAD_WARP0) {
+        const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
+        uint32_t bc = 0;
+        for (int step = blockIdx.x; step < p.n_steps; step += gridDim.x) {
+            for (int k = 0; k < nblk; ++k, ++bc) {
+                const bool isx = k < p.ab;
+                const float *src = isx ? p.x : p.y;
+                const int ld = isx ? p.ldx : p.ldy, width = isx ? p.a : p.b, f0 = (isx ? k : k - p.ab) * 128;
+                const int vec = isx ? p.vx : p.vy;
+                float4 v[2][2][2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const long long row = (long long)step * WROWS + lw * 8 + q * 4 + sub;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = f0 + h * 64 + kc * 8;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+                        if (row < p.rows && col < width) {
+                            const float *s = src + row * ld + col;
+                            if (vec && col + 8 <= width) {
+                                a = __ldg(reinterpret_cast<const float4 *>(s));
+                                c = __ldg(reinterpret_cast<const float4 *>(s + 4));
+                            } else {
+                                float t[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) t[e] = col + e < width ? __ldg(s + e) : 0.0f;
+                                a = make_float4(t[0], t[1], t[2], t[3]);
+                                c = make_float4(t[4], t[5], t[6], t[7]);
+                            }
+                        }
+                        v[q][h][0] = a; v[q][h][1] = c;
+                    }
+                }
+                const uint32_t s = bc % NB;
+                mbar_wait(&bar_empty[s], ((bc / NB) & 1u) ^ 1u, p.status, 12);
+                uint8_t *blk = smem + (size_t)s * BLOCK;
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 hh, mm, ll;
+                        split8_bf16(v[q][h][0], v[q][h][1], hh, mm, ll);
+                        uint8_t *d = blk + (uint32_t)(h * 8 + kc) * FB_LBO + (uint32_t)(lw * 8 + q * 4 + sub) * 16u;
+                        *reinterpret_cast<uint4 *>(d) = hh;
+                        *reinterpret_cast<uint4 *>(d + PLANE) = mm;
+                        *reinterpret_cast<uint4 *>(d + 2 * PLANE) = ll;
+                    }
+                fence_async_smem();
+                mbar_arrive(&bar_full[s]);
+            }
+        }
+    } else {
+        // epilogue: one partial [a][b] block per CTA; thread = x feature (accumulator row)
+        mbar_wait(&bar_done, 0, p.status, 13);
+        tc_fence_after();
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        float *dst = p.partial + (size_t)blockIdx.x * p.a * p.b;
+        for (int i = 0; i < p.ab; ++i) {
+            const int fa = i * 128 + warp * 32 + lane;
+            for (int j = 0; j < p.bb; ++j)
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)((i * p.bb + j) * 128 + c * 32), v);
+                    tmem_ld_wait();
+                    if (fa < p.a) {
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const int fb = j * 128 + c * 32 + t;
+                            if (fb < p.b) dst[(size_t)fa * p.b + fb] = __uint_as_float(v[t]);
+                        }
+                    }
+                }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc<512>(tmem);
+}
+
+__global__ void __launch_bounds__(256) tg_reduce_kernel(const float *partial, int n_part, int a, int b, float *out, int ldo, int accumulate) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a * b) return;
+    float s = 0.0f;
+    for (int c = 0; c < n_part; ++c) s += partial[(size_t)c * a * b + i];
+    float *d = out + (size_t)(i / b) * ldo + i % b;
+    *d = accumulate ? *d + s : s;
+}
+
+// ---- optimizer step ---------------------------------------------------------------------------------------------
+struct AdamParams {
+    TgTensor t[TG_MAX_TENSORS];
+    int n;
+    float lr, b1, b2, eps, max_norm;
+    const float *grad_scale;
+    long long *step;
+    float *scratch, *total_out;
+};
+constexpr int ADAM_BLOCKS = 128;
+static_assert(ADAM_BLOCKS <= TG_ADAM_SCRATCH_FLOATS, "one partial per block");
+
+__global__ void __launch_bounds__(256) tg_adam_norm_kernel(const AdamParams p) {
+    __shared__ float red[8];
+    const float gs = p.grad_scale != nullptr ? *p.grad_scale : 1.0f;
+    float acc = 0.0f;
+    for (int k = 0; k < p.n; ++k) {
+        float *g = p.t[k].g;
+        if (g == nullptr) continue;
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.t[k].numel; i += (long long)ADAM_BLOCKS * 256) {
+            const float x = g[i] * gs;
+            if (p.grad_scale != nullptr) g[i] = x;
+            acc = fmaf(x, x, acc);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        p.scratch[blockIdx.x] = s;
+        if (blockIdx.x == 0) *p.step += 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) tg_adam_update_kernel(const AdamParams p) {
+    __shared__ float s_coef, s_c1, s_c2;
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < ADAM_BLOCKS; ++i) s += p.scratch[i];
+        const float total = sqrtf(s);
+        if (blockIdx.x == 0 && p.total_out != nullptr) *p.total_out = total;
+        s_coef = p.max_norm > 0.0f ? fminf(1.0f, p.max_norm / (total + 1e-6f)) : 1.0f;
+        const double st = (double)*p.step;
+        s_c1 = (float)(1.0 - pow((double)p.b1, st));
+        s_c2 = (float)sqrt(1.0 - pow((double)p.b2, st));
+    }
+    __syncthreads();
+    const float coef = s_coef, step_size = p.lr / s_c1, c2 = s_c2;
+    for (int k = 0; k < p.n; ++k) {
+        const TgTensor t = p.t[k];
+        if (t.g == nullptr) continue;
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < t.numel; i += (long long)gridDim.x * 256) {
+            const float g = t.g[i] * coef;
+            const float m = p.b1 * t.m[i] + (1.0f - p.b1) * g;
+            const float v = p.b2 * t.v[i] + (1.0f - p.b2) * g * g;
+            t.m[i] = m; t.v[i] = v;
+            t.p[i] -= step_size * (m / (sqrtf(v) / c2 + p.eps));
+        }
+    }
+}
+
+}  // namespace tg
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+namespace {
+constexpr int MAX_DEVICES = 64;
+bool g_ready[MAX_DEVICES] = {};
+int g_sms[MAX_DEVICES] = {};
+uint32_t g_wg_lbo = 128, g_wg_sbo = tg::FB_LBO;
+
+int prepare(int *sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return fa_internal_fail(-3, "tg: no usable CUDA device");
+    if (!g_ready[dev]) {
+        e = cudaFuncSetAttribute(tg::tg_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::W_SMEM);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return fa_internal_fail(-2, "tg: device setup: %s", cudaGetErrorString(e));
+        g_ready[dev] = true;
+    }
+    if (sms) *sms = g_sms[dev];
+    return 0;
+}
+int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+}  // namespace
+
+extern "C" size_t tg_packed_bytes(int N, int K) { return (size_t)4 * pad_to(N, 16) * pad_to(K, 64) + 16; }
+
+extern "C" int tg_pack_weight(const float *d_w, int N, int K, int ld, int transposed, void *d_packed, void *stream) {
+    if (!d_w || !d_packed) return fa_internal_fail(-1, "tg_pack_weight: NULL pointer");
+    if (N < 1 || N > 256 || K < 1 || K > 256 || pad_to(N, 16) * pad_to(K, 64) > 32768 || ld < (transposed ? N : K))
+        return fa_internal_fail(-1, "tg_pack_weight: need 1 <= N, K <= 256, padded N * K <= 32768, ld >= row length (N=%d K=%d ld=%d)", N, K, ld);
+    if ((uintptr_t)d_packed & 15) return fa_internal_fail(-4, "tg_pack_weight: d_packed must be 16-byte aligned");
+    tg::tg_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_w, N, K, pad_to(N, 16), pad_to(K, 64), ld, transposed, (uint8_t *)d_packed);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "tg_pack_weight: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int tg_linear(const float *d_x, int ldx, long long rows, int K, const void *d_packed, int N, const float *d_bias,
+                         int relu, int accumulate, float *d_out, int ldo, uint32_t *d_status, void *stream) {
+    if (!d_x || !d_packed || !d_out || !d_status) return fa_internal_fail(-1, "tg_linear: NULL pointer");
+    if (rows < 1 || K < 1 || K > 256 || N < 1 || N > 256 || ldx < K || ldo < N)
+        return fa_internal_fail(-1, "tg_linear: need rows >= 1, 1 <= K, N <= 256, ldx >= K, ldo >= N");
+    const int Kp = pad_to(K, 64), Np = pad_to(N, 16);
+    if (Kp * Np > 32768) return fa_internal_fail(-1, "tg_linear: padded N * K must be <= 32768 (got %d x %d)", Np, Kp);
+    if ((uintptr_t)d_packed & 15) return fa_internal_fail(-4, "tg_linear: d_packed must be 16-byte aligned");
+    int sms = 0;
+    if (int rc = prepare(&sms)) return rc;
+    tg::LinParams p = {};
+    p.x = d_x; p.packed = (const uint8_t *)d_packed; p.bias = d_bias; p.out = d_out; p.status = d_status; p.rows = rows;
+    p.ldx = ldx; p.ldo = ldo; p.K = K; p.Kp = Kp; p.N = N; p.Np = Np; p.relu = relu; p.acc = accumulate;
+    p.n_tiles = (int)((rows + tg::ROWS - 1) / tg::ROWS);
+    p.gw = Kp >= 128 ? 128 : 64;
+    p.groups = Kp / p.gw;
+    p.wbytes = 4 * Np * Kp;
+    p.vec_ok = (ldx % 4 == 0) && (((uintptr_t)d_x & 15) == 0);
+    int nst = (tg::SMEM_LIMIT - tg::FIXED_BYTES - p.wbytes) / (int)tg::STAGE;
+    if (nst > tg::MAX_NST) nst = tg::MAX_NST;
+    if (nst < 2) return fa_internal_fail(-1, "tg_linear: weights too large for the shared-memory ring");
+    p.nst = nst;
+    const size_t smem = (size_t)p.wbytes + (size_t)nst * tg::STAGE + tg::FIXED_BYTES;
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    tg::tg_linear_kernel<<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "tg_linear: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" size_t tg_wgrad_scratch_bytes(int a, int b) { return (size_t)192 * a * b * sizeof(float); }
+
+extern "C" int tg_wgrad(const float *d_x, int ldx, int a, const float *d_y, int ldy, int b, long long rows, float *d_dw, int lddw,
+                        int accumulate, void *d_scratch, uint32_t *d_status, void *stream) {
+    if (!d_x || !d_y || !d_dw || !d_scratch || !d_status) return fa_internal_fail(-1, "tg_wgrad: NULL pointer");
+    if (rows < 1 || a < 1 || a > 256 || b < 1 || b > 256 || ldx < a || ldy < b || lddw < b)
+        return fa_internal_fail(-1, "tg_wgrad: need rows >= 1, 1 <= a, b <= 256, ld >= width");
+    int sms = 0;
+    if (int rc = prepare(&sms)) return rc;
+    if (sms > 192) sms = 192;
+    tg::WgParams p = {};
+    p.x = d_x; p.y = d_y; p.partial = (float *)d_scratch; p.status = d_status; p.rows = rows; p.ldx = ldx; p.ldy = ldy;
+    p.a = a; p.b = b; p.ab = (a + 127) / 128; p.bb = (b + 127) / 128;
+    p.n_steps = (int)((rows + tg::WROWS - 1) / tg::WROWS);
+    p.vx = (ldx % 4 == 0) && (((uintptr_t)d_x & 15) == 0);
+    p.vy = (ldy % 4 == 0) && (((uintptr_t)d_y & 15) == 0);
+    p.lbo = g_wg_lbo; p.sbo = g_wg_sbo;
+    const int grid = p.n_steps < sms ? p.n_steps : sms;
+    tg::tg_wgrad_kernel<<<grid, tg::THREADS, tg::W_SMEM, (cudaStream_t)stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "tg_wgrad: launch: %s", cudaGetErrorString(e));
+    tg::tg_reduce_kernel<<<(a * b + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float *)d_scratch, grid, a, b, d_dw, lddw, accumulate);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "tg_wgrad: reduce launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int tg_adam_step(const TgTensor *tensors, int n_tensors, float lr, float beta1, float beta2, float eps, float max_norm,
+                            const float *d_grad_scale, long long *d_step, float *d_scratch, float *d_total_norm, void *stream) {
+    if (!tensors || !d_step || !d_scratch) return fa_internal_fail(-1, "tg_adam_step: NULL pointer");
+    if (n_tensors < 1 || n_tensors > TG_MAX_TENSORS) return fa_internal_fail(-1, "tg_adam_step: 1 <= n_tensors <= %d", TG_MAX_TENSORS);
+    tg::AdamParams p = {};
+    for (int k = 0; k < n_tensors; ++k) {
+        if (!tensors[k].p || !tensors[k].m || !tensors[k].v || tensors[k].numel < 0)
+            return fa_internal_fail(-1, "tg_adam_step: tensor %d has a NULL parameter / moment pointer", k);
+        p.t[k] = tensors[k];
+    }
+    p.n = n_tensors; p.lr = lr; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.max_norm = max_norm; p.grad_scale = d_grad_scale;
+    p.step = d_step; p.scratch = d_scratch; p.total_out = d_total_norm;
+    tg::tg_adam_norm_kernel<<<tg::ADAM_BLOCKS, 256, 0, (cudaStream_t)stream>>>(p);
+    tg::tg_adam_update_kernel<<<tg::ADAM_BLOCKS, 256, 0, (cudaStream_t)stream>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "tg_adam_step: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t *smem) {
+    if (int rc = prepare(nullptr)) return rc;
+    cudaFuncAttributes at;
+    const cudaError_t e = which == 0 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel);
+    if (e != cudaSuccess) return fa_internal_fail(-2, "tg_kernel_info: %s", cudaGetErrorString(e));
+    if (regs) *regs = at.numRegs;
+    if (block) *block = tg::THREADS;
+    if (smem) *smem = (which == 0 ? tg::SMEM_LIMIT : tg::W_SMEM) + (int)at.sharedSizeBytes;
+    return 0;
+}
+
+extern "C" int tg_debug_wgrad_desc(uint32_t lbo, uint32_t sbo) {
+    g_wg_lbo = lbo ? lbo : 128;
+    g_wg_sbo = sbo ? sbo : tg::FB_LBO;
+    return 0;
+}

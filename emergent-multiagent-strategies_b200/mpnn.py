@@ -171,8 +171,10 @@ class MPNN(nn.Module):
         attn = None
         if self.fold_projections and n > 1 and self.h_dim <= 128:
             # Q/K/V/out projections folded into [d, d] products of the weights (rlcore/fused.py _MessageRound)
-            Mqk = ms.W_query[0] @ ms.W_key[0].t()
-            Wc = torch.cat((U1t, ms.W_val[0] @ ms.W_out[0] @ U2t), dim=0)
+            # the [d, d] folds go through the same dense functions (own kernels, hand-written backward): W_query ... W_out
+            # and update.0.weight receive their exact gradients through them
+            Mqk = fused.matmul_nt(ms.W_query[0], ms.W_key[0])                                  # W_query W_key^T
+            Wc = torch.cat((U1t, fused.matmul_nt(fused.matmul(ms.W_val[0], ms.W_out[0]), W[:, self.h_dim:])), dim=0)
             for _ in range(self.K):
                 h, attn = fused.message_round(h, Mqk, Wc, bias, n, ms.norm_factor)
             self._opp_attn = oattn
@@ -184,7 +186,7 @@ class MPNN(nn.Module):
                 msg, attn = fused.self_attention(h @ wqkv, n, ms.norm_factor)
                 h = torch.relu(torch.addmm(torch.addmm(bias, h, U1t), msg @ ms.W_out[0], U2t))
             else:                                                                  # a lone agent receives a zero message
-                h = torch.relu(torch.addmm(bias, h, U1t))
+                h = fused.linear(h, W[:, :self.h_dim], bias, True)
         self._opp_attn = oattn
         # a lone agent: the reference reports a zero attention matrix (mpnn.py:262-270)
         self._attn = attn.unsqueeze(0) if attn is not None else h.new_zeros(1, h.shape[0] // n, 1, 1)

@@ -55,7 +55,7 @@ def magent_feed_forward_generator(rollouts_list, opp_rollouts_list, advantages_l
 class JointPPO(object):
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
                  lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=False, process_group=None,
-                 allow_tf32=False, graph_update=False):
+                 allow_tf32=False, graph_update=False, tg_optimizer=True):
         self.actor_critic = actor_critic
         # graph_update (new, fused path): after three eager minibatch steps the whole optimizer step
         # (gather -> forward -> loss -> backward -> clip -> Adam) is captured in a CUDA graph and replayed; with TF32
@@ -73,9 +73,28 @@ class JointPPO(object):
         # eps is ignored by the reference too (:114); capturable keeps Adam's step counters on the device (graph capture)
         # on CUDA the whole Adam step is ONE fused kernel (24 parameter tensors; the foreach form cost 240 us of GPU time per
         # optimizer step, 7 % of it)
-        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, capturable=bool(graph_update) and on_cuda,
-                                    fused=True if on_cuda else None)
+        # on CUDA: gradient-norm clip + Adam are ONE pair of launches of this repo's own kernel (rlcore/fused.TgAdam ->
+        # tg_adam_step), step counter on the device; on the CPU (tests, the reference's --no-cuda runs) torch's Adam
+        self._tg_adam = False
+        if on_cuda and tg_optimizer:
+            try:
+                from .. import fused as _fused
+            except ImportError:
+                from rlcore import fused as _fused
+            self.optimizer = _fused.TgAdam(actor_critic.parameters(), lr=lr)
+            self._tg_adam = True
+        else:
+            self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, capturable=bool(graph_update) and on_cuda,
+                                        fused=True if on_cuda else None)
         self.process_group = process_group
+
+    def _clip_and_step(self):
+        if self._tg_adam:
+            self.optimizer.step(self.max_grad_norm)
+        else:
+            if self.max_grad_norm:
+                nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
+            self.optimizer.step()
 
     # -- distributed helpers (identity on one rank) ------------------------------------------------
     def _world(self):
@@ -183,8 +202,7 @@ class JointPPO(object):
             for g_ in grads:
                 g_.copy_(flat[off:off + g_.numel()].view_as(g_))
                 off += g_.numel()
-        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
-        self.optimizer.step()
+        self._clip_and_step()
         totals += stats[:3]
 
     def _graphed_step(self, fused, R, team, idx, advantages, totals, mini_batch_size, world):
@@ -285,8 +303,7 @@ class JointPPO(object):
                     for g_ in grads:
                         g_.copy_(flat[off:off + g_.numel()].view_as(g_))
                         off += g_.numel()
-                nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
-                self.optimizer.step()
+                self._clip_and_step()
                 totals += torch.stack([value_loss.detach(), action_loss.detach(), entropy.detach()])
                 n_updates += 1
         if world > 1:

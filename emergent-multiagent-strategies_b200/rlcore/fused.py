@@ -150,6 +150,92 @@ def cross_attention(a, bv, n, m, norm):
     return _CrossAttention.apply(a, bv, n, m, norm)
 
 
+# ---- the dense products themselves: hand-written tcgen05 kernels (csrc/tg_gemm.cu, include/fortattack_train.h) ---------
+# DENSE = "tcgen05": every product of the training forward / backward runs on this repo's kernels in fp32-grade split
+# arithmetic (fp16 hi/lo with power-of-two row scales; bf16 three-term split for the weight gradients).
+# DENSE = "cublas": the same functions on torch's library GEMMs -- kept as the checker the tests compare against.
+DENSE = "tcgen05"
+_TG = {}
+
+
+def _tg_state(dev):
+    st = _TG.get(dev)
+    if st is None:
+        st = _TG[dev] = {"status": torch.zeros(1, dtype=torch.int32, device=dev),
+                         "scratch": torch.empty(_lib().tg_wgrad_scratch_bytes(256, 128), dtype=torch.uint8, device=dev)}
+    return st
+
+
+def tg_check_status(dev):
+    """Synchronising: raises if any dense kernel so far reported a pipeline timeout (a protocol bug, never expected)."""
+    st = _TG.get(torch.device(dev))
+    if st is not None:
+        code = int(st["status"].item())
+        if code:
+            raise _capi.FaError("tg_gemm pipeline timeout (wait site %d)" % code)
+
+
+def _row_major(t):
+    """(tensor usable as a row-major operand, ld): last stride 1, row stride >= width."""
+    if t.dim() != 2:
+        raise ValueError("2-D operand expected")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1] or t.dtype != torch.float32:
+        t = t.contiguous().float()
+    return t, t.stride(0)
+
+
+def tg_pack(w, transposed):
+    """Pack B (the [N][K] operand of y = x B^T) for tg_linear.  w: [N, K] (transposed=False) or [K, N] (transposed=True),
+    fp32, row-major with any row stride.  Returns (packed uint8 tensor, N, K)."""
+    w, ld = _row_major(w.detach())
+    N, K = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+    packed = torch.empty(_lib().tg_packed_bytes(N, K), dtype=torch.uint8, device=w.device)
+    _capi.check(_lib().tg_pack_weight(w.data_ptr(), N, K, ld, int(bool(transposed)), packed.data_ptr(),
+                                      torch.cuda.current_stream(w.device).cuda_stream))
+    return packed, N, K
+
+
+def tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False):
+    """act(x B^T + bias) (+ out) with B packed by tg_pack; x [rows, K] fp32 row-major (row stride free)."""
+    packed, N, K = pack
+    x, ldx = _row_major(x.detach())
+    rows = x.shape[0]
+    if x.shape[1] != K:
+        raise ValueError("x has %d columns, the packed weight expects %d" % (x.shape[1], K))
+    if out is None:
+        out = torch.empty(rows, N, device=x.device)
+    elif out.shape != (rows, N) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("out must be a float32 [rows, N] tensor with unit column stride")
+    if rows == 0:
+        return out
+    st = _tg_state(x.device)
+    _capi.check(_lib().tg_linear(x.data_ptr(), ldx, rows, K, packed.data_ptr(), N, None if bias is None else bias.detach().data_ptr(),
+                                 int(bool(relu)), int(bool(accumulate)), out.data_ptr(), out.stride(0), st["status"].data_ptr(),
+                                 torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
+def tg_wgrad(x, y):
+    """x^T y for tall operands: [rows, a]^T [rows, b] -> [a, b]."""
+    x, ldx = _row_major(x.detach())
+    y, ldy = _row_major(y.detach())
+    a, b, rows = x.shape[1], y.shape[1], x.shape[0]
+    out = torch.empty(a, b, device=x.device)
+    if rows == 0:
+        return out.zero_()
+    st = _tg_state(x.device)
+    need = _lib().tg_wgrad_scratch_bytes(a, b)
+    if st["scratch"].numel() < need:
+        st["scratch"] = torch.empty(need, dtype=torch.uint8, device=x.device)
+    _capi.check(_lib().tg_wgrad(x.data_ptr(), ldx, a, y.data_ptr(), ldy, b, rows, out.data_ptr(), b, 0, st["scratch"].data_ptr(),
+                                st["status"].data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
+def _use_tg(x):
+    return DENSE == "tcgen05" and x.is_cuda and x.dtype == torch.float32
+
+
 # ---- dense layers of the training forward with a hand-written backward ------------------------------------------------
 def _relu_bwd_colsum_cuda(dout, out):
     """(dpre = dout * [out > 0], column sums of dpre) in one pass over [rows, cols] (rl_relu_bwd_colsum)."""
@@ -188,6 +274,8 @@ def xt_dy(x, dy):
     """x^T @ dy for tall operands ([rows, a]^T [rows, b] -> [a, b], rows ~ 2e5): the weight-gradient product of every
     dense layer.  As a plain GEMM its whole reduction dimension lands on a handful of CTAs (measured 90-170 us for
     200 MB of operands); as a batched GEMM over row chunks plus a sum of the [chunks, a, b] partials every SM works."""
+    if _use_tg(x):
+        return tg_wgrad(x, dy)
     rows = x.shape[0]
     S = _split(rows)
     if S == 1:
@@ -202,7 +290,9 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, b, relu):
-        if relu:
+        if _use_tg(x):
+            y = tg_linear(x, tg_pack(W, False), b, relu)
+        elif relu:
             y = torch._addmm_activation(b, x, W.t()) if x.is_cuda else torch.relu(torch.addmm(b, x, W.t()))
         else:
             y = torch.addmm(b, x, W.t())
@@ -219,7 +309,9 @@ class _Linear(torch.autograd.Function):
             dpre = dy.contiguous()
             db = dpre.sum(0)
         dW = xt_dy(dpre, x)
-        dx = dpre @ W if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = tg_linear(dpre, tg_pack(W, True)) if _use_tg(dpre) else dpre @ W
         return dx, dW, db, None
 
 
@@ -229,13 +321,36 @@ class _Matmul(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, M):
         ctx.save_for_backward(x, M)
-        return x @ M
+        return tg_linear(x, tg_pack(M, True)) if _use_tg(x) else x @ M
 
     @staticmethod
     def backward(ctx, dy):
         x, M = ctx.saved_tensors
         dy = dy.contiguous()
-        return (dy @ M.t() if ctx.needs_input_grad[0] else None), xt_dy(x, dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = tg_linear(dy, tg_pack(M, False)) if _use_tg(dy) else dy @ M.t()
+        return dx, (xt_dy(x, dy) if ctx.needs_input_grad[1] else None)
+
+
+class _MatmulNT(torch.autograd.Function):
+    """y = x B^T for B [N, K] (the folds of the attention projections: W_query W_key^T, ... U_2^T)."""
+
+    @staticmethod
+    def forward(ctx, x, B):
+        ctx.save_for_backward(x, B)
+        return tg_linear(x, tg_pack(B, False)) if _use_tg(x) else x @ B.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, B = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dB = None
+        if ctx.needs_input_grad[0]:
+            dx = tg_linear(dy, tg_pack(B, True)) if _use_tg(dy) else dy @ B
+        if ctx.needs_input_grad[1]:
+            dB = xt_dy(dy, x)
+        return dx, dB
 
 
 def linear(x, W, b, relu=False):
@@ -244,6 +359,10 @@ def linear(x, W, b, relu=False):
 
 def matmul(x, M):
     return _Matmul.apply(x, M)
+
+
+def matmul_nt(x, B):
+    return _MatmulNT.apply(x, B)
 
 
 # ---- one message-passing round with the projections folded into the weights --------------------------------------------
@@ -288,9 +407,13 @@ class _MessageRound(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, Mqk, Wc, bias, n, norm):
         h = h.contiguous()
-        g = h @ Mqk
+        tg = _use_tg(h)
+        g = tg_linear(h, tg_pack(Mqk, True)) if tg else h @ Mqk
         hm, attn = mix_forward(g, h, n, norm)
-        out = torch._addmm_activation(bias, hm, Wc) if h.is_cuda else torch.relu(torch.addmm(bias, hm, Wc))
+        if tg:
+            out = tg_linear(hm, tg_pack(Wc, True), bias, True)
+        else:
+            out = torch._addmm_activation(bias, hm, Wc) if h.is_cuda else torch.relu(torch.addmm(bias, hm, Wc))
         ctx.save_for_backward(g, hm, attn, out, Mqk, Wc)
         ctx.meta = (n, float(norm))
         ctx.mark_non_differentiable(attn)
@@ -302,13 +425,60 @@ class _MessageRound(torch.autograd.Function):
         n, norm = ctx.meta
         k = g.shape[1]
         dpre, dbias = relu_bwd_colsum(dout, out)
+        tg = _use_tg(dpre)
         dWc = xt_dy(hm, dpre)
-        dhm = dpre @ Wc.t()                                  # [dh through U1 | dmixed]
+        dhm = tg_linear(dpre, tg_pack(Wc, False)) if tg else dpre @ Wc.t()        # [dh through U1 | dmixed]
         dg, dh = mix_backward(dhm, g, hm, attn, n, norm)
         dMqk = xt_dy(hm[:, :k], dg)
-        dh.addmm_(dg, Mqk.t())
+        if tg:
+            tg_linear(dg, tg_pack(Mqk, False), out=dh, accumulate=True)
+        else:
+            dh.addmm_(dg, Mqk.t())
         return dh, dMqk, dWc, dbias, None, None
 
 
 def message_round(h, Mqk, Wc, bias, n, norm):
     return _MessageRound.apply(h, Mqk, Wc, bias, n, norm)
+
+
+# ---- optimizer step: gradient-norm clip + Adam for all parameters in two launches --------------------------------------
+class TgAdam(object):
+    """nn.utils.clip_grad_norm_(params, max_norm) followed by optim.Adam(params, lr).step() (rlcore/algo/ppo.py:114,191-192)
+    as tg_adam_step (csrc/tg_gemm.cu): same arithmetic as torch's, step counter on the device (graph-capturable)."""
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        if not self.params or not all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self.params):
+            raise ValueError("TgAdam needs contiguous float32 CUDA parameters")
+        if len(self.params) > 32:
+            raise ValueError("TgAdam handles up to 32 parameter tensors (TG_MAX_TENSORS)")
+        dev = self.params[0].device
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.scratch = torch.zeros(256, device=dev)
+        self.total_norm = torch.zeros(1, device=dev)
+        self.param_groups = [{"params": self.params, "lr": self.lr, "betas": self.betas, "eps": self.eps}]
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def step(self, max_norm=0.0, grad_scale=None):
+        """grad_scale: optional device scalar tensor every gradient is multiplied by first (in place)."""
+        arr = (_capi.TgTensor * len(self.params))()
+        for k, p in enumerate(self.params):
+            g = p.grad
+            if g is not None and (not g.is_contiguous() or g.dtype != torch.float32):
+                g = p.grad = g.contiguous().float()
+            arr[k] = _capi.TgTensor(p.data_ptr(), None if g is None else g.data_ptr(), self.exp_avg[k].data_ptr(),
+                                    self.exp_avg_sq[k].data_ptr(), p.numel())
+        dev = self.params[0].device
+        _capi.check(_lib().tg_adam_step(arr, len(self.params), self.param_groups[0]["lr"], self.betas[0], self.betas[1], self.eps,
+                                        float(max_norm or 0.0), None if grad_scale is None else grad_scale.data_ptr(),
+                                        self.step_count.data_ptr(), self.scratch.data_ptr(), self.total_norm.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream))

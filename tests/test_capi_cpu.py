@@ -26,7 +26,7 @@ def test_policy_and_rollout_headers_are_exported():
     they reject bad arguments without a GPU."""
     L = _capi.lib()
     for hdr_name, prefix in (("fortattack_policy.h", "mp_"), ("fortattack_rollout.h", "rl_"), ("mape_world.h", "mw_"),
-                             ("fortattack_render.h", "fr_")):
+                             ("fortattack_render.h", "fr_"), ("fortattack_train.h", "tg_")):
         hdr = open(os.path.join(ROOT, "include", hdr_name)).read()
         declared = set(re.findall(r"^int\s+(%s\w+)\(" % prefix, hdr, re.M))
         assert declared, hdr_name
@@ -38,6 +38,8 @@ def test_policy_and_rollout_headers_are_exported():
     assert L.mp_forward(*([None] * 3), 3, 3, 8, 0, 0, 0, None, 0, *([None] * 7), None, 0, None, None, None, None) == -1
     assert b"NULL" in L.fa_last_error()
     assert L.rl_gae(None, None, None, None, None, None, 4, 2, 8, 0.99, 0.95, None) == -1
+    assert L.tg_linear(None, 128, 1000, 128, None, 128, None, 0, 0, None, 128, None, None) == -1
+    assert L.tg_packed_bytes(128, 128) == 4 * 128 * 128 + 16 and L.tg_packed_bytes(8, 6) == 4 * 16 * 64 + 16
     blob_bytes = int(re.search(r"#define MP_BLOB_F16_BYTES (\d+)", open(os.path.join(ROOT, "include", "fortattack_policy.h")).read()).group(1))
     from importlib import import_module
     pk = import_module("emergent-multiagent-strategies_b200.policy_kernel")

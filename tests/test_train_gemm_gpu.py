@@ -1,0 +1,152 @@
+"""GPU: the hand-written tcgen05 dense kernels of the PPO update (csrc/tg_gemm.cu, include/fortattack_train.h) against
+float64 products, and the optimizer kernel against torch's clip_grad_norm_ + Adam (rlcore/algo/ppo.py:189-192).
+Gate: fp32-grade -- the split-operand products must be as close to the float64 result as an fp32 GEMM is."""
+from importlib import import_module
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+PKG = "emergent-multiagent-strategies_b200"
+fused = import_module(PKG + ".rlcore.fused")
+_capi = import_module(PKG + "._capi")
+
+
+def _rows(gen, rows, cols, wide):
+    x = torch.randn(rows, cols, generator=gen)
+    if wide:            # rows of very different magnitude (gradient rows of dead / alive agents, raw headings next to flags)
+        x = x * torch.pow(10.0, torch.rand(rows, 1, generator=gen) * 9 - 6)
+        x[::7] = 0.0
+    return x
+
+
+@pytest.mark.parametrize("rows,K,N", [(1000, 128, 128), (777, 256, 128), (300, 128, 256), (5000, 64, 64), (129, 64, 128),
+                                      (1000, 6, 64), (500, 128, 8), (500, 128, 1), (500, 8, 128), (500, 1, 128),
+                                      (1, 128, 128), (128, 128, 128), (40000, 128, 128), (20011, 256, 128)])
+@pytest.mark.parametrize("wide", [False, True])
+def test_linear_matches_float64(rows, K, N, wide):
+    gen = torch.Generator().manual_seed(rows * 7 + K + N)
+    x = _rows(gen, rows, K, wide).cuda()
+    W = (torch.randn(N, K, generator=gen) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=gen).cuda()
+    ref = x.double() @ W.double().t()
+    bound = (x.double().abs() @ W.double().abs().t())                   # what an fp32 dot product's error is relative to
+    y = fused.tg_linear(x, fused.tg_pack(W, False))
+    fused.tg_check_status("cuda:0")
+    err = ((y.double() - ref).abs() / (bound + 1e-30)).max()
+    assert float(err) < 2e-6, float(err)
+    # bias + ReLU epilogue, transposed pack (B given as [K, N]), accumulate into an existing output
+    y2 = fused.tg_linear(x, fused.tg_pack(W.t().contiguous(), True), b, relu=True)
+    assert float(((y2.double() - torch.relu(ref + b.double())).abs() / (bound + b.double().abs() + 1e-30)).max()) < 2e-6
+    base = torch.randn(rows, N, generator=gen).cuda()
+    y3 = fused.tg_linear(x, fused.tg_pack(W, False), out=base.clone(), accumulate=True)
+    assert float(((y3.double() - (ref + base.double())).abs() / (bound + base.double().abs() + 1e-30)).max()) < 2e-6
+
+
+def test_linear_strided_operands():
+    """x and out as column slices of wider row-major tensors (the [h | mixed] buffer of a message round)."""
+    gen = torch.Generator().manual_seed(3)
+    big = torch.randn(3000, 256, generator=gen).cuda()
+    W = torch.randn(128, 128, generator=gen).cuda() / 11
+    ref = big[:, 128:].double() @ W.double().t()
+    out = torch.zeros(3000, 256, device="cuda")
+    fused.tg_linear(big[:, 128:], fused.tg_pack(W, False), out=out[:, :128])
+    assert float((out[:, :128].double() - ref).abs().max()) < 2e-5 and float(out[:, 128:].abs().max()) == 0.0
+    Wv = torch.randn(128, 256, generator=gen).cuda()                       # weight given as a strided view: update.0.weight[:, 128:]
+    y = fused.tg_linear(big[:, :128], fused.tg_pack(Wv[:, 128:], False))
+    assert float((y.double() - big[:, :128].double() @ Wv[:, 128:].double().t()).abs().max()) < 1e-4
+
+
+def _wgrad_err(x, y):
+    ref = x.double().t() @ y.double()
+    bound = x.double().abs().t() @ y.double().abs()
+    got = fused.tg_wgrad(x, y)
+    return float(((got.double() - ref).abs() / (bound + 1e-30)).max()), float((got.double() - ref).abs().max() / ref.abs().max())
+
+
+def test_wgrad_descriptor_probe():
+    """Prints the error of the built-in MN-major descriptor fields and of the swapped pair (diagnostic for the layout)."""
+    gen = torch.Generator().manual_seed(0)
+    x, y = torch.randn(640, 128, generator=gen).cuda(), torch.randn(640, 128, generator=gen).cuda()
+    L = _capi.lib()
+    res = {}
+    for name, (lbo, sbo) in (("lbo=128,sbo=1040", (128, 1040)), ("lbo=1040,sbo=128", (1040, 128))):
+        L.tg_debug_wgrad_desc(lbo, sbo)
+        res[name] = _wgrad_err(x, y)
+        torch.cuda.synchronize()
+    L.tg_debug_wgrad_desc(0, 0)
+    print("tg_wgrad descriptor probe (err/bound, err/max):", res)
+    assert res["lbo=128,sbo=1040"][0] < 2e-6, res
+
+
+@pytest.mark.parametrize("rows,a,b", [(5000, 128, 128), (3001, 256, 128), (1000, 128, 256), (2000, 64, 6), (2000, 8, 128),
+                                      (2000, 1, 128), (64, 128, 128), (63, 64, 64), (100000, 128, 128), (196608, 256, 128)])
+@pytest.mark.parametrize("wide", [False, True])
+def test_wgrad_matches_float64(rows, a, b, wide):
+    gen = torch.Generator().manual_seed(rows + a * 3 + b)
+    x, y = _rows(gen, rows, a, wide).cuda(), _rows(gen, rows, b, False).cuda()
+    e_bound, e_max = _wgrad_err(x, y)
+    fused.tg_check_status("cuda:0")
+    assert e_bound < 2e-6, (e_bound, e_max)
+    # bit-reproducible (fixed-order partial sums, no atomics)
+    assert torch.equal(fused.tg_wgrad(x, y), fused.tg_wgrad(x, y))
+
+
+def test_wgrad_strided_operands():
+    gen = torch.Generator().manual_seed(5)
+    hm = torch.randn(4000, 256, generator=gen).cuda()
+    dg = torch.randn(4000, 128, generator=gen).cuda()
+    got = fused.tg_wgrad(hm[:, :128], dg)
+    ref = hm[:, :128].double().t() @ dg.double()
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) < 1e-6
+
+
+def test_adam_step_matches_torch():
+    torch.manual_seed(0)
+    shapes = [(128, 256), (128,), (64, 6), (1, 128, 128), (8, 128), (1,), (64, 128)]
+    ps = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.Adam(qs, lr=1e-3)
+    own = fused.TgAdam(ps, lr=1e-3)
+    for it in range(6):
+        scale = 10.0 if it % 2 == 0 else 1e-3                     # clipped and unclipped steps
+        for k, (p, q) in enumerate(zip(ps, qs)):
+            g = torch.randn_like(p) * scale
+            p.grad, q.grad = (None, None) if (k == 5 and it == 0) else (g.clone(), g.clone())
+        tn = torch.nn.utils.clip_grad_norm_(qs, 0.5)
+        ref.step()
+        own.step(0.5)
+        assert abs(float(own.total_norm) - float(tn)) < 1e-4 * float(tn)
+        for p, q in zip(ps, qs):
+            assert float((p - q).abs().max()) < 2e-6, it
+    assert int(own.step_count) == 6
+
+
+def test_dense_layers_match_library_path():
+    """fused.linear / matmul / matmul_nt / message_round with DENSE='tcgen05' against the same functions on cuBLAS:
+    outputs and every gradient."""
+    gen = torch.Generator().manual_seed(1)
+    n, B, d = 3, 700, 128
+    h = torch.randn(n * B, d, generator=gen).cuda().requires_grad_()
+    Mqk = (torch.randn(d, d, generator=gen) / d ** 0.5).cuda().requires_grad_()
+    Wc = (torch.randn(2 * d, d, generator=gen) / (2 * d) ** 0.5).cuda().requires_grad_()
+    bias = torch.randn(d, generator=gen).cuda().requires_grad_()
+    W2 = (torch.randn(8, d, generator=gen) / d ** 0.5).cuda().requires_grad_()
+    b2 = torch.zeros(8, device="cuda", requires_grad=True)
+    gout = torch.randn(n * B, 8, generator=gen).cuda()
+    res = {}
+    for mode in ("cublas", "tcgen05"):
+        fused.DENSE = mode
+        try:
+            for t in (h, Mqk, Wc, bias, W2, b2):
+                t.grad = None
+            x, attn = fused.message_round(h, Mqk, Wc, bias, n, d ** -0.5)
+            x = fused.matmul_nt(fused.matmul(x, Mqk), Wc[:d])
+            y = fused.linear(x, W2, b2)
+            (y * gout).sum().backward()
+            res[mode] = [y.detach().clone()] + [t.grad.clone() for t in (h, Mqk, Wc, bias, W2, b2)]
+        finally:
+            fused.DENSE = "tcgen05"
+    fused.tg_check_status("cuda:0")
+    for a, b in zip(res["cublas"], res["tcgen05"]):
+        assert float((a - b).abs().max()) < 2e-4 * max(1.0, float(a.abs().max())), float((a - b).abs().max())
