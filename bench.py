@@ -409,6 +409,11 @@ def run_ours(args):
         except Exception as exc:
             extra["rollout_ensemble"] = {"error": repr(exc)}
     del env
+    if not args.quick:
+        try:
+            extra["train"] = train_config4_share(torch, dev, dist, world, rank)
+        except Exception as exc:
+            extra["train"] = {"error": repr(exc)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -463,6 +468,15 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def shipped_models(torch, ckpt=2520):
+    """state_dicts of a shipped reference checkpoint (baseline/_ref/reference/marlsave/tmp_1/ep<ckpt>.pt: 10 entries,
+    guards first) or None when the reference install is absent."""
+    path = os.path.join(REF_DIR, "reference", "marlsave", "tmp_1", "ep%d.pt" % ckpt)
+    if not os.path.exists(path):
+        return None
+    return torch.load(path, map_location="cpu")["models"]
+
+
 def rollout_config3(fab, torch, dev, E=16384, T=128):
     """BASELINE.json configs[2]: 3v3, 16384 envs, full PPO rollout with the MPNN policy (fused tcgen05 forward +
     fused step + fused GAE), and one JointPPO update (4 epochs x 32 minibatches, torch autograd).  Reported next to
@@ -472,6 +486,9 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     pk = importlib.import_module("emergent-multiagent-strategies_b200.policy_kernel")
     torch.manual_seed(0)
     tr = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0)
+    models = shipped_models(torch)                                          # weights of marlsave/tmp_1/ep2520.pt
+    if models is not None:
+        tr.load_models(models)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     for _ in range(2):                                                      # eager warm-up, then the graph-capturing pass
         tr.collect(); tr.wrap_horizon(); tr.after_update()
@@ -480,6 +497,7 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     e0.record(); tr.collect(); e1.record(); tr.wrap_horizon(); e2.record()
     torch.cuda.synchronize(dev)
     collect_ms, wrap_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    tr.recompute_old(); tr.wrap_horizon()                                   # what train_once() does before the update
     # the policy kernel alone (guards' team), CUDA events over 20 launches
     R = tr.roll
     f = tr.fused[0]
@@ -506,22 +524,34 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     e0.record(); vals = tr.update(); e1.record()
     torch.cuda.synchronize(dev)
     update_ms = e0.elapsed_time(e1)
-    for trn in tr.trainers:                                                 # the same update with TF32 tensor-core GEMMs
-        trn.allow_tf32 = True
-    e0, e1 = ev(), ev()
-    e0.record(); tr.update(); e1.record()
-    torch.cuda.synchronize(dev)
-    update_tf32_ms = e0.elapsed_time(e1)
+    fused = importlib.import_module("emergent-multiagent-strategies_b200.rlcore.fused")
+    # comparison only: the same update with its dense products on cuBLAS fp32 (what round 1 measured; fused.DENSE is the
+    # checker switch of the tests).  No TF32 figures any more: single-pass TF32 misses the gradient gate by 2-3 orders.
+    fused.DENSE = "cublas"
+    try:
+        e0, e1 = ev(), ev()
+        e0.record(); tr.update(); e1.record()
+        torch.cuda.synchronize(dev)
+        update_cublas_ms = e0.elapsed_time(e1)
+    finally:
+        fused.DENSE = "tcgen05"
     # ... and with the optimizer step replayed from a CUDA graph (opt-in JointPPO(graph_update=True))
-    tr2 = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, allow_tf32=True, graph_update=True)
-    tr2.collect(); tr2.wrap_horizon()
+    tr2 = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, graph_update=True)
+    if models is not None:
+        tr2.load_models(models)
+    tr2.collect(); tr2.recompute_old(); tr2.wrap_horizon()
     tr2.update()                                                            # three eager steps, capture, replays
     torch.cuda.synchronize(dev)
     e0, e1 = ev(), ev()
     e0.record(); tr2.update(); e1.record()
     torch.cuda.synchronize(dev)
-    update_tf32_graph_ms = e0.elapsed_time(e1)
+    update_graph_ms = e0.elapsed_time(e1)
+    e0, e1 = ev(), ev()
+    e0.record(); tr2.recompute_old(); e1.record()
+    torch.cuda.synchronize(dev)
+    recompute_ms = e0.elapsed_time(e1)
     del tr2
+    fused.tg_check_status(dev)
     for fz in tr.fused:
         fz.check_status()
     flop_row = 2 * (64 * 64 * 2 + 3 * 3 * 128 * 128 + 2 * 128 * 128)       # tensor-core MACs x2 per (agent, env) row
@@ -534,11 +564,16 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     ach = NG * E * flop_row / (pol_us * 1e-6) / 1e12
     return {"workload": "FortAttack 3v3 (BASELINE.json configs[2]), %d envs, T=%d rollout with the MPNN policy + one JointPPO update" % (E, T),
             "rollout_agent_steps_per_s": E * A * T / (collect_ms * 1e-3), "collect_ms": collect_ms,
-            "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_tf32_ms": update_tf32_ms, "ppo_update_tf32_graph_ms": update_tf32_graph_ms,
-            "ppo_update": "4 epochs x 32 minibatches x 2 teams = 256 optimizer steps: message rounds with folded projections and "
-                          "hand-written forward/backward (rlcore/fused.py) over cuBLAS GEMMs (split-K weight gradients); attention "
-                          "forward/backward, ReLU-backward + bias gradient, minibatch gather and clipped-PPO loss are this repo's "
-                          "kernels (rl_attn_*, rl_attn_mix_*, rl_relu_bwd_colsum, rl_gather_minibatch, rl_ppo_loss)",
+            "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_graph_ms": update_graph_ms,
+            "ppo_update_cublas_fp32_ms": update_cublas_ms, "recompute_old_ms": recompute_ms,
+            "policy_weights": "marlsave/tmp_1/ep2520.pt (baseline/_ref)" if models is not None else "random init (baseline/_ref absent)",
+            "ppo_update": "4 epochs x 32 minibatches x 2 teams = 256 optimizer steps, fp32-grade arithmetic: every dense product on "
+                          "this repo's tcgen05 kernels (tg_linear: fp16 hi/lo split, 3 MMAs per product; tg_wgrad: bf16 3-term split, "
+                          "6 MMAs), folded message rounds with hand-written backward (rlcore/fused.py), attention forward/backward, "
+                          "ReLU-backward + bias gradient, minibatch gather, clipped-PPO loss, clip + Adam (tg_adam_step) all own "
+                          "kernels; ppo_update_cublas_fp32_ms = the same update with the products on cuBLAS fp32, for comparison; "
+                          "recompute_old_ms = re-evaluating the rollout's log-probs / values with the update's forward "
+                          "(BatchedTrainer.recompute_old, default in train_once)",
             "losses": vals,
             "policy_kernel": {"kernel": "mp::mp_policy_kernel", "us_per_team_forward": pol_us, "rows": NG * E,
                               "torch_module_act_us": torch_us, "speedup_vs_torch_module": torch_us / pol_us,
@@ -571,20 +606,97 @@ def rollout_config4_share(fab, torch, dev, E=8192, T=32):
             "envs_per_tile": tr.fused[0].kernel_info()["envs_per_tile"]}
 
 
+def train_config4_share(torch, dev, dist, world, rank, E=8192, T=128):
+    """BASELINE.json configs[3] (5v5, 65 536 envs over 8 GPUs = 8192 envs per GPU, PPO gradient all-reduce over NCCL): ONE full
+    training iteration of this rank's share -- graph-replayed rollout collection, recompute_old, GAE, and the update's 256
+    optimizer steps, each with ONE all-reduce of the flat gradient buffer (+ loss normaliser) when world > 1.  Runs on
+    every rank; times are CUDA-event times, max over ranks."""
+    import importlib
+    ro = importlib.import_module("emergent-multiagent-strategies_b200.rollout")
+    fused = importlib.import_module("emergent-multiagent-strategies_b200.rlcore.fused")
+    pg = dist.group.WORLD if world > 1 else None
+    torch.manual_seed(0)
+    tr = ro.BatchedTrainer(E, 5, 5, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, env_id0=rank * E,
+                           process_group=pg, graph_update=True)
+    models = shipped_models(torch)
+    if models is not None:
+        tr.load_models(models)
+    for _ in range(2):                       # eager pass, then the passes that capture the rollout and optimizer-step graphs
+        tr.train_once()
+    torch.cuda.synchronize(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev[0].record(); tr.collect(); ev[1].record(); tr.recompute_old(); tr.wrap_horizon(); ev[2].record()
+    vals = tr.update(); ev[3].record()
+    torch.cuda.synchronize(dev)
+    tr.after_update()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3])],
+                     device=dev, dtype=torch.float64)
+    ar_us, spread, nbytes = None, 0.0, 0
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        flat = torch.zeros(sum(p.numel() for p in tr.policies[0].parameters()) + 5, device=dev)
+        nbytes = flat.numel() * 4
+        for _ in range(5):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(50):
+            dist.all_reduce(flat)
+        a1.record()
+        torch.cuda.synchronize(dev)
+        ar = torch.tensor([a0.elapsed_time(a1) / 50 * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        ar_us = float(ar.item())
+        w = torch.cat([p.detach().reshape(-1) for pol in tr.policies for p in pol.parameters()])
+        lo, hi = w.clone(), w.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        spread = float((hi - lo).abs().max())
+    for f in tr.fused:
+        f.check_status()
+    fused.tg_check_status(dev)
+    for trn in tr.trainers:                  # the captured optimizer step holds NCCL kernels: drop it before the group goes away
+        trn.release_graphs()
+    tr._graph = None
+    col, wrap, upd, tot = [float(x) for x in t.tolist()]
+    out = {"workload": "FortAttack 5v5, %d envs per GPU x %d GPU(s) (BASELINE.json configs[3] = 65 536 envs on 8), T=%d: one training "
+                       "iteration = rollout + recompute_old + GAE + JointPPO update (4 epochs x 32 minibatches x 2 teams)" % (E, world, T),
+           "rollout_ms": col, "recompute_old_and_gae_ms": wrap, "update_ms": upd, "iteration_ms": tot,
+           "agent_steps_per_s_trained": world * E * 10 * T / (tot * 1e-3), "optimizer_steps": 256,
+           "collectives_per_optimizer_step": 1 if world > 1 else 0, "allreduce_us": ar_us, "allreduce_bytes": nbytes,
+           "allreduce_share_of_update": (256 * ar_us * 1e-3 / upd) if ar_us else 0.0, "replica_weight_spread": spread,
+           "update_path": "tcgen05 dense kernels + own attention / loss / Adam kernels, optimizer step replayed from a CUDA graph "
+                          "(NCCL all-reduce captured in it)",
+           "policy_weights": "marlsave/tmp_1/ep2520.pt" if models is not None else "random init",
+           "losses": [[float(x) for x in v] for v in vals]}
+    del tr
+    return out
+
+
 def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5):
     """One GPU's share of BASELINE.json configs[4] (guards-only training against an ensemble of 5 frozen attacker
     checkpoints, 32768 envs over 8 GPUs = 4096 envs per GPU, 5v5): rollout collection with a per-env, per-episode
     attacker draw = 1 guard forward + 1 ensemble forward (all K checkpoints in one launch) + 1 env step per rollout step (random-init checkpoints:
-    there is no network for the shipped ones; the arithmetic is the same)."""
+    the shipped checkpoints from baseline/_ref when present, else random-init stand-ins)."""
     import importlib
     ro = importlib.import_module("emergent-multiagent-strategies_b200.rollout")
     mp = importlib.import_module("emergent-multiagent-strategies_b200.mpnn")
-    sds = []
+    sds, ckpts = [], (220, 650, 1240, 1600, 2520)                       # arguments.py:62
+    shipped = [shipped_models(torch, c) for c in ckpts[:K]]
+    real = all(m is not None for m in shipped)
     for k in range(K):
-        torch.manual_seed(100 + k)
-        sds.append(mp.MPNN(action_space=ro._Shape(8), num_agents=5, num_opp_agents=5, input_size=6, hidden_dim=128).state_dict())
+        if real:
+            sds.append(shipped[k][-1])                                   # attackers = models[-1] (learner.py:131-140)
+        else:
+            torch.manual_seed(100 + k)
+            sds.append(mp.MPNN(action_space=ro._Shape(8), num_agents=5, num_opp_agents=5, input_size=6, hidden_dim=128).state_dict())
     torch.manual_seed(0)
     tr = ro.BatchedTrainer(E, 5, 5, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, attacker_ensemble=sds)
+    if real:
+        tr.load_models(shipped[-1])                                      # guards start from ep2520 (--pretrained-guard)
     for _ in range(2):
         tr.collect(); tr.wrap_horizon(); tr.after_update()
     torch.cuda.synchronize(dev)
@@ -597,7 +709,9 @@ def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5):
     return {"workload": "FortAttack 5v5 guards vs an ensemble of %d attacker checkpoints, %d envs (one GPU's share of BASELINE.json "
                         "configs[4]), T=%d rollout" % (K, E, T),
             "rollout_agent_steps_per_s": E * 10 * T / (ms * 1e-3), "us_per_rollout_step": ms * 1e3 / T,
-            "policy_launches_per_step": 2, "note": "one mp_forward for the guards, one mp_forward_ensemble serving all %d checkpoints" % K}
+            "policy_launches_per_step": 2, "note": "one mp_forward for the guards, one mp_forward_ensemble serving all %d checkpoints" % K,
+            "checkpoints": "marlsave/tmp_1/ep{220,650,1240,1600,2520}.pt attackers, ep2520 guards" if real else "random init (baseline/_ref absent)",
+            "ensemble_table": tr.ensemble_table().round(3).tolist()}
 
 
 def sweep(fab, torch, dev, peak):

@@ -7,7 +7,9 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfortattack_b200.so")
+# FORTATTACK_B200_LIB: load another build of the same library (the diagnostic build with the policy kernel's phase trace)
+LIB_PATH = os.environ.get("FORTATTACK_B200_LIB") or os.path.join(HERE, "libfortattack_b200.so")
+PROBE_PATH = os.path.join(HERE, "libfortattack_probe.so")
 CSRC = os.path.join(HERE, "csrc")
 
 FA_ABI_VERSION = 1
@@ -103,9 +105,6 @@ def lib():
     L.mp_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 7 + [vp, i32, vp, vp, vp, vp]
     L.mp_kernel_info.argtypes = [i32, i32, i32p, i32p, i32p, i32p, i32p]
     L.mp_forward_ensemble.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, u64, u64, vp, u64] + [vp] * 8
-    L.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, u32, u32, u32, vp, vp]
-    L.mp_set_trace.argtypes = [vp]
-    L.mp_probe_timing.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp]
     L.rl_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, vp]
     L.rl_rollout_bookkeeping.argtypes = [vp] * 7 + [i32, i32, vp]
     L.rl_gather_minibatch.argtypes = [vp] + [i32] * 8 + [vp] * 18
@@ -134,6 +133,22 @@ def lib():
         raise FaError("libfortattack_b200.so has ABI %d, binding expects %d" % (L.fa_abi_version(), FA_ABI_VERSION))
     _lib = L
     return L
+
+
+_probe = None
+
+
+def probe_lib():
+    """libfortattack_probe.so (include/fortattack_probe.h): hardware probes of the tensor-core operand layout used by the
+    tests and the profiling scripts; test infrastructure, separate from the product library."""
+    global _probe
+    if _probe is None:
+        P = ctypes.CDLL(PROBE_PATH)
+        vp, i32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32
+        P.mp_probe_gemm.argtypes = [vp, vp, vp, i32, i32, u32, u32, u32, vp, vp]
+        P.mp_probe_timing.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp]
+        _probe = P
+    return _probe
 
 
 def check(rc):

@@ -112,8 +112,10 @@ struct Params {
     int32_t sel_value;
     unsigned long long *counter;   // optional device call counter {count, ticket}: overrides `offset`, bumped by the last CTA
     int n_own, n_opp, E, ept, n_tiles, mode;
+#ifdef MP_TRACE                  // diagnostic build only (make trace): never in the product library
     unsigned long long *trace;   // optional: clock64() of row thread 0 of CTA 0 at every phase boundary of one of its tiles
     int trace_tile;              // which of CTA 0's tiles (0 = first)
+#endif
 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c[4]) {
@@ -400,7 +402,9 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 for (int c = 0; c < N_STREAM; ++c, ++g) {
                     const uint32_t s = g % NS, ph = (g / NS) & 1u;
                     mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 3);
+#ifdef MP_TRACE
                     if (p.trace != nullptr && blockIdx.x == 0 && tile == 0) p.trace[64 + c] = clock64();
+#endif
                     mbar_expect_tx(&bar_full[s], c_tab[c].bytes);
                     bulk_g2s(smem + OFF_RING + s * STAGE_BYTES, blob + c_tab[c].off, c_tab[c].bytes, &bar_full[s]);
                 }
@@ -436,7 +440,9 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 }
                 umma_commit(&bar_empty[s]);
                 if (ch.commit_acc) umma_commit(&bar_acc);
+#ifdef MP_TRACE
                 if (p.trace != nullptr && blockIdx.x == 0 && g < 6) p.trace[72 + c] = clock64();
+#endif
             }
             __syncwarp();
             ++g;
@@ -481,9 +487,15 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         const int n_oth = n_own - 1;
         const float *DW = DW_IN_SMEM ? C + C_DW : reinterpret_cast<const float *>(blob + MP_BLOB_F16_BYTES) + C_DW;   // [128][8]
         uint32_t pc = 0;
+#ifdef MP_TRACE
         int ti = 0;
+#endif
 #define ARRIVE_A() do { tc_fence_before(); fence_async_smem(); mbar_arrive(&bar_a_ready); } while (0)
+#ifdef MP_TRACE
 #define TS() do { if (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && tile == tile0 + p.trace_tile * tile_stride && ti < 96) p.trace[ti++] = clock64(); } while (0)
+#else
+#define TS() do { } while (0)
+#endif
 #define WAIT_ACC(code) do { mbar_wait(&bar_acc, pc, p.status, code); pc ^= 1u; tc_fence_after(); } while (0)
 
         float o_own[6], o_opp[6];                                  // this tile's observations (prefetched one tile ahead)
@@ -679,8 +691,10 @@ namespace {
 constexpr int MAX_DEVICES = 64;
 bool g_attr_done[MAX_DEVICES] = {};
 int g_sms[MAX_DEVICES] = {};
+#ifdef MP_TRACE
 unsigned long long *g_trace = nullptr;
 int g_trace_tile = 0;
+#endif
 
 int prepare(int *sms) {
     int dev = 0;
@@ -718,7 +732,10 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     p.env_order = d_env_order; p.env_offsets = d_env_offsets;
     if ((d_env_order == nullptr) != (d_env_offsets == nullptr) || (d_env_order != nullptr && sel_value < 0))
         return fa_internal_fail(-1, "mp_forward: d_env_order and d_env_offsets come together, with sel_value >= 0");
-    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = g_trace; p.trace_tile = g_trace_tile;
+    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode;
+#ifdef MP_TRACE
+    p.trace = g_trace; p.trace_tile = g_trace_tile;
+#endif
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
@@ -751,7 +768,7 @@ extern "C" int mp_forward_ensemble(const void *const *d_blobs, int n_ckpt, const
     p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.value = d_value; p.logp = d_logp; p.action = d_action;
     p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0;
     p.counter = (unsigned long long *)d_counter; p.env_order = d_env_order; p.env_offsets = d_env_offsets;
-    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.trace = nullptr;
+    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode;
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;
     // every checkpoint may own up to all tiles: one CTA per SM, at least one per checkpoint
@@ -780,11 +797,13 @@ extern "C" int mp_kernel_info(int n_own, int n_opp, int32_t *regs, int32_t *bloc
     return 0;
 }
 
-// Debug aid: device buffer of 96 uint64 that receives clock64() of one row thread at every phase boundary of
-// the first tile of CTA 0 (NULL switches it off).  Not part of the product API.
+#ifdef MP_TRACE
+// Diagnostic build (make -C csrc trace -> libfortattack_b200_trace.so): device buffer of 96 uint64 that receives clock64()
+// of one row thread at every phase boundary of one tile of CTA 0 (NULL switches it off).  Not in the product library.
 extern "C" int mp_set_trace(unsigned long long *d_trace) {
     g_trace = d_trace;
     g_trace_tile = 0;
     if (const char *ev = getenv("MP_TRACE_TILE")) g_trace_tile = atoi(ev);
     return 0;
 }
+#endif

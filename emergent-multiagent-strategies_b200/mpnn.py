@@ -224,7 +224,7 @@ class MPNN(nn.Module):
                 from rlcore import fused
                 from rlcore.distributions import FixedCategorical
             logits = fused.linear(p, self.dist.linear.weight, self.dist.linear.bias)
-            return FixedCategorical(logits=logits, validate_args=False if torch.cuda.is_current_stream_capturing() else None)
+            return FixedCategorical(logits=logits, validate_args=False if (p.is_cuda and torch.cuda.is_current_stream_capturing()) else None)
         return self.dist(p)
 
     def _value(self, x):

@@ -170,8 +170,7 @@ class JointPPO(object):
                     continue
                 self._minibatch_step(fused, R, (a0, n, o0, m), idx, advantages, totals, params, world)
                 n_updates += 1
-        if world > 1:
-            totals = self._allreduce(totals) / world
+        # (several ranks: the per-step sums were made global inside _minibatch_step, nothing left to reduce)
         # the reference divides the summed losses by ppo_epoch * num_mini_batch whatever the number of minibatches the
         # sampler produced (ppo.py:198-202: a ragged tail adds one more term to the sums)
         v, a, e = (totals / (self.ppo_epoch * self.num_mini_batch)).tolist()
@@ -186,24 +185,57 @@ class JointPPO(object):
         count = mask.new_full((1,), float(mask.numel()))
         if world == 1:
             norm = torch.where(alive_sum != 0, alive_sum, count)          # mask.mean() != 0 else 1 (ppo.py:150-187)
-        else:
-            g = self._allreduce(torch.cat([alive_sum, count]))
-            norm = torch.where(g[0:1] != 0, g[0:1], g[1:2]) / world
+            loss, stats = fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch,
+                                         old_log_probs_batch, adv_targ, mask, norm, self.clip_param,
+                                         self.value_loss_coef, self.entropy_coef)
+            self.optimizer.zero_grad()
+            loss.backward()
+            self._clip_and_step()
+            totals += stats[:3]
+            return
+        # Several ranks: ONE collective per optimizer step.  Every loss term is sum_r(local sum) / sum_r(local alive count)
+        # (ppo.py:150-187 with global sums), so each rank differentiates its UN-normalised local sums (norm = 1), the
+        # gradients travel together with the two normaliser terms and the three loss sums in one persistent flat buffer,
+        # and the division by the global normaliser happens after the all-reduce (inside the optimizer kernel).
+        if getattr(self, "_one", None) is None or self._one.device != mask.device:
+            self._one = torch.ones(1, device=mask.device)
         loss, stats = fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch,
-                                     old_log_probs_batch, adv_targ, mask, norm, self.clip_param,
+                                     old_log_probs_batch, adv_targ, mask, self._one, self.clip_param,
                                      self.value_loss_coef, self.entropy_coef)
         self.optimizer.zero_grad()
         loss.backward()
-        if world > 1:
-            grads = [p.grad for p in params if p.grad is not None]
-            flat = torch.cat([g_.reshape(-1) for g_ in grads])
-            self._allreduce(flat).div_(world)
-            off = 0
-            for g_ in grads:
-                g_.copy_(flat[off:off + g_.numel()].view_as(g_))
-                off += g_.numel()
-        self._clip_and_step()
-        totals += stats[:3]
+        flat, views = self._flat_grads(params)
+        total = flat.numel() - 5
+        torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params], out=flat[:total])
+        torch.cat([alive_sum, count, stats[:3]], out=flat[total:])
+        self._allreduce(flat)
+        inv = 1.0 / torch.where(flat[total:total + 1] != 0, flat[total:total + 1], flat[total + 1:total + 2])
+        if self._tg_adam:
+            self.optimizer.step(self.max_grad_norm, grad_scale=inv, grads=views)
+        else:
+            for p, v in zip(params, views):
+                p.grad = v * inv
+            self._clip_and_step()
+        totals += flat[total + 2:] * inv
+
+    def _flat_grads(self, params):
+        """Persistent flat buffer [sum(numel) + 5] and its per-parameter views (allocated once per parameter set)."""
+        key = tuple(id(p) for p in params)
+        fg = getattr(self, "_fg", None)
+        if fg is None or fg[0] != key:
+            total = sum(p.numel() for p in params)
+            flat = torch.zeros(total + 5, device=params[0].device)
+            views, off = [], 0
+            for p in params:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            fg = self._fg = (key, flat, views)
+        return fg[1], fg[2]
+
+    def release_graphs(self):
+        """Drop the captured optimizer-step graph (it holds this process group's NCCL kernels): call before
+        dist.destroy_process_group(), or teardown waits on the graph's communicator references."""
+        self._g = None
 
     def _graphed_step(self, fused, R, team, idx, advantages, totals, mini_batch_size, world):
         """Replay (or, on its fourth call, capture) the optimizer step as one CUDA graph.  Returns False when the step

@@ -179,9 +179,10 @@ def _row_major(t):
     """(tensor usable as a row-major operand, ld): last stride 1, row stride >= width."""
     if t.dim() != 2:
         raise ValueError("2-D operand expected")
-    if t.stride(1) != 1 or t.stride(0) < t.shape[1] or t.dtype != torch.float32:
+    if t.dtype != torch.float32 or (t.shape[1] > 1 and t.stride(1) != 1) or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
         t = t.contiguous().float()
-    return t, t.stride(0)
+    # (the stride of a size-1 dimension is arbitrary: a [1, n] or [n, 1] tensor reports whatever its history left there)
+    return t, (t.stride(0) if t.shape[0] > 1 else max(int(t.shape[1]), 1))
 
 
 def tg_pack(w, transposed):
@@ -468,12 +469,16 @@ class TgAdam(object):
             elif p.grad is not None:
                 p.grad.zero_()
 
-    def step(self, max_norm=0.0, grad_scale=None):
-        """grad_scale: optional device scalar tensor every gradient is multiplied by first (in place)."""
+    def step(self, max_norm=0.0, grad_scale=None, grads=None):
+        """grad_scale: optional device scalar tensor every gradient is multiplied by first (in place).
+        grads: optional list (one per parameter, None = skip) to read the gradients from instead of p.grad -- the views of
+        a flat all-reduced buffer in a multi-rank step."""
         arr = (_capi.TgTensor * len(self.params))()
         for k, p in enumerate(self.params):
-            g = p.grad
+            g = p.grad if grads is None else grads[k]
             if g is not None and (not g.is_contiguous() or g.dtype != torch.float32):
+                if grads is not None:
+                    raise ValueError("explicit gradients must be contiguous float32")
                 g = p.grad = g.contiguous().float()
             arr[k] = _capi.TgTensor(p.data_ptr(), None if g is None else g.data_ptr(), self.exp_avg[k].data_ptr(),
                                     self.exp_avg_sq[k].data_ptr(), p.numel())

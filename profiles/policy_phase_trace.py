@@ -1,3 +1,6 @@
+import ctypes
+# needs the diagnostic build: make -C emergent-multiagent-strategies_b200/csrc trace; run with
+#   FORTATTACK_B200_LIB=emergent-multiagent-strategies_b200/libfortattack_b200_trace.so python profiles/policy_phase_trace.py
 import sys, os, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from importlib import import_module
@@ -39,7 +42,7 @@ for EE in (42, 4096, 16384, 65536, 262144):
     print("E=%d: %.1f us per team forward, %.3e agent-forwards/s, %.1f TFLOP/s (0.7 MFLOP/row)  status %d" % (EE, us, n*EE/us*1e6, n*EE*0.7e6/us*1e6/1e12, int(fp.status.item())), flush=True)
     if EE in (42, 16384):
         tr = torch.zeros(96, dtype=torch.int64, device="cuda")
-        L.mp_set_trace(tr.data_ptr())
+        L.mp_set_trace.argtypes = [ctypes.c_void_p]; L.mp_set_trace(tr.data_ptr())
         fp.forward(own, opp, pk.MODE_SAMPLE, out=out)
         torch.cuda.synchronize()
         L.mp_set_trace(None)

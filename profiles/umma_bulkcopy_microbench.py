@@ -1,7 +1,7 @@
 import sys, torch
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fortattack_b200 as fab
-L = fab._capi.lib()
+L = fab._capi.probe_lib()      # libfortattack_probe.so (test infrastructure)
 buf = torch.randn(8 * 16384 // 2, device="cuda").half()
 out = torch.zeros(3, dtype=torch.int64, device="cuda"); err = torch.zeros(1, dtype=torch.int32, device="cuda")
 for grid in (1, 148):

@@ -101,3 +101,105 @@ def test_folded_rounds_match_the_mirror(n, hid, monkeypatch):
     assert torch.allclose(xa, xb, rtol=1e-10, atol=1e-12) and torch.allclose(aa.reshape(ab.shape), ab, atol=1e-12)
     for a, b in zip(ga, gb):
         assert torch.allclose(a, b, rtol=1e-9, atol=1e-11), float((a - b).abs().max())
+
+
+# ---- the tcgen05 wiring (DENSE = "tcgen05"): which operand is packed how, on exact CPU stand-ins of the three primitives ----
+def _tg_pack(w, transposed):
+    B = (w.detach().t() if transposed else w.detach()).clone()
+    return (B, B.shape[0], B.shape[1])
+
+
+def _tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False):
+    B, N, K = pack
+    assert x.shape[1] == K, (tuple(x.shape), K)
+    y = x.detach() @ B.t()
+    if bias is not None:
+        y = y + bias.detach()
+    if relu:
+        y = torch.relu(y)
+    if out is None:
+        return y
+    assert out.shape == y.shape
+    if accumulate:
+        out += y
+    else:
+        out.copy_(y)
+    return out
+
+
+def _tg_wgrad(x, y):
+    return x.detach().t() @ y.detach()
+
+
+def _patch_tg(monkeypatch):
+    monkeypatch.setattr(fused, "tg_pack", _tg_pack)
+    monkeypatch.setattr(fused, "tg_linear", _tg_linear)
+    monkeypatch.setattr(fused, "tg_wgrad", _tg_wgrad)
+    monkeypatch.setattr(fused, "_use_tg", lambda x: True)
+    monkeypatch.setattr(fused, "mix_forward", mix_forward)
+    monkeypatch.setattr(fused, "mix_backward", mix_backward)
+    monkeypatch.setattr(fused, "relu_bwd_colsum", relu_bwd_colsum)
+
+
+def test_tcgen05_wiring_of_dense_functions(monkeypatch):
+    """fused.linear / matmul / matmul_nt routed through tg_pack / tg_linear / tg_wgrad (stand-ins with the kernels' contract:
+    y = act(x B^T + b), dW = x^T y) reproduce autograd: every operand is packed in the right orientation."""
+    _patch_tg(monkeypatch)
+    torch.manual_seed(1)
+    x = torch.randn(50, 24, dtype=torch.float64, requires_grad=True)
+    W = torch.randn(16, 24, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(16, dtype=torch.float64, requires_grad=True)
+    M = torch.randn(16, 8, dtype=torch.float64, requires_grad=True)
+    Bn = torch.randn(5, 8, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(50, 5, dtype=torch.float64)
+    for relu in (True, False):
+        ref = torch.nn.functional.linear(x, W, b)
+        ref = ((torch.relu(ref) if relu else ref) @ M) @ Bn.t()
+        got = fused.matmul_nt(fused.matmul(fused.linear(x, W, b, relu), M), Bn)
+        assert torch.allclose(ref, got, rtol=1e-12, atol=1e-12)
+        for a, c in zip(torch.autograd.grad((ref * w).sum(), (x, W, b, M, Bn)), torch.autograd.grad((got * w).sum(), (x, W, b, M, Bn))):
+            assert torch.allclose(a, c, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,m", [(3, 3), (1, 2), (4, 2)])
+def test_tcgen05_wiring_of_the_whole_network(n, m, monkeypatch):
+    """MPNN.evaluate_actions through the fused path with the dense products on the (stand-in) tcgen05 primitives ==
+    the bmm mirror of mpnn.py:117-205: outputs and every parameter gradient, in float64."""
+    _patch_tg(monkeypatch)
+
+    def cross(a, bv, n_, m_, norm):                       # torch restatement of rl_attn_forward/backward (mpnn.py:409-437)
+        Bsz, k = a.shape[0] // n_, a.shape[1]
+        A = a.view(n_, Bsz, k).transpose(0, 1)
+        Bq, V = bv[:, :k].reshape(m_, Bsz, k).transpose(0, 1), bv[:, k:].reshape(m_, Bsz, k).transpose(0, 1)
+        attn = torch.softmax(norm * A @ Bq.transpose(1, 2), dim=-1)
+        return (attn @ V).transpose(0, 1).reshape(n_ * Bsz, k), attn
+    monkeypatch.setattr(fused, "cross_attention", cross)
+    torch.manual_seed(n * 7 + m)
+    net = mp.MPNN(action_space=Shape(8), num_agents=n, num_opp_agents=m, input_size=6, hidden_dim=128).double()
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.3, 0.3)
+    monkeypatch.setattr(mp.MPNN, "_use_fused", lambda self, x: self.fused_attention)
+    Bsz = 23
+    own, opp = torch.randn(n * Bsz, 6, dtype=torch.float64), torch.randn(m * Bsz, 6, dtype=torch.float64)
+    act = torch.randint(0, 8, (n * Bsz, 1))
+    w = torch.randn(n * Bsz, 1, dtype=torch.float64)
+    res = []
+    for fused_on in (False, True):
+        net.zero_grad()
+        net.fused_attention = fused_on
+        if fused_on:
+            x = net._fwd_fused(own, opp)
+            v, dist = net._value(x), net._dist(net._policy(x))
+            lp, ent = dist.log_probs(act), dist.entropy()
+        else:
+            v, lp, ent, _ = net.evaluate_actions(own, None, opp, None, act)
+        ((v * w).sum() + (lp * w).sum() * 0.7 + ent.sum() * 0.3).backward()
+        res.append((v.detach(), lp.detach(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+        net.fused_attention = False
+    (v0, lp0, g0), (v1, lp1, g1) = res
+    assert torch.allclose(v0, v1, rtol=1e-10, atol=1e-10) and torch.allclose(lp0, lp1, rtol=1e-10, atol=1e-10)
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert torch.allclose(g0[k], g1[k], rtol=1e-8, atol=1e-9), (k, float((g0[k] - g1[k]).abs().max()))

@@ -17,7 +17,7 @@ _capi = import_module(PKG + "._capi")
 
 def test_tcgen05_gemm_probe():
     """One 128 x N x K tile through tcgen05.mma with the canonical no-swizzle K-major descriptors."""
-    L = _capi.lib()
+    L = _capi.probe_lib()
     g = torch.Generator().manual_seed(0)
     for K, N in ((64, 64), (128, 64), (128, 256), (256, 128), (64, 16)):
         a = torch.randn(128, K, generator=g).half().cuda()
