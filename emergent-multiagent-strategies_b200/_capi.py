@@ -15,12 +15,12 @@ CSRC = os.path.join(HERE, "csrc")
 FA_ABI_VERSION = 1
 FA_F32, FA_F64 = 0, 1
 FA_MAX_TEAM = 5
-FA_MAP_AUTO, FA_MAP_ENV, FA_MAP_AGENT = 0, 1, 2
+FA_MAP_AUTO, FA_MAP_ENV, FA_MAP_AGENT, FA_MAP_GROUP = 0, 1, 2, 3
 
 # every symbol include/fortattack.h declares
 SYMBOLS = ("fa_abi_version", "fa_last_error", "fa_workspace_bytes", "fa_create", "fa_destroy", "fa_reset",
            "fa_step", "fa_step_many", "fa_step_host", "fa_step_many_host", "fa_host_stage_bytes", "fa_host_layout", "fa_get_state", "fa_set_state", "fa_alive_counts",
-           "fa_set_max_steps", "fa_set_alive_end_buffer", "fa_launch_count", "fa_kernel_info")
+           "fa_set_max_steps", "fa_set_alive_end_buffer", "fa_set_rollout_outputs", "fa_launch_count", "fa_kernel_info")
 
 
 class FaConfig(ctypes.Structure):
@@ -96,6 +96,7 @@ def lib():
     L.fa_alive_counts.argtypes = [vp, vp, vp]
     L.fa_set_max_steps.argtypes = [vp, i32]
     L.fa_set_alive_end_buffer.argtypes = [vp, vp]
+    L.fa_set_rollout_outputs.argtypes = [vp, vp, vp, vp]
     L.fa_launch_count.argtypes = [vp, u64p]
     L.fa_kernel_info.argtypes = [vp, i32p, i32p, i32p, i32p, i32p]
     # every other entry point of the library (include/fortattack_policy.h, fortattack_rollout.h, mape_world.h).  ALL

@@ -29,7 +29,7 @@ class FortAttackBatch(object):
         self.cfg = _capi.FaConfig(self.E, self.n_guards, self.n_attackers, int(max_steps),
                                   _capi.FA_F64 if dtype == torch.float64 else _capi.FA_F32,
                                   dev.index if dev.index is not None else torch.cuda.current_device(),
-                                  {"auto": _capi.FA_MAP_AUTO, "env": _capi.FA_MAP_ENV, "agent": _capi.FA_MAP_AGENT}[mapping],
+                                  {"auto": _capi.FA_MAP_AUTO, "env": _capi.FA_MAP_ENV, "agent": _capi.FA_MAP_AGENT, "group": _capi.FA_MAP_GROUP}[mapping],
                                   0, int(seed), int(env_id0))
         nbytes = ctypes.c_size_t()
         _capi.check(self._lib.fa_workspace_bytes(ctypes.byref(self.cfg), ctypes.byref(nbytes)))
@@ -49,14 +49,15 @@ class FortAttackBatch(object):
     def _new(self, *shape, dtype=None):
         return torch.empty(shape, dtype=dtype or self.dtype, device=self.device)
 
-    def _dev(self, name, t, shape, dtype, optional=False):
+    def _dev(self, name, t, shape, dtype, optional=False, numel=None):
         """The library reads / writes through raw pointers: refuse anything that is not a contiguous tensor of exactly
-        the documented shape and type on this handle's device."""
+        the documented shape (or, with shape None, element count) and type on this handle's device."""
         if t is None and optional:
             return None
-        if (t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.workspace.device
-                or not t.is_contiguous()):
-            raise ValueError("%s must be a contiguous %s tensor of shape %r on %s" % (name, dtype, tuple(shape), self.device))
+        if (t is None or (shape is not None and tuple(t.shape) != tuple(shape)) or (numel is not None and t.numel() != numel)
+                or (dtype is not None and t.dtype != dtype) or t.device != self.workspace.device or not t.is_contiguous()):
+            raise ValueError("%s must be a contiguous %s tensor of %s on %s"
+                             % (name, dtype, "shape %r" % (tuple(shape),) if shape is not None else "%d elements" % numel, self.device))
         return t
 
     def _guard(self):
@@ -88,8 +89,10 @@ class FortAttackBatch(object):
                                            self._stream()))
         return obs
 
-    def step(self, actions, auto_reset=True, out=None):
-        """actions int32 [A, E] -> (obs [A,E,6], reward [A,E], done u8 [E], result u8 [E])."""
+    def step(self, actions, auto_reset=True, out=None, bookkeeping=None):
+        """actions int32 [A, E] -> (obs [A,E,6], reward [A,E], done u8 [E], result u8 [E]).
+        bookkeeping = (mask_next float32 [A, E], end_next uint8/bool [E], episode_reward float32 [A, E]) (entries may be None):
+        the rollout loop's per-step glue written by the same launch (fa_set_rollout_outputs; train_fortattack.py:53,97-104)."""
         a = self._actions(actions, (self.A, self.E))
         if out is None:
             out = (self._new(self.A, self.E, 6), self._new(self.A, self.E),
@@ -103,9 +106,25 @@ class FortAttackBatch(object):
             self._dev("out[3] (result)", out[3], (self.E,), torch.uint8)
         self._check_alive_end(1)
         obs, rew, done, result = out
+        bk = None
+        if bookkeeping is not None:
+            if len(bookkeeping) != 3:
+                raise ValueError("bookkeeping = (mask_next, end_next, episode_reward)")
+            self._dev("bookkeeping[0] (mask_next)", bookkeeping[0], None, torch.float32, optional=True, numel=self.A * self.E)
+            if bookkeeping[1] is not None and bookkeeping[1].dtype not in (torch.uint8, torch.bool):
+                raise ValueError("bookkeeping[1] (end_next) must be uint8 or bool")
+            self._dev("bookkeeping[1] (end_next)", bookkeeping[1], None, None, optional=True, numel=self.E)
+            self._dev("bookkeeping[2] (episode_reward)", bookkeeping[2], None, torch.float32, optional=True, numel=self.A * self.E)
+            bk = [None if t is None else t.data_ptr() for t in bookkeeping]
         with self._guard():
-            _capi.check(self._lib.fa_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                                          result.data_ptr(), int(bool(auto_reset)), self._stream()))
+            if bk is not None:
+                _capi.check(self._lib.fa_set_rollout_outputs(self._h, *bk))
+            try:
+                _capi.check(self._lib.fa_step(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                              result.data_ptr(), int(bool(auto_reset)), self._stream()))
+            finally:
+                if bk is not None:
+                    _capi.check(self._lib.fa_set_rollout_outputs(self._h, None, None, None))
         return obs, rew, done, result
 
     def step_many(self, actions, out=None, store_obs=True):
@@ -274,5 +293,5 @@ class FortAttackBatch(object):
         v = [ctypes.c_int32() for _ in range(5)]
         _capi.check(self._lib.fa_kernel_info(self._h, *[ctypes.byref(x) for x in v]))
         d = dict(zip(("regs", "block", "grid", "smem", "mapping"), [x.value for x in v]))
-        d["mapping"] = {_capi.FA_MAP_ENV: "env", _capi.FA_MAP_AGENT: "agent"}[d["mapping"]]
+        d["mapping"] = {_capi.FA_MAP_ENV: "env", _capi.FA_MAP_AGENT: "agent", _capi.FA_MAP_GROUP: "group"}[d["mapping"]]
         return d

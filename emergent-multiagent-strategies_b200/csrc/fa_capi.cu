@@ -26,14 +26,14 @@ __global__ void fa_alive_counts_kernel(const uint32_t *fl, int32_t *counts, int 
 }
 
 #define FA_EXTERN(NG)                                                                                                  \
-    extern template cudaError_t launch_step_g<NG, float>(int, bool, bool, const StepParams<float> &, int, int, cudaStream_t);  \
-    extern template cudaError_t launch_step_g<NG, double>(int, bool, bool, const StepParams<double> &, int, int, cudaStream_t); \
+    extern template cudaError_t launch_step_g<NG, float>(int, bool, int, const StepParams<float> &, int, int, cudaStream_t);  \
+    extern template cudaError_t launch_step_g<NG, double>(int, bool, int, const StepParams<double> &, int, int, cudaStream_t); \
     extern template cudaError_t launch_reset_g<NG, float>(int, const StateView<float> &, const uint8_t *, float *, int,  \
                                                           uint64_t, uint64_t, int, int, cudaStream_t);                   \
     extern template cudaError_t launch_reset_g<NG, double>(int, const StateView<double> &, const uint8_t *, double *,    \
                                                            int, uint64_t, uint64_t, int, int, cudaStream_t);             \
-    extern template cudaError_t step_attr_g<NG, float>(int, bool, bool, cudaFuncAttributes *);                                 \
-    extern template cudaError_t step_attr_g<NG, double>(int, bool, bool, cudaFuncAttributes *);
+    extern template cudaError_t step_attr_g<NG, float>(int, bool, int, cudaFuncAttributes *);                                 \
+    extern template cudaError_t step_attr_g<NG, double>(int, bool, int, cudaFuncAttributes *);
 FA_EXTERN(1) FA_EXTERN(2) FA_EXTERN(3) FA_EXTERN(4) FA_EXTERN(5)
 
 #define FA_DISPATCH_NG(ng, CALL)          \
@@ -47,9 +47,9 @@ FA_EXTERN(1) FA_EXTERN(2) FA_EXTERN(3) FA_EXTERN(4) FA_EXTERN(5)
     }
 
 template <typename R>
-static cudaError_t launch_step(int ng, int na, bool many, bool wide, const StepParams<R> &p, int grid, int block,
+static cudaError_t launch_step(int ng, int na, bool many, int mapping, const StepParams<R> &p, int grid, int block,
                                cudaStream_t s) {
-#define CALL(NG) launch_step_g<NG, R>(na, many, wide, p, grid, block, s)
+#define CALL(NG) launch_step_g<NG, R>(na, many, mapping, p, grid, block, s)
     FA_DISPATCH_NG(ng, CALL)
 #undef CALL
 }
@@ -60,8 +60,8 @@ static cudaError_t launch_reset(int ng, int na, const StateView<R> &st, const ui
     FA_DISPATCH_NG(ng, CALL)
 #undef CALL
 }
-template <typename R> static cudaError_t step_attr(int ng, int na, bool many, bool wide, cudaFuncAttributes *out) {
-#define CALL(NG) step_attr_g<NG, R>(na, many, wide, out)
+template <typename R> static cudaError_t step_attr(int ng, int na, bool many, int mapping, cudaFuncAttributes *out) {
+#define CALL(NG) step_attr_g<NG, R>(na, many, mapping, out)
     FA_DISPATCH_NG(ng, CALL)
 #undef CALL
 }
@@ -106,7 +106,10 @@ struct FaHandle {
     int block, grid;
     int pdl;            // launch fa_step with programmatic stream serialization (FA_PDL=1 enables)
     uint8_t *alive_end; // optional extra output of every step (fa_set_alive_end_buffer)
-    bool wide;          // one thread per agent (small batches) instead of one thread per env
+    int kmap;           // FA_MAP_ENV / FA_MAP_AGENT / FA_MAP_GROUP actually in use
+    float *mask_next;   // optional rollout bookkeeping outputs of every step (fa_set_rollout_outputs)
+    uint8_t *end_next;
+    float *ep_rew;
     int sm_count;
     uint64_t launches;
     int host_path;      // fa_step_host: 0 auto, 1 staged only, 2 mapped only (env FA_HOST_PATH)
@@ -169,7 +172,7 @@ static int check_cfg(const FaConfig *c) {
                     c->n_guards, c->n_attackers, FA_MAX_TEAM, FA_MAX_TEAM);
     if (c->max_steps < 1) return fail(FA_EINVAL, "max_steps must be >= 1 (got %d)", c->max_steps);
     if (c->scalar != FA_F32 && c->scalar != FA_F64) return fail(FA_EINVAL, "scalar must be FA_F32 or FA_F64");
-    if (c->mapping < FA_MAP_AUTO || c->mapping > FA_MAP_AGENT) return fail(FA_EINVAL, "mapping must be FA_MAP_AUTO/ENV/AGENT");
+    if (c->mapping < FA_MAP_AUTO || c->mapping > FA_MAP_GROUP) return fail(FA_EINVAL, "mapping must be FA_MAP_AUTO/ENV/AGENT/GROUP");
     if ((uint64_t)c->n_envs * (uint64_t)(c->n_guards + c->n_attackers) * 6ull >= (1ull << 40))
         return fail(FA_EINVAL, "n_envs too large");
     return FA_OK;
@@ -189,12 +192,27 @@ template <typename R> static fa::StateView<R> view(const FaHandle *h) {
 // SMs busy); many envs: 128-thread blocks (4 warps share one 6/12 KB obs stage).
 static void pick_launch(FaHandle *h) {
     const int E = h->cfg.n_envs;
-    // FA_MAP_AUTO: thread-per-agent while thread-per-env could not even put two warps on every SM
-    // sub-partition (E < 2 * 4 * 32 * #SM = 37 888 on a B200); measured crossover in DESIGN.md
-    h->wide = h->cfg.mapping == FA_MAP_AGENT || (h->cfg.mapping == FA_MAP_AUTO && E < 2 * 4 * 32 * h->sm_count);
-    if (h->wide) {
+    // FA_MAP_AUTO (measured crossovers in DESIGN.md / profiles/r2i_step_mappings.jsonl):
+    //   sub-warp group per env   while its warps number at most 4 per SM sub-partition (3v3: E <= 9 472, 5v5: E <= 4 736 on a
+    //                            B200): a step lasts one warp's instruction chain, and the group kernel's is the shortest
+    //   thread per agent         up to the batch where thread-per-env puts two warps on every sub-partition (E < 37 888)
+    //   thread per env           beyond: the bandwidth-bound regime
+    const int Gw = h->A <= 2 ? 2 : (h->A <= 4 ? 4 : (h->A <= 8 ? 8 : 16));
+    const long long group_warps = ((long long)E * Gw + 31) / 32;
+    h->kmap = h->cfg.mapping != FA_MAP_AUTO ? h->cfg.mapping
+              : (group_warps <= 4ll * 4 * h->sm_count ? FA_MAP_GROUP : (E < 2 * 4 * 32 * h->sm_count ? FA_MAP_AGENT : FA_MAP_ENV));
+    if (h->kmap == FA_MAP_AGENT) {
         h->block = 32 * h->A;
         h->grid = (E + 31) / 32;
+        return;
+    }
+    if (h->kmap == FA_MAP_GROUP) {
+        const int G = h->A <= 2 ? 2 : (h->A <= 4 ? 4 : (h->A <= 8 ? 8 : 16));
+        const int warps = (E + 32 / G - 1) / (32 / G);
+        int bw = 4;                                        // warps per block: fewer while the blocks would not cover the SMs twice
+        while (bw > 1 && (warps + bw - 1) / bw < 2 * h->sm_count) bw >>= 1;
+        h->block = 32 * bw;
+        h->grid = (warps + bw - 1) / bw;
         return;
     }
     int block = 128;
@@ -208,7 +226,7 @@ static void pick_launch(FaHandle *h) {
 
 template <typename R>
 static cudaError_t do_step(FaHandle *h, bool many, int T, const int32_t *act, void *obs, void *rew, uint8_t *done,
-                           uint8_t *result, int auto_reset, cudaStream_t s) {
+                           uint8_t *result, int auto_reset, cudaStream_t s, bool rollout) {
     const FaConfig &c = h->cfg;
     fa::StepParams<R> p;
     p.st = view<R>(h);
@@ -226,12 +244,15 @@ static cudaError_t do_step(FaHandle *h, bool many, int T, const int32_t *act, vo
     p.seed = c.seed;
     p.env_id0 = c.env_id0;
     p.alive_end = h->alive_end;
+    p.mask_next = rollout ? h->mask_next : nullptr;
+    p.end_next = rollout ? h->end_next : nullptr;
+    p.ep_rew = rollout ? h->ep_rew : nullptr;
     p.pdl = h->pdl && !many;     // single-step launches chain through programmatic dependent launch
-    return fa::launch_step<R>(c.n_guards, c.n_attackers, many, h->wide, p, h->grid, h->block, s);
+    return fa::launch_step<R>(c.n_guards, c.n_attackers, many, h->kmap, p, h->grid, h->block, s);
 }
 
 static int step_common(FaHandle *h, bool many, int T, const int32_t *d_actions, void *d_obs, void *d_reward,
-                       uint8_t *d_done, uint8_t *d_result, int auto_reset, void *stream) {
+                       uint8_t *d_done, uint8_t *d_result, int auto_reset, void *stream, bool rollout = false) {
     NEED_HANDLE(h);
     DevGuard dev_guard(h);
     if (!d_actions) return fail(FA_EINVAL, "actions is NULL");
@@ -239,8 +260,8 @@ static int step_common(FaHandle *h, bool many, int T, const int32_t *d_actions, 
     if (d_obs && (uintptr_t)d_obs % (2 * h->rs)) return fail(FA_EALIGN, "obs must be aligned to %zu bytes", 2 * h->rs);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e = h->cfg.scalar == FA_F64
-                        ? do_step<double>(h, many, T, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, s)
-                        : do_step<float>(h, many, T, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, s);
+                        ? do_step<double>(h, many, T, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, s, rollout)
+                        : do_step<float>(h, many, T, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, s, rollout);
     CUDA_TRY(e);
     h->launches += 1;
     return FA_OK;
@@ -302,6 +323,9 @@ int fa_create(const FaConfig *cfg, void *d_workspace, FaHandle **out) {
     // (5.7 vs 3.7 us/step).
     h->pdl = 0;
     h->alive_end = nullptr;
+    h->mask_next = nullptr;
+    h->end_next = nullptr;
+    h->ep_rew = nullptr;
     h->pipe_ready = false;
     if (const char *ev = getenv("FA_PDL")) h->pdl = ev[0] == '1';
     if (const char *hp = getenv("FA_HOST_PATH")) h->host_path = !strcmp(hp, "staged") ? 1 : (!strcmp(hp, "mapped") ? 2 : 0);
@@ -358,12 +382,12 @@ int fa_reset(FaHandle *h, const uint8_t *d_env_mask, void *d_obs, void *stream) 
 
 int fa_step(FaHandle *h, const int32_t *d_actions, void *d_obs, void *d_reward, uint8_t *d_done, uint8_t *d_result,
             int auto_reset, void *stream) {
-    return step_common(h, false, 1, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, stream);
+    return step_common(h, false, 1, d_actions, d_obs, d_reward, d_done, d_result, auto_reset, stream, true);
 }
 
 int fa_step_many(FaHandle *h, int T, const int32_t *d_actions, void *d_obs, void *d_reward, uint8_t *d_done,
                  uint8_t *d_result, void *stream) {
-    return step_common(h, true, T, d_actions, d_obs, d_reward, d_done, d_result, 1, stream);
+    return step_common(h, true, T, d_actions, d_obs, d_reward, d_done, d_result, 1, stream, true);
 }
 
 // Device-visible alias of a host pointer if it is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a
@@ -615,6 +639,14 @@ int fa_set_alive_end_buffer(FaHandle *h, uint8_t *d_alive_end) {
     return FA_OK;
 }
 
+int fa_set_rollout_outputs(FaHandle *h, float *d_mask_next, uint8_t *d_end_next, float *d_ep_reward) {
+    NEED_HANDLE(h);
+    h->mask_next = d_mask_next;
+    h->end_next = d_end_next;
+    h->ep_rew = d_ep_reward;
+    return FA_OK;
+}
+
 int fa_launch_count(const FaHandle *h, uint64_t *out) {
     NEED_HANDLE(h);
     if (!out) return fail(FA_EINVAL, "out is NULL");
@@ -626,14 +658,14 @@ int fa_kernel_info(const FaHandle *h, int32_t *regs, int32_t *block, int32_t *gr
     NEED_HANDLE(h);
     cudaFuncAttributes a;
     cudaError_t e = h->cfg.scalar == FA_F64
-                        ? fa::step_attr<double>(h->cfg.n_guards, h->cfg.n_attackers, false, h->wide, &a)
-                        : fa::step_attr<float>(h->cfg.n_guards, h->cfg.n_attackers, false, h->wide, &a);
+                        ? fa::step_attr<double>(h->cfg.n_guards, h->cfg.n_attackers, false, h->kmap, &a)
+                        : fa::step_attr<float>(h->cfg.n_guards, h->cfg.n_attackers, false, h->kmap, &a);
     CUDA_TRY(e);
     if (regs) *regs = a.numRegs;
     if (block) *block = h->block;
     if (grid) *grid = h->grid;
     if (smem) *smem = (int32_t)a.sharedSizeBytes;
-    if (mapping) *mapping = h->wide ? FA_MAP_AGENT : FA_MAP_ENV;
+    if (mapping) *mapping = h->kmap;
     return FA_OK;
 }
 

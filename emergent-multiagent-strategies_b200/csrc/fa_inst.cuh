@@ -24,12 +24,15 @@ static cudaError_t launch_one(K kernel, const StepParams<R> &p, int grid, int bl
 }
 
 template <int NG, typename R>
-cudaError_t launch_step_g(int na, bool many, bool wide, const StepParams<R> &p, int grid, int block, cudaStream_t stream) {
+cudaError_t launch_step_g(int na, bool many, int mapping, const StepParams<R> &p, int grid, int block, cudaStream_t stream) {
     cudaError_t e = cudaSuccess;
     switch (na) {
 #define FA_CASE(NA)                                                                                   \
     case NA:                                                                                          \
-        if (wide) {                                                                                   \
+        if (mapping == FA_KMAP_GROUP) {                                                               \
+            if (many) e = launch_one(fa_step_group_kernel<NG, NA, R, true>, p, grid, block, stream);  \
+            else e = launch_one(fa_step_group_kernel<NG, NA, R, false>, p, grid, block, stream);      \
+        } else if (mapping == FA_KMAP_AGENT) {                                                        \
             if (many) e = launch_one(fa_step_wide_kernel<NG, NA, R, true>, p, grid, block, stream);   \
             else e = launch_one(fa_step_wide_kernel<NG, NA, R, false>, p, grid, block, stream);       \
         } else {                                                                                      \
@@ -57,11 +60,14 @@ cudaError_t launch_reset_g(int na, const StateView<R> &st, const uint8_t *mask, 
     return cudaGetLastError();
 }
 
-template <int NG, typename R> cudaError_t step_attr_g(int na, bool many, bool wide, cudaFuncAttributes *out) {
+template <int NG, typename R> cudaError_t step_attr_g(int na, bool many, int mapping, cudaFuncAttributes *out) {
     switch (na) {
 #define FA_CASE(NA)                                                                                            \
     case NA:                                                                                                   \
-        if (wide)                                                                                              \
+        if (mapping == FA_KMAP_GROUP)                                                                          \
+            return many ? cudaFuncGetAttributes(out, (const void *)fa_step_group_kernel<NG, NA, R, true>)      \
+                        : cudaFuncGetAttributes(out, (const void *)fa_step_group_kernel<NG, NA, R, false>);    \
+        if (mapping == FA_KMAP_AGENT)                                                                          \
             return many ? cudaFuncGetAttributes(out, (const void *)fa_step_wide_kernel<NG, NA, R, true>)       \
                         : cudaFuncGetAttributes(out, (const void *)fa_step_wide_kernel<NG, NA, R, false>);     \
         return many ? cudaFuncGetAttributes(out, (const void *)fa_step_kernel<NG, NA, R, true>)                \
@@ -73,13 +79,13 @@ template <int NG, typename R> cudaError_t step_attr_g(int na, bool many, bool wi
 }
 
 #define FA_INSTANTIATE(NG)                                                                                        \
-    template cudaError_t launch_step_g<NG, float>(int, bool, bool, const StepParams<float> &, int, int, cudaStream_t);  \
-    template cudaError_t launch_step_g<NG, double>(int, bool, bool, const StepParams<double> &, int, int, cudaStream_t); \
+    template cudaError_t launch_step_g<NG, float>(int, bool, int, const StepParams<float> &, int, int, cudaStream_t);  \
+    template cudaError_t launch_step_g<NG, double>(int, bool, int, const StepParams<double> &, int, int, cudaStream_t); \
     template cudaError_t launch_reset_g<NG, float>(int, const StateView<float> &, const uint8_t *, float *, int,  \
                                                    uint64_t, uint64_t, int, int, cudaStream_t);                   \
     template cudaError_t launch_reset_g<NG, double>(int, const StateView<double> &, const uint8_t *, double *,    \
                                                     int, uint64_t, uint64_t, int, int, cudaStream_t);             \
-    template cudaError_t step_attr_g<NG, float>(int, bool, bool, cudaFuncAttributes *);                                 \
-    template cudaError_t step_attr_g<NG, double>(int, bool, bool, cudaFuncAttributes *);
+    template cudaError_t step_attr_g<NG, float>(int, bool, int, cudaFuncAttributes *);                                 \
+    template cudaError_t step_attr_g<NG, double>(int, bool, int, cudaFuncAttributes *);
 
 }  // namespace fa

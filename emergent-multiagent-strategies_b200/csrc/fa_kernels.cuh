@@ -72,12 +72,29 @@ template <typename R> struct StepParams {
     uint8_t *alive_end;   // [T][E] (may be null): alive guards | alive attackers << 4 at the END of the step, before any reset
     int pdl;              // launched with programmatic stream serialization: the state is read after griddepcontrol.wait
     uint64_t seed, env_id0;
+    // optional rollout bookkeeping, fused into the step (fa_set_rollout_outputs; train_fortattack.py:53,97-104, storage.py:41):
+    float *mask_next;     // [T][A][E]  done ? alive flag of the (reset) observation : alive flag before the step
+    uint8_t *end_next;    // [T][E]     done
+    float *ep_rew;        // [A][E]     += reward * alive flag before the step
 };
+
+// the three bookkeeping outputs of one (agent, env) pair; alive0 = alive before the step, alive2 = alive in the new observation
+template <typename R>
+__device__ __forceinline__ void rollout_outputs(const StepParams<R> &p, size_t t, int A, size_t E, int i, int e, bool alive0,
+                                                bool alive2, bool dn, R rew) {
+    const size_t k = (size_t)i * E + e;
+    if (p.mask_next != nullptr) p.mask_next[t * A * E + k] = (dn ? alive2 : alive0) ? 1.0f : 0.0f;
+    if (p.ep_rew != nullptr && alive0) p.ep_rew[k] += (float)rew;
+    if (p.end_next != nullptr && i == 0) p.end_next[t * E + e] = dn ? 1 : 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // scalar helpers (float: SFU approximations are ~1e-7 relative, far inside the 1e-5 parity budget)
 __device__ __forceinline__ float rsqrt_t(float v) { return rsqrtf(v); }
 __device__ __forceinline__ double rsqrt_t(double v) { return 1.0 / sqrt(v); }
+// rsqrtf pinned where it is written (the select-style code below wants it issued unconditionally, ahead of its use)
+__device__ __forceinline__ float rsqrt_pinned(float v) { float r; asm volatile("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ double rsqrt_pinned(double v) { return 1.0 / sqrt(v); }
 __device__ __forceinline__ float sqrt_t(float v) { return sqrtf(v); }
 __device__ __forceinline__ double sqrt_t(double v) { return sqrt(v); }
 __device__ __forceinline__ float max_t(float a, float b) { return fmaxf(a, b); }
@@ -487,6 +504,9 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) fa_step_kernel(const StepParam
         }
         R rew[A];
         int result;
+        uint32_t alive_before = 0;
+#pragma unroll
+        for (int i = 0; i < A; ++i) alive_before |= (s.fl[i] & F_ALIVE) << i;
         const bool dn = step_env<NG, NA, R>(s, act, p.max_steps, rew, result);
         if (p.alive_end != nullptr && valid) {         // world.numAliveGuards / numAliveAttackers as the episode's last step leaves them
             int ag = 0, aa = 0;
@@ -509,6 +529,11 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) fa_step_kernel(const StepParam
         }
         if (p.done != nullptr && valid) p.done[(size_t)t * E + e] = dn ? 1 : 0;
         if (p.result != nullptr && valid) p.result[(size_t)t * E + e] = (uint8_t)result;
+        if ((p.mask_next != nullptr || p.ep_rew != nullptr || p.end_next != nullptr) && valid) {
+#pragma unroll
+            for (int i = 0; i < A; ++i)
+                rollout_outputs<R>(p, (size_t)t, A, E, i, e, alive_before >> i & 1u, s.fl[i] & F_ALIVE, dn, rew[i]);
+        }
         if (p.obs != nullptr) store_obs<A, R>(s, p.obs + plane * E * OBS_DIM, E, e, lane, valid, vec, stage[warp]);
         if (MANY) {
 #pragma unroll
@@ -712,6 +737,7 @@ __global__ void __launch_bounds__(32 * (NG + NA)) fa_step_wide_kernel(const Step
         // ---- outputs ----------------------------------------------------------------------------
         const size_t plane = (size_t)t * A;
         if (p.rew != nullptr && valid) p.rew[(plane + i) * E + e] = r;
+        if (valid) rollout_outputs<R>(p, (size_t)t, A, E, i, e, alive0, s.fl[0] & F_ALIVE, dn, r);
         if (i == 0 && valid) {
             if (p.done != nullptr) p.done[(size_t)t * E + e] = dn ? 1 : 0;
             if (p.result != nullptr) p.result[(size_t)t * E + e] = (uint8_t)result;
@@ -755,6 +781,232 @@ __global__ void __launch_bounds__(32 * (NG + NA)) fa_step_wide_kernel(const Step
         p.st.ap[i * E + e] = w;
         p.st.fl[i * E + e] = s.fl[0];
         if (i == 0) { p.st.tstep[e] = s.t; p.st.episode[e] = ep; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same step with one SUB-WARP GROUP per env: G = 2/4/8/16 consecutive lanes (the power of two >= A) hold the agents of
+// one env, 32 / G envs per warp, and nothing crosses a warp -- no block barrier anywhere in the step.
+//   agent block   each lane publishes (x, y, cos, sin) of its agent as ONE 16-byte shared-memory word in the warp's
+//                 stage (double-buffered by step parity, one __syncwarp per step) and reads the A words of its env:
+//                 the O(A^2) laser and contact tests then run on registers
+//   masks         alive-before / shoots / alive-after-the-kill / inside-the-fort are warp ballots, shifted down to the
+//                 group: "who was hit", "how many attackers are left" and "did the nearest alive attacker reach the
+//                 fort" (min over the team < FORT_DIM  <=>  any member < FORT_DIM) are popc / != 0 on those masks
+// Per-agent arithmetic is statement for statement that of fa_step_wide_kernel, so the two mappings agree bit for bit.
+// Global accesses: a warp touches 32 / G consecutive envs of each agent plane (whole 32-byte sectors for pv / ap / obs); this
+// mapping is chosen for batches that live in L2 (FA_MAP_AUTO: E < 37 888), where latency, not sector efficiency, is the limit.
+template <int A> struct GroupOf { static constexpr int G = A <= 2 ? 2 : (A <= 4 ? 4 : (A <= 8 ? 8 : 16)); };
+
+template <typename R>
+__device__ __forceinline__ bool in_cone(R sx, R sy, R cs, R sn, R qx, R qy) {
+    typedef K<R> C;
+    const R dx = qx - (sx + C::SIZE * cs), dy = qy - (sy + C::SIZE * sn);     // q relative to the apex (core.py:376)
+    const R a = (dx * cs + dy * sn) * C::INV_LC8, b = (dy * cs - dx * sn) * C::INV_LS8;
+    return a <= R(1) && a + b >= R(0) && a - b >= R(0);
+}
+
+template <int NG, int NA, typename R, bool MANY>
+__global__ void __launch_bounds__(32 * MAX_WARPS) fa_step_group_kernel(const StepParams<R> p) {
+    constexpr int A = NG + NA, G = GroupOf<A>::G, EPW = 32 / G;
+    constexpr uint32_t GM = (1u << A) - 1u, GRD_BITS = (1u << NG) - 1u, ATT_BITS = GM & ~GRD_BITS, FULL = 0xffffffffu;
+    typedef K<R> C;
+    typedef typename VecT<R>::T4 T4;
+    typedef typename VecT<R>::T2 T2;
+    __shared__ __align__(32) T4 block_stage[MAX_WARPS][2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int il = lane & (G - 1), base = lane - il;                   // lane within the group, first lane of the group
+    const long long e0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * EPW;
+    if (e0 >= p.E) return;                                             // whole warp out of range
+    const int e = (int)e0 + lane / G;
+    const bool agent = il < A;                                         // padding lanes (A < G) shadow the last agent, never store
+    const bool valid = agent && e < p.E;
+    const int ec = e < p.E ? e : p.E - 1, i = agent ? il : A - 1;
+    const size_t E = (size_t)p.E;
+    const bool attacker = i >= NG;
+    const uint32_t opp_bits = attacker ? GRD_BITS : ATT_BITS;
+    constexpr int NOPP_MAX = NG > NA ? NG : NA;
+    const int j0 = attacker ? 0 : NG, nopp = attacker ? NG : NA;       // the other team
+
+    pdl_launch_dependents();
+    int act = p.act[i * E + ec], nxt1 = 0, nxt2 = 0;
+    if (MANY && p.T > 1) nxt1 = p.act[((size_t)A + i) * E + ec];
+    pdl_wait();
+    R x, y, vx, vy, ang, pd;
+    uint32_t fl;
+    {
+        const T4 v = p.st.pv[i * E + ec];
+        const T2 w = p.st.ap[i * E + ec];
+        x = v.x; y = v.y; vx = v.z; vy = v.w; ang = w.x; pd = w.y;
+        fl = p.st.fl[i * E + ec];
+    }
+    int32_t ts = p.st.tstep[ec];
+    uint32_t ep = p.st.episode[ec];
+    const int T = MANY ? p.T : 1;
+    size_t off_ae = (size_t)i * E + ec, off_e = (size_t)ec;            // this lane's element in [t][A][E] / [t][E] outputs
+    for (int t = 0; t < T; ++t) {
+        if (MANY && t + 2 < T) nxt2 = p.act[((size_t)(t + 2) * A + i) * E + ec];    // two steps ahead: a step is shorter than an L2 round trip
+        // ---- publish the agent block ---------------------------------------------------------------
+        // Everything from here to the reward is written as straight-line selects, not branches: with ~7 warps per SM at the
+        // batch sizes this mapping serves, a step's duration is one warp's dependent-instruction chain, and the A cone tests
+        // and A - 1 contact pairs of a lane are independent of each other -- the compiler can only overlap them if no
+        // divergent region separates them.  (The selected values are those the branches of fa_step_wide_kernel compute.)
+        const bool alive0 = agent && (fl & F_ALIVE), shoot = act == 7, shooter = shoot && alive0;
+        fl = alive0 ? (fl & ~(F_HIT | F_WASHIT)) : fl;
+        R sn, cs;
+        AngOps<R>::sincos_heading(ang, sn, cs);
+        sn = shooter ? sn : R(0); cs = shooter ? cs : R(0);
+        T4 *stg = block_stage[warp][t & 1];
+        {
+            T4 me; me.x = x; me.y = y; me.z = cs; me.w = sn;
+            stg[lane] = me;
+        }
+        const uint32_t m_alive0 = (__ballot_sync(FULL, alive0) >> base) & GM;
+        const uint32_t m_shoot = (__ballot_sync(FULL, shooter) >> base) & GM;
+        __syncwarp();
+        // ---- apply_laser_effect: as shooter and as victim (core.py:254-302) ----------------------
+        {
+            const uint32_t targets = alive0 ? (opp_bits & m_alive0) : 0u;      // alive opponents of an alive agent
+            const uint32_t as_shooter = (shoot ? targets : 0u) >> j0, as_victim = (targets & m_shoot) >> j0;
+            int n_hit = 0, n_was = 0;
+#pragma unroll
+            for (int jj = 0; jj < NOPP_MAX; ++jj) {                            // opponent jj of this lane's team (lane-dependent address)
+                const T4 q = stg[base + j0 + (jj < nopp ? jj : 0)];
+                const bool h = in_cone<R>(x, y, cs, sn, q.x, q.y);
+                const bool w = in_cone<R>(q.x, q.y, q.z, q.w, x, y);
+                n_hit += (h && (as_shooter >> jj & 1u)) ? 1 : 0;
+                n_was += (w && (as_victim >> jj & 1u)) ? 1 : 0;
+            }
+            const int c_hit = min((int)((fl >> F_NHIT_SHIFT) & F_CNT_MASK) + n_hit, (int)F_CNT_MASK);
+            const int c_was = min((int)((fl >> F_NWAS_SHIFT) & F_CNT_MASK) + n_was, (int)F_CNT_MASK);
+            fl = (fl & ~((F_CNT_MASK << F_NHIT_SHIFT) | (F_CNT_MASK << F_NWAS_SHIFT))) | ((uint32_t)c_hit << F_NHIT_SHIFT) |
+                 ((uint32_t)c_was << F_NWAS_SHIFT) | (n_hit ? F_HIT : 0u) | (n_was ? F_WASHIT : 0u);
+        }
+        fl = !(fl & F_ALIVE) ? (fl & ~F_JD) : ((fl & F_WASHIT) ? ((fl & ~F_ALIVE) | F_JD) : fl);
+        const bool alive1 = agent && (fl & F_ALIVE);
+        const uint32_t m_alive1 = (__ballot_sync(FULL, alive1) >> base) & GM;
+        // ---- forces on this agent + integrate (core.py:204-213) ---------------------------------
+        {
+            R fx = act == 1 ? C::ACCEL : (act == 2 ? -C::ACCEL : R(0));
+            R fy = act == 3 ? C::ACCEL : (act == 4 ? -C::ACCEL : R(0));
+            const uint32_t others = m_alive1 & ~(1u << i);
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                const T2 q = *reinterpret_cast<const T2 *>(&stg[base + j]);
+                const R dx = x - q.x, dy = y - q.y;
+                const R r2 = dx * dx + dy * dy;
+                const bool touch = (others >> j & 1u) && r2 < ContactGate<R>::R2;
+                if (sizeof(R) == 4) {
+                    const R rinv = rsqrt_pinned(r2);
+                    const R g = touch ? C::CONTACT_FORCE * penetration(C::DIST_MIN - r2 * rinv) * rinv : R(0);
+                    fx += g * dx; fy += g * dy;
+                } else if (touch) {                                   // double: the softplus itself (log1p / exp), rarely needed
+                    const R rinv = rsqrt_t(r2);
+                    const R g = C::CONTACT_FORCE * penetration(C::DIST_MIN - r2 * rinv) * rinv;
+                    fx += g * dx; fy += g * dy;
+                }
+            }
+            fx += C::CONTACT_FORCE * (penetration(-C::WALL_X - x) - penetration(x - C::WALL_X));
+            fy += C::CONTACT_FORCE * (penetration(-C::WALL_Y - y) - penetration(y - C::WALL_Y));
+            R nvx = vx * C::DAMP + fx * C::DT, nvy = vy * C::DAMP + fy * C::DT;
+            const R sp2 = nvx * nvx + nvy * nvy;
+            const R k = sp2 > C::MAX_SPEED * C::MAX_SPEED ? C::MAX_SPEED * rsqrt_t(sp2) : R(1);
+            nvx = sp2 > C::MAX_SPEED * C::MAX_SPEED ? nvx * k : nvx;
+            nvy = sp2 > C::MAX_SPEED * C::MAX_SPEED ? nvy * k : nvy;
+            if (alive1) {
+                AngOps<R>::advance(ang, fl, act);
+                vx = nvx; vy = nvy;
+                x += nvx * C::DT; y += nvy * C::DT;
+            }
+        }
+        const R ddy = y - C::DOOR_Y;
+        const R d = sqrt_t(x * x + ddy * ddy);
+        // ---- reward, done (fortattack_env_v1.py:87-188, fortattack.py:202-225) -------------------
+        const bool reached = ((__ballot_sync(FULL, alive1 && attacker && d < C::FORT_DIM) >> base) & GM) != 0u;
+        const int n_alive_att = __popc(m_alive1 & ATT_BITS);
+        R r = R(0);
+        if (fl & (F_ALIVE | F_JD)) {
+            const bool has_prev = pd == pd;
+            if (attacker) {
+                if (has_prev) r += R(2) * (pd - d);
+                if (d < C::FORT_DIM) r += R(10);
+                if (shoot) r -= R(1);
+                if (fl & F_HIT) r += R(3);
+                if (fl & F_WASHIT) r -= R(3);
+                if (n_alive_att == 0) r -= R(10);
+            } else {
+                if (has_prev) {
+                    if (d > C::GUARD_RING && pd <= C::GUARD_RING) r = R(-1);
+                    else if (d <= C::GUARD_RING && pd > C::GUARD_RING) r = R(1);
+                }
+                if (reached) r -= R(10);
+                if (shoot) r -= R(0.1);
+                if (fl & F_HIT) r += R(3);
+                if (fl & F_WASHIT) r -= R(3);
+                if (n_alive_att == 0) r += R(10);
+            }
+            pd = d;
+        }
+        int result;
+        bool dn = true;
+        if (reached) result = 3;
+        else if (n_alive_att == 0) result = 1;
+        else if (ts == p.max_steps - 1) result = 2;
+        else { result = 0; dn = false; }
+        ts += 1;
+        if (dn && (MANY || p.auto_reset)) {
+            // reset_world for this lane's agent: Philox block of its pair, words (2h, 2h+1)
+            const uint64_t id = p.env_id0 + (uint64_t)ec;
+            uint32_t c[4] = {(uint32_t)id, (uint32_t)(id >> 32), ep, (uint32_t)(i >> 1)};
+            philox4x32_10((uint32_t)p.seed, (uint32_t)(p.seed >> 32), c);
+            const int h = i & 1;
+            const double ux = u01(h ? c[2] : c[0]), uy = u01(h ? c[3] : c[1]);
+            double px, py;
+            if (attacker) {
+                px = __dadd_rn(-1.0, __dmul_rn(1.0 - (-1.0), ux));
+                py = __dadd_rn(-0.8, __dmul_rn(0.8 * -0.8 - (-0.8), uy));
+            } else {
+                const double lo = -0.8 * 0.15 / 2, hi = 0.8 * 0.15 / 2;
+                px = __dadd_rn(lo, __dmul_rn(hi - lo, ux));
+                py = __dadd_rn(0.8 * 0.8, __dmul_rn(0.8 - 0.8 * 0.8, uy));
+            }
+            x = (R)px; y = (R)py; vx = R(0); vy = R(0);
+            fl = (fl & (F_JD | (~0u << F_WRAP_SHIFT))) | F_ALIVE;
+            AngOps<R>::set_reset(ang, fl, attacker);
+            ts = 0;
+            ep += 1;
+        }
+        // ---- outputs (element offsets of this step advance by one plane set per step) -------------
+        if (valid) {
+            if (p.rew != nullptr) p.rew[off_ae] = r;
+            if (p.mask_next != nullptr) p.mask_next[off_ae] = ((dn ? (fl & F_ALIVE) != 0u : alive0)) ? 1.0f : 0.0f;
+            if (p.ep_rew != nullptr && alive0) p.ep_rew[(size_t)i * E + e] += (float)r;
+            if (i == 0) {
+                if (p.end_next != nullptr) p.end_next[off_e] = dn ? 1 : 0;
+                if (p.done != nullptr) p.done[off_e] = dn ? 1 : 0;
+                if (p.result != nullptr) p.result[off_e] = (uint8_t)result;
+                if (p.alive_end != nullptr)
+                    p.alive_end[off_e] = (uint8_t)(__popc(m_alive1 & GRD_BITS) | (__popc(m_alive1 & ATT_BITS) << 4));
+            }
+            if (p.obs != nullptr) {
+                T2 o0, o1, o2;
+                o0.x = (fl & F_ALIVE) ? R(1) : R(0); o0.y = x;
+                o1.x = y; o1.y = AngOps<R>::full(ang, fl);
+                o2.x = vx; o2.y = vy;
+                T2 *gdst = reinterpret_cast<T2 *>(p.obs + off_ae * OBS_DIM);
+                gdst[0] = o0; gdst[1] = o1; gdst[2] = o2;
+            }
+        }
+        off_ae += (size_t)A * E; off_e += E;
+        if (MANY) { act = nxt1; nxt1 = nxt2; }
+    }
+    if (valid) {
+        T4 v; v.x = x; v.y = y; v.z = vx; v.w = vy;
+        T2 w; w.x = ang; w.y = pd;
+        p.st.pv[i * E + e] = v;
+        p.st.ap[i * E + e] = w;
+        p.st.fl[i * E + e] = fl;
+        if (i == 0) { p.st.tstep[e] = ts; p.st.episode[e] = ep; }
     }
 }
 

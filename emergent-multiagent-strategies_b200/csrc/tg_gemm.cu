@@ -36,10 +36,11 @@ using namespace mp;
 constexpr int ROWS = 128, KC = 64;
 constexpr uint32_t A_SBO = 128, A_LBO = ROWS * 16 + 16;           // bytes
 constexpr uint32_t HALF = (KC / 8) * A_LBO, STAGE = 2 * HALF;     // 16512, 33024
-constexpr int EPI_WARPS = 4, LOAD_WARPS = 8, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS;
+constexpr int EPI_WARPS = 8, LOAD_WARPS = 8, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS;
 constexpr int THREADS = (MMA_WARP + 1) * 32, LOAD_THREADS = LOAD_WARPS * 32;
 constexpr int MAX_NST = 6, SCALE_SLOTS = 2;
-constexpr int TB_BYTES = EPI_WARPS * 32 * 33 * 4, RS_BYTES = SCALE_SLOTS * 2 * ROWS * 4, BIAS_BYTES = 256 * 4;
+constexpr int TB_STRIDE = 20;                                     // floats per row of a warp's 32 x 16 transposition block
+constexpr int TB_BYTES = EPI_WARPS * 32 * TB_STRIDE * 4, RS_BYTES = SCALE_SLOTS * 2 * ROWS * 4, BIAS_BYTES = 2 * 256 * 4;
 constexpr int FIXED_BYTES = TB_BYTES + RS_BYTES + BIAS_BYTES;
 constexpr int SMEM_LIMIT = 232448 - 1024;                         // 227 KB minus the static barriers
 
@@ -91,8 +92,9 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *ring = smem + p.wbytes;
     float *tb = reinterpret_cast<float *>(ring + (size_t)p.nst * STAGE);
-    float *rowscale = tb + EPI_WARPS * 32 * 33;                  // [SCALE_SLOTS][2][ROWS]
-    float *bias_s = rowscale + SCALE_SLOTS * 2 * ROWS;            // [256]
+    float *rowscale = tb + EPI_WARPS * 32 * TB_STRIDE;            // [SCALE_SLOTS][2][ROWS]
+    float *bias_s = rowscale + SCALE_SLOTS * 2 * ROWS;            // [256] bias, then [256] inverse weight scale per column
+    float *winv_s = bias_s + 256;
 
     if (tid == 0) {
         for (int s = 0; s < p.nst; ++s) { mbar_init(&bar_full[s], LOAD_THREADS); mbar_init(&bar_empty[s], 1); }
@@ -101,7 +103,10 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
-    for (int i = tid; i < 256; i += THREADS) bias_s[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
+    for (int i = tid; i < 256; i += THREADS) {
+        bias_s[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
+        winv_s[i] = i < p.Np ? reinterpret_cast<const float *>(p.packed + p.wbytes)[i] : 0.0f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -157,110 +162,156 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
         }
     } else if (warp >= LOAD_WARP0) {
         // ================= loaders =================
+        // lane = (row-in-pass sub, 8-column chunk kc): a warp reads 4 rows x 256 contiguous bytes per pass.  A group (<= 128
+        // columns of a 128-row tile) is processed in two batches of two passes (32 data registers in flight per thread);
+        // both ring stages of the group are acquired first and released together.
         const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
         const int halves = p.gw / KC;                             // 64-column halves of a group: 1 or 2
         uint32_t sc = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             for (int g = 0; g < p.groups; ++g) {
-                float4 v[4][2][2];
+                const uint32_t s0 = sc % (uint32_t)p.nst, ph0 = (sc / (uint32_t)p.nst) & 1u;
+                const uint32_t s1 = (sc + 1) % (uint32_t)p.nst, ph1 = ((sc + 1) / (uint32_t)p.nst) & 1u;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const long long row = (long long)tile * ROWS + lw * 16 + q * 4 + sub;
-                    const float *src = p.x + row * p.ldx;
+                for (int batch = 0; batch < 2; ++batch) {
+                    float4 v[2][2][2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = g * p.gw + h * KC + kc * 8;
-                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-                        if (h < halves && row < p.rows) {
-                            if (p.vec_ok && col + 8 <= p.K) {
-                                a = __ldg(reinterpret_cast<const float4 *>(src + col));
-                                c = __ldg(reinterpret_cast<const float4 *>(src + col + 4));
-                            } else if (col < p.K) {
-                                float t[8];
+                    for (int q = 0; q < 2; ++q) {
+                        const long long row = (long long)tile * ROWS + lw * 16 + (batch * 2 + q) * 4 + sub;
+                        const float *src = p.x + row * p.ldx;
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) t[e] = col + e < p.K ? __ldg(src + col + e) : 0.0f;
-                                a = make_float4(t[0], t[1], t[2], t[3]);
-                                c = make_float4(t[4], t[5], t[6], t[7]);
+                        for (int h = 0; h < 2; ++h) {
+                            const int col = g * p.gw + h * KC + kc * 8;
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+                            if (h < halves && row < p.rows) {
+                                if (p.vec_ok && col + 8 <= p.K) {
+                                    a = __ldg(reinterpret_cast<const float4 *>(src + col));
+                                    c = __ldg(reinterpret_cast<const float4 *>(src + col + 4));
+                                } else if (col < p.K) {
+                                    float t[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) t[e] = col + e < p.K ? __ldg(src + col + e) : 0.0f;
+                                    a = make_float4(t[0], t[1], t[2], t[3]);
+                                    c = make_float4(t[4], t[5], t[6], t[7]);
+                                }
+                            }
+                            v[q][h][0] = a; v[q][h][1] = c;
+                        }
+                    }
+                    if (batch == 0) {
+                        // the row scales of tile `it` live in slot it & 1, which the epilogue of tile it - 2 may still be reading:
+                        // wait for it exactly as the MMA issuer does (the loads above are already in flight)
+                        if (g == 0) mbar_wait(&bar_acc_empty[it & 1], (uint32_t)(((it >> 1) & 1) ^ 1), p.status, 6);
+                        mbar_wait(&bar_empty[s0], ph0 ^ 1u, p.status, 4);
+                        if (halves > 1) mbar_wait(&bar_empty[s1], ph1 ^ 1u, p.status, 4);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int r = lw * 16 + (batch * 2 + q) * 4 + sub;
+                        float m = fmaxf(fmaxf(amax4(v[q][0][0]), amax4(v[q][0][1])), fmaxf(amax4(v[q][1][0]), amax4(v[q][1][1])));
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                        float inv;
+                        const float s = pow2_scale(m, &inv);
+                        if (kc == 0) rowscale[((it & (SCALE_SLOTS - 1)) * 2 + g) * ROWS + r] = inv;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (h < halves) {
+                                scale4(v[q][h][0], s); scale4(v[q][h][1], s);
+                                uint4 hi, lo;
+                                split8_f16(v[q][h][0], v[q][h][1], hi, lo);
+                                uint8_t *st = ring + (size_t)(h == 0 ? s0 : s1) * STAGE + (uint32_t)kc * A_LBO + (uint32_t)r * 16u;
+                                *reinterpret_cast<uint4 *>(st) = hi;
+                                *reinterpret_cast<uint4 *>(st + HALF) = lo;
                             }
                         }
-                        v[q][h][0] = a; v[q][h][1] = c;
                     }
                 }
-                // the row scales of tile `it` live in slot it & 1, which the epilogue of tile it - 2 may still be reading: wait
-                // for it exactly as the MMA issuer does (the loads above are already in flight)
-                if (g == 0) mbar_wait(&bar_acc_empty[it & 1], (uint32_t)(((it >> 1) & 1) ^ 1), p.status, 6);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float m = fmaxf(fmaxf(amax4(v[q][0][0]), amax4(v[q][0][1])), fmaxf(amax4(v[q][1][0]), amax4(v[q][1][1])));
-                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                    float inv;
-                    const float s = pow2_scale(m, &inv);
-                    if (kc == 0) rowscale[((it & (SCALE_SLOTS - 1)) * 2 + g) * ROWS + lw * 16 + q * 4 + sub] = inv;
-                    scale4(v[q][0][0], s); scale4(v[q][0][1], s); scale4(v[q][1][0], s); scale4(v[q][1][1], s);
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h < halves) {
-                        const uint32_t s = sc % (uint32_t)p.nst, ph = (sc / (uint32_t)p.nst) & 1u;
-                        mbar_wait(&bar_empty[s], ph ^ 1u, p.status, 4);
-                        uint8_t *st = ring + (size_t)s * STAGE + (uint32_t)kc * A_LBO;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 hi, lo;
-                            split8_f16(v[q][h][0], v[q][h][1], hi, lo);
-                            const uint32_t off = (uint32_t)(lw * 16 + q * 4 + sub) * 16u;
-                            *reinterpret_cast<uint4 *>(st + off) = hi;
-                            *reinterpret_cast<uint4 *>(st + HALF + off) = lo;
-                        }
-                        fence_async_smem();
-                        mbar_arrive(&bar_full[s]);
-                        ++sc;
-                    }
-                }
+                fence_async_smem();
+                mbar_arrive(&bar_full[s0]);
+                if (halves > 1) mbar_arrive(&bar_full[s1]);
+                sc += (uint32_t)halves;
             }
         }
     } else {
-        // ================= epilogue: thread = accumulator row =================
-        const int r = warp * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        float *tbw = tb + warp * 32 * 33;
-        const float w_inv = *reinterpret_cast<const float *>(p.packed + p.wbytes);
-        const int chunks = (p.N + 31) / 32;
+        // ================= epilogue: thread = accumulator row (phase A), 4 columns x 4 row octets (phase B) ==========
+        // warps w and w + 4 share tensor-memory lanes 32 (w % 4) .. + 31 and split the 16-column blocks between them.
+        // Phase A: tcgen05.ld of 16 columns of the thread's row, times the row's inverse scale, into the warp's 32 x 16
+        // transposition block.  Phase B: lane = (row octet member l & 7, column quad l >> 3): 16-byte loads from the block,
+        // times the column's inverse weight scale, + bias, ReLU, (+ previous output), 16-byte global stores -- one warp
+        // store covers 8 rows x 64 contiguous bytes.
+        const int lw = warp & 3, half = warp >> 2;
+        const int r = lw * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(lw * 32) << 16);
+        float *tbw = tb + warp * 32 * TB_STRIDE;
+        const int nblk = (p.N + 15) / 16;                              // 16-column blocks of the output
+        const int rq = lane & 7, cq = lane >> 3;                       // phase-B row (within an octet) and column quad
+        const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out & 15) == 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
+            const long long row0 = (long long)tile * ROWS + lw * 32;
+            // accumulate mode: the previous output does not depend on the MMAs -- fetch the first block's values early
             mbar_wait(&bar_acc_full[b], (uint32_t)((it >> 1) & 1), p.status, 5);
             tc_fence_after();
             const float *rs = rowscale + (it & (SCALE_SLOTS - 1)) * 2 * ROWS;
-            const float inv0 = rs[r] * w_inv, inv1 = p.groups > 1 ? rs[ROWS + r] * w_inv : 0.0f;
-            const long long row0 = (long long)tile * ROWS + warp * 32;
-            for (int c = 0; c < chunks; ++c) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(trow + (uint32_t)(b * acc_cols + c * 32), v0);
-                if (p.groups > 1) tmem_ld32(trow + (uint32_t)(b * acc_cols + p.Np + c * 32), v1);
+            const float inv0 = rs[r], inv1 = p.groups > 1 ? rs[ROWS + r] : 0.0f;
+            for (int c = half; c < nblk; c += 2) {
+                const int col = c * 16 + cq * 4;
+                float4 old[4];
+                if (p.acc) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long row = row0 + i * 8 + rq;
+                        old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < p.rows && col < p.N) {
+                            const float *src = p.out + row * p.ldo + col;
+                            if (vec_out && col + 4 <= p.N) old[i] = *reinterpret_cast<const float4 *>(src);
+                            else {
+                                old[i].x = src[0];
+                                if (col + 1 < p.N) old[i].y = src[1];
+                                if (col + 2 < p.N) old[i].z = src[2];
+                                if (col + 3 < p.N) old[i].w = src[3];
+                            }
+                        }
+                    }
+                }
+                uint32_t v0[16], v1[16];
+                tmem_ld16(trow + (uint32_t)(b * acc_cols + c * 16), v0);
+                if (p.groups > 1) tmem_ld16(trow + (uint32_t)(b * acc_cols + p.Np + c * 16), v1);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = __uint_as_float(v0[j]) * inv0;
-                    if (p.groups > 1) f = fmaf(__uint_as_float(v1[j]), inv1, f);
-                    tbw[lane * 33 + j] = f;
+                for (int j = 0; j < 16; j += 4) {
+                    float4 f;
+                    f.x = __uint_as_float(v0[j]) * inv0; f.y = __uint_as_float(v0[j + 1]) * inv0;
+                    f.z = __uint_as_float(v0[j + 2]) * inv0; f.w = __uint_as_float(v0[j + 3]) * inv0;
+                    if (p.groups > 1) {
+                        f.x = fmaf(__uint_as_float(v1[j]), inv1, f.x); f.y = fmaf(__uint_as_float(v1[j + 1]), inv1, f.y);
+                        f.z = fmaf(__uint_as_float(v1[j + 2]), inv1, f.z); f.w = fmaf(__uint_as_float(v1[j + 3]), inv1, f.w);
+                    }
+                    *reinterpret_cast<float4 *>(tbw + lane * TB_STRIDE + j) = f;
                 }
                 __syncwarp();
-                const int col = c * 32 + lane;
-                if (col < p.N) {
-                    const float bias = bias_s[col];
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const long long row = row0 + rr;
-                        if (row < p.rows) {
-                            float f = tbw[rr * 33 + lane] + bias;
-                            if (p.relu) f = fmaxf(f, 0.0f);
-                            float *dst = p.out + row * p.ldo + col;
-                            if (p.acc) f += *dst;
-                            *dst = f;
+                const float4 wi = *reinterpret_cast<const float4 *>(winv_s + col);
+                const float4 bi = *reinterpret_cast<const float4 *>(bias_s + col);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = i * 8 + rq;
+                    const long long row = row0 + rr;
+                    float4 f = *reinterpret_cast<const float4 *>(tbw + rr * TB_STRIDE + cq * 4);
+                    f.x = fmaf(f.x, wi.x, bi.x); f.y = fmaf(f.y, wi.y, bi.y); f.z = fmaf(f.z, wi.z, bi.z); f.w = fmaf(f.w, wi.w, bi.w);
+                    if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+                    if (p.acc) { f.x += old[i].x; f.y += old[i].y; f.z += old[i].z; f.w += old[i].w; }
+                    if (row < p.rows && col < p.N) {
+                        float *dst = p.out + row * p.ldo + col;
+                        if (vec_out && col + 4 <= p.N) *reinterpret_cast<float4 *>(dst) = f;
+                        else {
+                            dst[0] = f.x;
+                            if (col + 1 < p.N) dst[1] = f.y;
+                            if (col + 2 < p.N) dst[2] = f.z;
+                            if (col + 3 < p.N) dst[3] = f.w;
                         }
                     }
                 }
@@ -278,35 +329,24 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
 // ---- weight packing ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tg_pack_kernel(const float *w, int N, int K, int Np, int Kp, int ld, int transposed,
                                                       uint8_t *out) {
-    __shared__ float red[8];
-    __shared__ float s_scale;
-    const int tid = threadIdx.x;
+    // one CTA = 8 consecutive rows n of B (one row group of core matrices); one warp = one row: its own power-of-two
+    // scale (the epilogue multiplies column n of the product by the inverse), then the hi / lo planes of that row
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     float m = 0.0f;
-    for (int i = tid; i < N * K; i += 256) {
-        const int n = transposed ? i % N : i / K, k = transposed ? i / N : i % K;      // coalesced in either orientation
-        m = fmaxf(m, fabsf(w[transposed ? (size_t)k * ld + n : (size_t)n * ld + k]));
-    }
+    if (n < N)
+        for (int k = lane; k < K; k += 32) m = fmaxf(m, fabsf(w[transposed ? (size_t)k * ld + n : (size_t)n * ld + k]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0) red[tid >> 5] = m;
-    __syncthreads();
-    if (tid == 0) {
-        float t = red[0];
-        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
-        float inv;
-        s_scale = pow2_scale(t, &inv);
-        *reinterpret_cast<float *>(out + (size_t)4 * Np * Kp) = inv;
-    }
-    __syncthreads();
-    const float s = s_scale;
+    float inv;
+    const float s = pow2_scale(m, &inv);
+    if (lane == 0) reinterpret_cast<float *>(out + (size_t)4 * Np * Kp)[n] = n < N ? inv : 0.0f;
     __half *hi = reinterpret_cast<__half *>(out), *lo = hi + (size_t)Np * Kp;
-    for (int i = tid; i < Np * Kp; i += 256) {
-        // i runs over the canonical order: ((n/8) * (Kp/8) + k/8) * 64 + (n%8) * 8 + k%8
-        const int k8 = i & 7, n8 = (i >> 3) & 7, blk = i >> 6, kb = blk % (Kp / 8), nb = blk / (Kp / 8);
-        const int n = nb * 8 + n8, k = kb * 8 + k8;
+    // element (n, k) of the canonical K-major order: ((n/8) * (Kp/8) + k/8) * 64 + (n%8) * 8 + k%8
+    for (int k = lane; k < Kp; k += 32) {
         float x = 0.0f;
         if (n < N && k < K) x = w[transposed ? (size_t)k * ld + n : (size_t)n * ld + k] * s;
         const __half h = __float2half_rn(x);
+        const size_t i = ((size_t)(n >> 3) * (Kp >> 3) + (k >> 3)) * 64 + (size_t)(n & 7) * 8 + (k & 7);
         hi[i] = h;
         lo[i] = __float2half_rn(x - __half2float(h));
     }
@@ -418,66 +458,81 @@ __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) 
         if (elect_one()) umma_commit(&bar_done);
         __syncwarp();
     } else if (warp >= LOAD_WARP0) {
+        // loaders: the global loads of operand block idx + 1 are in flight while block idx is split and stored (two register
+        // buffers), so the load latency is paid once per CTA, not once per block
         const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
-        uint32_t bc = 0;
-        for (int step = blockIdx.x; step < p.n_steps; step += gridDim.x) {
-            for (int k = 0; k < nblk; ++k, ++bc) {
-                const bool isx = k < p.ab;
-                const float *src = isx ? p.x : p.y;
-                const int ld = isx ? p.ldx : p.ldy, width = isx ? p.a : p.b, f0 = (isx ? k : k - p.ab) * 128;
-                const int vec = isx ? p.vx : p.vy;
-                float4 v[2][2][2];
+        const int my_steps = (p.n_steps - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = my_steps * nblk;
+        auto load_block = [&](int idx, float4 (&v)[2][2][2]) {
+            const int step = (int)blockIdx.x + (idx / nblk) * (int)gridDim.x, k = idx % nblk;
+            const bool isx = k < p.ab;
+            const float *src = isx ? p.x : p.y;
+            const int ld = isx ? p.ldx : p.ldy, width = isx ? p.a : p.b, f0 = (isx ? k : k - p.ab) * 128;
+            const int vec = isx ? p.vx : p.vy;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const long long row = (long long)step * WROWS + lw * 8 + q * 4 + sub;
+            for (int q = 0; q < 2; ++q) {
+                const long long row = (long long)step * WROWS + lw * 8 + q * 4 + sub;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = f0 + h * 64 + kc * 8;
-                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-                        if (row < p.rows && col < width) {
-                            const float *s = src + row * ld + col;
-                            if (vec && col + 8 <= width) {
-                                a = __ldg(reinterpret_cast<const float4 *>(s));
-                                c = __ldg(reinterpret_cast<const float4 *>(s + 4));
-                            } else {
-                                float t[8];
+                for (int h = 0; h < 2; ++h) {
+                    const int col = f0 + h * 64 + kc * 8;
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+                    if (idx < total && row < p.rows && col < width) {
+                        const float *s = src + row * ld + col;
+                        if (vec && col + 8 <= width) {
+                            a = __ldg(reinterpret_cast<const float4 *>(s));
+                            c = __ldg(reinterpret_cast<const float4 *>(s + 4));
+                        } else {
+                            float t[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) t[e] = col + e < width ? __ldg(s + e) : 0.0f;
-                                a = make_float4(t[0], t[1], t[2], t[3]);
-                                c = make_float4(t[4], t[5], t[6], t[7]);
-                            }
+                            for (int e = 0; e < 8; ++e) t[e] = col + e < width ? __ldg(s + e) : 0.0f;
+                            a = make_float4(t[0], t[1], t[2], t[3]);
+                            c = make_float4(t[4], t[5], t[6], t[7]);
                         }
-                        v[q][h][0] = a; v[q][h][1] = c;
                     }
+                    v[q][h][0] = a; v[q][h][1] = c;
                 }
-                const uint32_t s = bc % NB;
-                mbar_wait(&bar_empty[s], ((bc / NB) & 1u) ^ 1u, p.status, 12);
-                uint8_t *blk = smem + (size_t)s * BLOCK;
+            }
+        };
+        auto emit_block = [&](int idx, const float4 (&v)[2][2][2]) {
+            const uint32_t bc = (uint32_t)idx, s = bc % NB;
+            mbar_wait(&bar_empty[s], ((bc / NB) & 1u) ^ 1u, p.status, 12);
+            uint8_t *blk = smem + (size_t)s * BLOCK;
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint4 hh, mm, ll;
-                        split8_bf16(v[q][h][0], v[q][h][1], hh, mm, ll);
-                        uint8_t *d = blk + (uint32_t)(h * 8 + kc) * FB_LBO + (uint32_t)(lw * 8 + q * 4 + sub) * 16u;
-                        *reinterpret_cast<uint4 *>(d) = hh;
-                        *reinterpret_cast<uint4 *>(d + PLANE) = mm;
-                        *reinterpret_cast<uint4 *>(d + 2 * PLANE) = ll;
-                    }
-                fence_async_smem();
-                mbar_arrive(&bar_full[s]);
+                for (int h = 0; h < 2; ++h) {
+                    uint4 hh, mm, ll;
+                    split8_bf16(v[q][h][0], v[q][h][1], hh, mm, ll);
+                    uint8_t *d = blk + (uint32_t)(h * 8 + kc) * FB_LBO + (uint32_t)(lw * 8 + q * 4 + sub) * 16u;
+                    *reinterpret_cast<uint4 *>(d) = hh;
+                    *reinterpret_cast<uint4 *>(d + PLANE) = mm;
+                    *reinterpret_cast<uint4 *>(d + 2 * PLANE) = ll;
+                }
+            fence_async_smem();
+            mbar_arrive(&bar_full[s]);
+        };
+        float4 va[2][2][2], vb[2][2][2];
+        load_block(0, va);
+        for (int idx = 0; idx < total; idx += 2) {
+            load_block(idx + 1, vb);
+            emit_block(idx, va);
+            if (idx + 1 < total) {
+                load_block(idx + 2, va);
+                emit_block(idx + 1, vb);
             }
         }
     } else {
-        // epilogue: one partial [a][b] block per CTA; thread = x feature (accumulator row)
+        // epilogue: one partial [a][b] block per CTA; thread = x feature (accumulator row); warps w and w + 4 share a lane
+        // window and split the 32-column chunks
         mbar_wait(&bar_done, 0, p.status, 13);
         tc_fence_after();
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const int lw = warp & 3, half = warp >> 2;
+        const uint32_t trow = tmem + ((uint32_t)(lw * 32) << 16);
         float *dst = p.partial + (size_t)blockIdx.x * p.a * p.b;
         for (int i = 0; i < p.ab; ++i) {
-            const int fa = i * 128 + warp * 32 + lane;
+            const int fa = i * 128 + lw * 32 + lane;
             for (int j = 0; j < p.bb; ++j)
-                for (int c = 0; c < 4; ++c) {
+                for (int c = half; c < 4; c += 2) {
                     uint32_t v[32];
                     tmem_ld32(trow + (uint32_t)((i * p.bb + j) * 128 + c * 32), v);
                     tmem_ld_wait();
@@ -499,8 +554,16 @@ __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) 
 __global__ void __launch_bounds__(256) tg_reduce_kernel(const float *partial, int n_part, int a, int b, float *out, int ldo, int accumulate) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= a * b) return;
-    float s = 0.0f;
-    for (int c = 0; c < n_part; ++c) s += partial[(size_t)c * a * b + i];
+    // four interleaved partial sums (independent loads in flight), combined in a fixed order: bit-reproducible
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    const size_t stride = (size_t)a * b;
+    int c = 0;
+    for (; c + 4 <= n_part; c += 4) {
+        s0 += partial[(size_t)c * stride + i]; s1 += partial[(size_t)(c + 1) * stride + i];
+        s2 += partial[(size_t)(c + 2) * stride + i]; s3 += partial[(size_t)(c + 3) * stride + i];
+    }
+    for (; c < n_part; ++c) s0 += partial[(size_t)c * stride + i];
+    const float s = (s0 + s1) + (s2 + s3);
     float *d = out + (size_t)(i / b) * ldo + i % b;
     *d = accumulate ? *d + s : s;
 }
@@ -595,14 +658,14 @@ int prepare(int *sms) {
 int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 }  // namespace
 
-extern "C" size_t tg_packed_bytes(int N, int K) { return (size_t)4 * pad_to(N, 16) * pad_to(K, 64) + 16; }
+extern "C" size_t tg_packed_bytes(int N, int K) { return (size_t)4 * pad_to(N, 16) * pad_to(K, 64) + (size_t)4 * pad_to(N, 16); }
 
 extern "C" int tg_pack_weight(const float *d_w, int N, int K, int ld, int transposed, void *d_packed, void *stream) {
     if (!d_w || !d_packed) return fa_internal_fail(-1, "tg_pack_weight: NULL pointer");
     if (N < 1 || N > 256 || K < 1 || K > 256 || pad_to(N, 16) * pad_to(K, 64) > 32768 || ld < (transposed ? N : K))
         return fa_internal_fail(-1, "tg_pack_weight: need 1 <= N, K <= 256, padded N * K <= 32768, ld >= row length (N=%d K=%d ld=%d)", N, K, ld);
     if ((uintptr_t)d_packed & 15) return fa_internal_fail(-4, "tg_pack_weight: d_packed must be 16-byte aligned");
-    tg::tg_pack_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_w, N, K, pad_to(N, 16), pad_to(K, 64), ld, transposed, (uint8_t *)d_packed);
+    tg::tg_pack_kernel<<<pad_to(N, 16) / 8, 256, 0, (cudaStream_t)stream>>>(d_w, N, K, pad_to(N, 16), pad_to(K, 64), ld, transposed, (uint8_t *)d_packed);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_pack_weight: launch: %s", cudaGetErrorString(e));
     return 0;

@@ -247,10 +247,10 @@ class BatchedTrainer(object):
             masks = R.obs[step, :, :, 0]                                   # alive flags before the step (:53)
             actions = self.act(step)
             # obs of step+1, rewards of step, done/result are written in place by the kernel
-            self.env.step(actions, auto_reset=True, out=(R.obs[step + 1], R.rewards[step], R.done[step], R.result[step]))
-            # RolloutStorage.insert's masks (storage.py:41), the end point (train_fortattack.py:98), initialize_new_episode's
-            # masks for finished envs (:100-104: the reset obs is already in place) and the episode reward sums: one launch
-            R.bookkeeping(step, self.episode_rewards)
+            # ... and so are RolloutStorage.insert's masks (storage.py:41), the end point (train_fortattack.py:98),
+            # initialize_new_episode's masks for finished envs (:100-104) and the episode reward sums: same launch
+            self.env.step(actions, auto_reset=True, out=(R.obs[step + 1], R.rewards[step], R.done[step], R.result[step]),
+                          bookkeeping=(R.masks[step + 1], R.ends[step + 1], self.episode_rewards))
             if self.ensemble is not None:
                 K = len(self.ensemble)
                 finished = R.done[step] != 0

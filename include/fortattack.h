@@ -56,9 +56,11 @@ enum {
 
 enum { FA_F32 = 0, FA_F64 = 1 };
 
-/* Thread mapping of the step kernel: one thread per env (large batches, register-resident agent block) or one
- * thread per agent (small batches, shared-memory agent block); AUTO picks by batch size. */
-enum { FA_MAP_AUTO = 0, FA_MAP_ENV = 1, FA_MAP_AGENT = 2 };
+/* Thread mapping of the step kernel: one thread per env (large batches, register-resident agent block), one thread per
+ * agent with one warp per agent index (shared-memory agent block, block barriers), or one sub-warp group of 2/4/8/16
+ * lanes per env (small batches: agent block staged per warp, hit / alive / fort-reached resolution by warp ballots, no
+ * block barrier); AUTO picks by batch size (GROUP, then AGENT, then ENV as the batch grows). */
+enum { FA_MAP_AUTO = 0, FA_MAP_ENV = 1, FA_MAP_AGENT = 2, FA_MAP_GROUP = 3 };
 
 #define FA_MAX_TEAM 5    /* kernels are instantiated for 1..5 guards x 1..5 attackers */
 
@@ -73,7 +75,7 @@ typedef struct FaConfig {
     int32_t max_steps;     /* world.max_time_steps, episode cap (fortattack.py:21) */
     int32_t scalar;        /* FA_F32 (production) or FA_F64 (parity mode, same kernels in double) */
     int32_t device;        /* CUDA device ordinal */
-    int32_t mapping;       /* FA_MAP_AUTO / FA_MAP_ENV / FA_MAP_AGENT */
+    int32_t mapping;       /* FA_MAP_AUTO / FA_MAP_ENV / FA_MAP_AGENT / FA_MAP_GROUP */
     int32_t reserved;      /* 0 */
     uint64_t seed;         /* Philox key of the reset streams */
     uint64_t env_id0;      /* global id of env 0 of this shard: resets are keyed by (seed, env_id0+e, episode) */
@@ -181,12 +183,21 @@ int fa_set_max_steps(FaHandle *h, int32_t max_steps);
  * NULL (the default) switches it off. */
 int fa_set_alive_end_buffer(FaHandle *h, uint8_t *d_alive_end);
 
+/* Optional rollout bookkeeping written by every subsequent fa_step / fa_step_many (device calls; the host-buffer calls
+ * ignore it), replacing the per-step glue of the reference's collection loop (train_fortattack.py:53,97-104;
+ * RolloutStorage.insert, rlcore/storage.py:41).  Each pointer may be NULL; all NULL (the default) switches it off.
+ *   d_mask_next float [A][E] ([T][A][E] for fa_step_many): done ? alive flag of the new (reset) observation
+ *                                                                : alive flag before the step
+ *   d_end_next  uint8 [E]    ([T][E]):                     done
+ *   d_ep_reward float [A][E] (accumulated in place):       += reward * alive flag before the step */
+int fa_set_rollout_outputs(FaHandle *h, float *d_mask_next, uint8_t *d_end_next, float *d_ep_reward);
+
 /* Number of kernel launches this handle has enqueued so far (bench.py's gpu_launches). */
 int fa_launch_count(const FaHandle *h, uint64_t *out);
 
 /* Static facts about the step kernel chosen for this handle (for DESIGN.md / bench.py):
  * registers per thread, threads per block, blocks per launch, static shared memory bytes, and the mapping in
- * use (FA_MAP_ENV or FA_MAP_AGENT). */
+ * use (FA_MAP_ENV, FA_MAP_AGENT or FA_MAP_GROUP). */
 int fa_kernel_info(const FaHandle *h, int32_t *regs, int32_t *block, int32_t *grid, int32_t *smem, int32_t *mapping);
 
 #ifdef __cplusplus

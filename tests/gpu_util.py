@@ -11,7 +11,7 @@ TOL = {torch.float32: (1e-5, 1e-5), torch.float64: (1e-11, 1e-11)}
 MARGIN_F32 = 1e-5
 
 
-MAPPINGS = ["env", "agent"]      # thread-per-env and thread-per-agent kernels: both must pass every parity gate
+MAPPINGS = ["env", "agent", "group"]      # thread-per-env, thread-per-agent and sub-warp-group kernels: all must pass every parity gate
 
 
 def make(E, ng, na, dtype, max_steps=100, seed=0, env_id0=0, mapping="auto"):
@@ -68,3 +68,4 @@ def close(got, ref, dtype, what, slack=None):
     bad = np.argwhere(~(err <= 0))          # NaN-safe
     assert bad.size == 0, "%s: %d mismatches, first at %s got %r ref %r (max |d| %.3g)" % (
         what, len(bad), bad[0], got[tuple(bad[0])], ref[tuple(bad[0])], np.nanmax(np.abs(got - ref)))
+

@@ -39,7 +39,7 @@ def test_policy_and_rollout_headers_are_exported():
     assert b"NULL" in L.fa_last_error()
     assert L.rl_gae(None, None, None, None, None, None, 4, 2, 8, 0.99, 0.95, None) == -1
     assert L.tg_linear(None, 128, 1000, 128, None, 128, None, 0, 0, None, 128, None, None) == -1
-    assert L.tg_packed_bytes(128, 128) == 4 * 128 * 128 + 16 and L.tg_packed_bytes(8, 6) == 4 * 16 * 64 + 16
+    assert L.tg_packed_bytes(128, 128) == 4 * 128 * 128 + 4 * 128 and L.tg_packed_bytes(8, 6) == 4 * 16 * 64 + 4 * 16
     blob_bytes = int(re.search(r"#define MP_BLOB_F16_BYTES (\d+)", open(os.path.join(ROOT, "include", "fortattack_policy.h")).read()).group(1))
     from importlib import import_module
     pk = import_module("emergent-multiagent-strategies_b200.policy_kernel")

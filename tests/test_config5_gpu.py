@@ -64,11 +64,12 @@ def test_ensemble_table_matches_reference_evaluation():
 @needs_ckpts
 def test_reference_eval_script_runs_on_cuda_env(tmp_path):
     """The reference's UNCHANGED test_fortattack_v2.py (guards ep2520 vs attacker ckpts 220 and 2520, 25 episodes each) on
-    the CUDA env facade; its own stats file must land near the fixture."""
+    the CUDA env facade; its own stats file must land near the fixture.  (--no-cuda: the script's np.average over a torch
+    tensor, :100-101, only works with the policies on the CPU; the env is the CUDA engine either way.)"""
     os.makedirs(tmp_path / "marlsave" / "stats")
     shutil.copytree(CKDIR, tmp_path / "marlsave" / "tmp_1")
     cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_config1.py"), "--env", "ours", "--rl", "ours", "--teams", "5v5",
-           "--workdir", str(tmp_path), "--script", "test_fortattack_v2.py", "--", "--test", "--train-guards-only",
+           "--workdir", str(tmp_path), "--script", "test_fortattack_v2.py", "--", "--test", "--train-guards-only", "--no-cuda",
            "--num-eval-episodes", "25", "--load-dir", "tmp_1", "--ckpt", "2520", "--attacker-load-dir", "tmp_1",
            "--attacker-ckpts", "220", "2520", "--seed", "2"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)

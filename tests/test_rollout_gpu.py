@@ -302,23 +302,47 @@ def test_fused_training_attention_matches_bmm_path(n, m, hid):
     own, opp = torch.randn(n * B, 6, device="cuda"), torch.randn(m * B, 6, device="cuda")
     act = torch.randint(0, 8, (n * B, 1), device="cuda")
     w = torch.randn(n * B, 1, device="cuda")
-    res = []
-    for fused_on, fold in ((False, False), (True, False), (True, True)):
-        net.fused_attention, net.fold_projections = fused_on, fold
-        net.zero_grad()
-        v, lp, ent, _ = net.evaluate_actions(own, None, opp, None, act)
-        ((v * w).sum() + (lp * w).sum() * 0.7 + ent.sum() * 0.3).backward()
+    fused = import_module(PKG + ".rlcore.fused")
+
+    def run(fused_on, fold, dense, trace=None):
+        net.fused_attention, net.fold_projections, fused.DENSE, fused.RELU_TRACE = fused_on, fold, dense, trace
+        try:
+            net.zero_grad()
+            v, lp, ent, _ = net.evaluate_actions(own, None, opp, None, act)
+            ((v * w).sum() + (lp * w).sum() * 0.7 + ent.sum() * 0.3).backward()
+        finally:
+            fused.DENSE, fused.RELU_TRACE = "tcgen05", None
         grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
-        res.append((v.detach(), lp.detach(), ent.detach(), net.attn_mat, net.opp_attn_mat, grads))
-    a = res[0]
-    for b in res[1:]:        # attention kernels with explicit projections, then with the projections folded into the weights
+        return (v.detach(), lp.detach(), ent.detach(), net.attn_mat, net.opp_attn_mat, grads)
+
+    def same(a, b, what):
         for x, y in zip(a[:3], b[:3]):
-            assert torch.allclose(x, y, rtol=1e-4, atol=2e-5)
-        assert np.allclose(a[3], b[3], atol=1e-5) and np.allclose(a[4], b[4], atol=1e-5)
+            assert torch.allclose(x, y, rtol=1e-4, atol=2e-5), what
+        assert np.allclose(a[3], b[3], atol=1e-5) and np.allclose(a[4], b[4], atol=1e-5), what
         assert set(a[5]) == set(b[5])
         for k in a[5]:
             scale = float(a[5][k].abs().max()) + 1e-6
-            assert float((a[5][k] - b[5][k]).abs().max()) < 2e-4 * scale, (k, float((a[5][k] - b[5][k]).abs().max()), scale)
+            err = float((a[5][k] - b[5][k]).abs().max())
+            assert err < 2e-4 * scale, (what, k, err, scale)
+
+    # (1) the restructuring: attention kernels with explicit projections, then with the projections folded into the weights,
+    #     against the bmm/softmax mirror, all three on the library GEMMs (the same products round the same way)
+    mirror = run(False, False, "cublas")
+    same(mirror, run(True, False, "cublas"), "attention kernels")
+    rec = {"mode": "record", "outs": []}
+    folded_lib = run(True, True, "cublas", rec)
+    same(mirror, folded_lib, "folded projections")
+    # (2) the arithmetic: the production path (folded, every dense product on the tcgen05 kernels) against the same path
+    #     on the library GEMMs, with the ReLU decisions of the backward pinned to the library run's (fused.RELU_TRACE:
+    #     a pre-activation within rounding of zero may legitimately fall either side) -- and those are counted
+    rep = {"mode": "replay", "outs": rec["outs"], "pos": 0, "flips": 0}
+    folded_tg = run(True, True, "tcgen05", rep)
+    fused.tg_check_status("cuda:0")
+    assert rep["pos"] == len(rec["outs"]) > 0
+    n_act = sum(o.numel() for o in rec["outs"])
+    assert rep["flips"] <= max(4, n_act // 200000), (rep["flips"], n_act)      # observed: 0-2 sign flips in ~1.5M activations
+    same(folded_lib, folded_tg, "tcgen05 dense kernels (%d ReLU sign flips of %d pinned)" % (rep["flips"], n_act))
+    same(mirror, folded_tg, "production path against the mirror")
 
 
 def test_graph_captured_update_tracks_eager_update():

@@ -360,8 +360,56 @@ def test_both_mappings_agree_and_auto_picks_by_batch_size():
     ob, rb, db, sb = eb.step_many(acts)
     assert torch.equal(da, db) and torch.equal(sa, sb) and torch.equal(oa[..., 0], ob[..., 0])
     assert (oa - ob).abs().max() < 1e-9 and (ra - rb).abs().max() < 1e-9
-    assert make(4096, 3, 3, torch.float32).kernel_info()["mapping"] == "agent"
+    assert make(4096, 3, 3, torch.float32).kernel_info()["mapping"] == "group"
     assert make(1 << 17, 3, 3, torch.float32).kernel_info()["mapping"] == "env"
+
+
+@pytest.mark.parametrize("ng,na,E", [(3, 3, 2050), (5, 5, 1001), (1, 1, 515), (2, 1, 300), (4, 2, 777), (5, 4, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_group_mapping_is_bit_equal_to_agent_mapping(ng, na, E, dtype):
+    """The sub-warp-group kernel (2/4/8/16 lanes per env, ballots instead of block barriers) performs the per-agent
+    arithmetic of the thread-per-agent kernel statement for statement: free-running, with resets, every output and the
+    final state are identical bit for bit -- for every group width, with ragged tails (E not a multiple of 32 / G)."""
+    T, A = 50, ng + na
+    g = torch.Generator(device="cuda").manual_seed(ng * 10 + na)
+    acts = torch.randint(0, 8, (T, A, E), generator=g, device="cuda", dtype=torch.int32)
+    ea, eb = make(E, ng, na, dtype, max_steps=17, seed=4, mapping="agent"), make(E, ng, na, dtype, max_steps=17, seed=4, mapping="group")
+    assert eb.kernel_info()["mapping"] == "group"
+    assert torch.equal(ea.reset(), eb.reset())
+    for x, y in zip(ea.step_many(acts[:30]), eb.step_many(acts[:30])):
+        assert torch.equal(x, y)
+    for t in range(30, T):                       # single-step launches, auto-reset on
+        for x, y in zip(ea.step(acts[t]), eb.step(acts[t])):
+            assert torch.equal(x, y)
+    for x, y in zip(ea.get_state(), eb.get_state()):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("mapping", MAPPINGS)
+def test_fused_rollout_bookkeeping_equals_separate_kernel(mapping):
+    """fa_set_rollout_outputs (mask of the next slot, end point, episode reward sums written by the step launch itself)
+    == rl_rollout_bookkeeping run on the step's outputs afterwards (train_fortattack.py:53,97-104, storage.py:41)."""
+    from importlib import import_module
+    ro = import_module("emergent-multiagent-strategies_b200.rollout")
+    ng, na, E, T = 3, 3, 1500, 40
+    A = ng + na
+    env = make(E, ng, na, torch.float32, max_steps=11, seed=5, mapping=mapping)
+    env2 = make(E, ng, na, torch.float32, max_steps=11, seed=5, mapping=mapping)
+    R1, R2 = ro.SharedRollouts(T, A, E, "cuda"), ro.SharedRollouts(T, A, E, "cuda")
+    ep1, ep2 = torch.zeros(A, E, device="cuda"), torch.zeros(A, E, device="cuda")
+    o0 = env.reset()
+    assert torch.equal(o0, env2.reset())
+    R1.obs[0].copy_(o0); R2.obs[0].copy_(o0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(T):
+        a = torch.randint(0, 8, (A, E), generator=g, device="cuda", dtype=torch.int32)
+        env.step(a, out=(R1.obs[t + 1], R1.rewards[t], R1.done[t], R1.result[t]))
+        R1.bookkeeping(t, ep1)
+        env2.step(a, out=(R2.obs[t + 1], R2.rewards[t], R2.done[t], R2.result[t]), bookkeeping=(R2.masks[t + 1], R2.ends[t + 1], ep2))
+    assert torch.equal(R1.obs, R2.obs) and torch.equal(R1.masks, R2.masks) and torch.equal(R1.ends, R2.ends)
+    assert torch.equal(ep1, ep2) and int(R1.ends.sum()) > E and float(R1.masks.min()) == 0.0
+    with pytest.raises(ValueError):
+        env.step(a, bookkeeping=(R2.masks[0, :, :5], None, None))
 
 
 def test_step_many_host_errors_are_loud():

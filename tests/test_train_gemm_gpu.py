@@ -136,8 +136,11 @@ def test_dense_layers_match_library_path():
     b2 = torch.zeros(8, device="cuda", requires_grad=True)
     gout = torch.randn(n * B, 8, generator=gen).cuda()
     res = {}
+    rec = {"mode": "record", "outs": []}
+    rep = {"mode": "replay", "outs": rec["outs"], "pos": 0, "flips": 0}
     for mode in ("cublas", "tcgen05"):
         fused.DENSE = mode
+        fused.RELU_TRACE = rec if mode == "cublas" else rep      # ReLU decisions of the backward pinned to the library run's
         try:
             for t in (h, Mqk, Wc, bias, W2, b2):
                 t.grad = None
@@ -147,7 +150,8 @@ def test_dense_layers_match_library_path():
             (y * gout).sum().backward()
             res[mode] = [y.detach().clone()] + [t.grad.clone() for t in (h, Mqk, Wc, bias, W2, b2)]
         finally:
-            fused.DENSE = "tcgen05"
+            fused.DENSE, fused.RELU_TRACE = "tcgen05", None
     fused.tg_check_status("cuda:0")
+    assert rep["pos"] == len(rec["outs"]) == 1 and rep["flips"] <= 2, rep["flips"]
     for a, b in zip(res["cublas"], res["tcgen05"]):
         assert float((a - b).abs().max()) < 2e-4 * max(1.0, float(a.abs().max())), float((a - b).abs().max())
