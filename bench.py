@@ -227,9 +227,10 @@ def run_reference(args):
 
 
 def bind_host_to_gpu(torch, local):
-    """Restrict this rank's host threads to the CPUs NVML reports as NUMA-local to its GPU, so that the pinned host
-    buffers it allocates afterwards (first touch) and the thread that drives the copies sit on the GPU's own socket.
-    Returns a small report for the JSON line; never fatal."""
+    """Place this rank's host side next to its GPU before any pinned allocation: (1) restrict the rank's threads to the CPUs
+    NVML reports as NUMA-local to the GPU (when the container's cpuset has any), (2) ask the kernel to take this process's
+    new pages -- the pinned buffers allocated afterwards -- from the GPU's own NUMA node (set_mempolicy MPOL_PREFERRED with
+    the node sysfs names for the GPU's PCI function).  Returns a small report for the JSON line; never fatal."""
     rep = {"bound": False}
     try:
         import pynvml
@@ -249,6 +250,22 @@ def bind_host_to_gpu(torch, local):
             rep["bound"] = True
         elif use:
             rep["note"] = "all allowed CPUs are already local to the GPU"
+        else:
+            rep["note"] = "none of the CPUs this container may use is local to the GPU"
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        rep["gpu_numa_node"] = node
+        if node >= 0:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            nodemask = (ctypes.c_ulong * 2)(0, 0)
+            nodemask[node // 64] = 1 << (node % 64)
+            rc = libc.syscall(238, 1, ctypes.byref(nodemask), 129)          # x86-64 set_mempolicy(MPOL_PREFERRED, mask, maxnode)
+            rep["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy failed: errno %d" % ctypes.get_errno()
     except Exception as exc:
         rep["error"] = repr(exc)[:200]
     return rep
@@ -270,6 +287,12 @@ def run_ours(args):
     binding = bind_host_to_gpu(torch, local)               # before any pinned allocation: first-touch places it NUMA-local
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        nodes = torch.tensor([binding.get("gpu_numa_node", -9), binding.get("used_cpus", -1),
+                              1 if str(binding.get("mempolicy", "")).startswith("preferred") else 0], device=dev)
+        allr = [torch.zeros_like(nodes) for _ in range(world)]
+        dist.all_gather(allr, nodes)
+        binding["by_rank"] = {"gpu_numa_node": [int(t[0]) for t in allr], "local_cpus_used": [int(t[1]) for t in allr],
+                              "mempolicy_set": [int(t[2]) for t in allr]}
     K, W, E = args.steps, max(3, args.warmup), args.envs
 
     def barrier():
@@ -507,6 +530,11 @@ def run_ours(args):
             extra["train"] = train_config4_share(torch, dev, dist, world, rank)
         except Exception as exc:
             extra["train"] = {"error": repr(exc)}
+        if world > 1:                         # config 5 sharded over the ranks (at world == 1 it is in rollout_ensemble above)
+            try:
+                extra["rollout_ensemble"] = rollout_config5_share(fab, torch, dev, dist=dist, world=world, rank=rank)
+            except Exception as exc:
+                extra["rollout_ensemble"] = {"error": repr(exc)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -776,7 +804,7 @@ def train_config4_share(torch, dev, dist, world, rank, E=8192, T=128):
     return out
 
 
-def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5):
+def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5, dist=None, world=1, rank=0):
     """One GPU's share of BASELINE.json configs[4] (guards-only training against an ensemble of 5 frozen attacker
     checkpoints, 32768 envs over 8 GPUs = 4096 envs per GPU, 5v5): rollout collection with a per-env, per-episode
     attacker draw = 1 guard forward + 1 ensemble forward (all K checkpoints in one launch) + 1 env step per rollout step (random-init checkpoints:
@@ -794,21 +822,29 @@ def rollout_config5_share(fab, torch, dev, E=4096, T=32, K=5):
             torch.manual_seed(100 + k)
             sds.append(mp.MPNN(action_space=ro._Shape(8), num_agents=5, num_opp_agents=5, input_size=6, hidden_dim=128).state_dict())
     torch.manual_seed(0)
-    tr = ro.BatchedTrainer(E, 5, 5, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, attacker_ensemble=sds)
+    tr = ro.BatchedTrainer(E, 5, 5, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, env_id0=rank * E, attacker_ensemble=sds)
     if real:
         tr.load_models(shipped[-1])                                      # guards start from ep2520 (--pretrained-guard)
     for _ in range(2):
         tr.collect(); tr.wrap_horizon(); tr.after_update()
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); tr.collect(); e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     for fz in tr.fused + tr.ensemble:
         fz.check_status()
-    return {"workload": "FortAttack 5v5 guards vs an ensemble of %d attacker checkpoints, %d envs (one GPU's share of BASELINE.json "
-                        "configs[4]), T=%d rollout" % (K, E, T),
-            "rollout_agent_steps_per_s": E * 10 * T / (ms * 1e-3), "us_per_rollout_step": ms * 1e3 / T,
+    if world > 1:                            # envs are independent: the job's time is the slowest rank's, the table sums the shards
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.all_reduce(tr.ensemble_results)
+        dist.all_reduce(tr.ensemble_sums)
+    return {"workload": "FortAttack 5v5 guards vs an ensemble of %d attacker checkpoints, %d envs per GPU x %d GPU(s) (BASELINE.json "
+                        "configs[4] = 32 768 envs on 8), T=%d rollout" % (K, E, world, T),
+            "rollout_agent_steps_per_s": world * E * 10 * T / (ms * 1e-3), "us_per_rollout_step": ms * 1e3 / T,
             "policy_launches_per_step": 2, "note": "one mp_forward for the guards, one mp_forward_ensemble serving all %d checkpoints" % K,
             "checkpoints": "marlsave/tmp_1/ep{220,650,1240,1600,2520}.pt attackers, ep2520 guards" if real else "random init (baseline/_ref absent)",
             "ensemble_table": tr.ensemble_table().round(3).tolist()}
