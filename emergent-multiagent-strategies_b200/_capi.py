@@ -127,6 +127,9 @@ def lib():
     L.tg_kernel_info.argtypes = [i32, i32p, i32p, i32p]
     L.tg_debug_wgrad_desc.argtypes = [u32, u32]
     L.mw_step.argtypes = [vp, vp, vp, vp, vp]
+    L.mw_scenario_obs_dim.argtypes = [i32, i32, i32, i32]
+    L.mw_scenario_callbacks.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp]
+    L.mw_scenario_reset.argtypes = [vp, f64, f64, f64, f64, u64, u32, vp, vp, vp, vp]
     L.fr_render.argtypes = [ctypes.POINTER(FrConfig), vp, vp, vp, vp, i32, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)   # AttributeError here = the library does not match the header

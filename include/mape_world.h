@@ -39,6 +39,30 @@ typedef struct MwConfig {
  *   d_u           Real [n_agents][E][2]     agent.action.u, already scaled by the caller (environment.py _set_action) */
 int mw_step(const MwConfig *cfg, void *d_pos, void *d_vel, const void *d_u, void *stream);
 
+/* Scenario callbacks of two of the reference's scenarios, evaluated for every agent of every world the way
+ * MultiAgentEnv.step does after world.step() (multiagent/environment.py:97-108):
+ *   MW_SIMPLE_SPREAD  observation = [vel, pos, landmarks - pos, other agents - pos, other agents' comm (zeros, dim_c 2)],
+ *                     reward = -sum_l min_a |a - l| - #{a : |a - i| < size_a + size_i} (the agent itself included), then
+ *                     shared: every agent receives the sum over agents (world.collaborative)
+ *                                                                        multiagent/scenarios/simple_spread.py:72-101
+ *   MW_SIMPLE_TAG     the first n_adversaries agents chase the others: observation = [vel, pos, landmarks - pos, other
+ *                     agents - pos, velocities of the other good agents]; adversaries get +10 per (good, adversary) pair in
+ *                     contact, a good agent -10 per adversary touching it and the screen-exit penalty bound(|x|), bound(|y|)
+ *                                                                        multiagent/scenarios/simple_tag.py:83-179
+ *   d_obs     Real [n_agents][E][obs_stride] (rows zero-padded to obs_stride >= mw_scenario_obs_dim)
+ *   d_reward  Real [n_agents][E] */
+enum { MW_SIMPLE_SPREAD = 0, MW_SIMPLE_TAG = 1 };
+int mw_scenario_obs_dim(int scenario, int n_agents, int n_entities, int n_adversaries);
+int mw_scenario_callbacks(const MwConfig *cfg, int scenario, int n_adversaries, const void *d_pos, const void *d_vel,
+                          void *d_obs, int obs_stride, void *d_reward, void *stream);
+
+/* reset_world of those scenarios (simple_spread.py:32-45, simple_tag.py:43-58) for the worlds with d_mask[e] != 0 (all when
+ * d_mask is NULL): agent positions uniform in [lo_agents, hi_agents)^2, landmark positions uniform in
+ * [lo_landmarks, hi_landmarks)^2, velocities zero.  Philox4x32-10 keyed by (seed; env, entity, episode) -- the reference
+ * draws from numpy's global MT19937 stream, which a batched engine cannot reproduce; parity tests set the state. */
+int mw_scenario_reset(const MwConfig *cfg, double lo_agents, double hi_agents, double lo_landmarks, double hi_landmarks,
+                      uint64_t seed, uint32_t episode, const uint8_t *d_mask, void *d_pos, void *d_vel, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

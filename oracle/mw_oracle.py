@@ -61,3 +61,56 @@ def step(pos, vel, u, cfg, na, world):
         vel[:, i] = v
         pos[:, i] = pos[:, i] + v * dt
     return pos, vel
+
+
+# ---- scenario callbacks (multiagent/scenarios/simple_spread.py:72-101, simple_tag.py:83-179; MultiAgentEnv.step,
+# multiagent/environment.py:97-108), vectorised over environments.  Pinned by tests/golden/mape_scenarios.npz.
+def _dist(a, b):
+    return np.sqrt(np.sum(np.square(a - b), axis=-1))
+
+
+def spread_callbacks(pos, vel, size, na):
+    """pos, vel [E, NE, 2] -> (obs [E, na, 4 + 2L + 4(na-1)], reward [E, na]) with the shared (summed) reward."""
+    E, NE, _ = pos.shape
+    obs, rew = [], np.zeros((E, na))
+    cover = np.zeros(E)
+    for l in range(na, NE):
+        cover -= np.min(np.stack([_dist(pos[:, a], pos[:, l]) for a in range(na)], axis=1), axis=1)
+    for i in range(na):
+        r = cover.copy()
+        for a in range(na):
+            r -= (_dist(pos[:, a], pos[:, i]) < size[a] + size[i]).astype(float)
+        rew[:, i] = r
+        others = [j for j in range(na) if j != i]
+        obs.append(np.concatenate([vel[:, i], pos[:, i]] + [pos[:, l] - pos[:, i] for l in range(na, NE)] +
+                                  [pos[:, j] - pos[:, i] for j in others] + [np.zeros((E, 2)) for _ in others], axis=1))
+    total = rew.sum(axis=1, keepdims=True)
+    return np.stack(obs, axis=1), np.repeat(total, na, axis=1)
+
+
+def _bound(x):
+    return np.where(x < 0.9, 0.0, np.where(x < 1.0, (x - 0.9) * 10, np.minimum(np.exp(2 * x - 2), 10)))
+
+
+def tag_callbacks(pos, vel, size, na, n_adv):
+    """-> (list of per-agent obs [E, d_i], reward [E, na])."""
+    E, NE, _ = pos.shape
+    obs, rew = [], np.zeros((E, na))
+    catches = np.zeros(E)
+    for g in range(n_adv, na):
+        for a in range(n_adv):
+            catches += 10.0 * (_dist(pos[:, g], pos[:, a]) < size[g] + size[a])
+    for i in range(na):
+        if i < n_adv:
+            rew[:, i] = catches
+        else:
+            r = np.zeros(E)
+            for a in range(n_adv):
+                r -= 10.0 * (_dist(pos[:, a], pos[:, i]) < size[a] + size[i])
+            for d in range(2):
+                r -= _bound(np.abs(pos[:, i, d]))
+            rew[:, i] = r
+        others = [j for j in range(na) if j != i]
+        obs.append(np.concatenate([vel[:, i], pos[:, i]] + [pos[:, l] - pos[:, i] for l in range(na, NE)] +
+                                  [pos[:, j] - pos[:, i] for j in others] + [vel[:, j] for j in others if j >= n_adv], axis=1))
+    return obs, rew

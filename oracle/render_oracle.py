@@ -3,10 +3,11 @@ csrc/fr_render.cu), i.e. of the scene FortAttackGlobalEnv.render draws (gym_fort
 rectangle, fort disc, attention halos, dead / alive agents with head, laser triangle and body, grey strips; colours from
 fortattack_env_v1.py:57 and core.py:297; 700 x 700 viewer over [-1, 1]^2, rendering.py:90).
 
-Parity status: UNPINNED against the reference's pixels -- its renderer needs an OpenGL display (pyglet) and approximates
-circles by 30-gons, so there is no golden image to reproduce bit for bit.  What IS pinned to the reference's artefacts:
-the geometry constants, and the pixel area of an agent's body disc in the recorded out_files/1.gif (945..981 px per
-isolated agent blob at 700 x 700, measured here; pi * 17.5^2 = 962).  The CUDA kernel is compared with THIS restatement
+Parity status: pinned to the reference's own pixels as far as they exist -- its renderer needs an OpenGL display (pyglet)
+and approximates circles by 30-gons, so no golden image can be reproduced bit for bit, but two frames of its recording
+out_files/1.gif are committed (tests/golden/render_ref_frames.npz) and tests/test_render_cpu.py compares against them: the
+strip rows, the fort disc (IoU 0.99) and the agent blobs of the reset frame (position fitted, body + head IoU > 0.9, area within
+5 %); plus the geometry constants and the blob area over further frames (945..981 px; pi * 17.5^2 = 962).  The CUDA kernel is compared with THIS restatement
 bit for bit: every operation below is a single float32 operation in the kernel's order, trigonometry in float64 rounded
 once to float32."""
 import numpy as np

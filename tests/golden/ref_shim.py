@@ -74,7 +74,7 @@ def install_stubs():
     spaces = _mod("gym.spaces", Space=Space, Discrete=Discrete, Box=Box, Tuple=Tuple, Dict=Dict)
     seeding = _mod("gym.utils.seeding")
     gutils = _mod("gym.utils", seeding=seeding)
-    registration = _mod("gym.envs.registration", register=register)
+    registration = _mod("gym.envs.registration", register=register, EnvSpec=object)
     envs = _mod("gym.envs", registration=registration)
     error = _mod("gym.error")
     wrappers = _mod("gym.wrappers", Monitor=object)

@@ -73,3 +73,51 @@ def test_large_batch_matches_oracle_and_is_loud():
         w.step(torch.zeros(1, 2, 2, device="cuda"))
     with pytest.raises(Exception):
         mw.MapeWorldBatch(4, [dict()], device="cpu")
+
+
+@pytest.mark.parametrize("name", ["simple_spread", "simple_tag"])
+@pytest.mark.parametrize("dtype,atol", [(torch.float64, 1e-10), (torch.float32, 2e-4)])
+def test_scenario_env_matches_reference(name, dtype, atol):
+    """MultiAgentEnvBatch.step (set_action -> mw_step -> mw_scenario_callbacks) against the transitions recorded from the
+    reference's MultiAgentEnv with its own simple_spread / simple_tag scenarios (tests/golden/mape_scenarios.npz)."""
+    from importlib import import_module
+    mwm = import_module("emergent-multiagent-strategies_b200.mape_world")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mape_scenarios.npz"))
+    T, E = g[name + "/act"].shape[:2]
+    env = mwm.MultiAgentEnvBatch(name, E, dtype=dtype)
+    assert env.n == int(g[name + "/na"]) and env.obs_dims == [int(d) for d in g[name + "/obs_dims"]]
+    assert env.shared_reward == bool(g[name + "/shared"])
+    flips = 0
+    for t in range(T):
+        env.world.pos.copy_(torch.from_numpy(g[name + "/pos_before"][t]).transpose(0, 1).to(dtype))      # teacher-forced
+        env.world.vel.copy_(torch.from_numpy(g[name + "/vel_before"][t]).transpose(0, 1).to(dtype))
+        act = g[name + "/act"][t]
+        obs_n, rew_n, done_n, info = env.step([torch.from_numpy(act[:, i]) for i in range(env.n)])
+        assert np.allclose(env.world.pos.transpose(0, 1).cpu().numpy(), g[name + "/pos_after"][t], rtol=0, atol=atol)
+        for i in range(env.n):
+            assert tuple(obs_n[i].shape) == (E, env.obs_dims[i])
+            assert np.allclose(obs_n[i].cpu().numpy(), g["%s/obs%d" % (name, i)][t], rtol=0, atol=atol * 10), (t, i)
+            d = np.abs(rew_n[i].cpu().numpy() - g[name + "/rew"][t][:, i])
+            # a contact / catch decided within float rounding of the threshold moves a reward by a whole unit: count, do not hide
+            flips += int((d > 0.5).sum())
+            assert (d[d <= 0.5] < atol * 50).all(), (t, i, d.max())
+        assert not any(bool(x.any()) for x in done_n)
+    assert flips == 0 if dtype == torch.float64 else flips <= 2
+
+
+def test_scenario_reset_and_discrete_actions():
+    from importlib import import_module
+    mwm = import_module("emergent-multiagent-strategies_b200.mape_world")
+    env = mwm.MultiAgentEnvBatch("simple_tag", 4096, discrete_action_input=True, seed=3)
+    obs = env.reset()
+    p = env.world.pos
+    assert float(p[:4].abs().max()) < 1.0 and float(p[4:].abs().max()) < 0.9 and float(p[4:].abs().max()) > 0.85
+    assert abs(float(p[:4].mean())) < 0.02 and abs(float(p[:4].var()) - 1 / 3) < 0.02 and float(env.world.vel.abs().max()) == 0.0
+    assert torch.equal(obs[0][:, 2:4], p[0])
+    before = p.clone()
+    mask = torch.zeros(4096, dtype=torch.uint8, device="cuda"); mask[::2] = 1
+    env.reset(mask)
+    assert torch.equal(p[:, 1::2], before[:, 1::2]) and not torch.equal(p[:, ::2], before[:, ::2])
+    # discrete input: 1 -> -x, 2 -> +x, 3 -> -y, 4 -> +y (environment.py:163-168), times accel 4
+    u = env.set_action([torch.full((4096,), k, device="cuda") for k in (1, 2, 3, 4)])
+    assert torch.equal(u[:, 0].cpu(), torch.tensor([[-4.0, 0.0], [4.0, 0.0], [0.0, -4.0], [0.0, 4.0]]))

@@ -87,3 +87,73 @@ def test_attention_halos_pick_the_reference_agent_like_the_reference():
         for i in range(ng + na):
             want = -1.0 if i == k else float(team[e, k, i] if i < ng else opp[e, k, i - ng])     # :452-458
             assert float(halo[i, e]) == want
+
+
+# ---- against the reference's own pixels: two frames decoded from out_files/1.gif (tests/golden/make_render_golden.py) ----------
+FRAMES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_ref_frames.npz")
+
+
+def ref_frame(k):
+    g = np.load(FRAMES)
+    return g["frame%d/palette" % k][g["frame%d/index" % k]].astype(int)            # [700, 700, 3]
+
+
+def near(img, rgb, tol=60):
+    return np.abs(img.astype(int) - np.array(rgb)).sum(-1) < tol
+
+
+def iou(a, b):
+    return (a & b).sum() / max(1, (a | b).sum())
+
+
+def test_static_scene_matches_reference_frames():
+    """World rectangle, strips and fort disc of the reference's recorded frames against the rasteriser: the strip rows are the
+    same rows, and the fort disc of frame 8 (nothing in front of it) covers the same pixels (IoU > 0.97; the reference draws
+    a 30-gon, rendering.py:260-270)."""
+    ours = ro.render(one_guard(alive=0.0), 1)
+    for k in (0, 8):
+        ref = ref_frame(k)
+        nonblack = ref.sum(-1) > 150                               # the recording's edges are one blurred row wide: half intensity decides
+        col = nonblack[:, 40]                                      # a column no agent crosses in either frame
+        assert col[:70].all() and not col[70:630].any() and col[630:].all()
+        assert ((ours[:, 40] != 0).any(-1) == col).all()
+    from scipy import ndimage
+    ref = ref_frame(8)
+    # the recording is dithered over a palette with four blue levels: cyan-ish pixels, closed over the dither pattern, largest blob
+    m = (ref[..., 1] >= 144) & (ref[..., 2] >= 85) & (ref[..., 0] <= 110)
+    m[:70] = False
+    lab, n = ndimage.label(ndimage.binary_fill_holes(ndimage.binary_closing(m, np.ones((3, 3)))))
+    fort_ref = lab == 1 + int(np.argmax(ndimage.sum(np.ones_like(lab), lab, range(1, n + 1))))
+    fort_ours = near(ours, CYAN, 1)
+    assert iou(fort_ref, fort_ours) > 0.97, iou(fort_ref, fort_ours)
+
+
+def test_agent_blobs_match_reference_frame():
+    """Frame 0 of the recording is a reset state: attackers head up (pi/2), no lasers, no halos.  For the two attackers that are
+    isolated and fully inside the world, the position is fitted from the blob and the rasteriser's agent (body disc + head) must
+    cover the same pixels as the reference's (IoU > 0.9, area within 5 %; the black digits the reference prints on the
+    agents are filled first)."""
+    from scipy import ndimage
+    ref = ref_frame(0)
+    red = ndimage.binary_fill_holes(near(ref, (252, 0, 0), 120))
+    lab, n = ndimage.label(red)
+    checked = 0
+    for b in range(1, n + 1):
+        m = lab == b
+        ys, xs = np.nonzero(m)
+        if m.sum() < 900 or m.sum() > 1300 or xs.min() < 5 or ys.max() > 625:       # merged, clipped by the frame or by the strip
+            continue
+        # fit: place the agent so that the rasterised blob's centroid coincides with the recorded blob's
+        x, y = (xs.mean() + 0.5) / 350 - 1, 1 - (ys.mean() + 0.5) / 350
+        for _ in range(3):
+            obs = np.zeros((2, 6), np.float32)
+            obs[0] = [0.0, 0, 0, 0, 0, 0]
+            obs[1] = [1.0, x, y, math.pi / 2, 0, 0]
+            mine = near(ro.render(obs, 1), RED, 1)
+            my, mx = np.nonzero(mine)
+            x += (xs.mean() - mx.mean()) / 350
+            y -= (ys.mean() - my.mean()) / 350
+        assert iou(m, mine) > 0.9, (b, iou(m, mine))
+        assert abs(int(mine.sum()) - int(m.sum())) < 0.05 * m.sum(), (int(mine.sum()), int(m.sum()))
+        checked += 1
+    assert checked >= 2
