@@ -200,16 +200,18 @@ def run_reference(args):
     port_rate, port_dt = cpu_oracle_rate(kp, args.warmup, cores)
     port = {"value": port_rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d env.step() calls of %d envs (oracle/fa_oracle.c float64, %d pthreads), %.3f s" % (kp, E_PER_GPU, cores, port_dt)}
-    # K steps of the 4096-env batch = K*4096 env-steps; bounded to ~25 s at ~1.4e3 env-steps/s per core
+    # the job's batch at N GPUs is N x 4096 envs (weak scaling): K steps of it = K * N * 4096 env.step() calls, bounded to
+    # ~25 s at ~1.4e3 env-steps/s per core
+    E_JOB = max(1, args.gpus) * E_PER_GPU
     budget = int(25.0 * 1400 * cores)
-    k = max(1, min(args.steps, budget // E_PER_GPU))
-    ref = python_reference_rate(k * E_PER_GPU, cores)
+    k = max(1, min(args.steps, budget // E_JOB))
+    ref = python_reference_rate(k * E_JOB, cores)
     if ref is not None:
         rate, dt, n = ref
         kind = "reference"
-        sample = ("%d steps of the %d-env batch = %d env.step() calls of the unmodified Python reference "
+        sample = ("%d steps of the job's %d-env batch (%d GPU(s) x %d) = %d env.step() calls of the unmodified Python reference "
                   "(baseline/_ref/reference/gym_fortattack, numpy float64), one process per core x %d, %.1f s"
-                  % (k, E_PER_GPU, n, cores, dt))
+                  % (k, E_JOB, max(1, args.gpus), E_PER_GPU, n, cores, dt))
         what = ("the reference's own gym_fortattack env.step (byte copy of /root/reference under baseline/_ref, imported through "
                 "stub modules for gym/pygame/pyglet), one Python process per host core, each stepping its own env")
     else:
@@ -218,7 +220,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm runs one shard of %d envs on the host cores whatever N is" % E_PER_GPU,
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E_PER_GPU, "envs_total": E_JOB,
+                       "note": "the CPU arm steps the whole job's batch (N x %d envs) on the host cores of rank 0's box" % E_PER_GPU,
                        "what_runs": what},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "port": port},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

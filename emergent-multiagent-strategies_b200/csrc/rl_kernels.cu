@@ -426,10 +426,24 @@ extern "C" int rl_attn_mix_backward(const RlAttnOperand *dout, const RlAttnOpera
     return 0;
 }
 
+// 8 resident blocks per SM of the current device (the count is a property of the chip, queried once per device; it only
+// sizes grids -- without a device, e.g. in the CPU-side symbol tests, the B200's 148 is assumed)
+static int grid_cap() {
+    static int cap[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * 8;
+    if (cap[dev] == 0) {
+        int sms = 0;
+        cap[dev] = (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0 ? sms : 148) * 8;
+    }
+    return cap[dev];
+}
+
 extern "C" int rl_relu_bwd_colsum_blocks(long long rows, int cols) {
     if (rows < 1 || (cols != 32 && cols != 64 && cols != 128 && cols != 256)) return -1;
     const long long rpi = 256 / (cols / 4), need = (rows + rpi - 1) / rpi;
-    return (int)(need < 148 * 8 ? need : 148 * 8);
+    const int cap = grid_cap();
+    return (int)(need < cap ? need : cap);
 }
 
 extern "C" int rl_relu_bwd_colsum(const float *d_dout, const float *d_out, float *d_dpre, float *d_partial, long long rows,
@@ -493,7 +507,7 @@ extern "C" int rl_ppo_loss(const float *d_values, const float *d_logp, const flo
         return fa_internal_fail(-1, "rl_ppo_loss: NULL pointer");
     if (N < 1) return fa_internal_fail(-1, "rl_ppo_loss: N must be >= 1");
     int blocks = (N + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > grid_cap()) blocks = grid_cap();
     rl::ppo_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_values, d_logp, d_entropy, d_old_values, d_returns,
                                                                   d_old_logp, d_adv, d_mask, d_norm, N, clip, vcoef, ecoef,
                                                                   d_out, d_gvalues, d_glogp, d_gentropy);
