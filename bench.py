@@ -134,6 +134,52 @@ def cpu_oracle_rate(n_steps, warm, threads, rank_seed=0):
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
+def parity_sample(fab, torch, dev, steps=60):
+    """Part of the cpu_baseline leg (the one place bench.py runs oracle/, as the CHECKER): the bench workload's float kernel
+    teacher-forced against the float64 oracle for `steps` steps of E_PER_GPU envs -- every step starts from the oracle's own
+    state.  Counts how many env-steps hold a laser decision whose float64 barycentric margin is below 1e-5 (the only place
+    where a float-state predicate may legitimately decide differently) and how the masks compare inside and outside it."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import fa_oracle
+    E = E_PER_GPU
+    rng = np.random.RandomState(7)
+    ora = fa_oracle.OracleEnv(E, NG, NA, max_steps=CAP, seed=3, n_threads=len(os.sched_getaffinity(0)))
+    env = fab.FortAttackBatch(E, NG, NA, max_steps=CAP, seed=3, device=dev)
+    ora.reset(); env.reset()
+    near = differ_near = differ_far = contact_steps = 0
+    worst = worst_contact = 0.0
+    for _ in range(steps):
+        act = rng.randint(0, 8, size=(E, A)).astype(np.int32)
+        pos, alive = ora.st_f[:, :, 0:2].copy(), ora.st_i[:, :, 0] > 0
+        dist = np.sqrt(((pos[:, :, None, :] - pos[:, None, :, :]) ** 2).sum(-1))
+        touching = ((dist < 0.1) & alive[:, :, None] & alive[:, None, :] & ~np.eye(A, dtype=bool)[None]).any(axis=(1, 2))
+        env.set_state(torch.from_numpy(ora.st_f.copy()), torch.from_numpy(ora.st_i.copy()), torch.from_numpy(ora.time_step.copy()),
+                      torch.from_numpy(ora.episode.astype(np.int64)))
+        obs, rew, done, res, margin = ora.step(act, auto_reset=True, want_margin=True)
+        o, r, d, rs = env.step(torch.from_numpy(np.ascontiguousarray(act.T)).to(dev))
+        o = o.cpu().numpy().swapaxes(0, 1)
+        tight = margin < 1e-5
+        bad = (d.cpu().numpy() != done) | (rs.cpu().numpy() != res) | (o[:, :, 0] != obs[:, :, 0]).any(axis=1)
+        near += int(tight.sum()); differ_near += int((bad & tight).sum()); differ_far += int((bad & ~tight).sum())
+        ok = ~tight & ~bad
+        gate = np.abs(o - obs) / (1e-5 + 1e-5 * np.abs(obs))              # <= 1: inside the 1e-5 gate of the north star
+        if (ok & ~touching).any():
+            worst = max(worst, float(gate[ok & ~touching].max()))
+        if (ok & touching).any():
+            worst_contact = max(worst_contact, float(gate[ok & touching].max()))
+        contact_steps += int(touching.sum())
+    return {"env_steps": steps * E, "mapping": env.kernel_info()["mapping"], "margin": 1e-5,
+            "env_steps_with_a_decision_inside_the_margin": near, "mask_mismatches_inside_the_margin": differ_near,
+            "mask_mismatches_outside_the_margin": differ_far,
+            "obs_error_over_gate_no_contact": worst, "obs_error_over_gate_in_contact": worst_contact,
+            "env_steps_in_contact": contact_steps,
+            "gate": "|got - ref| / (1e-5 + 1e-5 |ref|) <= 1; env-steps with two alive agents closer than 0.1 are listed separately: "
+                    "the contact force amplifies the rounding of the float64 state to float32 by 1 / distance (tests/gpu_util.contact_slack)",
+            "what": "float32 step kernel vs the float64 oracle, teacher-forced, alive / done / result masks compared per env-step; "
+                    "double mode (FA_F64) has no such margin (tests)"}
+
+
 def _pyref_worker(rank, n_env_steps, warm, barrier, q):
     """One process = one core stepping the UNMODIFIED reference env (baseline/_ref/reference, imported through the stub
     modules of ref_shim.py) with uniform random actions; resets on done as train_fortattack.py:97-100 does."""
@@ -593,6 +639,10 @@ def run_ours(args):
                                     "per_core": ref[0] / cores, "port": port}
         else:
             line["cpu_baseline"] = port
+        try:
+            line["cpu_baseline"]["parity_sample"] = parity_sample(fab, torch, dev)
+        except Exception as exc:
+            line["cpu_baseline"]["parity_sample"] = {"error": repr(exc)[:300]}
     if rank == 0:
         emit(line)
     if world > 1:

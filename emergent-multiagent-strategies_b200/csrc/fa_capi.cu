@@ -211,6 +211,10 @@ static void pick_launch(FaHandle *h) {
         const int warps = (E + 32 / G - 1) / (32 / G);
         int bw = 4;                                        // warps per block: fewer while the blocks would not cover the SMs twice
         while (bw > 1 && (warps + bw - 1) / bw < 2 * h->sm_count) bw >>= 1;
+        if (const char *ev = getenv("FA_GROUP_BLOCK_WARPS")) {           // experiments (profiles/step_mappings.py)
+            const int v = atoi(ev);
+            if (v == 1 || v == 2 || v == 4) bw = v;
+        }
         h->block = 32 * bw;
         h->grid = (warps + bw - 1) / bw;
         return;

@@ -552,20 +552,26 @@ __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) 
 }
 
 __global__ void __launch_bounds__(256) tg_reduce_kernel(const float *partial, int n_part, int a, int b, float *out, int ldo, int accumulate) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= a * b) return;
-    // four interleaved partial sums (independent loads in flight), combined in a fixed order: bit-reproducible
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    // eight lanes per output element: lane q adds partials q, q + 8, ... (consecutive lanes of an octet read the SAME element
+    // of eight different partial blocks; the four octets of a warp read four consecutive elements), then a three-step
+    // butterfly in a fixed order -- bit-reproducible, no atomics, and 8 x the loads in flight of one thread per element
+    const int t = blockIdx.x * 256 + threadIdx.x, i = t >> 3, q = t & 7;
+    const bool live = i < a * b;
     const size_t stride = (size_t)a * b;
-    int c = 0;
-    for (; c + 4 <= n_part; c += 4) {
-        s0 += partial[(size_t)c * stride + i]; s1 += partial[(size_t)(c + 1) * stride + i];
-        s2 += partial[(size_t)(c + 2) * stride + i]; s3 += partial[(size_t)(c + 3) * stride + i];
+    float s0 = 0.0f, s1 = 0.0f;
+    if (live) {
+        int c = q;
+        for (; c + 8 < n_part; c += 16) { s0 += partial[(size_t)c * stride + i]; s1 += partial[(size_t)(c + 8) * stride + i]; }
+        if (c < n_part) s0 += partial[(size_t)c * stride + i];
     }
-    for (; c < n_part; ++c) s0 += partial[(size_t)c * stride + i];
-    const float s = (s0 + s1) + (s2 + s3);
-    float *d = out + (size_t)(i / b) * ldo + i % b;
-    *d = accumulate ? *d + s : s;
+    float s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (live && q == 0) {
+        float *d = out + (size_t)(i / b) * ldo + i % b;
+        *d = accumulate ? *d + s : s;
+    }
 }
 
 // ---- optimizer step ---------------------------------------------------------------------------------------------
@@ -722,7 +728,7 @@ extern "C" int tg_wgrad(const float *d_x, int ldx, int a, const float *d_y, int 
     tg::tg_wgrad_kernel<<<grid, tg::THREADS, tg::W_SMEM, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_wgrad: launch: %s", cudaGetErrorString(e));
-    tg::tg_reduce_kernel<<<(a * b + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float *)d_scratch, grid, a, b, d_dw, lddw, accumulate);
+    tg::tg_reduce_kernel<<<(a * b * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float *)d_scratch, grid, a, b, d_dw, lddw, accumulate);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_wgrad: reduce launch: %s", cudaGetErrorString(e));
     return 0;
