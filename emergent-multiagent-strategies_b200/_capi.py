@@ -110,6 +110,9 @@ def lib():
     L.rl_rollout_bookkeeping.argtypes = [vp] * 7 + [i32, i32, vp]
     L.rl_gather_minibatch.argtypes = [vp] + [i32] * 8 + [vp] * 18
     L.rl_ppo_loss.argtypes = [vp] * 9 + [i32, f32, f32, f32] + [vp] * 5
+    L.rl_ppo_loss_logits.argtypes = [vp] * 9 + [i32, i32, f32, f32, f32] + [vp] * 7
+    L.rl_ppo_loss_logits_scratch_floats.argtypes = []
+    L.rl_ppo_loss_logits_scratch_floats.restype = ctypes.c_size_t
     L.rl_attn_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]
     L.rl_attn_backward.argtypes = [P, P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
     L.rl_attn_mix_forward.argtypes = [P, P, P, P, vp, i32, i32, i32, i32, f32, i32, vp]

@@ -158,6 +158,98 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
     }
 }
 
+// ---- the same loss taken from the action head's LOGITS: Categorical log-prob / entropy (rlcore/distributions.py:9-17,
+// mpnn.py:199-200) and their gradient folded in, per-block partial sums added in block order by the last block ----------
+constexpr int LOSS_ACTIONS = 8;
+__global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const float *__restrict__ values, const float *__restrict__ logits,
+                                                              const long long *__restrict__ actions, const float *__restrict__ old_values,
+                                                              const float *__restrict__ returns, const float *__restrict__ old_logp,
+                                                              const float *__restrict__ adv, const float *__restrict__ mask,
+                                                              const float *__restrict__ norm, int N, float clip, float vcoef, float ecoef,
+                                                              float *out, float *gvalues, float *glogits, float *logp_out,
+                                                              float *entropy_out, float *scratch) {
+    const float inv = norm != nullptr ? 1.0f / norm[0] : 1.0f;
+    float sv = 0.0f, sa = 0.0f, se = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const float4 l0 = *reinterpret_cast<const float4 *>(logits + (size_t)i * LOSS_ACTIONS);
+        const float4 l1 = *reinterpret_cast<const float4 *>(logits + (size_t)i * LOSS_ACTIONS + 4);
+        const float lg[LOSS_ACTIONS] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        float mx = lg[0];
+#pragma unroll
+        for (int k = 1; k < LOSS_ACTIONS; ++k) mx = fmaxf(mx, lg[k]);
+        float pr[LOSS_ACTIONS], sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < LOSS_ACTIONS; ++k) { pr[k] = expf(lg[k] - mx); sum += pr[k]; }
+        const float lse = mx + logf(sum), rs = 1.0f / sum;
+        int act = (int)actions[i];
+        act = act < 0 ? 0 : (act > LOSS_ACTIONS - 1 ? LOSS_ACTIONS - 1 : act);
+        float lp = 0.0f, ent = 0.0f, ln[LOSS_ACTIONS];
+#pragma unroll
+        for (int k = 0; k < LOSS_ACTIONS; ++k) {
+            pr[k] *= rs;
+            ln[k] = lg[k] - lse;
+            ent -= pr[k] * ln[k];
+            lp = k == act ? ln[k] : lp;
+        }
+        if (logp_out != nullptr) logp_out[i] = lp;
+        if (entropy_out != nullptr) entropy_out[i] = ent;
+        if (out == nullptr) continue;                          // evaluation only (the behaviour log-probs of recompute_old)
+        const float m = mask[i], v = values[i], ov = old_values[i], ret = returns[i], a = adv[i];
+        se += ent * m;
+        const float gen = -ecoef * m * inv;
+        const float ratio = m * expf(lp - old_logp[i]);
+        const float clamped = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
+        const float s1 = ratio * a, s2 = clamped * a;
+        sa += m * -fminf(s1, s2);
+        const float d1 = ratio * a, d2 = (ratio >= 1.0f - clip && ratio <= 1.0f + clip) ? ratio * a : 0.0f;
+        const float dmin = s1 < s2 ? d1 : (s1 > s2 ? d2 : 0.5f * (d1 + d2));
+        const float glp = -m * dmin * inv;
+        // d logp_a / d l_j = [j == a] - p_j ;  d H / d l_j = -p_j (log p_j + H)
+        float g[LOSS_ACTIONS];
+#pragma unroll
+        for (int k = 0; k < LOSS_ACTIONS; ++k) g[k] = glp * ((k == act ? 1.0f : 0.0f) - pr[k]) - gen * pr[k] * (ln[k] + ent);
+        *reinterpret_cast<float4 *>(glogits + (size_t)i * LOSS_ACTIONS) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4 *>(glogits + (size_t)i * LOSS_ACTIONS + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        const float dv = v - ov;
+        const float vc = ov + fminf(fmaxf(dv, -clip), clip);
+        const float e1 = v - ret, e2 = vc - ret;
+        const float A1 = e1 * e1, A2 = e2 * e2;
+        sv += 0.5f * fmaxf(A1, A2) * m;
+        const float g1 = 2.0f * e1, g2 = (dv >= -clip && dv <= clip) ? 2.0f * e2 : 0.0f;
+        const float dmax = A1 > A2 ? g1 : (A1 < A2 ? g2 : 0.5f * (g1 + g2));
+        gvalues[i] = vcoef * 0.5f * dmax * m * inv;
+    }
+    if (out == nullptr) return;
+    __shared__ float red[3][8];
+    __shared__ bool last;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, s);
+        sa += __shfl_xor_sync(0xffffffffu, sa, s);
+        se += __shfl_xor_sync(0xffffffffu, se, s);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = sa; red[2][threadIdx.x >> 5] = se; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tv = 0.0f, ta = 0.0f, te = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tv += red[0][w]; ta += red[1][w]; te += red[2][w]; }
+        float *mine = scratch + 4 + 3 * blockIdx.x;
+        mine[0] = tv; mine[1] = ta; mine[2] = te;
+        __threadfence();
+        unsigned int *ticket = reinterpret_cast<unsigned int *>(scratch);
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (last) {                                            // block order, not arrival order: the sums are reproducible
+            __threadfence();
+            tv = ta = te = 0.0f;
+            const volatile float *part = scratch + 4;
+            for (unsigned int b = 0; b < gridDim.x; ++b) { tv += part[3 * b]; ta += part[3 * b + 1]; te += part[3 * b + 2]; }
+            tv *= inv; ta *= inv; te *= inv;
+            out[0] = tv; out[1] = ta; out[2] = te; out[3] = tv * vcoef + ta - te * ecoef;
+            *ticket = 0u;
+        }
+    }
+}
+
 // ---- tiny attention: one warp per batch element, the 32 lanes split the feature dimension (VEC floats each) --------
 constexpr int ATT_MAX = 5;
 struct Opnd { float *p; long long bs, rs; };
@@ -513,6 +605,32 @@ extern "C" int rl_ppo_loss(const float *d_values, const float *d_logp, const flo
                                                                   d_out, d_gvalues, d_glogp, d_gentropy);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_ppo_loss: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" size_t rl_ppo_loss_logits_scratch_floats(void) { return (size_t)4 + 3 * (size_t)grid_cap(); }
+
+extern "C" int rl_ppo_loss_logits(const float *d_values, const float *d_logits, const int64_t *d_actions, const float *d_old_values,
+                                  const float *d_returns, const float *d_old_logp, const float *d_adv, const float *d_mask,
+                                  const float *d_norm, int N, int n_actions, float clip, float vcoef, float ecoef, float *d_out,
+                                  float *d_gvalues, float *d_glogits, float *d_logp, float *d_entropy, float *d_scratch,
+                                  void *stream) {
+    if (!d_logits || !d_actions) return fa_internal_fail(-1, "rl_ppo_loss_logits: NULL logits / actions");
+    if (d_out != nullptr && (!d_values || !d_old_values || !d_returns || !d_old_logp || !d_adv || !d_mask || !d_gvalues ||
+                             !d_glogits || !d_scratch))
+        return fa_internal_fail(-1, "rl_ppo_loss_logits: NULL pointer (the loss form needs every input, both gradients and the scratch)");
+    if (d_out == nullptr && !d_logp && !d_entropy) return fa_internal_fail(-1, "rl_ppo_loss_logits: nothing to compute");
+    if (N < 1 || n_actions != rl::LOSS_ACTIONS)
+        return fa_internal_fail(-1, "rl_ppo_loss_logits: N >= 1 and n_actions == %d expected (got %d, %d)", rl::LOSS_ACTIONS, N, n_actions);
+    if (((uintptr_t)d_logits & 15) || ((uintptr_t)d_glogits & 15))
+        return fa_internal_fail(-4, "rl_ppo_loss_logits: logits / gradient rows must be 16-byte aligned");
+    int blocks = (N + 255) / 256;
+    if (blocks > grid_cap()) blocks = grid_cap();
+    rl::ppo_loss_logits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_values, d_logits, (const long long *)d_actions, d_old_values, d_returns, d_old_logp, d_adv, d_mask, d_norm, N, clip, vcoef,
+        ecoef, d_out, d_gvalues, d_glogits, d_logp, d_entropy, d_scratch);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_ppo_loss_logits: launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

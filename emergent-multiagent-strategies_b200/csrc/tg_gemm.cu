@@ -36,7 +36,12 @@ using namespace mp;
 constexpr int ROWS = 128, KC = 64;
 constexpr uint32_t A_SBO = 128, A_LBO = ROWS * 16 + 16;           // bytes
 constexpr uint32_t HALF = (KC / 8) * A_LBO, STAGE = 2 * HALF;     // 16512, 33024
-constexpr int EPI_WARPS = 8, LOAD_WARPS = 8, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS;
+#ifndef TG_LOAD_WARPS
+#define TG_LOAD_WARPS 8                                           // 8 or 16 loader warps per CTA (measured: profiles/r2r_*)
+#endif
+constexpr int EPI_WARPS = 8, LOAD_WARPS = TG_LOAD_WARPS, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS;
+static_assert(LOAD_WARPS == 8 || LOAD_WARPS == 16, "8 or 16 loader warps");
+constexpr int RPW = ROWS / LOAD_WARPS, NBATCH = RPW / 8;          // tile rows per loader warp; batches of 2 passes x 4 rows
 constexpr int THREADS = (MMA_WARP + 1) * 32, LOAD_THREADS = LOAD_WARPS * 32;
 constexpr int MAX_NST = 6, SCALE_SLOTS = 2;
 constexpr int TB_STRIDE = 20;                                     // floats per row of a warp's 32 x 16 transposition block
@@ -174,11 +179,11 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
                 const uint32_t s0 = sc % (uint32_t)p.nst, ph0 = (sc / (uint32_t)p.nst) & 1u;
                 const uint32_t s1 = (sc + 1) % (uint32_t)p.nst, ph1 = ((sc + 1) / (uint32_t)p.nst) & 1u;
 #pragma unroll
-                for (int batch = 0; batch < 2; ++batch) {
+                for (int batch = 0; batch < NBATCH; ++batch) {
                     float4 v[2][2][2];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const long long row = (long long)tile * ROWS + lw * 16 + (batch * 2 + q) * 4 + sub;
+                        const long long row = (long long)tile * ROWS + lw * RPW + (batch * 2 + q) * 4 + sub;
                         const float *src = p.x + row * p.ldx;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
                     }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const int r = lw * 16 + (batch * 2 + q) * 4 + sub;
+                        const int r = lw * RPW + (batch * 2 + q) * 4 + sub;
                         float m = fmaxf(fmaxf(amax4(v[q][0][0]), amax4(v[q][0][1])), fmaxf(amax4(v[q][1][0]), amax4(v[q][1][1])));
                         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
                         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
@@ -463,15 +468,16 @@ __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) 
         const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
         const int my_steps = (p.n_steps - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = my_steps * nblk;
-        auto load_block = [&](int idx, float4 (&v)[2][2][2]) {
+        constexpr int WQ = WROWS / LOAD_WARPS / 4;                 // passes of 4 rows per loader warp and operand block
+        auto load_block = [&](int idx, float4 (&v)[WQ][2][2]) {
             const int step = (int)blockIdx.x + (idx / nblk) * (int)gridDim.x, k = idx % nblk;
             const bool isx = k < p.ab;
             const float *src = isx ? p.x : p.y;
             const int ld = isx ? p.ldx : p.ldy, width = isx ? p.a : p.b, f0 = (isx ? k : k - p.ab) * 128;
             const int vec = isx ? p.vx : p.vy;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const long long row = (long long)step * WROWS + lw * 8 + q * 4 + sub;
+            for (int q = 0; q < WQ; ++q) {
+                const long long row = (long long)step * WROWS + lw * (WQ * 4) + q * 4 + sub;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int col = f0 + h * 64 + kc * 8;
@@ -493,17 +499,17 @@ __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) 
                 }
             }
         };
-        auto emit_block = [&](int idx, const float4 (&v)[2][2][2]) {
+        auto emit_block = [&](int idx, const float4 (&v)[WQ][2][2]) {
             const uint32_t bc = (uint32_t)idx, s = bc % NB;
             mbar_wait(&bar_empty[s], ((bc / NB) & 1u) ^ 1u, p.status, 12);
             uint8_t *blk = smem + (size_t)s * BLOCK;
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < WQ; ++q)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint4 hh, mm, ll;
                     split8_bf16(v[q][h][0], v[q][h][1], hh, mm, ll);
-                    uint8_t *d = blk + (uint32_t)(h * 8 + kc) * FB_LBO + (uint32_t)(lw * 8 + q * 4 + sub) * 16u;
+                    uint8_t *d = blk + (uint32_t)(h * 8 + kc) * FB_LBO + (uint32_t)(lw * (WQ * 4) + q * 4 + sub) * 16u;
                     *reinterpret_cast<uint4 *>(d) = hh;
                     *reinterpret_cast<uint4 *>(d + PLANE) = mm;
                     *reinterpret_cast<uint4 *>(d + 2 * PLANE) = ll;
@@ -511,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) 
             fence_async_smem();
             mbar_arrive(&bar_full[s]);
         };
-        float4 va[2][2][2], vb[2][2][2];
+        float4 va[WQ][2][2], vb[WQ][2][2];
         load_block(0, va);
         for (int idx = 0; idx < total; idx += 2) {
             load_block(idx + 1, vb);

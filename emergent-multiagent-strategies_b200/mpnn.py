@@ -255,9 +255,46 @@ class MPNN(nn.Module):
 
     def evaluate_actions(self, inp, state, oppInp, mask, action):
         x = self._fwd(inp, oppInp, mask)
+        if self._logits_path(x):
+            value, logits = self._heads(x)
+            if not torch.is_grad_enabled():
+                # no autograd wanted (BatchedTrainer.recompute_old): log-prob and entropy in the arithmetic of the update's loss kernel
+                lp, ent = self._fused_module().categorical_eval(logits, action)
+                return value, lp.view(-1, 1), ent, state
+            try:
+                from .rlcore.distributions import FixedCategorical
+            except ImportError:
+                from rlcore.distributions import FixedCategorical
+            dist = FixedCategorical(logits=logits, validate_args=False if torch.cuda.is_current_stream_capturing() else None)
+            return value, dist.log_probs(action), dist.entropy(), state
         value = self._value(x)
         dist = self._dist(self._policy(x))
         return value, dist.log_probs(action), dist.entropy(), state
+
+    @staticmethod
+    def _fused_module():
+        try:
+            from .rlcore import fused
+        except ImportError:
+            from rlcore import fused
+        return fused
+
+    def _logits_path(self, x):
+        return (self._use_fused(x) and self.policy_layers == 1
+                and self.dist.linear.out_features == self._fused_module().LOSS_ACTIONS)
+
+    def _heads(self, x):
+        """(value [N, 1], logits [N, 8]) through rlcore/fused.heads: the two hidden layers of the heads as one stacked product."""
+        v0, v2, p0, dl = self.value_head[0], self.value_head[2], self.policy_head[0], self.dist.linear
+        return self._fused_module().heads(x, v0.weight, v0.bias, p0.weight, p0.bias, v2.weight, v2.bias, dl.weight, dl.bias)
+
+    def evaluate_logits(self, inp, oppInp):
+        """(value [N, 1], action-head logits [N, 8]) of the fused training forward, or None when that path does not apply:
+        JointPPO feeds them to rlcore/fused.ppo_loss_logits, which holds the Categorical (mpnn.py:199-200) and its backward."""
+        if not (self.fused_attention and inp.is_cuda and inp.dtype == torch.float32 and self.nonlin is nn.ReLU
+                and self.policy_layers == 1 and self.dist.linear.out_features == self._fused_module().LOSS_ACTIONS):
+            return None
+        return self._heads(self._fwd(inp, oppInp, None))
 
     def get_value(self, inp, state, oppInp, mask):
         return self._value(self._fwd(inp, oppInp, mask))

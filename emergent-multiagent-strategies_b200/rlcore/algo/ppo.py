@@ -180,14 +180,27 @@ class JointPPO(object):
         a0, n, o0, m = team
         (obs_batch, mask, obs_opp_batch, actions_batch, value_preds_batch, return_batch, masks_batch,
          old_log_probs_batch, adv_targ, alive_sum) = fused.gather_minibatch(R, idx, a0, n, o0, m, advantages)
-        values, action_log_probs, dist_entropy, _ = self.actor_critic.evaluate_actions(
-            obs_batch, None, obs_opp_batch, masks_batch, actions_batch)
+        # the Categorical head (log-prob, entropy) and its backward live inside the loss kernel when the policy offers its
+        # logits (MPNN.evaluate_logits on the fused path); otherwise the distribution is evaluated by torch as before
+        head = getattr(self.actor_critic, "evaluate_logits", None)
+        vl = head(obs_batch, obs_opp_batch) if head is not None and torch.is_grad_enabled() else None
+        if vl is not None:
+            values, logits = vl
+
+            def loss_of(norm_):
+                return fused.ppo_loss_logits(values, logits, actions_batch, value_preds_batch, return_batch, old_log_probs_batch,
+                                             adv_targ, mask, norm_, self.clip_param, self.value_loss_coef, self.entropy_coef)
+        else:
+            values, action_log_probs, dist_entropy, _ = self.actor_critic.evaluate_actions(
+                obs_batch, None, obs_opp_batch, masks_batch, actions_batch)
+
+            def loss_of(norm_):
+                return fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch, old_log_probs_batch,
+                                      adv_targ, mask, norm_, self.clip_param, self.value_loss_coef, self.entropy_coef)
         count = mask.new_full((1,), float(mask.numel()))
         if world == 1:
             norm = torch.where(alive_sum != 0, alive_sum, count)          # mask.mean() != 0 else 1 (ppo.py:150-187)
-            loss, stats = fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch,
-                                         old_log_probs_batch, adv_targ, mask, norm, self.clip_param,
-                                         self.value_loss_coef, self.entropy_coef)
+            loss, stats = loss_of(norm)
             self.optimizer.zero_grad()
             loss.backward()
             self._clip_and_step()
@@ -199,9 +212,7 @@ class JointPPO(object):
         # and the division by the global normaliser happens after the all-reduce (inside the optimizer kernel).
         if getattr(self, "_one", None) is None or self._one.device != mask.device:
             self._one = torch.ones(1, device=mask.device)
-        loss, stats = fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch,
-                                     old_log_probs_batch, adv_targ, mask, self._one, self.clip_param,
-                                     self.value_loss_coef, self.entropy_coef)
+        loss, stats = loss_of(self._one)
         self.optimizer.zero_grad()
         loss.backward()
         flat, views = self._flat_grads(params)

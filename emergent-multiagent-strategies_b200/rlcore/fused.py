@@ -65,6 +65,68 @@ def ppo_loss(values, logp, entropy, old_values, returns, old_logp, adv, mask, no
     return _PPOLoss.apply(values, logp, entropy, old_values, returns, old_logp, adv, mask, norm, clip, vcoef, ecoef)
 
 
+# ---- the loss taken from the action head's logits: Categorical log-prob / entropy and their backward inside the loss kernel --
+LOSS_ACTIONS = 8
+_LOSS_SCRATCH = {}
+
+
+def _loss_scratch(dev):
+    s = _LOSS_SCRATCH.get(dev)
+    if s is None:
+        s = _LOSS_SCRATCH[dev] = torch.zeros(int(_lib().rl_ppo_loss_logits_scratch_floats()), device=dev)
+    return s
+
+
+def categorical_eval(logits, actions):
+    """(log-prob of `actions` [N], entropy [N]) of Categorical(logits=logits [N, 8]) in the loss kernel's arithmetic, no
+    autograd (BatchedTrainer.recompute_old: the behaviour log-probs the update's ratio starts from)."""
+    lg = logits.detach().contiguous().float()
+    act = actions.detach().reshape(-1).contiguous()
+    N = lg.shape[0]
+    if lg.shape[1] != LOSS_ACTIONS or act.dtype != torch.int64 or act.numel() != N:
+        raise ValueError("categorical_eval: logits [N, %d] float and int64 actions [N] expected" % LOSS_ACTIONS)
+    lp, ent = torch.empty(N, device=lg.device), torch.empty(N, device=lg.device)
+    if N:
+        _capi.check(_lib().rl_ppo_loss_logits(None, lg.data_ptr(), act.data_ptr(), None, None, None, None, None, None, N, LOSS_ACTIONS,
+                                              0.0, 0.0, 0.0, None, None, None, lp.data_ptr(), ent.data_ptr(), None,
+                                              torch.cuda.current_stream(lg.device).cuda_stream))
+    return lp, ent
+
+
+class _PPOLossLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, values, logits, actions, old_values, returns, old_logp, adv, mask, norm, clip, vcoef, ecoef):
+        c = lambda t: t.detach().reshape(-1).contiguous().float()
+        v, lg = c(values), logits.detach().contiguous().float()
+        act = actions.detach().reshape(-1).contiguous()
+        N = v.numel()
+        if lg.shape != (N, LOSS_ACTIONS) or act.dtype != torch.int64 or act.numel() != N:
+            raise ValueError("ppo_loss_logits: logits [N, %d] float and int64 actions [N] expected" % LOSS_ACTIONS)
+        out = torch.empty(4, device=v.device)
+        gv, glg = torch.empty_like(v), torch.empty_like(lg)
+        _capi.check(_lib().rl_ppo_loss_logits(v.data_ptr(), lg.data_ptr(), act.data_ptr(), c(old_values).data_ptr(),
+                                              c(returns).data_ptr(), c(old_logp).data_ptr(), c(adv).data_ptr(), c(mask).data_ptr(),
+                                              c(norm).data_ptr(), N, LOSS_ACTIONS, float(clip), float(vcoef), float(ecoef),
+                                              out.data_ptr(), gv.data_ptr(), glg.data_ptr(), None, None,
+                                              _loss_scratch(v.device).data_ptr(), torch.cuda.current_stream(v.device).cuda_stream))
+        ctx.save_for_backward(gv, glg)
+        ctx.shapes = (values.shape, logits.shape)
+        ctx.mark_non_differentiable(out)
+        return out[3].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_total, _g_out):
+        gv, glg = ctx.saved_tensors
+        sv, sl = ctx.shapes
+        return ((gv * g_total).view(sv), (glg * g_total).view(sl)) + (None,) * 10
+
+
+def ppo_loss_logits(values, logits, actions, old_values, returns, old_logp, adv, mask, norm, clip, vcoef, ecoef):
+    """ppo_loss with the Categorical head inside: -> (total loss with autograd through values and logits, stats
+    [value_loss, action_loss, entropy, total] detached)."""
+    return _PPOLossLogits.apply(values, logits, actions, old_values, returns, old_logp, adv, mask, norm, clip, vcoef, ecoef)
+
+
 # ---- attention over a handful of agents: forward + backward kernels behind autograd ---------------------------------
 _Opnd = _capi.RlAttnOperand
 
@@ -384,6 +446,53 @@ def matmul(x, M):
 
 def matmul_nt(x, B):
     return _MatmulNT.apply(x, B)
+
+
+# ---- value head + policy head + action head as one function of the final features -----------------------------------------
+class _Heads(torch.autograd.Function):
+    """(value, logits) = (value_head.2(ReLU(value_head.0 x)), dist.linear(ReLU(policy_head.0 x)))  (mpnn.py:174-205 with
+    policy_layers = 1).  The two 128 -> 128 hidden layers read the same x: they run as ONE product with the weights stacked
+    ([2d, d], ReLU in the epilogue), and backward as ONE K = 2d product for dx and ONE weight-gradient product, instead of two
+    of each plus the sum of the two dx; the small heads read / write their halves of the stacked activation in place."""
+
+    @staticmethod
+    def forward(ctx, x, Wv0, bv0, Wp0, bp0, Wv2, bv2, Wd, bd):
+        x = x.contiguous()
+        d = Wv0.shape[0]
+        Wcat, bcat = torch.cat((Wv0, Wp0), 0), torch.cat((bv0, bp0), 0)
+        if _use_tg(x):
+            hv = tg_linear(x, tg_pack(Wcat, False), bcat, True)
+            value = tg_linear(hv[:, :d], tg_pack(Wv2, False), bv2)
+            logits = tg_linear(hv[:, d:], tg_pack(Wd, False), bd)
+        else:
+            hv = torch.relu(torch.addmm(bcat, x, Wcat.t()))
+            value, logits = torch.addmm(bv2, hv[:, :d], Wv2.t()), torch.addmm(bd, hv[:, d:], Wd.t())
+        ctx.save_for_backward(x, hv, Wcat, Wv2, Wd)
+        return value, logits
+
+    @staticmethod
+    def backward(ctx, dvalue, dlogits):
+        x, hv, Wcat, Wv2, Wd = ctx.saved_tensors
+        d = Wcat.shape[0] // 2
+        dvalue, dlogits = dvalue.contiguous(), dlogits.contiguous()
+        dhv = torch.empty_like(hv)
+        if _use_tg(x):
+            tg_linear(dvalue, tg_pack(Wv2, True), out=dhv[:, :d])
+            tg_linear(dlogits, tg_pack(Wd, True), out=dhv[:, d:])
+        else:
+            dhv[:, :d] = dvalue @ Wv2
+            dhv[:, d:] = dlogits @ Wd
+        dWv2, dWd = xt_dy(dvalue, hv[:, :d]), xt_dy(dlogits, hv[:, d:])
+        dpre, dbcat = relu_bwd_colsum(dhv, _relu_mask_source(hv))
+        dWcat = xt_dy(dpre, x)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = tg_linear(dpre, tg_pack(Wcat, True)) if _use_tg(dpre) else dpre @ Wcat
+        return dx, dWcat[:d], dbcat[:d], dWcat[d:], dbcat[d:], dWv2, dvalue.sum(0), dWd, dlogits.sum(0)
+
+
+def heads(x, Wv0, bv0, Wp0, bp0, Wv2, bv2, Wd, bd):
+    return _Heads.apply(x, Wv0, bv0, Wp0, bp0, Wv2, bv2, Wd, bd)
 
 
 # ---- one message-passing round with the projections folded into the weights --------------------------------------------

@@ -71,6 +71,21 @@ int rl_ppo_loss(const float *d_values, const float *d_logp, const float *d_entro
                 const float *d_norm, int N, float clip, float vcoef, float ecoef, float *d_out, float *d_gvalues,
                 float *d_glogp, float *d_gentropy, void *stream);
 
+/* The same loss taken from the action head's LOGITS [N][8] and the actions int64 [N]: the Categorical's log-prob and
+ * entropy (rlcore/distributions.py:9-17 as used by mpnn.py:199-200) and their gradients are evaluated inside, so the ~50
+ * elementwise launches of log_softmax / gather / entropy and their autograd backward disappear from the optimizer step:
+ *   logp_i = l_{i,a_i} - logsumexp_j l_ij,  H_i = -sum_j p_ij log p_ij,
+ *   d total / d l_ij = glogp_i ([j == a_i] - p_ij) - gentropy_i p_ij (log p_ij + H_i).
+ * d_out float [4] is OVERWRITTEN with {value_loss, action_loss, entropy, total}: per-block partial sums are added in block
+ * order by the last block (d_scratch: rl_ppo_loss_logits_scratch_floats() floats, its first word zero before the first
+ * call; the kernel leaves it zero), so the statistics are bit-reproducible.  d_logp / d_entropy (optional) receive
+ * the per-row values.  d_out == NULL: evaluation only (d_logp and / or d_entropy), nothing else is read. */
+size_t rl_ppo_loss_logits_scratch_floats(void);
+int rl_ppo_loss_logits(const float *d_values, const float *d_logits, const int64_t *d_actions, const float *d_old_values,
+                       const float *d_returns, const float *d_old_logp, const float *d_adv, const float *d_mask,
+                       const float *d_norm, int N, int n_actions, float clip, float vcoef, float ecoef, float *d_out,
+                       float *d_gvalues, float *d_glogits, float *d_logp, float *d_entropy, float *d_scratch, void *stream);
+
 /* Single-head attention over a handful of agents, forward and backward, for the TRAINING forward of the MPNN
  * (mpnn.py:249-331 MultiHeadAttention without self-messages, mpnn.py:376-443 MultiHeadOppAttention): replaces
  * bmm -> mask -> softmax -> bmm (and their four backward bmm's) over [batch, <=5, <=5] matrices by one warp per

@@ -286,6 +286,50 @@ def test_fused_gather_and_loss_match_torch_path():
         assert np.allclose(a, b, rtol=2e-3, atol=2e-4), (trs[0], trs[1])
 
 
+def test_loss_from_logits_matches_categorical_and_torch_loss():
+    """rl_ppo_loss_logits == FixedCategorical(logits).log_probs / .entropy (rlcore/distributions.py:9-17) fed to the torch
+    expressions of ppo.py:150-187: statistics, the gradient with respect to values and LOGITS (torch autograd through
+    log_softmax / gather / entropy), bit-reproducible statistics, and the evaluation-only form."""
+    fused = import_module(PKG + ".rlcore.fused")
+    dist = import_module(PKG + ".rlcore.distributions")
+    gen = torch.Generator().manual_seed(5)
+    for N in (1, 777, 70001):
+        r = lambda *s: torch.randn(*s, generator=gen).cuda()
+        logits = (2.0 * r(N, 8)).requires_grad_()
+        values = r(N, 1).requires_grad_()
+        actions = torch.randint(0, 8, (N, 1), generator=gen).cuda()
+        old_v, ret, adv = values.detach() + 0.3 * r(N, 1), r(N, 1), r(N, 1)
+        mask = (torch.rand(N, 1, generator=gen) < 0.8).float().cuda()
+        mask[0] = 1.0
+        clip, vc, ec = 0.2, 0.5, 0.01
+        d = dist.FixedCategorical(logits=logits)
+        logp, ent = d.log_probs(actions), d.entropy()
+        old_lp = logp.detach() + 0.3 * r(N, 1)
+        norm = mask.sum().view(1)
+        total, stats = fused.ppo_loss_logits(values, logits, actions, old_v, ret, old_lp, adv, mask, norm, clip, vc, ec)
+        total.backward()
+        got = [values.grad.clone(), logits.grad.clone()]
+        values.grad = logits.grad = None
+        mm = lambda x: x.mean() / mask.mean()
+        entropy = mm(ent * mask[:, 0])
+        ratio = mask * torch.exp(logp - old_lp)
+        action_loss = mm(mask * -torch.min(ratio * adv, torch.clamp(ratio, 1 - clip, 1 + clip) * adv))
+        clipped = old_v + (values - old_v).clamp(-clip, clip)
+        value_loss = mm(0.5 * torch.max((values - ret).pow(2), (clipped - ret).pow(2)) * mask)
+        ref_total = value_loss * vc + action_loss - entropy * ec
+        ref_total.backward()
+        assert torch.allclose(stats[:3], torch.stack([value_loss, action_loss, entropy]).detach(), rtol=3e-5, atol=1e-6)
+        assert abs(float(total) - float(ref_total)) < 3e-5 * max(1.0, abs(float(ref_total)))
+        assert torch.allclose(got[0], values.grad, rtol=1e-4, atol=1e-9)
+        scale = float(logits.grad.abs().max())
+        assert float((got[1] - logits.grad).abs().max()) < 2e-5 * scale + 1e-10, (N, float((got[1] - logits.grad).abs().max()), scale)
+        # same inputs, same bits (block-ordered partial sums, no atomics on the statistics)
+        _, again = fused.ppo_loss_logits(values, logits, actions, old_v, ret, old_lp, adv, mask, norm, clip, vc, ec)
+        assert torch.equal(again, stats)
+        lp2, ent2 = fused.categorical_eval(logits, actions)
+        assert float((lp2 - logp.detach()[:, 0]).abs().max()) < 2e-6 and float((ent2 - ent.detach()).abs().max()) < 2e-6
+
+
 @pytest.mark.parametrize("n,m,hid", [(3, 3, 128), (5, 4, 128), (1, 2, 128), (2, 5, 64)])
 def test_fused_training_attention_matches_bmm_path(n, m, hid):
     """MPNN.evaluate_actions with the attention kernels (rl_attn_forward / rl_attn_backward) == the bmm/softmax mirror
