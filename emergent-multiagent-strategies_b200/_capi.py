@@ -129,6 +129,7 @@ def lib():
     L.tg_adam_step.argtypes = [ctypes.POINTER(TgTensor), i32, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp]
     L.tg_kernel_info.argtypes = [i32, i32p, i32p, i32p]
     L.tg_debug_wgrad_desc.argtypes = [u32, u32]
+    L.tg_debug_staged.argtypes = [i32]
     L.mw_step.argtypes = [vp, vp, vp, vp, vp]
     L.mw_scenario_obs_dim.argtypes = [i32, i32, i32, i32]
     L.mw_scenario_callbacks.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp]

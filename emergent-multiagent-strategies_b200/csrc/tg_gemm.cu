@@ -42,8 +42,12 @@ constexpr uint32_t HALF = (KC / 8) * A_LBO, STAGE = 2 * HALF;     // 16512, 3302
 constexpr int EPI_WARPS = 8, LOAD_WARPS = TG_LOAD_WARPS, LOAD_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + LOAD_WARPS;
 static_assert(LOAD_WARPS == 8 || LOAD_WARPS == 16, "8 or 16 loader warps");
 constexpr int RPW = ROWS / LOAD_WARPS, NBATCH = RPW / 8;          // tile rows per loader warp; batches of 2 passes x 4 rows
-constexpr int THREADS = (MMA_WARP + 1) * 32, LOAD_THREADS = LOAD_WARPS * 32;
+constexpr int THREADS = (MMA_WARP + 1) * 32, LOAD_THREADS = LOAD_WARPS * 32, THREADS_STAGED = THREADS + 32;
 constexpr int MAX_NST = 6, SCALE_SLOTS = 2;
+// staged form (K = 64 or 128): a producer warp streams raw fp32 rows of x into a ring of RAW_ROWS-row chunks with bulk copies
+// (TMA engine: the requests do not pass through registers or L1TEX); the loader warps become converters that read the chunks
+// from shared memory.  Chunk = one pass of the converters: RAW_ROWS = LOAD_WARPS x 4 rows.
+constexpr int RAW_ROWS = LOAD_WARPS * 4, NRAW = 4, PROD_WARP = MMA_WARP + 1;
 constexpr int TB_STRIDE = 20;                                     // floats per row of a warp's 32 x 16 transposition block
 constexpr int TB_BYTES = EPI_WARPS * 32 * TB_STRIDE * 4, RS_BYTES = SCALE_SLOTS * 2 * ROWS * 4, BIAS_BYTES = 2 * 256 * 4;
 constexpr int FIXED_BYTES = TB_BYTES + RS_BYTES + BIAS_BYTES;
@@ -90,9 +94,11 @@ __device__ __forceinline__ float pow2_scale(float amax, float *inv) {
     return __uint_as_float((uint32_t)(127 + 14 - e) << 23);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p) {
+template <bool STAGED>
+__global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linear_kernel(const LinParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_acc_full[2], bar_acc_empty[2], bar_w;
+    __shared__ __align__(8) uint64_t bar_raw_full[NRAW], bar_raw_empty[NRAW];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *ring = smem + p.wbytes;
@@ -100,15 +106,18 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
     float *rowscale = tb + EPI_WARPS * 32 * TB_STRIDE;            // [SCALE_SLOTS][2][ROWS]
     float *bias_s = rowscale + SCALE_SLOTS * 2 * ROWS;            // [256] bias, then [256] inverse weight scale per column
     float *winv_s = bias_s + 256;
+    uint8_t *raw = reinterpret_cast<uint8_t *>(winv_s + 256);     // STAGED: [NRAW][RAW_ROWS][K] fp32
 
     if (tid == 0) {
         for (int s = 0; s < p.nst; ++s) { mbar_init(&bar_full[s], LOAD_THREADS); mbar_init(&bar_empty[s], 1); }
+        if (STAGED)
+            for (int s = 0; s < NRAW; ++s) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], LOAD_WARPS); }
         for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_WARPS * 32); }
         mbar_init(&bar_w, 1);
         mbar_fence_init();
     }
     if (warp == MMA_WARP) tmem_alloc<512>(&tmem_base_s);
-    for (int i = tid; i < 256; i += THREADS) {
+    for (int i = tid; i < 256; i += (int)blockDim.x) {
         bias_s[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
         winv_s[i] = i < p.Np ? reinterpret_cast<const float *>(p.packed + p.wbytes)[i] : 0.0f;
     }
@@ -164,6 +173,89 @@ __global__ void __launch_bounds__(THREADS, 1) tg_linear_kernel(const LinParams p
                 }
                 __syncwarp();
             }
+        }
+    } else if (STAGED && warp == PROD_WARP) {
+        // ================= producer (staged form): raw fp32 rows of x -> ring of RAW_ROWS-row chunks ==================
+        // one bulk copy per chunk when the rows are contiguous (ldx == K), else one per row (lane = row of the chunk)
+        const uint32_t row_bytes = (uint32_t)p.K * 4u, chunk_bytes = RAW_ROWS * row_bytes;
+        uint32_t rc = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int c = 0; c < ROWS / RAW_ROWS; ++c, ++rc) {
+                const uint32_t rs = rc % NRAW, rph = (rc / NRAW) & 1u;
+                mbar_wait(&bar_raw_empty[rs], rph ^ 1u, p.status, 8);
+                const long long row0 = (long long)tile * ROWS + c * RAW_ROWS, left = p.rows - row0;
+                const int nrows = left <= 0 ? 0 : (left > RAW_ROWS ? RAW_ROWS : (int)left);
+                if (lane == 0) mbar_expect_tx(&bar_raw_full[rs], (uint32_t)nrows * row_bytes);
+                __syncwarp();
+                uint8_t *dst = raw + rs * chunk_bytes;
+                if (p.ldx == p.K) {
+                    if (lane == 0 && nrows > 0) bulk_g2s(dst, p.x + row0 * p.ldx, (uint32_t)nrows * row_bytes, &bar_raw_full[rs]);
+                } else if (lane < nrows) {
+                    bulk_g2s(dst + (uint32_t)lane * row_bytes, p.x + (row0 + lane) * p.ldx, row_bytes, &bar_raw_full[rs]);
+                }
+            }
+        }
+    } else if (STAGED && warp >= LOAD_WARP0) {
+        // ================= converters (staged form) =================
+        // lane = (row of the pass sub, 8-column chunk kc) as in the register loaders below; a chunk of the raw ring is one
+        // pass of the eight warps (warp lw converts rows 4 lw .. 4 lw + 3 of the chunk).  One group (K = gw <= 128).
+        const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
+        const int halves = p.gw / KC;
+        const uint32_t row_bytes = (uint32_t)p.K * 4u, chunk_bytes = RAW_ROWS * row_bytes;
+        uint32_t sc = 0, rc = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s0 = sc % (uint32_t)p.nst, ph0 = (sc / (uint32_t)p.nst) & 1u;
+            const uint32_t s1 = (sc + 1) % (uint32_t)p.nst, ph1 = ((sc + 1) / (uint32_t)p.nst) & 1u;
+            for (int c = 0; c < ROWS / RAW_ROWS; ++c, ++rc) {
+                const uint32_t rs = rc % NRAW, rph = (rc / NRAW) & 1u;
+                const int r = c * RAW_ROWS + lw * 4 + sub;
+                const bool live = (long long)tile * ROWS + r < p.rows;
+                mbar_wait(&bar_raw_full[rs], rph, p.status, 7);
+                const uint8_t *src = raw + rs * chunk_bytes + (uint32_t)(lw * 4 + sub) * row_bytes + (uint32_t)kc * 32u;
+                float4 v[2][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    v[h][0] = v[h][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (h < halves && live) {
+                        v[h][0] = *reinterpret_cast<const float4 *>(src + h * 256);
+                        v[h][1] = *reinterpret_cast<const float4 *>(src + h * 256 + 16);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_raw_empty[rs]);       // the chunk's values are in registers: hand it back
+                float m = fmaxf(fmaxf(amax4(v[0][0]), amax4(v[0][1])), fmaxf(amax4(v[1][0]), amax4(v[1][1])));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                float inv;
+                const float s = pow2_scale(m, &inv);
+                uint4 hi[2], lo[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    scale4(v[h][0], s); scale4(v[h][1], s);
+                    split8_f16(v[h][0], v[h][1], hi[h], lo[h]);
+                }
+                if (c == 0) {
+                    // row-scale slot it & 1 may still be read by the epilogue of tile it - 2; the operand stages by the MMAs
+                    mbar_wait(&bar_acc_empty[it & 1], (uint32_t)(((it >> 1) & 1) ^ 1), p.status, 6);
+                    mbar_wait(&bar_empty[s0], ph0 ^ 1u, p.status, 4);
+                    if (halves > 1) mbar_wait(&bar_empty[s1], ph1 ^ 1u, p.status, 4);
+                }
+                if (kc == 0) rowscale[((it & (SCALE_SLOTS - 1)) * 2) * ROWS + r] = inv;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h < halves) {
+                        uint8_t *st = ring + (size_t)(h == 0 ? s0 : s1) * STAGE + (uint32_t)kc * A_LBO + (uint32_t)r * 16u;
+                        *reinterpret_cast<uint4 *>(st) = hi[h];
+                        *reinterpret_cast<uint4 *>(st + HALF) = lo[h];
+                    }
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(&bar_full[s0]);
+            if (halves > 1) mbar_arrive(&bar_full[s1]);
+            sc += (uint32_t)halves;
         }
     } else if (warp >= LOAD_WARP0) {
         // ================= loaders =================
@@ -652,13 +744,15 @@ constexpr int MAX_DEVICES = 64;
 bool g_ready[MAX_DEVICES] = {};
 int g_sms[MAX_DEVICES] = {};
 uint32_t g_wg_lbo = 128, g_wg_sbo = tg::FB_LBO;
+bool g_staged = true;          // tg_debug_staged(0): keep tg_linear on the register loaders (A/B measurements, tests of both forms)
 
 int prepare(int *sms) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return fa_internal_fail(-3, "tg: no usable CUDA device");
     if (!g_ready[dev]) {
-        e = cudaFuncSetAttribute(tg::tg_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
+        e = cudaFuncSetAttribute(tg::tg_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::W_SMEM);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return fa_internal_fail(-2, "tg: device setup: %s", cudaGetErrorString(e));
@@ -701,13 +795,19 @@ extern "C" int tg_linear(const float *d_x, int ldx, long long rows, int K, const
     p.groups = Kp / p.gw;
     p.wbytes = 4 * Np * Kp;
     p.vec_ok = (ldx % 4 == 0) && (((uintptr_t)d_x & 15) == 0);
-    int nst = (tg::SMEM_LIMIT - tg::FIXED_BYTES - p.wbytes) / (int)tg::STAGE;
+    // staged form: K = 64 or 128 exactly (one scale group, rows are whole 16-byte multiples), 16-byte aligned rows, and room
+    // for the raw ring beside the weights and at least one tile of operand stages
+    const int raw_bytes = tg::NRAW * tg::RAW_ROWS * K * 4;
+    const bool staged = g_staged && (K == 64 || K == 128) && p.vec_ok &&
+                        tg::SMEM_LIMIT - tg::FIXED_BYTES - p.wbytes - raw_bytes >= 2 * (int)tg::STAGE;
+    int nst = (tg::SMEM_LIMIT - tg::FIXED_BYTES - p.wbytes - (staged ? raw_bytes : 0)) / (int)tg::STAGE;
     if (nst > tg::MAX_NST) nst = tg::MAX_NST;
     if (nst < 2) return fa_internal_fail(-1, "tg_linear: weights too large for the shared-memory ring");
     p.nst = nst;
-    const size_t smem = (size_t)p.wbytes + (size_t)nst * tg::STAGE + tg::FIXED_BYTES;
+    const size_t smem = (size_t)p.wbytes + (size_t)nst * tg::STAGE + tg::FIXED_BYTES + (staged ? raw_bytes : 0);
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    tg::tg_linear_kernel<<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p);
+    if (staged) tg::tg_linear_kernel<true><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p);
+    else tg::tg_linear_kernel<false><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_linear: launch: %s", cudaGetErrorString(e));
     return 0;
@@ -762,10 +862,11 @@ extern "C" int tg_adam_step(const TgTensor *tensors, int n_tensors, float lr, fl
 extern "C" int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t *smem) {
     if (int rc = prepare(nullptr)) return rc;
     cudaFuncAttributes at;
-    const cudaError_t e = which == 0 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel);
+    const cudaError_t e = which == 0 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<false>)
+                        : (which == 2 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<true>) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel));
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_kernel_info: %s", cudaGetErrorString(e));
     if (regs) *regs = at.numRegs;
-    if (block) *block = tg::THREADS;
+    if (block) *block = which == 2 ? tg::THREADS_STAGED : tg::THREADS;
     if (smem) *smem = (which == 0 ? tg::SMEM_LIMIT : tg::W_SMEM) + (int)at.sharedSizeBytes;
     return 0;
 }
@@ -773,5 +874,10 @@ extern "C" int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t 
 extern "C" int tg_debug_wgrad_desc(uint32_t lbo, uint32_t sbo) {
     g_wg_lbo = lbo ? lbo : 128;
     g_wg_sbo = sbo ? sbo : tg::FB_LBO;
+    return 0;
+}
+
+extern "C" int tg_debug_staged(int on) {
+    g_staged = on != 0;
     return 0;
 }

@@ -82,6 +82,12 @@ int tg_adam_step(const TgTensor *tensors, int n_tensors, float lr, float beta1, 
 /* Static facts for reports: registers / block / dynamic shared memory of the two GEMM kernels. */
 int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t *smem);
 
+/* tg_linear has two loader forms with identical arithmetic: the STAGED form (K = 64 or 128, 16-byte aligned rows: a producer
+ * warp streams raw fp32 rows into a shared-memory ring with bulk copies and the loader warps convert from there) and the
+ * register form (every other shape).  tg_debug_staged(0) keeps every call on the register form (measurements, tests of
+ * both forms); tg_debug_staged(1) restores the default. */
+int tg_debug_staged(int on);
+
 /* Debug: override the descriptor fields of the MN-major operands of tg_wgrad (lbo, sbo in bytes; 0 = built-in). */
 int tg_debug_wgrad_desc(uint32_t lbo, uint32_t sbo);
 

@@ -7,6 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 fused = import_module("emergent-multiagent-strategies_b200.rlcore.fused")
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 196608
 dev = "cuda:0"
+if os.environ.get("TG_BENCH_STAGED") == "0":       # A/B: keep tg_linear on the register loaders
+    import_module("emergent-multiagent-strategies_b200._capi").lib().tg_debug_staged(0)
 
 def timed(fn, n=20):
     for _ in range(3):

@@ -43,6 +43,35 @@ def test_linear_matches_float64(rows, K, N, wide):
     assert float(((y3.double() - (ref + base.double())).abs() / (bound + base.double().abs() + 1e-30)).max()) < 2e-6
 
 
+@pytest.mark.parametrize("rows,K,N,ld", [(1000, 128, 128, 128), (129, 64, 128, 64), (5000, 64, 64, 192), (20011, 128, 64, 256),
+                                         (31, 128, 8, 128), (40000, 128, 128, 128), (4097, 128, 1, 132)])
+def test_linear_staged_form_equals_register_form(rows, K, N, ld):
+    """The bulk-copy staged loader (default for K = 64 / 128) and the register loader convert the same values with the same
+    arithmetic: outputs are bit-equal, for contiguous and strided rows, ragged tails, with bias / ReLU / accumulate."""
+    L = _capi.lib()
+    gen = torch.Generator().manual_seed(rows + K + N + ld)
+    big = _rows(gen, rows, ld, True).cuda()
+    x = big[:, ld - K:]
+    W = (torch.randn(N, K, generator=gen) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=gen).cuda()
+    base = torch.randn(rows, N, generator=gen).cuda()
+    outs = []
+    for on in (1, 0):
+        L.tg_debug_staged(on)
+        try:
+            pack = fused.tg_pack(W, False)
+            outs.append((fused.tg_linear(x, pack), fused.tg_linear(x, pack, b, relu=True),
+                         fused.tg_linear(x, pack, out=base.clone(), accumulate=True)))
+        finally:
+            L.tg_debug_staged(1)
+    fused.tg_check_status("cuda:0")
+    for a, c in zip(*outs):
+        assert torch.equal(a, c)
+    ref = x.double() @ W.double().t()
+    bound = x.double().abs() @ W.double().abs().t()
+    assert float(((outs[0][0].double() - ref).abs() / (bound + 1e-30)).max()) < 2e-6
+
+
 def test_linear_strided_operands():
     """x and out as column slices of wider row-major tensors (the [h | mixed] buffer of a message round)."""
     gen = torch.Generator().manual_seed(3)
