@@ -119,10 +119,12 @@ def lib():
     L.rl_attn_mix_backward.argtypes = [P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
     L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
     L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    L.rl_relu_bwd_colsum_ld.argtypes = [vp, i32, vp, i32, vp, i32, vp, i64, i32, vp]
     L.tg_packed_bytes.argtypes = [i32, i32]
     L.tg_packed_bytes.restype = ctypes.c_size_t
     L.tg_pack_weight.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.tg_linear.argtypes = [vp, i32, i64, i32, vp, i32, vp, i32, i32, vp, i32, vp, vp]
+    L.tg_linear_res.argtypes = [vp, i32, i64, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp]
     L.tg_wgrad_scratch_bytes.argtypes = [i32, i32]
     L.tg_wgrad_scratch_bytes.restype = ctypes.c_size_t
     L.tg_wgrad.argtypes = [vp, i32, i32, vp, i32, i32, i64, vp, i32, i32, vp, vp, vp]
@@ -130,6 +132,7 @@ def lib():
     L.tg_kernel_info.argtypes = [i32, i32p, i32p, i32p]
     L.tg_debug_wgrad_desc.argtypes = [u32, u32]
     L.tg_debug_staged.argtypes = [i32]
+    L.tg_debug_wgrad_rows.argtypes = [i32]
     L.mw_step.argtypes = [vp, vp, vp, vp, vp]
     L.mw_scenario_obs_dim.argtypes = [i32, i32, i32, i32]
     L.mw_scenario_callbacks.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp]

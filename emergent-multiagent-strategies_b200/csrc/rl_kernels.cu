@@ -230,23 +230,38 @@ __global__ void __launch_bounds__(256) ppo_loss_logits_kernel(const float *__res
     }
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = sa; red[2][threadIdx.x >> 5] = se; }
     __syncthreads();
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(scratch);
     if (threadIdx.x == 0) {
         float tv = 0.0f, ta = 0.0f, te = 0.0f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tv += red[0][w]; ta += red[1][w]; te += red[2][w]; }
         float *mine = scratch + 4 + 3 * blockIdx.x;
         mine[0] = tv; mine[1] = ta; mine[2] = te;
         __threadfence();
-        unsigned int *ticket = reinterpret_cast<unsigned int *>(scratch);
         last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-        if (last) {                                            // block order, not arrival order: the sums are reproducible
-            __threadfence();
-            tv = ta = te = 0.0f;
-            const volatile float *part = scratch + 4;
-            for (unsigned int b = 0; b < gridDim.x; ++b) { tv += part[3 * b]; ta += part[3 * b + 1]; te += part[3 * b + 2]; }
-            tv *= inv; ta *= inv; te *= inv;
-            out[0] = tv; out[1] = ta; out[2] = te; out[3] = tv * vcoef + ta - te * ecoef;
-            *ticket = 0u;
-        }
+    }
+    __syncthreads();
+    if (!last) return;
+    // the last block to arrive adds the per-block partials in a FIXED order (thread t: blocks t, t + 256, ...; then the same
+    // shuffle / warp-order tree as above), so the statistics do not depend on the order the blocks finished in
+    __threadfence();
+    const volatile float *part = scratch + 4;
+    sv = sa = se = 0.0f;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) { sv += part[3 * b]; sa += part[3 * b + 1]; se += part[3 * b + 2]; }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, s);
+        sa += __shfl_xor_sync(0xffffffffu, sa, s);
+        se += __shfl_xor_sync(0xffffffffu, se, s);
+    }
+    __syncthreads();                                           // (red is reused)
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = sa; red[2][threadIdx.x >> 5] = se; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tv = 0.0f, ta = 0.0f, te = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tv += red[0][w]; ta += red[1][w]; te += red[2][w]; }
+        tv *= inv; ta *= inv; te *= inv;
+        out[0] = tv; out[1] = ta; out[2] = te; out[3] = tv * vcoef + ta - te * ecoef;
+        *ticket = 0u;
     }
 }
 
@@ -400,15 +415,15 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(Opnd G, Opnd A, Opnd B, O
 // caller adds the [blocks, cols] partials), so the result is reproducible run to run.
 __global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(const float4 *__restrict__ dout, const float4 *__restrict__ out,
                                                               float4 *__restrict__ dpre, float4 *__restrict__ partial,
-                                                              long long rows, int c4) {
+                                                              long long rows, int c4, long long ldd4, long long ldo4, long long ldp4) {
     __shared__ float4 sm[256];
     const int lane = threadIdx.x % c4, rsub = threadIdx.x / c4, rpi = 256 / c4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long r = (long long)blockIdx.x * rpi + rsub; r < rows; r += (long long)gridDim.x * rpi) {
-        float4 g = dout[r * c4 + lane];
-        const float4 o = out[r * c4 + lane];
+        float4 g = dout[r * ldd4 + lane];
+        const float4 o = out[r * ldo4 + lane];
         g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
-        dpre[r * c4 + lane] = g;
+        dpre[r * ldp4 + lane] = g;
         acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
     }
     sm[threadIdx.x] = acc;
@@ -540,14 +555,21 @@ extern "C" int rl_relu_bwd_colsum_blocks(long long rows, int cols) {
 
 extern "C" int rl_relu_bwd_colsum(const float *d_dout, const float *d_out, float *d_dpre, float *d_partial, long long rows,
                                   int cols, void *stream) {
+    return rl_relu_bwd_colsum_ld(d_dout, cols, d_out, cols, d_dpre, cols, d_partial, rows, cols, stream);
+}
+
+extern "C" int rl_relu_bwd_colsum_ld(const float *d_dout, int ldd, const float *d_out, int ldo, float *d_dpre, int ldp,
+                                     float *d_partial, long long rows, int cols, void *stream) {
     if (!d_dout || !d_out || !d_dpre || !d_partial) return fa_internal_fail(-1, "rl_relu_bwd_colsum: NULL pointer");
     const int blocks = rl_relu_bwd_colsum_blocks(rows, cols);
     if (blocks < 1) return fa_internal_fail(-1, "rl_relu_bwd_colsum: need rows >= 1 and cols in {32, 64, 128, 256} (got %lld x %d)", rows, cols);
     if (((uintptr_t)d_dout | (uintptr_t)d_out | (uintptr_t)d_dpre | (uintptr_t)d_partial) % 16)
         return fa_internal_fail(-4, "rl_relu_bwd_colsum: pointers must be 16-byte aligned");
+    if (ldd < cols || ldo < cols || ldp < cols || (ldd | ldo | ldp) % 4)
+        return fa_internal_fail(-1, "rl_relu_bwd_colsum: row strides must be >= cols and multiples of 4 floats");
     rl::relu_bwd_colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(d_dout), reinterpret_cast<const float4 *>(d_out), reinterpret_cast<float4 *>(d_dpre),
-        reinterpret_cast<float4 *>(d_partial), rows, cols / 4);
+        reinterpret_cast<float4 *>(d_partial), rows, cols / 4, ldd / 4, ldo / 4, ldp / 4);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_relu_bwd_colsum: launch: %s", cudaGetErrorString(e));
     return 0;

@@ -58,9 +58,10 @@ struct LinParams {
     const uint8_t *packed;
     const float *bias;
     float *out;
+    const float *res;                                             // acc: out = act(..) + res (row stride ldr); may alias out
     uint32_t *status;
     long long rows;
-    int ldx, ldo, K, Kp, N, Np, relu, acc, n_tiles, nst, groups, gw, vec_ok, wbytes;
+    int ldx, ldo, ldr, K, Kp, N, Np, relu, acc, n_tiles, nst, groups, gw, vec_ok, wbytes;
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
         const int nblk = (p.N + 15) / 16;                              // 16-column blocks of the output
         const int rq = lane & 7, cq = lane >> 3;                       // phase-B row (within an octet) and column quad
         const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out & 15) == 0);
+        const bool vec_res = (p.ldr % 4 == 0) && (((uintptr_t)p.res & 15) == 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
@@ -364,8 +366,8 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
                         const long long row = row0 + i * 8 + rq;
                         old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (row < p.rows && col < p.N) {
-                            const float *src = p.out + row * p.ldo + col;
-                            if (vec_out && col + 4 <= p.N) old[i] = *reinterpret_cast<const float4 *>(src);
+                            const float *src = p.res + row * p.ldr + col;
+                            if (vec_res && col + 4 <= p.N) old[i] = *reinterpret_cast<const float4 *>(src);
                             else {
                                 old[i].x = src[0];
                                 if (col + 1 < p.N) old[i].y = src[1];
@@ -454,10 +456,14 @@ __global__ void __launch_bounds__(256) tg_pack_kernel(const float *w, int N, int
 // the tiles above (feature chunk kc at kc * FB_LBO, row r at + r * 16).  Read as an MN-major operand: mn = feature
 // (M = N = 128), k = row: 8 features of one row are the 16 contiguous bytes, 8 rows the 128-byte core matrix,
 // SBO = FB_LBO (next 8 features), LBO = 128 (next 8 rows); one MMA consumes 16 rows (+256 bytes).
-constexpr int WROWS = 64;
-constexpr uint32_t FB_LBO = WROWS * 16 + 16, PLANE = 16 * FB_LBO, BLOCK = 3 * PLANE;      // 1040, 16640, 49920
-constexpr int NB = 4;                                                                       // ring of operand blocks
-constexpr int W_SMEM = NB * BLOCK;
+// Two block heights: 64 rows (ring of 4 blocks: two row steps of a one-block-per-operand product in flight) and 32 rows
+// (ring of 8) for products with a 256-wide operand, whose row step needs THREE blocks -- with 64-row blocks only one more
+// block fits beside a step, and the loaders idle while its twelve-MMA groups run.
+template <int WR> struct WG {
+    static constexpr uint32_t LBO = WR * 16 + 16, PLANE = 16 * LBO, BLOCK = 3 * PLANE;      // 64: 1040, 16640, 49920; 32: 528, 8448, 25344
+    static constexpr int NB = WR == 64 ? 4 : 8, SMEM = NB * (int)BLOCK;
+};
+constexpr int MAX_NB = 8;
 __device__ uint32_t g_dbg_lbo = 0, g_dbg_sbo = 0;
 
 struct WgParams {
@@ -497,9 +503,12 @@ __device__ __forceinline__ void split8_bf16(const float4 &a, const float4 &b, ui
     l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
 }
 
+template <int WROWS>
 __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) {
+    constexpr uint32_t FB_LBO = WG<WROWS>::LBO, PLANE = WG<WROWS>::PLANE, BLOCK = WG<WROWS>::BLOCK;
+    constexpr int NB = WG<WROWS>::NB;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[NB], bar_empty[NB], bar_done;
+    __shared__ __align__(8) uint64_t bar_full[MAX_NB], bar_empty[MAX_NB], bar_done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -743,7 +752,8 @@ namespace {
 constexpr int MAX_DEVICES = 64;
 bool g_ready[MAX_DEVICES] = {};
 int g_sms[MAX_DEVICES] = {};
-uint32_t g_wg_lbo = 128, g_wg_sbo = tg::FB_LBO;
+uint32_t g_wg_lbo = 128, g_wg_sbo = 0;      // descriptor fields of tg_wgrad's MN-major operands (sbo 0 = the block's feature-chunk stride)
+int g_wg_rows = 0;             // tg_debug_wgrad_rows: force the block height of tg_wgrad (32 / 64; 0 = by shape)
 bool g_staged = true;          // tg_debug_staged(0): keep tg_linear on the register loaders (A/B measurements, tests of both forms)
 
 int prepare(int *sms) {
@@ -753,7 +763,8 @@ int prepare(int *sms) {
     if (!g_ready[dev]) {
         e = cudaFuncSetAttribute(tg::tg_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::W_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<64>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<32>::SMEM);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return fa_internal_fail(-2, "tg: device setup: %s", cudaGetErrorString(e));
         g_ready[dev] = true;
@@ -779,9 +790,15 @@ extern "C" int tg_pack_weight(const float *d_w, int N, int K, int ld, int transp
 
 extern "C" int tg_linear(const float *d_x, int ldx, long long rows, int K, const void *d_packed, int N, const float *d_bias,
                          int relu, int accumulate, float *d_out, int ldo, uint32_t *d_status, void *stream) {
+    return tg_linear_res(d_x, ldx, rows, K, d_packed, N, d_bias, relu, accumulate ? d_out : nullptr, ldo, d_out, ldo, d_status, stream);
+}
+
+extern "C" int tg_linear_res(const float *d_x, int ldx, long long rows, int K, const void *d_packed, int N, const float *d_bias,
+                             int relu, const float *d_res, int ldr, float *d_out, int ldo, uint32_t *d_status, void *stream) {
+    const int accumulate = d_res != nullptr;
     if (!d_x || !d_packed || !d_out || !d_status) return fa_internal_fail(-1, "tg_linear: NULL pointer");
-    if (rows < 1 || K < 1 || K > 256 || N < 1 || N > 256 || ldx < K || ldo < N)
-        return fa_internal_fail(-1, "tg_linear: need rows >= 1, 1 <= K, N <= 256, ldx >= K, ldo >= N");
+    if (rows < 1 || K < 1 || K > 256 || N < 1 || N > 256 || ldx < K || ldo < N || (accumulate && ldr < N))
+        return fa_internal_fail(-1, "tg_linear: need rows >= 1, 1 <= K, N <= 256, ldx >= K, ldo >= N, ldr >= N");
     const int Kp = pad_to(K, 64), Np = pad_to(N, 16);
     if (Kp * Np > 32768) return fa_internal_fail(-1, "tg_linear: padded N * K must be <= 32768 (got %d x %d)", Np, Kp);
     if ((uintptr_t)d_packed & 15) return fa_internal_fail(-4, "tg_linear: d_packed must be 16-byte aligned");
@@ -789,6 +806,7 @@ extern "C" int tg_linear(const float *d_x, int ldx, long long rows, int K, const
     if (int rc = prepare(&sms)) return rc;
     tg::LinParams p = {};
     p.x = d_x; p.packed = (const uint8_t *)d_packed; p.bias = d_bias; p.out = d_out; p.status = d_status; p.rows = rows;
+    p.res = d_res; p.ldr = accumulate ? ldr : ldo;
     p.ldx = ldx; p.ldo = ldo; p.K = K; p.Kp = Kp; p.N = N; p.Np = Np; p.relu = relu; p.acc = accumulate;
     p.n_tiles = (int)((rows + tg::ROWS - 1) / tg::ROWS);
     p.gw = Kp >= 128 ? 128 : 64;
@@ -826,12 +844,14 @@ extern "C" int tg_wgrad(const float *d_x, int ldx, int a, const float *d_y, int 
     tg::WgParams p = {};
     p.x = d_x; p.y = d_y; p.partial = (float *)d_scratch; p.status = d_status; p.rows = rows; p.ldx = ldx; p.ldy = ldy;
     p.a = a; p.b = b; p.ab = (a + 127) / 128; p.bb = (b + 127) / 128;
-    p.n_steps = (int)((rows + tg::WROWS - 1) / tg::WROWS);
+    const int wr = (g_wg_rows == 32 || g_wg_rows == 64) ? g_wg_rows : (p.ab + p.bb >= 3 ? 32 : 64);
+    p.n_steps = (int)((rows + wr - 1) / wr);
     p.vx = (ldx % 4 == 0) && (((uintptr_t)d_x & 15) == 0);
     p.vy = (ldy % 4 == 0) && (((uintptr_t)d_y & 15) == 0);
-    p.lbo = g_wg_lbo; p.sbo = g_wg_sbo;
+    p.lbo = g_wg_lbo; p.sbo = g_wg_sbo ? g_wg_sbo : (wr == 64 ? tg::WG<64>::LBO : tg::WG<32>::LBO);
     const int grid = p.n_steps < sms ? p.n_steps : sms;
-    tg::tg_wgrad_kernel<<<grid, tg::THREADS, tg::W_SMEM, (cudaStream_t)stream>>>(p);
+    if (wr == 64) tg::tg_wgrad_kernel<64><<<grid, tg::THREADS, tg::WG<64>::SMEM, (cudaStream_t)stream>>>(p);
+    else tg::tg_wgrad_kernel<32><<<grid, tg::THREADS, tg::WG<32>::SMEM, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_wgrad: launch: %s", cudaGetErrorString(e));
     tg::tg_reduce_kernel<<<(a * b * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float *)d_scratch, grid, a, b, d_dw, lddw, accumulate);
@@ -863,17 +883,22 @@ extern "C" int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t 
     if (int rc = prepare(nullptr)) return rc;
     cudaFuncAttributes at;
     const cudaError_t e = which == 0 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<false>)
-                        : (which == 2 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<true>) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel));
+                        : (which == 2 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<true>) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel<64>));
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_kernel_info: %s", cudaGetErrorString(e));
     if (regs) *regs = at.numRegs;
     if (block) *block = which == 2 ? tg::THREADS_STAGED : tg::THREADS;
-    if (smem) *smem = (which == 0 ? tg::SMEM_LIMIT : tg::W_SMEM) + (int)at.sharedSizeBytes;
+    if (smem) *smem = (which == 1 ? tg::WG<64>::SMEM : tg::SMEM_LIMIT) + (int)at.sharedSizeBytes;
     return 0;
 }
 
 extern "C" int tg_debug_wgrad_desc(uint32_t lbo, uint32_t sbo) {
     g_wg_lbo = lbo ? lbo : 128;
-    g_wg_sbo = sbo ? sbo : tg::FB_LBO;
+    g_wg_sbo = sbo;
+    return 0;
+}
+
+extern "C" int tg_debug_wgrad_rows(int rows) {
+    g_wg_rows = rows;
     return 0;
 }
 

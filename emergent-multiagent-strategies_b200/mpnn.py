@@ -153,6 +153,7 @@ class MPNN(nn.Module):
     fused_attention = False
     fused_no_grad = False       # also take the fused path under torch.no_grad() (BatchedTrainer.recompute_old: same arithmetic as the update)
     fold_projections = True     # within the fused path: message rounds with the attention projections folded (see _fwd_fused)
+    front_end_fused = True      # within the fused path: encoders + opponent attention + feature block as rlcore/fused.front_end
 
     def _fwd_fused(self, inp, oppInp):
         try:
@@ -161,11 +162,17 @@ class MPNN(nn.Module):
             from rlcore import fused
         n, m = self.num_agents, self.num_opp_agents
         oa, ms = self.oppAttn, self.messages
-        h0 = fused.linear(inp, self.encoder[0].weight, self.encoder[0].bias, True)  # [n*B, 64] agent-major rows
-        hO = fused.linear(oppInp, self.oppEncoder[0].weight, self.oppEncoder[0].bias, True)   # [m*B, 64]
-        e, oattn = fused.cross_attention(fused.matmul(h0, oa.W_key[0]),
-                                         fused.matmul(hO, torch.cat((oa.W_query[0], oa.W_val[0]), dim=1)), n, m, oa.norm_factor)
-        h = torch.cat((h0, fused.matmul(e, oa.W_out[0])), dim=1)                   # [n*B, 128]
+        if self.front_end_fused:
+            # encoders, opponent attention and the [h0 | eOpp] block as one function with a hand-written backward
+            h, oattn = fused.front_end(inp, oppInp, self.encoder[0].weight, self.encoder[0].bias, self.oppEncoder[0].weight,
+                                       self.oppEncoder[0].bias, oa.W_key[0], oa.W_query[0], oa.W_val[0], oa.W_out[0], n, m,
+                                       oa.norm_factor)
+        else:
+            h0 = fused.linear(inp, self.encoder[0].weight, self.encoder[0].bias, True)  # [n*B, 64] agent-major rows
+            hO = fused.linear(oppInp, self.oppEncoder[0].weight, self.oppEncoder[0].bias, True)   # [m*B, 64]
+            e, oattn = fused.cross_attention(fused.matmul(h0, oa.W_key[0]),
+                                             fused.matmul(hO, torch.cat((oa.W_query[0], oa.W_val[0]), dim=1)), n, m, oa.norm_factor)
+            h = torch.cat((h0, fused.matmul(e, oa.W_out[0])), dim=1)               # [n*B, 128]
         W, bias = self.update[0].weight, self.update[0].bias
         U1t, U2t = W[:, :self.h_dim].t(), W[:, self.h_dim:].t()
         attn = None

@@ -258,8 +258,9 @@ def tg_pack(w, transposed):
     return packed, N, K
 
 
-def tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False):
-    """act(x B^T + bias) (+ out) with B packed by tg_pack; x [rows, K] fp32 row-major (row stride free)."""
+def tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False, res=None):
+    """act(x B^T + bias) (+ out | + res) with B packed by tg_pack; x [rows, K] fp32 row-major (row stride free).
+    res: float32 [rows, N] with unit column stride, added in the epilogue (accumulate=True is res = out)."""
     packed, N, K = pack
     x, ldx = _row_major(x.detach())
     rows = x.shape[0]
@@ -272,9 +273,14 @@ def tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False):
     if rows == 0:
         return out
     st = _tg_state(x.device)
-    _capi.check(_lib().tg_linear(x.data_ptr(), ldx, rows, K, packed.data_ptr(), N, None if bias is None else bias.detach().data_ptr(),
-                                 int(bool(relu)), int(bool(accumulate)), out.data_ptr(), out.stride(0), st["status"].data_ptr(),
-                                 torch.cuda.current_stream(x.device).cuda_stream))
+    if accumulate:
+        res = out
+    if res is not None and (res.shape != (rows, N) or res.stride(1) != 1 or res.dtype != torch.float32):
+        raise ValueError("res must be a float32 [rows, N] tensor with unit column stride")
+    _capi.check(_lib().tg_linear_res(x.data_ptr(), ldx, rows, K, packed.data_ptr(), N, None if bias is None else bias.detach().data_ptr(),
+                                     int(bool(relu)), None if res is None else res.data_ptr(), 0 if res is None else res.stride(0),
+                                     out.data_ptr(), out.stride(0), st["status"].data_ptr(),
+                                     torch.cuda.current_stream(x.device).cuda_stream))
     return out
 
 
@@ -305,14 +311,18 @@ def _relu_bwd_colsum_cuda(dout, out):
     L = _lib()
     rows, cols = out.shape
     blocks = L.rl_relu_bwd_colsum_blocks(rows, cols)
+    strided = lambda t: t.stride(1) == 1 and t.stride(0) >= cols and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0
     if blocks < 1:                                   # widths the kernel does not cover
         dpre = torch.ops.aten.threshold_backward(dout, out, 0)
         return dpre, dpre.sum(0)
-    dout = dout.contiguous()
-    dpre = torch.empty_like(out)
+    if not strided(dout):
+        dout = dout.contiguous()
+    if not strided(out):
+        out = out.contiguous()
+    dpre = torch.empty(rows, cols, device=out.device)
     partial = torch.empty(blocks, cols, device=out.device)
-    _capi.check(L.rl_relu_bwd_colsum(dout.data_ptr(), out.data_ptr(), dpre.data_ptr(), partial.data_ptr(), rows, cols,
-                                     torch.cuda.current_stream(out.device).cuda_stream))
+    _capi.check(L.rl_relu_bwd_colsum_ld(dout.data_ptr(), dout.stride(0), out.data_ptr(), out.stride(0), dpre.data_ptr(), cols,
+                                        partial.data_ptr(), rows, cols, torch.cuda.current_stream(out.device).cuda_stream))
     return dpre, partial.sum(0)
 
 
@@ -448,6 +458,94 @@ def matmul_nt(x, B):
     return _MatmulNT.apply(x, B)
 
 
+# ---- encoders + attention over the opponents + the [h0 | eOpp] feature block as one function ---------------------------------
+def _cross_forward(kk, qv, n, m, norm):
+    """kk [n*B, k] (keys of the own team), qv [m*B, 2k] (queries | values of the opponents) -> (e [n*B, k], attn [B, n, m])."""
+    B, k = kk.shape[0] // n, kk.shape[1]
+    e, attn = torch.empty(n * B, k, device=kk.device), torch.empty(B, n, m, device=kk.device)
+    kk, qv = kk.contiguous(), qv.contiguous()
+    _capi.check(_attn_lib().rl_attn_forward(_op(kk, 0, k, B), _op(qv, 0, 2 * k, B), _op(qv, k, 2 * k, B), _op(e, 0, k, B),
+                                            attn.data_ptr(), B, n, m, k, float(norm), 0, torch.cuda.current_stream(kk.device).cuda_stream))
+    return e, attn
+
+
+def _cross_backward(de, kk, qv, attn, n, m, norm):
+    B, k = kk.shape[0] // n, kk.shape[1]
+    dkk, dqv = torch.empty_like(kk), torch.empty_like(qv)
+    de = de.contiguous()
+    _capi.check(_attn_lib().rl_attn_backward(_op(de, 0, k, B), _op(kk, 0, k, B), _op(qv, 0, 2 * k, B), _op(qv, k, 2 * k, B),
+                                             attn.data_ptr(), _op(dkk, 0, k, B), _op(dqv, 0, 2 * k, B), _op(dqv, k, 2 * k, B),
+                                             B, n, m, k, float(norm), torch.cuda.current_stream(kk.device).cuda_stream))
+    return dkk, dqv
+
+
+def _prod(x, B, transposed, bias=None, relu=False, out=None, res=None):
+    """act(x B'^T + bias) (+ res), B' = B^T if transposed: tg_linear, or the same on torch's library GEMM when DENSE = "cublas"
+    (the checker the tests compare the tcgen05 path against)."""
+    if _use_tg(x):
+        return tg_linear(x, tg_pack(B, transposed), bias, relu, out=out, res=res)
+    y = x @ (B if transposed else B.t())
+    if bias is not None:
+        y = y + bias
+    if relu:
+        y = torch.relu(y)
+    if res is not None:
+        y = y + res
+    if out is None:
+        return y
+    out.copy_(y)
+    return out
+
+
+class _FrontEnd(torch.autograd.Function):
+    """h = [ReLU(encoder own) | (softmax(K(h0) Q(hOpp)^T / sqrt(dk)) V(hOpp)) W_out]   (mpnn.py:127-142, 376-443) on this repo's dense
+    kernels.  The two halves of the feature block are written in place by the products that make them (no concatenation),
+    backward reads the halves of dh in place, the encoder's gradient dh0 = dh[:, :d] + dK W_key^T comes out of ONE product with
+    the first term added in its epilogue, and the ReLU masks are read from the stored block -- no slice copies, zero fills or
+    gradient sums between the kernels."""
+
+    @staticmethod
+    def forward(ctx, inp, oppInp, We, be, Wo, bo, Wk, Wq, Wv, Wout, n, m, norm):
+        d = We.shape[0]
+        We, be, Wo, bo, Wk, Wout = (t.detach() for t in (We, be, Wo, bo, Wk, Wout))
+        Wqv = torch.cat((Wq.detach(), Wv.detach()), dim=1)                          # [d, 2k]
+        h = torch.empty(inp.shape[0], d + Wout.shape[1], device=inp.device, dtype=inp.dtype)
+        _prod(inp, We, False, be, True, out=h[:, :d])
+        hO = _prod(oppInp, Wo, False, bo, True)
+        kk = _prod(h[:, :d], Wk, True)
+        qv = _prod(hO, Wqv, True)
+        e, attn = cross_forward(kk, qv, n, m, norm)
+        _prod(e, Wout, True, out=h[:, d:])
+        ctx.save_for_backward(inp, oppInp, h, hO, kk, qv, e, attn, Wk, Wqv, Wout)
+        ctx.meta = (n, m, float(norm), d)
+        ctx.mark_non_differentiable(attn)
+        return h, attn
+
+    @staticmethod
+    def backward(ctx, dh, _dattn):
+        inp, oppInp, h, hO, kk, qv, e, attn, Wk, Wqv, Wout = ctx.saved_tensors
+        n, m, norm, d = ctx.meta
+        k = Wk.shape[1]
+        if dh.stride(1) != 1 or dh.stride(0) % 4 or dh.data_ptr() % 16:
+            dh = dh.contiguous()
+        dE, h0 = dh[:, d:], h[:, :d]
+        de = _prod(dE, Wout, False)
+        dWout = xt_dy(e, dE)
+        dkk, dqv = cross_backward(de, kk, qv, attn, n, m, norm)
+        dWk, dWqv = xt_dy(h0, dkk), xt_dy(hO, dqv)
+        dh0 = _prod(dkk, Wk, False, res=dh[:, :d])                                  # dh[:, :d] + dK W_key^T
+        dpre0, dbe = relu_bwd_colsum(dh0, _relu_mask_source(h0))
+        dWe = xt_dy(dpre0, inp)
+        dhO = _prod(dqv, Wqv, False)
+        dpreO, dbo = relu_bwd_colsum(dhO, _relu_mask_source(hO))
+        dWo = xt_dy(dpreO, oppInp)
+        return None, None, dWe, dbe, dWo, dbo, dWk, dWqv[:, :k], dWqv[:, k:], dWout, None, None, None
+
+
+def front_end(inp, oppInp, We, be, Wo, bo, Wk, Wq, Wv, Wout, n, m, norm):
+    return _FrontEnd.apply(inp, oppInp, We, be, Wo, bo, Wk, Wq, Wv, Wout, n, m, norm)
+
+
 # ---- value head + policy head + action head as one function of the final features -----------------------------------------
 class _Heads(torch.autograd.Function):
     """(value, logits) = (value_head.2(ReLU(value_head.0 x)), dist.linear(ReLU(policy_head.0 x)))  (mpnn.py:174-205 with
@@ -523,6 +621,7 @@ def _mix_backward_cuda(dhm, g, hm, attn, n, norm):
 
 # the two device steps of a round; tests substitute torch restatements to check the hand-written backward on the CPU
 mix_forward, mix_backward = _mix_forward_cuda, _mix_backward_cuda
+cross_forward, cross_backward = _cross_forward, _cross_backward          # likewise for the attention over the opponents
 
 
 class _MessageRound(torch.autograd.Function):

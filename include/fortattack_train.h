@@ -50,6 +50,12 @@ int tg_pack_weight(const float *d_w, int N, int K, int ld, int transposed, void 
 int tg_linear(const float *d_x, int ldx, long long rows, int K, const void *d_packed, int N, const float *d_bias, int relu,
               int accumulate, float *d_out, int ldo, uint32_t *d_status, void *stream);
 
+/* The same with the accumulated term read from its own matrix:  out = act(x B^T + bias) + res  (d_res float [rows][N], row
+ * stride ldr; NULL = no accumulated term; d_res == d_out is tg_linear's accumulate form).  dh = dh_direct + dg Mqk^T without a
+ * copy of dh_direct (mpnn.py's backward through the encoder / message rounds). */
+int tg_linear_res(const float *d_x, int ldx, long long rows, int K, const void *d_packed, int N, const float *d_bias, int relu,
+                  const float *d_res, int ldr, float *d_out, int ldo, uint32_t *d_status, void *stream);
+
 /* Bytes of scratch tg_wgrad needs for an [a][b] result. */
 size_t tg_wgrad_scratch_bytes(int a, int b);
 
@@ -81,6 +87,10 @@ int tg_adam_step(const TgTensor *tensors, int n_tensors, float lr, float beta1, 
 
 /* Static facts for reports: registers / block / dynamic shared memory of the two GEMM kernels. */
 int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t *smem);
+
+/* tg_wgrad stages its operands in blocks of 64 rows (ring of 4), or of 32 rows (ring of 8) when an operand is wider than 128
+ * columns (three blocks per row step).  tg_debug_wgrad_rows(32 | 64) forces one height, 0 restores the choice by shape. */
+int tg_debug_wgrad_rows(int rows);
 
 /* tg_linear has two loader forms with identical arithmetic: the STAGED form (K = 64 or 128, 16-byte aligned rows: a producer
  * warp streams raw fp32 rows into a shared-memory ring with bulk copies and the loader warps convert from there) and the

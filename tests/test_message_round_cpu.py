@@ -109,7 +109,7 @@ def _tg_pack(w, transposed):
     return (B, B.shape[0], B.shape[1])
 
 
-def _tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False):
+def _tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False, res=None):
     B, N, K = pack
     assert x.shape[1] == K, (tuple(x.shape), K)
     y = x.detach() @ B.t()
@@ -117,6 +117,8 @@ def _tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False):
         y = y + bias.detach()
     if relu:
         y = torch.relu(y)
+    if res is not None:
+        y = y + res.detach()
     if out is None:
         return y
     assert out.shape == y.shape
@@ -125,6 +127,21 @@ def _tg_linear(x, pack, bias=None, relu=False, out=None, accumulate=False):
     else:
         out.copy_(y)
     return out
+
+
+def _cross_forward(kk, qv, n, m, norm):                  # torch restatement of rl_attn_forward (mpnn.py:409-437), agent-major rows
+    Bsz, k = kk.shape[0] // n, kk.shape[1]
+    A = kk.view(n, Bsz, k).transpose(0, 1)
+    Q, V = qv[:, :k].reshape(m, Bsz, k).transpose(0, 1), qv[:, k:].reshape(m, Bsz, k).transpose(0, 1)
+    attn = torch.softmax(norm * A @ Q.transpose(1, 2), dim=-1)
+    return (attn @ V).transpose(0, 1).reshape(n * Bsz, k), attn
+
+
+def _cross_backward(de, kk, qv, attn, n, m, norm):       # ... and of rl_attn_backward, by autograd on the restatement
+    with torch.enable_grad():
+        kk2, qv2 = kk.detach().requires_grad_(), qv.detach().requires_grad_()
+        e, _ = _cross_forward(kk2, qv2, n, m, norm)
+        return torch.autograd.grad((e * de).sum(), (kk2, qv2))
 
 
 def _tg_wgrad(x, y):
@@ -139,6 +156,8 @@ def _patch_tg(monkeypatch):
     monkeypatch.setattr(fused, "mix_forward", mix_forward)
     monkeypatch.setattr(fused, "mix_backward", mix_backward)
     monkeypatch.setattr(fused, "relu_bwd_colsum", relu_bwd_colsum)
+    monkeypatch.setattr(fused, "cross_forward", _cross_forward)
+    monkeypatch.setattr(fused, "cross_backward", _cross_backward)
 
 
 def test_tcgen05_wiring_of_dense_functions(monkeypatch):
@@ -190,8 +209,11 @@ def test_tcgen05_wiring_of_the_whole_network(n, m, monkeypatch):
         net.zero_grad()
         net.fused_attention = fused_on
         if fused_on:
+            # the production path of the update: front_end + folded rounds + stacked heads (what evaluate_actions /
+            # evaluate_logits run on CUDA)
             x = net._fwd_fused(own, opp)
-            v, dist = net._value(x), net._dist(net._policy(x))
+            v, logits = net._heads(x)
+            dist = import_module(PKG + ".rlcore.distributions").FixedCategorical(logits=logits)
             lp, ent = dist.log_probs(act), dist.entropy()
         else:
             v, lp, ent, _ = net.evaluate_actions(own, None, opp, None, act)

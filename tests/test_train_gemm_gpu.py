@@ -93,6 +93,23 @@ def _wgrad_err(x, y):
     return float(((got.double() - ref).abs() / (bound + 1e-30)).max()), float((got.double() - ref).abs().max() / ref.abs().max())
 
 
+@pytest.mark.parametrize("rows,a,b", [(5000, 256, 128), (4099, 128, 256), (1000, 128, 128), (33, 64, 8), (70000, 256, 64)])
+def test_wgrad_block_heights(rows, a, b):
+    """Both block heights of tg_wgrad (64-row blocks, and 32-row blocks = the default when an operand is wider than 128 columns)
+    against float64, ragged row counts included."""
+    L = _capi.lib()
+    gen = torch.Generator().manual_seed(rows + a + b)
+    x, y = _rows(gen, rows, a, False).cuda(), _rows(gen, rows, b, True).cuda()
+    for wr in (32, 64, 0):
+        L.tg_debug_wgrad_rows(wr)
+        try:
+            e_rel, e_abs = _wgrad_err(x, y)
+        finally:
+            L.tg_debug_wgrad_rows(0)
+        fused.tg_check_status("cuda:0")
+        assert e_rel < 2e-6, (wr, e_rel, e_abs)
+
+
 def test_wgrad_descriptor_probe():
     """Prints the error of the built-in MN-major descriptor fields and of the swapped pair (diagnostic for the layout)."""
     gen = torch.Generator().manual_seed(0)
