@@ -177,6 +177,13 @@ class JointPPO(object):
         return v, a, e
 
     def _minibatch_step(self, fused, R, team, idx, advantages, totals, params, world):
+        fused.pack_cache(True)               # weights are constant from here to the optimizer kernel: packs are reused
+        try:
+            self._minibatch_step_body(fused, R, team, idx, advantages, totals, params, world)
+        finally:
+            fused.pack_cache(False)
+
+    def _minibatch_step_body(self, fused, R, team, idx, advantages, totals, params, world):
         a0, n, o0, m = team
         (obs_batch, mask, obs_opp_batch, actions_batch, value_preds_batch, return_batch, masks_batch,
          old_log_probs_batch, adv_targ, alive_sum) = fused.gather_minibatch(R, idx, a0, n, o0, m, advantages)

@@ -247,14 +247,34 @@ def _row_major(t):
     return t, (t.stride(0) if t.shape[0] > 1 else max(int(t.shape[1]), 1))
 
 
+# Within one optimizer step the same weight is packed several times (the folded round weights: once per round and
+# orientation).  JointPPO brackets a step with pack_cache(True) / pack_cache(False); inside the bracket a pack is reused while
+# the tensor it was made from is alive and unchanged (the entry keeps the tensor alive, so its storage cannot be handed to
+# another weight).  Outside the bracket nothing is cached: parameters change in place between steps.
+_PACKS = None
+
+
+def pack_cache(on):
+    global _PACKS
+    _PACKS = {} if on else None
+
+
 def tg_pack(w, transposed):
     """Pack B (the [N][K] operand of y = x B^T) for tg_linear.  w: [N, K] (transposed=False) or [K, N] (transposed=True),
     fp32, row-major with any row stride.  Returns (packed uint8 tensor, N, K)."""
     w, ld = _row_major(w.detach())
+    key = None
+    if _PACKS is not None:
+        key = (w.data_ptr(), tuple(w.shape), ld, bool(transposed), w._version)
+        hit = _PACKS.get(key)
+        if hit is not None:
+            return hit[0]
     N, K = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
     packed = torch.empty(_lib().tg_packed_bytes(N, K), dtype=torch.uint8, device=w.device)
     _capi.check(_lib().tg_pack_weight(w.data_ptr(), N, K, ld, int(bool(transposed)), packed.data_ptr(),
                                       torch.cuda.current_stream(w.device).cuda_stream))
+    if key is not None:
+        _PACKS[key] = ((packed, N, K), w)
     return packed, N, K
 
 

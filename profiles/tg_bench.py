@@ -9,6 +9,8 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 196608
 dev = "cuda:0"
 if os.environ.get("TG_BENCH_STAGED") == "0":       # A/B: keep tg_linear on the register loaders
     import_module("emergent-multiagent-strategies_b200._capi").lib().tg_debug_staged(0)
+if os.environ.get("TG_BENCH_WGRAD_ROWS"):          # A/B: force tg_wgrad's block height (32 / 64)
+    import_module("emergent-multiagent-strategies_b200._capi").lib().tg_debug_wgrad_rows(int(os.environ["TG_BENCH_WGRAD_ROWS"]))
 
 def timed(fn, n=20):
     for _ in range(3):
@@ -41,7 +43,7 @@ for K, N, relu, acc in ((6, 64, True, False), (64, 64, False, False), (64, 128, 
     print(json.dumps({"op": "tg_linear", "K": K, "N": N, "relu": relu, "acc": acc, "us": round(us, 1), "gbs": round(b / us / 1e3, 1),
                       "mb": round(b / 1e6, 1)}), flush=True)
     del xs, outs
-for a, b_ in ((64, 6), (64, 64), (64, 128), (128, 128), (256, 128), (128, 8), (128, 1), (128, 64)):
+for a, b_ in ((64, 6), (64, 64), (64, 128), (128, 128), (256, 128), (128, 256), (128, 8), (128, 1), (128, 64)):
     sets = max(2, int(400e6 / (rows * (a + b_) * 4)) + 1)
     xs = [torch.randn(rows, a, device=dev) for _ in range(sets)]
     ys = [torch.randn(rows, b_, device=dev) for _ in range(sets)]
