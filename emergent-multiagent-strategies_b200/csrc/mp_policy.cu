@@ -112,6 +112,7 @@ struct Params {
     int32_t sel_value;
     unsigned long long *counter;   // optional device call counter {count, ticket}: overrides `offset`, bumped by the last CTA
     int n_own, n_opp, E, ept, n_tiles, mode;
+    int opt;                       // bit 0: balanced heads, bit 1: next tile's opponent encoder under the heads' MMAs (MP_OPT, default 2)
 #ifdef MP_TRACE                  // diagnostic build only (make trace): never in the product library
     unsigned long long *trace;   // optional: clock64() of row thread 0 of CTA 0 at every phase boundary of one of its tiles
     int trace_tile;              // which of CTA 0's tiles (0 = first)
@@ -342,7 +343,11 @@ __device__ __forceinline__ void combine_scores(float (&s)[MP_MAX_TEAM], float (*
 
 __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_a_ready, bar_acc, bar_res;
+    // bar_acc[2]: accumulator hand-offs alternate between two barriers (commit k -> bar_acc[k & 1], phase (k >> 1) & 1), so the
+    // MMA issuer may finish TWO groups before the rows look at the first (policy and value hidden layers while the rows encode
+    // the next tile's opponents): with one barrier the second completion flips the phase parity back and the rows' wait for
+    // the first never returns
+    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_a_ready, bar_acc[2], bar_res;
     __shared__ uint32_t tmem_base_s;
     __shared__ float sc[NQ][128][MP_MAX_TEAM];         // partial sums exchanged between the NQ threads of a row
     uint8_t *bufH = smem + OFF_H, *bufX = smem + OFF_X;
@@ -358,7 +363,8 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_a_ready, ROW_THREADS);
-        mbar_init(&bar_acc, 1);
+        mbar_init(&bar_acc[0], 1);
+        mbar_init(&bar_acc[1], 1);
         mbar_init(&bar_res, 1);
         mbar_fence_init();
     }
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
         const uint32_t idesc64 = idesc_f16(128, 64), idesc128 = idesc_f16(128, 128);
         const uint32_t sbase = smem_u32(smem);
         const uint64_t hdesc = smem_desc(sbase + OFF_H, A_LBO, A_SBO), wdesc = smem_desc(sbase + OFF_WRES, A_LBO, A_SBO);
-        uint32_t g = 0, pa = 0;
+        uint32_t g = 0, pa = 0, ac = 0;                    // ac: accumulator groups committed so far (warp-uniform)
         auto stream_chunk = [&](int c) {
             const Chunk ch = c_tab[c];
             const uint32_t s = g % NS, ph = (g / NS) & 1u;
@@ -439,12 +445,13 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                     for (uint32_t k = 0; k < 4; ++k) umma_f16(dcol, ad0 + k * 16u, bd0 + k * 16u, idesc64, k > 0);
                 }
                 umma_commit(&bar_empty[s]);
-                if (ch.commit_acc) umma_commit(&bar_acc);
+                if (ch.commit_acc) umma_commit(&bar_acc[ac & 1u]);
 #ifdef MP_TRACE
                 if (p.trace != nullptr && blockIdx.x == 0 && g < 6) p.trace[72 + c] = clock64();
 #endif
             }
             __syncwarp();
+            ac += ch.commit_acc;
             ++g;
         };
         mbar_wait(&bar_res, 0, p.status, 2);
@@ -461,10 +468,11 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
 #pragma unroll
                         for (uint32_t k = 0; k < 8; ++k)
                             umma_f16(tmem + j * 128u, hdesc + k * 16u, wdesc + (j * 32768u >> 4) + k * 16u, idesc128, k > 0);
-                        if (j != 1) umma_commit(&bar_acc);        // T ready (the rows start the scores), then Z | Y
+                        if (j != 1) umma_commit(&bar_acc[(ac + (j >> 1)) & 1u]);   // T ready (the rows start the scores), then Z | Y
                     }
                 }
                 __syncwarp();
+                ac += 2;
             }
             for (int c = 2; c < N_STREAM; ++c) stream_chunk(c);
         }
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
 #else
 #define TS() do { } while (0)
 #endif
-#define WAIT_ACC(code) do { mbar_wait(&bar_acc, pc, p.status, code); pc ^= 1u; tc_fence_after(); } while (0)
+#define WAIT_ACC(code) do { mbar_wait(&bar_acc[pc & 1u], (pc >> 1) & 1u, p.status, code); ++pc; tc_fence_after(); } while (0)
 
         float o_own[6], o_opp[6];                                  // this tile's observations (prefetched one tile ahead)
         // global env id of list entry li (p.E = "none": load_obs and the output guard treat it as out of range)
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             TS();
             // ---- input encoders (mpnn.py:127-128): h0 -> bufH[:, 0:64), hOpp -> bufX[:, 0:64); QC64 outputs per thread
             encode(C + C_ENC, o_own, bufH, r, q * QC64);
-            encode(C + C_OENC, o_opp, bufX, r, q * QC64);
+            if (tile == tile0 || !(p.opt & 2)) encode(C + C_OENC, o_opp, bufX, r, q * QC64);   // later tiles: encoded under the previous tile's heads
             ARRIVE_A();
             TS();
             // ---- attention over the opponents (mpnn.py:409-437), folded: T' = h0 G', z' = hOpp Wz' -------
@@ -533,6 +541,13 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
 
             // ---- three message-passing rounds (mpnn.py:156-158) ------------------------------------------
             for (int round = 0; round < 3; ++round) {
+                if (round == 2) {      // the next tile's observations: the loads fly during the last round and the heads
+                    const int nt = tile + tile_stride;
+                    if (nt < n_tiles) {
+                        load_obs(p.obs_own, n_own, a, p.E, env_of(nt * ept + e), o_own);
+                        load_obs(p.obs_opp, n_opp, a, p.E, env_of(nt * ept + e), o_opp);
+                    }
+                }
                 float s[MP_MAX_TEAM] = {0.f, 0.f, 0.f, 0.f, 0.f};
                 WAIT_ACC(8);                                      // T ready; Z | Y are still being computed
                 TS();
@@ -551,12 +566,13 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 ARRIVE_A();
                 TS();
             }
-            {   // the next tile's observations: the loads fly while the heads are computed
-                const int nt = tile + tile_stride;
-                if (nt < n_tiles) {
-                    load_obs(p.obs_own, n_own, a, p.E, env_of(nt * ept + e), o_own);
-                    load_obs(p.obs_opp, n_opp, a, p.E, env_of(nt * ept + e), o_opp);
-                }
+            // this tile's identity, before the observation registers move on (eg / a are per-tile constants already)
+            if ((p.opt & 2) && tile + tile_stride < n_tiles) {
+                // The heads' MMAs read bufH only; bufX is free once every row has finished the last update (which reads the z
+                // rows of its team mates): one barrier, then the opponents' encoder of the NEXT tile runs while the tensor pipe
+                // works on the heads (ncu / phase trace: the rows idled ~1.8k cycles here).
+                bar_rows();
+                encode(C + C_OENC, o_opp, bufX, r, q * QC64);
             }
 
             // ---- heads (mpnn.py:174-205).  Threads q < NQ/2 evaluate the value head, the others policy_head +
@@ -569,6 +585,52 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
             const bool live = a < n_own && eg < p.E && (p.env_sel == nullptr || p.env_sel[eg] == p.sel_value);
             const size_t row = (size_t)a * p.E + eg;
             float value = 0.0f, lg[MP_ACTIONS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (NQ == 2 && (p.opt & 1)) {
+                // balanced form: each of the two threads of a row takes 64 hidden units of the action head AND of the value head
+                // (before: one thread 128 x 8 FMAs, the other 128 FMAs -- the row waited for the long one), partial sums meet in sc
+                const int k0 = q * 64;
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 16) {
+                    uint32_t w[16];
+                    tmem_ld16(trow + (uint32_t)(128 + k0 + c), w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = k0 + c + j;
+                        const float x = fmaxf(__uint_as_float(w[j]) + C[C_PB + k], 0.0f);
+                        const float4 d0 = *reinterpret_cast<const float4 *>(DW + k * 8);
+                        const float4 d1 = *reinterpret_cast<const float4 *>(DW + k * 8 + 4);
+                        lg[0] = fmaf(x, d0.x, lg[0]); lg[1] = fmaf(x, d0.y, lg[1]); lg[2] = fmaf(x, d0.z, lg[2]);
+                        lg[3] = fmaf(x, d0.w, lg[3]); lg[4] = fmaf(x, d1.x, lg[4]); lg[5] = fmaf(x, d1.y, lg[5]);
+                        lg[6] = fmaf(x, d1.z, lg[6]); lg[7] = fmaf(x, d1.w, lg[7]);
+                    }
+                }
+                WAIT_ACC(12);    // value hidden layer; also: it still reads bufH, nobody may start the next tile before it is done
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(trow + (uint32_t)(k0 + c), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = k0 + c + j;
+                        value = fmaf(fmaxf(__uint_as_float(v[j]) + C[C_VB + k], 0.0f), C[C_VW + k], value);
+                    }
+                }
+                if (q == 0) {                                     // hand the partial logits to the thread that finishes the Categorical
+#pragma unroll
+                    for (int k = 0; k < MP_ACTIONS; ++k) sc[k / MP_MAX_TEAM][r][k % MP_MAX_TEAM] = lg[k];
+                } else {
+                    sc[1][r][MP_MAX_TEAM - 1] = value;            // (logits use sc[0][r][0..4], sc[1][r][0..2])
+                }
+                bar_rows();
+                if (q == 0) {
+                    value += sc[1][r][MP_MAX_TEAM - 1];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < MP_ACTIONS; ++k) lg[k] = sc[k / MP_MAX_TEAM][r][k % MP_MAX_TEAM] + lg[k];
+                }
+            } else {
             if (q >= HG) {
                 const int k0 = (q - HG) * HC;
 #pragma unroll 1
@@ -609,6 +671,7 @@ __global__ void __launch_bounds__(THREADS, 1) mp_policy_kernel(const Params p) {
                 if (q > 0) sc[1][r][0] = value;
             }
             if (NQ > 2) bar_rows();
+            }
             if (q == 0) {
                 if (NQ > 2) value += sc[1][r][0];
                 if (live && p.value) p.value[row] = value + C[S_VB2];
@@ -696,6 +759,18 @@ unsigned long long *g_trace = nullptr;
 int g_trace_tile = 0;
 #endif
 
+// MP_OPT=0..3 switches two measures (measured, profiles/r3f_policy_time.log, 3v3 x 16384 / x 65536 envs, us per forward):
+//   bit 0  balanced heads (each thread of a row takes 64 hidden units of both heads)      55.6 -> 56.2 / 178.3 -> 181.2  (off)
+//   bit 1  the next tile's opponent encoder runs while the tensor pipe works on the heads 55.6 -> 54.9 / 178.3 -> 174.6  (on)
+int g_opt() {
+    static int v = -1;
+    if (v < 0) {
+        const char *ev = getenv("MP_OPT");
+        v = ev ? (atoi(ev) & 3) : 2;
+    }
+    return v;
+}
+
 int prepare(int *sms) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -732,7 +807,7 @@ extern "C" int mp_forward(const void *d_blob, const float *d_obs_own, const floa
     p.env_order = d_env_order; p.env_offsets = d_env_offsets;
     if ((d_env_order == nullptr) != (d_env_offsets == nullptr) || (d_env_order != nullptr && sel_value < 0))
         return fa_internal_fail(-1, "mp_forward: d_env_order and d_env_offsets come together, with sel_value >= 0");
-    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode;
+    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.opt = g_opt();
 #ifdef MP_TRACE
     p.trace = g_trace; p.trace_tile = g_trace_tile;
 #endif
@@ -768,7 +843,7 @@ extern "C" int mp_forward_ensemble(const void *const *d_blobs, int n_ckpt, const
     p.obs_own = d_obs_own; p.obs_opp = d_obs_opp; p.value = d_value; p.logp = d_logp; p.action = d_action;
     p.action_i32 = d_action_i32; p.status = d_status; p.seed = seed; p.offset = offset; p.env_id0 = env_id0;
     p.counter = (unsigned long long *)d_counter; p.env_order = d_env_order; p.env_offsets = d_env_offsets;
-    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode;
+    p.n_own = n_own; p.n_opp = n_opp; p.E = n_envs; p.mode = mode; p.opt = g_opt();
     p.ept = 128 / (n_own > n_opp ? n_own : n_opp);
     p.n_tiles = (n_envs + p.ept - 1) / p.ept;
     // every checkpoint may own up to all tiles: one CTA per SM, at least one per checkpoint
