@@ -8,6 +8,7 @@ take: learner.py:239-243, rlcore/storage.py:33-43).  All arithmetic happens in t
 (csrc/, through include/fortattack.h); PyTorch only owns the memory and the stream.
 """
 import ctypes
+import os
 
 import torch
 
@@ -205,7 +206,8 @@ class FortAttackBatch(object):
 
     def step_many_host(self, h_actions, h_obs, h_rew, h_done, h_result, chunk_steps=None):
         """T env.step() calls of every env with HOST streams (fa_step_many_host), synchronous.
-        chunk_steps=None: chunks of about 8 MB of results, copied by the DMA engines while the neighbouring chunks
+        chunk_steps=None: chunks of about 16 MB of results (measured: profiles/r3g_e2e_chunks.log -- smaller chunks pay the
+        per-chunk copy / event calls, larger ones the pipeline fill), copied by the DMA engines while the neighbouring chunks
         compute; chunk_steps=0: no staging, one persistent launch working through mapped pinned memory."""
         T = self._check_host_streams(h_actions, h_obs, h_rew, h_done, h_result)
         self._check_alive_end(T)
@@ -213,7 +215,8 @@ class FortAttackBatch(object):
         stage, nbytes = None, 0
         if chunk_steps is None:
             rs = 8 if self.dtype == torch.float64 else 4
-            chunk_steps = max(1, min(T, (8 << 20) // (self.A * self.E * 7 * rs + 2 * self.E)))
+            target = int(float(os.environ.get("FA_HOST_CHUNK_MB", "16")) * (1 << 20))      # (experiments: chunk size of the pipeline)
+            chunk_steps = max(1, min(T, target // (self.A * self.E * 7 * rs + 2 * self.E)))
         if chunk_steps > 0:
             need = ctypes.c_size_t()
             _capi.check(self._lib.fa_host_stage_bytes(self._h, int(chunk_steps), ctypes.byref(need)))
