@@ -119,6 +119,8 @@ def lib():
     L.rl_attn_mix_backward.argtypes = [P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
     L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
     L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    L.rl_colsum_blocks.argtypes = [i64, i32]
+    L.rl_colsum.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     L.rl_relu_bwd_colsum_ld.argtypes = [vp, i32, vp, i32, vp, i32, vp, i64, i32, vp]
     L.tg_packed_bytes.argtypes = [i32, i32]
     L.tg_packed_bytes.restype = ctypes.c_size_t

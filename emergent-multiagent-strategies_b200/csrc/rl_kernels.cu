@@ -437,6 +437,51 @@ __global__ void __launch_bounds__(256) relu_bwd_colsum_kernel(const float4 *__re
     }
 }
 
+// ---- column sums of a tall matrix (bias gradients: sum over the rows of dpre, or of relu_bwd_colsum's per-block partials) ----
+// cols is a power of two <= 256: thread t owns column t % cols and every (256 / cols)-th row of the block's row range; the
+// row lanes of a column are added in lane order, the blocks' partials in block order by the last block to arrive.
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ x, long long rows, int cols, long long ld,
+                                                     float *__restrict__ out, float *scratch) {
+    __shared__ float sm[256];
+    __shared__ bool last;
+    const int c = threadIdx.x % cols, lane = threadIdx.x / cols, lanes = 256 / cols;
+    const long long per = (rows + gridDim.x - 1) / gridDim.x, r0 = (long long)blockIdx.x * per;
+    const long long r1 = r0 + per < rows ? r0 + per : rows;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    long long r = r0 + lane;
+    for (; r + 3ll * lanes < r1; r += 4ll * lanes) {
+        a0 += x[r * ld + c]; a1 += x[(r + lanes) * ld + c]; a2 += x[(r + 2ll * lanes) * ld + c]; a3 += x[(r + 3ll * lanes) * ld + c];
+    }
+    for (; r < r1; r += lanes) a0 += x[r * ld + c];
+    sm[threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(scratch);
+    float *part = scratch + 4;
+    if (lane == 0) {
+        float t = sm[c];
+        for (int q = 1; q < lanes; ++q) t += sm[q * cols + c];
+        part[(size_t)blockIdx.x * cols + c] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const volatile float *vp = part;
+    float t = 0.0f;
+    for (unsigned int b = lane; b < gridDim.x; b += lanes) t += vp[(size_t)b * cols + c];
+    __syncthreads();
+    sm[threadIdx.x] = t;
+    __syncthreads();
+    if (lane == 0) {
+        t = sm[c];
+        for (int q = 1; q < lanes; ++q) t += sm[q * cols + c];
+        out[c] = t;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
 }  // namespace rl
 
 static int attn_check(const char *who, int batch, int n, int m, int k, const RlAttnOperand *const *ops, int nops) {
@@ -572,6 +617,24 @@ extern "C" int rl_relu_bwd_colsum_ld(const float *d_dout, int ldd, const float *
         reinterpret_cast<float4 *>(d_partial), rows, cols / 4, ldd / 4, ldo / 4, ldp / 4);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_relu_bwd_colsum: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rl_colsum_blocks(long long rows, int cols) {
+    if (rows < 1 || cols < 1 || cols > 256 || (cols & (cols - 1))) return -1;
+    const long long lanes = 256 / cols, need = (rows + lanes * 16 - 1) / (lanes * 16);
+    const int cap = 4 * grid_cap() < 1024 ? 4 * grid_cap() : 1024;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+extern "C" int rl_colsum(const float *d_x, long long rows, int cols, int ld, float *d_out, float *d_scratch, void *stream) {
+    if (!d_x || !d_out || !d_scratch) return fa_internal_fail(-1, "rl_colsum: NULL pointer");
+    const int blocks = rl_colsum_blocks(rows, cols);
+    if (blocks < 1 || ld < cols)
+        return fa_internal_fail(-1, "rl_colsum: need rows >= 1, cols a power of two <= 256, ld >= cols (got %lld x %d, ld %d)", rows, cols, ld);
+    rl::colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, rows, cols, ld, d_out, d_scratch);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_colsum: launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -326,6 +326,31 @@ def _use_tg(x):
 
 
 # ---- dense layers of the training forward with a hand-written backward ------------------------------------------------
+_COLSUM_SCRATCH = {}
+
+
+def colsum(x):
+    """x.sum(0) of a tall float32 CUDA matrix [rows, cols] (cols a power of two <= 256, unit column stride) in one launch with a
+    fixed summation order (rl_colsum); anything else falls back to torch."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0 and (x.shape[1] == 1 or x.stride(1) == 1)):
+        return x.sum(0)
+    rows, cols = x.shape
+    L = _lib()
+    blocks = L.rl_colsum_blocks(rows, cols)
+    if blocks < 1:
+        return x.sum(0)
+    ld = x.stride(0) if rows > 1 else cols
+    if ld < cols:
+        return x.sum(0)
+    need = 4 + 1024 * 256
+    sc = _COLSUM_SCRATCH.get(x.device)
+    if sc is None:
+        sc = _COLSUM_SCRATCH[x.device] = torch.zeros(need, device=x.device)
+    out = torch.empty(cols, device=x.device)
+    _capi.check(L.rl_colsum(x.data_ptr(), rows, cols, ld, out.data_ptr(), sc.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
 def _relu_bwd_colsum_cuda(dout, out):
     """(dpre = dout * [out > 0], column sums of dpre) in one pass over [rows, cols] (rl_relu_bwd_colsum)."""
     L = _lib()
@@ -343,7 +368,7 @@ def _relu_bwd_colsum_cuda(dout, out):
     partial = torch.empty(blocks, cols, device=out.device)
     _capi.check(L.rl_relu_bwd_colsum_ld(dout.data_ptr(), dout.stride(0), out.data_ptr(), out.stride(0), dpre.data_ptr(), cols,
                                         partial.data_ptr(), rows, cols, torch.cuda.current_stream(out.device).cuda_stream))
-    return dpre, partial.sum(0)
+    return dpre, colsum(partial)
 
 
 relu_bwd_colsum = _relu_bwd_colsum_cuda               # tests substitute a torch restatement on the CPU
@@ -420,7 +445,7 @@ class _Linear(torch.autograd.Function):
             dpre, db = relu_bwd_colsum(dy, _relu_mask_source(y))
         else:
             dpre = dy.contiguous()
-            db = dpre.sum(0)
+            db = colsum(dpre)
         dW = xt_dy(dpre, x)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -606,7 +631,7 @@ class _Heads(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = tg_linear(dpre, tg_pack(Wcat, True)) if _use_tg(dpre) else dpre @ Wcat
-        return dx, dWcat[:d], dbcat[:d], dWcat[d:], dbcat[d:], dWv2, dvalue.sum(0), dWd, dlogits.sum(0)
+        return dx, dWcat[:d], dbcat[:d], dWcat[d:], dbcat[d:], dWv2, colsum(dvalue), dWd, colsum(dlogits)
 
 
 def heads(x, Wv0, bv0, Wp0, bp0, Wv2, bv2, Wd, bd):

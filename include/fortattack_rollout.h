@@ -130,6 +130,12 @@ int rl_attn_mix_backward(const RlAttnOperand *dout, const RlAttnOperand *A, cons
 int rl_relu_bwd_colsum_blocks(long long rows, int cols);     /* number of partial rows, or -1 for unsupported sizes */
 int rl_relu_bwd_colsum(const float *d_dout, const float *d_out, float *d_dpre, float *d_partial, long long rows, int cols,
                        void *stream);
+/* out[c] = sum_r x[r][c] for a tall row-major matrix (cols a power of two <= 256, row stride ld): the bias gradients of the
+ * dense layers (rows of dpre, or relu_bwd_colsum's per-block partials) in one launch, partial sums added in a fixed order
+ * (bit-reproducible).  d_scratch: 4 + rl_colsum_blocks(rows, cols) * cols floats, first word zero before the first call. */
+int rl_colsum_blocks(long long rows, int cols);
+int rl_colsum(const float *d_x, long long rows, int cols, int ld, float *d_out, float *d_scratch, void *stream);
+
 /* The same on row-major operands with row strides (floats, multiples of 4): column slices of wider matrices (the encoder half
  * of the [h0 | eOpp] feature block) are masked in place of a contiguous copy. */
 int rl_relu_bwd_colsum_ld(const float *d_dout, int ldd, const float *d_out, int ldo, float *d_dpre, int ldp, float *d_partial,

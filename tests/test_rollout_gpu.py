@@ -286,6 +286,22 @@ def test_fused_gather_and_loss_match_torch_path():
         assert np.allclose(a, b, rtol=2e-3, atol=2e-4), (trs[0], trs[1])
 
 
+@pytest.mark.parametrize("rows,cols,ld", [(1, 8, 8), (1184, 128, 128), (196608, 1, 1), (70001, 8, 8), (5000, 64, 192), (333, 256, 256),
+                                          (100000, 32, 32), (7, 3, 3)])
+def test_colsum_matches_float64_and_is_reproducible(rows, cols, ld):
+    """rl_colsum (bias gradients) == the float64 column sums within fp32 summation error, bit-reproducible; widths the kernel
+    does not cover (not a power of two) fall back to torch."""
+    fused = import_module(PKG + ".rlcore.fused")
+    gen = torch.Generator().manual_seed(rows + cols)
+    big = torch.randn(rows, ld, generator=gen).cuda()
+    x = big[:, :cols]
+    got = fused.colsum(x)
+    ref = x.double().sum(0)
+    bound = x.double().abs().sum(0)
+    assert got.shape == (cols,) and float(((got.double() - ref).abs() / (bound + 1e-30)).max()) < 2e-6
+    assert torch.equal(got, fused.colsum(x))
+
+
 def test_loss_from_logits_matches_categorical_and_torch_loss():
     """rl_ppo_loss_logits == FixedCategorical(logits).log_probs / .entropy (rlcore/distributions.py:9-17) fed to the torch
     expressions of ppo.py:150-187: statistics, the gradient with respect to values and LOGITS (torch autograd through
