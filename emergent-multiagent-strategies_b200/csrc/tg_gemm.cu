@@ -20,10 +20,12 @@
 //   (fp16 hi/lo planes, packed by tg_pack_weight) resident in shared memory for the whole launch.
 // K = 256 is handled as two 128-column groups with their own row scales and their own accumulators (summed in the
 // epilogue), so the per-row scale never has to wait for more than 128 columns.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/fortattack_train.h"
 #include "mp_umma.cuh"
@@ -62,6 +64,7 @@ struct LinParams {
     uint32_t *status;
     long long rows;
     int ldx, ldo, ldr, K, Kp, N, Np, relu, acc, n_tiles, nst, groups, gw, vec_ok, wbytes;
+    int tma_out;                                                  // epilogue stores through the TMA engine (tensor map `omap`)
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -95,8 +98,23 @@ __device__ __forceinline__ float pow2_scale(float amax, float *inv) {
     return __uint_as_float((uint32_t)(127 + 14 - e) << 23);
 }
 
-template <bool STAGED>
-__global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linear_kernel(const LinParams p) {
+// ---- epilogue stores through the TMA engine -------------------------------------------------------------------------------
+// ncu on the STG epilogue: one warp-wide STG.E.128 (512 bytes) costs ~34 wavefronts of the LSU data pipe, the output stores
+// were 53 % of that pipe's work and the pipe the busiest unit of the kernel (70 %).  A 32-row x 16-column block leaves instead as
+// ONE cp.async.bulk.tensor store from a dense shared-memory tile (rows of 64 bytes, SWIZZLE_64B: the 16-byte chunk j of row r
+// lives at chunk j ^ ((r >> 1) & 3), which also makes the row-per-thread STS.128 conflict-free); rows past the matrix are
+// clipped by the tensor map.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t smem_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(smem_addr)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <bool STAGED, bool TMA_OUT>
+__global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linear_kernel(const LinParams p, const __grid_constant__ CUtensorMap omap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_acc_full[2], bar_acc_empty[2], bar_w;
     __shared__ __align__(8) uint64_t bar_raw_full[NRAW], bar_raw_empty[NRAW];
@@ -357,6 +375,46 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
             tc_fence_after();
             const float *rs = rowscale + (it & (SCALE_SLOTS - 1)) * 2 * ROWS;
             const float inv0 = rs[r], inv1 = p.groups > 1 ? rs[ROWS + r] : 0.0f;
+            if constexpr (TMA_OUT) {
+                // thread = row: scale, bias, ReLU in registers, 4 x STS.128 into the warp's swizzled 32 x 16 tile, one tensor store
+                uint8_t *tile_s = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tb) + 511) & ~(uintptr_t)511) + warp * 2048;
+                const uint32_t tile_a = smem_u32(tile_s), sw = (uint32_t)((lane >> 1) & 3);
+                for (int c = half; c < nblk; c += 2) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(trow + (uint32_t)(b * acc_cols + c * 16), v0);
+                    if (p.groups > 1) tmem_ld16(trow + (uint32_t)(b * acc_cols + p.Np + c * 16), v1);
+                    float4 rs[4];                                     // accumulate mode: this row's 16 values of the added matrix
+                    if (p.acc) {
+                        const float *src = p.res + (row0 + lane) * p.ldr + c * 16;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            rs[j] = (row0 + lane < p.rows && c * 16 + j * 4 < p.N) ? __ldg(reinterpret_cast<const float4 *>(src + j * 4))
+                                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    tmem_ld_wait();
+                    if (lane == 0) tma_store_wait_read();             // the previous block's store has read the tile
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 wi = *reinterpret_cast<const float4 *>(winv_s + c * 16 + j);
+                        const float4 bi = *reinterpret_cast<const float4 *>(bias_s + c * 16 + j);
+                        float4 f;
+                        f.x = __uint_as_float(v0[j]) * inv0; f.y = __uint_as_float(v0[j + 1]) * inv0;
+                        f.z = __uint_as_float(v0[j + 2]) * inv0; f.w = __uint_as_float(v0[j + 3]) * inv0;
+                        if (p.groups > 1) {
+                            f.x = fmaf(__uint_as_float(v1[j]), inv1, f.x); f.y = fmaf(__uint_as_float(v1[j + 1]), inv1, f.y);
+                            f.z = fmaf(__uint_as_float(v1[j + 2]), inv1, f.z); f.w = fmaf(__uint_as_float(v1[j + 3]), inv1, f.w);
+                        }
+                        f.x = fmaf(f.x, wi.x, bi.x); f.y = fmaf(f.y, wi.y, bi.y); f.z = fmaf(f.z, wi.z, bi.z); f.w = fmaf(f.w, wi.w, bi.w);
+                        if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+                        if (p.acc) { f.x += rs[j >> 2].x; f.y += rs[j >> 2].y; f.z += rs[j >> 2].z; f.w += rs[j >> 2].w; }
+                        *reinterpret_cast<float4 *>(tile_s + lane * 64 + ((((uint32_t)j >> 2) ^ sw) << 4)) = f;
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&omap, tile_a, c * 16, (int)(row0));
+                }
+            } else
             for (int c = half; c < nblk; c += 2) {
                 const int col = c * 16 + cq * 4;
                 float4 old[4];
@@ -420,6 +478,7 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
             mbar_arrive(&bar_acc_empty[b]);
         }
     }
+    if (TMA_OUT && warp < EPI_WARPS && lane == 0) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc<512>(tmem);
@@ -754,6 +813,22 @@ bool g_ready[MAX_DEVICES] = {};
 int g_sms[MAX_DEVICES] = {};
 uint32_t g_wg_lbo = 128, g_wg_sbo = 0;      // descriptor fields of tg_wgrad's MN-major operands (sbo 0 = the block's feature-chunk stride)
 int g_wg_rows = 0;             // tg_debug_wgrad_rows: force the block height of tg_wgrad (32 / 64; 0 = by shape)
+int g_tma_out = 1;             // tg_debug_tma_out: 0 keeps tg_linear's epilogue on STG stores, 2 also sends accumulating calls through TMA
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {     // the driver entry point, looked up once (no link-time dependency on libcuda)
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
 bool g_staged = true;          // tg_debug_staged(0): keep tg_linear on the register loaders (A/B measurements, tests of both forms)
 
 int prepare(int *sms) {
@@ -761,8 +836,10 @@ int prepare(int *sms) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return fa_internal_fail(-3, "tg: no usable CUDA device");
     if (!g_ready[dev]) {
-        e = cudaFuncSetAttribute(tg::tg_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
+        e = cudaFuncSetAttribute(tg::tg_linear_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<64>::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<32>::SMEM);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
@@ -824,8 +901,24 @@ extern "C" int tg_linear_res(const float *d_x, int ldx, long long rows, int K, c
     p.nst = nst;
     const size_t smem = (size_t)p.wbytes + (size_t)nst * tg::STAGE + tg::FIXED_BYTES + (staged ? raw_bytes : 0);
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    if (staged) tg::tg_linear_kernel<true><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p);
-    else tg::tg_linear_kernel<false><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p);
+    // output through the TMA engine: at least one whole 16-column block, rows (of the output and of an accumulated term, which
+    // the row threads read 64 bytes at a time) that are 16-byte multiples apart
+    CUtensorMap omap;
+    memset(&omap, 0, sizeof(omap));
+    // (with an accumulated term the row threads would read it 64 bytes at a time: measured 111 us against 91 us on the STG
+    // epilogue at 128 -> 128, so those calls stay there unless tg_debug_tma_out(2) forces the tensor-store form)
+    if (g_tma_out && N >= 16 && N % 4 == 0 && ldo % 4 == 0 && (((uintptr_t)d_out) & 15) == 0 &&
+        (!accumulate || (g_tma_out == 2 && ldr % 4 == 0 && (((uintptr_t)d_res) & 15) == 0)) && encode_tiled()) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)rows}, gstride[1] = {(cuuint64_t)ldo * 4};
+        const cuuint32_t box[2] = {16, 32}, estr[2] = {1, 1};
+        const CUresult r = encode_tiled()(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        p.tma_out = r == CUDA_SUCCESS;
+    }
+    if (staged && p.tma_out) tg::tg_linear_kernel<true, true><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p, omap);
+    else if (staged) tg::tg_linear_kernel<true, false><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p, omap);
+    else if (p.tma_out) tg::tg_linear_kernel<false, true><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p, omap);
+    else tg::tg_linear_kernel<false, false><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p, omap);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_linear: launch: %s", cudaGetErrorString(e));
     return 0;
@@ -882,8 +975,8 @@ extern "C" int tg_adam_step(const TgTensor *tensors, int n_tensors, float lr, fl
 extern "C" int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t *smem) {
     if (int rc = prepare(nullptr)) return rc;
     cudaFuncAttributes at;
-    const cudaError_t e = which == 0 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<false>)
-                        : (which == 2 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<true>) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel<64>));
+    const cudaError_t e = which == 0 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<false, true>)
+                        : (which == 2 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<true, true>) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel<64>));
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_kernel_info: %s", cudaGetErrorString(e));
     if (regs) *regs = at.numRegs;
     if (block) *block = which == 2 ? tg::THREADS_STAGED : tg::THREADS;
@@ -904,5 +997,10 @@ extern "C" int tg_debug_wgrad_rows(int rows) {
 
 extern "C" int tg_debug_staged(int on) {
     g_staged = on != 0;
+    return 0;
+}
+
+extern "C" int tg_debug_tma_out(int on) {
+    g_tma_out = on < 0 ? 0 : (on > 2 ? 2 : on);
     return 0;
 }

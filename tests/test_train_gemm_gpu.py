@@ -44,10 +44,12 @@ def test_linear_matches_float64(rows, K, N, wide):
 
 
 @pytest.mark.parametrize("rows,K,N,ld", [(1000, 128, 128, 128), (129, 64, 128, 64), (5000, 64, 64, 192), (20011, 128, 64, 256),
-                                         (31, 128, 8, 128), (40000, 128, 128, 128), (4097, 128, 1, 132)])
+                                         (31, 128, 8, 128), (40000, 128, 128, 128), (4097, 128, 1, 132), (3000, 256, 128, 256),
+                                         (2777, 128, 256, 128), (1500, 6, 64, 8), (999, 128, 20, 128)])
 def test_linear_staged_form_equals_register_form(rows, K, N, ld):
     """The bulk-copy staged loader (default for K = 64 / 128) and the register loader convert the same values with the same
-    arithmetic: outputs are bit-equal, for contiguous and strided rows, ragged tails, with bias / ReLU / accumulate."""
+    arithmetic, and the TMA tensor-store epilogue writes what the STG epilogue writes: outputs are bit-equal across the four
+    combinations, for contiguous and strided rows / outputs, ragged tails, partial column blocks, with bias / ReLU / accumulate."""
     L = _capi.lib()
     gen = torch.Generator().manual_seed(rows + K + N + ld)
     big = _rows(gen, rows, ld, True).cuda()
@@ -56,17 +58,23 @@ def test_linear_staged_form_equals_register_form(rows, K, N, ld):
     b = torch.randn(N, generator=gen).cuda()
     base = torch.randn(rows, N, generator=gen).cuda()
     outs = []
-    for on in (1, 0):
-        L.tg_debug_staged(on)
+    for staged, tma in ((1, 1), (1, 0), (0, 1), (0, 0)):          # loader form x epilogue form (TMA tensor stores / STG)
+        L.tg_debug_staged(staged)
+        L.tg_debug_tma_out(tma)
         try:
             pack = fused.tg_pack(W, False)
+            wide = torch.full((rows, N + 4), 7.0, device="cuda")    # strided output: the column beside it must stay untouched
+            fused.tg_linear(x, pack, b, relu=True, out=wide[:, :N])
             outs.append((fused.tg_linear(x, pack), fused.tg_linear(x, pack, b, relu=True),
-                         fused.tg_linear(x, pack, out=base.clone(), accumulate=True)))
+                         fused.tg_linear(x, pack, out=base.clone(), accumulate=True), wide))
         finally:
             L.tg_debug_staged(1)
+            L.tg_debug_tma_out(1)
     fused.tg_check_status("cuda:0")
-    for a, c in zip(*outs):
-        assert torch.equal(a, c)
+    for o in outs[1:]:
+        for a, c in zip(outs[0], o):
+            assert torch.equal(a, c)
+    assert torch.equal(outs[0][3][:, :N], outs[0][1]) and float((outs[0][3][:, N:] - 7.0).abs().max()) == 0.0
     ref = x.double() @ W.double().t()
     bound = x.double().abs() @ W.double().abs().t()
     assert float(((outs[0][0].double() - ref).abs() / (bound + 1e-30)).max()) < 2e-6
