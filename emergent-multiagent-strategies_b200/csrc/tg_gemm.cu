@@ -65,6 +65,7 @@ struct LinParams {
     long long rows;
     int ldx, ldo, ldr, K, Kp, N, Np, relu, acc, n_tiles, nst, groups, gw, vec_ok, wbytes;
     int tma_out;                                                  // epilogue stores through the TMA engine (tensor map `omap`)
+    int nraw, tb_bytes;                                           // chunks of the raw ring (staged form); bytes of the epilogue's tile area
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -110,19 +111,24 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sm
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint32_t smem_addr, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <bool STAGED, bool TMA_OUT>
-__global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linear_kernel(const LinParams p, const __grid_constant__ CUtensorMap omap) {
+__global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linear_kernel(const LinParams p, const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap rmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_acc_full[2], bar_acc_empty[2], bar_w;
-    __shared__ __align__(8) uint64_t bar_raw_full[NRAW], bar_raw_empty[NRAW];
+    __shared__ __align__(8) uint64_t bar_raw_full[NRAW], bar_raw_empty[NRAW], bar_res[EPI_WARPS];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *ring = smem + p.wbytes;
     float *tb = reinterpret_cast<float *>(ring + (size_t)p.nst * STAGE);
-    float *rowscale = tb + EPI_WARPS * 32 * TB_STRIDE;            // [SCALE_SLOTS][2][ROWS]
+    float *rowscale = tb + p.tb_bytes / 4;                        // [SCALE_SLOTS][2][ROWS]
     float *bias_s = rowscale + SCALE_SLOTS * 2 * ROWS;            // [256] bias, then [256] inverse weight scale per column
     float *winv_s = bias_s + 256;
     uint8_t *raw = reinterpret_cast<uint8_t *>(winv_s + 256);     // STAGED: [NRAW][RAW_ROWS][K] fp32
@@ -131,6 +137,8 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
         for (int s = 0; s < p.nst; ++s) { mbar_init(&bar_full[s], LOAD_THREADS); mbar_init(&bar_empty[s], 1); }
         if (STAGED)
             for (int s = 0; s < NRAW; ++s) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], LOAD_WARPS); }
+        if (TMA_OUT)
+            for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&bar_res[w], 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_WARPS * 32); }
         mbar_init(&bar_w, 1);
         mbar_fence_init();
@@ -197,10 +205,9 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
         // ================= producer (staged form): raw fp32 rows of x -> ring of RAW_ROWS-row chunks ==================
         // one bulk copy per chunk when the rows are contiguous (ldx == K), else one per row (lane = row of the chunk)
         const uint32_t row_bytes = (uint32_t)p.K * 4u, chunk_bytes = RAW_ROWS * row_bytes;
-        uint32_t rc = 0;
+        uint32_t rs = 0, rph = 0;                                 // ring slot and its phase (the ring has 3 or 4 chunks)
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            for (int c = 0; c < ROWS / RAW_ROWS; ++c, ++rc) {
-                const uint32_t rs = rc % NRAW, rph = (rc / NRAW) & 1u;
+            for (int c = 0; c < ROWS / RAW_ROWS; ++c, rph ^= (rs + 1 == (uint32_t)p.nraw), rs = (rs + 1 == (uint32_t)p.nraw) ? 0u : rs + 1) {
                 mbar_wait(&bar_raw_empty[rs], rph ^ 1u, p.status, 8);
                 const long long row0 = (long long)tile * ROWS + c * RAW_ROWS, left = p.rows - row0;
                 const int nrows = left <= 0 ? 0 : (left > RAW_ROWS ? RAW_ROWS : (int)left);
@@ -221,13 +228,12 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
         const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
         const int halves = p.gw / KC;
         const uint32_t row_bytes = (uint32_t)p.K * 4u, chunk_bytes = RAW_ROWS * row_bytes;
-        uint32_t sc = 0, rc = 0;
+        uint32_t sc = 0, rs = 0, rph = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s0 = sc % (uint32_t)p.nst, ph0 = (sc / (uint32_t)p.nst) & 1u;
             const uint32_t s1 = (sc + 1) % (uint32_t)p.nst, ph1 = ((sc + 1) / (uint32_t)p.nst) & 1u;
-            for (int c = 0; c < ROWS / RAW_ROWS; ++c, ++rc) {
-                const uint32_t rs = rc % NRAW, rph = (rc / NRAW) & 1u;
+            for (int c = 0; c < ROWS / RAW_ROWS; ++c, rph ^= (rs + 1 == (uint32_t)p.nraw), rs = (rs + 1 == (uint32_t)p.nraw) ? 0u : rs + 1) {
                 const int r = c * RAW_ROWS + lw * 4 + sub;
                 const bool live = (long long)tile * ROWS + r < p.rows;
                 mbar_wait(&bar_raw_full[rs], rph, p.status, 7);
@@ -366,6 +372,13 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
         const int rq = lane & 7, cq = lane >> 3;                       // phase-B row (within an octet) and column quad
         const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out & 15) == 0);
         const bool vec_res = (p.ldr % 4 == 0) && (((uintptr_t)p.res & 15) == 0);
+        const bool two_groups = !STAGED && p.groups > 1;               // (the staged form has one scale group: K <= 128)
+        uint32_t res_ph = 0;
+        if (TMA_OUT && p.acc && lane == 0 && (int)blockIdx.x < p.n_tiles && half < nblk) {      // first block of the added matrix
+            const uint8_t *res0 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tb) + 511) & ~(uintptr_t)511) + (EPI_WARPS + warp) * 2048;
+            mbar_expect_tx(&bar_res[warp], 2048u);
+            tma_load_2d(&rmap, smem_u32(res0), half * 16, (int)blockIdx.x * ROWS + lw * 32, &bar_res[warp]);
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
@@ -379,17 +392,26 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
                 // thread = row: scale, bias, ReLU in registers, 4 x STS.128 into the warp's swizzled 32 x 16 tile, one tensor store
                 uint8_t *tile_s = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tb) + 511) & ~(uintptr_t)511) + warp * 2048;
                 const uint32_t tile_a = smem_u32(tile_s), sw = (uint32_t)((lane >> 1) & 3);
+                // accumulate mode: the 32 x 16 block of the added matrix arrives by a tensor-map LOAD into a second swizzled tile
+                // (one block ahead, across tile boundaries), and the row thread reads its 64 bytes from there
+                const uint8_t *res_s = tile_s + EPI_WARPS * 2048;
                 for (int c = half; c < nblk; c += 2) {
                     uint32_t v0[16], v1[16];
                     tmem_ld16(trow + (uint32_t)(b * acc_cols + c * 16), v0);
-                    if (p.groups > 1) tmem_ld16(trow + (uint32_t)(b * acc_cols + p.Np + c * 16), v1);
-                    float4 rs[4];                                     // accumulate mode: this row's 16 values of the added matrix
+                    if (two_groups) tmem_ld16(trow + (uint32_t)(b * acc_cols + p.Np + c * 16), v1);
+                    float4 rs[4];
                     if (p.acc) {
-                        const float *src = p.res + (row0 + lane) * p.ldr + c * 16;
+                        mbar_wait(&bar_res[warp], res_ph, p.status, 9);
+                        res_ph ^= 1u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            rs[j] = (row0 + lane < p.rows && c * 16 + j * 4 < p.N) ? __ldg(reinterpret_cast<const float4 *>(src + j * 4))
-                                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < 4; ++j) rs[j] = *reinterpret_cast<const float4 *>(res_s + lane * 64 + (((uint32_t)j ^ sw) << 4));
+                        __syncwarp();                                  // every lane has its values: the tile may be refilled
+                        int tn = tile, cn = c + 2;
+                        if (cn >= nblk) { tn += (int)gridDim.x; cn = half; }
+                        if (lane == 0 && tn < p.n_tiles && cn < nblk) {
+                            mbar_expect_tx(&bar_res[warp], 2048u);
+                            tma_load_2d(&rmap, smem_u32(res_s), cn * 16, tn * ROWS + lw * 32, &bar_res[warp]);
+                        }
                     }
                     tmem_ld_wait();
                     if (lane == 0) tma_store_wait_read();             // the previous block's store has read the tile
@@ -401,7 +423,7 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
                         float4 f;
                         f.x = __uint_as_float(v0[j]) * inv0; f.y = __uint_as_float(v0[j + 1]) * inv0;
                         f.z = __uint_as_float(v0[j + 2]) * inv0; f.w = __uint_as_float(v0[j + 3]) * inv0;
-                        if (p.groups > 1) {
+                        if (two_groups) {
                             f.x = fmaf(__uint_as_float(v1[j]), inv1, f.x); f.y = fmaf(__uint_as_float(v1[j + 1]), inv1, f.y);
                             f.z = fmaf(__uint_as_float(v1[j + 2]), inv1, f.z); f.w = fmaf(__uint_as_float(v1[j + 3]), inv1, f.w);
                         }
@@ -813,7 +835,7 @@ bool g_ready[MAX_DEVICES] = {};
 int g_sms[MAX_DEVICES] = {};
 uint32_t g_wg_lbo = 128, g_wg_sbo = 0;      // descriptor fields of tg_wgrad's MN-major operands (sbo 0 = the block's feature-chunk stride)
 int g_wg_rows = 0;             // tg_debug_wgrad_rows: force the block height of tg_wgrad (32 / 64; 0 = by shape)
-int g_tma_out = 1;             // tg_debug_tma_out: 0 keeps tg_linear's epilogue on STG stores, 2 also sends accumulating calls through TMA
+int g_tma_out = 1;             // tg_debug_tma_out(0): keep tg_linear's epilogue on STG stores
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -890,35 +912,49 @@ extern "C" int tg_linear_res(const float *d_x, int ldx, long long rows, int K, c
     p.groups = Kp / p.gw;
     p.wbytes = 4 * Np * Kp;
     p.vec_ok = (ldx % 4 == 0) && (((uintptr_t)d_x & 15) == 0);
+    // output through the TMA engine: at least one whole 16-column block, rows (of the output and of an accumulated term, which
+    // then arrives by tensor-map loads) that are 16-byte multiples apart
+    CUtensorMap omap, rmap;
+    memset(&omap, 0, sizeof(omap));
+    memset(&rmap, 0, sizeof(rmap));
+    if (g_tma_out && N >= 16 && N % 4 == 0 && ldo % 4 == 0 && (((uintptr_t)d_out) & 15) == 0 &&
+        (!accumulate || (ldr % 4 == 0 && (((uintptr_t)d_res) & 15) == 0)) && encode_tiled()) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)rows}, gstride[1] = {(cuuint64_t)ldo * 4}, rstride[1] = {(cuuint64_t)ldr * 4};
+        const cuuint32_t box[2] = {16, 32}, estr[2] = {1, 1};
+        CUresult r = encode_tiled()(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS && accumulate)
+            r = encode_tiled()(&rmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d_res), gdim, rstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        p.tma_out = r == CUDA_SUCCESS;
+    }
+    // epilogue tile area: the transposition blocks of the STG form, or 512-byte aligned 2 KB tiles per warp (output; + added term)
+    p.tb_bytes = !p.tma_out ? tg::TB_BYTES : (512 + tg::EPI_WARPS * 2048 * (accumulate ? 2 : 1));
+    if (p.tb_bytes < tg::TB_BYTES) p.tb_bytes = tg::TB_BYTES;
+    if (tg::SMEM_LIMIT - (p.tb_bytes + tg::RS_BYTES + tg::BIAS_BYTES) - p.wbytes < 2 * (int)tg::STAGE) {
+        p.tma_out = 0;                          // (256-wide weights + an added term: no room for the second tile set)
+        p.tb_bytes = tg::TB_BYTES;
+    }
+    const int fixed = p.tb_bytes + tg::RS_BYTES + tg::BIAS_BYTES;
     // staged form: K = 64 or 128 exactly (one scale group, rows are whole 16-byte multiples), 16-byte aligned rows, and room
-    // for the raw ring beside the weights and at least one tile of operand stages
-    const int raw_bytes = tg::NRAW * tg::RAW_ROWS * K * 4;
-    const bool staged = g_staged && (K == 64 || K == 128) && p.vec_ok &&
-                        tg::SMEM_LIMIT - tg::FIXED_BYTES - p.wbytes - raw_bytes >= 2 * (int)tg::STAGE;
-    int nst = (tg::SMEM_LIMIT - tg::FIXED_BYTES - p.wbytes - (staged ? raw_bytes : 0)) / (int)tg::STAGE;
+    // for a raw ring of 4 (or 3) chunks beside the weights and at least one tile of operand stages
+    const int chunk = tg::RAW_ROWS * K * 4;
+    bool staged = g_staged && (K == 64 || K == 128) && p.vec_ok;
+    p.nraw = tg::NRAW;
+    if (staged && tg::SMEM_LIMIT - fixed - p.wbytes - p.nraw * chunk < 2 * (int)tg::STAGE) p.nraw = tg::NRAW - 1;
+    if (staged && tg::SMEM_LIMIT - fixed - p.wbytes - p.nraw * chunk < 2 * (int)tg::STAGE) staged = false;
+    const int raw_bytes = staged ? p.nraw * chunk : 0;
+    int nst = (tg::SMEM_LIMIT - fixed - p.wbytes - raw_bytes) / (int)tg::STAGE;
     if (nst > tg::MAX_NST) nst = tg::MAX_NST;
     if (nst < 2) return fa_internal_fail(-1, "tg_linear: weights too large for the shared-memory ring");
     p.nst = nst;
-    const size_t smem = (size_t)p.wbytes + (size_t)nst * tg::STAGE + tg::FIXED_BYTES + (staged ? raw_bytes : 0);
+    const size_t smem = (size_t)p.wbytes + (size_t)nst * tg::STAGE + fixed + raw_bytes;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    // output through the TMA engine: at least one whole 16-column block, rows (of the output and of an accumulated term, which
-    // the row threads read 64 bytes at a time) that are 16-byte multiples apart
-    CUtensorMap omap;
-    memset(&omap, 0, sizeof(omap));
-    // (with an accumulated term the row threads would read it 64 bytes at a time: measured 111 us against 91 us on the STG
-    // epilogue at 128 -> 128, so those calls stay there unless tg_debug_tma_out(2) forces the tensor-store form)
-    if (g_tma_out && N >= 16 && N % 4 == 0 && ldo % 4 == 0 && (((uintptr_t)d_out) & 15) == 0 &&
-        (!accumulate || (g_tma_out == 2 && ldr % 4 == 0 && (((uintptr_t)d_res) & 15) == 0)) && encode_tiled()) {
-        const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)rows}, gstride[1] = {(cuuint64_t)ldo * 4};
-        const cuuint32_t box[2] = {16, 32}, estr[2] = {1, 1};
-        const CUresult r = encode_tiled()(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        p.tma_out = r == CUDA_SUCCESS;
-    }
-    if (staged && p.tma_out) tg::tg_linear_kernel<true, true><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p, omap);
-    else if (staged) tg::tg_linear_kernel<true, false><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p, omap);
-    else if (p.tma_out) tg::tg_linear_kernel<false, true><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p, omap);
-    else tg::tg_linear_kernel<false, false><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p, omap);
+    if (staged && p.tma_out) tg::tg_linear_kernel<true, true><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p, omap, rmap);
+    else if (staged) tg::tg_linear_kernel<true, false><<<grid, tg::THREADS_STAGED, smem, (cudaStream_t)stream>>>(p, omap, rmap);
+    else if (p.tma_out) tg::tg_linear_kernel<false, true><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p, omap, rmap);
+    else tg::tg_linear_kernel<false, false><<<grid, tg::THREADS, smem, (cudaStream_t)stream>>>(p, omap, rmap);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_linear: launch: %s", cudaGetErrorString(e));
     return 0;
@@ -1001,6 +1037,6 @@ extern "C" int tg_debug_staged(int on) {
 }
 
 extern "C" int tg_debug_tma_out(int on) {
-    g_tma_out = on < 0 ? 0 : (on > 2 ? 2 : on);
+    g_tma_out = on != 0;
     return 0;
 }

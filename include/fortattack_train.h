@@ -88,9 +88,10 @@ int tg_adam_step(const TgTensor *tensors, int n_tensors, float lr, float beta1, 
 /* Static facts for reports: registers / block / dynamic shared memory of the two GEMM kernels. */
 int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t *smem);
 
-/* tg_linear's epilogue leaves through the TMA engine (one cp.async.bulk.tensor store per 32 x 16 block) whenever N >= 16 and
- * the rows of the output (and of an accumulated term) are 16-byte multiples apart; tg_debug_tma_out(0) keeps it on plain
- * stores.  Both epilogues compute the same values in the same order (bit-equal, test). */
+/* tg_linear's epilogue leaves through the TMA engine (one cp.async.bulk.tensor store per 32 x 16 block; an accumulated term
+ * arrives by tensor-map loads of the same blocks) whenever N >= 16 and the rows of the output (and of the added matrix) are
+ * 16-byte multiples apart; tg_debug_tma_out(0) keeps it on plain loads / stores.  Both epilogues compute the same values in
+ * the same order (bit-equal, test). */
 int tg_debug_tma_out(int on);
 
 /* tg_wgrad stages its operands in blocks of 64 rows (ring of 4), or of 32 rows (ring of 8) when an operand is wider than 128
