@@ -378,9 +378,9 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
         const bool two_groups = !STAGED && p.groups > 1;               // (the staged form has one scale group: K <= 128)
         uint32_t res_ph = 0;
         if (TMA_OUT && p.acc && lane == 0 && (int)blockIdx.x < p.n_tiles && half < nblk) {      // first block of the added matrix
-            const uint8_t *res0 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tb) + 511) & ~(uintptr_t)511) + (EPI_WARPS + warp) * 2048;
+            const uint32_t tb_a = smem_u32(tb);
             mbar_expect_tx(&bar_res[warp], 2048u);
-            tma_load_2d(&rmap, smem_u32(res0), half * 16, (int)blockIdx.x * ROWS + lw * 32, &bar_res[warp]);
+            tma_load_2d(&rmap, ((tb_a + 511u) & ~511u) + (EPI_WARPS + warp) * 2048u, half * 16, (int)blockIdx.x * ROWS + lw * 32, &bar_res[warp]);
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -393,7 +393,9 @@ __global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1) tg_linea
             const float inv0 = rs[r], inv1 = p.groups > 1 ? rs[ROWS + r] : 0.0f;
             if constexpr (TMA_OUT) {
                 // thread = row: scale, bias, ReLU in registers, 4 x STS.128 into the warp's swizzled 32 x 16 tile, one tensor store
-                uint8_t *tile_s = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tb) + 511) & ~(uintptr_t)511) + warp * 2048;
+                // (offsets from the shared array, not a rounded pointer: the compiler must still see shared-memory accesses)
+                const uint32_t tb_a = smem_u32(tb), tile_off = (uint32_t)(reinterpret_cast<uint8_t *>(tb) - smem) + (((tb_a + 511u) & ~511u) - tb_a);
+                uint8_t *tile_s = smem + tile_off + warp * 2048;
                 const uint32_t tile_a = smem_u32(tile_s), sw = (uint32_t)((lane >> 1) & 3);
                 // accumulate mode: the 32 x 16 block of the added matrix arrives by a tensor-map LOAD into a second swizzled tile
                 // (one block ahead, across tile boundaries), and the row thread reads its 64 bytes from there
