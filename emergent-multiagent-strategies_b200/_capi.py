@@ -34,6 +34,13 @@ class FaState(ctypes.Structure):
                 ("d_episode", ctypes.c_void_p)]
 
 
+class RlSmallMatmul(ctypes.Structure):
+    """include/fortattack_rollout.h RlSmallMatmul"""
+    _fields_ = [("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("C", ctypes.c_void_p), ("M", ctypes.c_int32), ("N", ctypes.c_int32),
+                ("K", ctypes.c_int32), ("lda", ctypes.c_int32), ("ldb", ctypes.c_int32), ("ldc", ctypes.c_int32),
+                ("trans_a", ctypes.c_int32), ("trans_b", ctypes.c_int32), ("accumulate", ctypes.c_int32)]
+
+
 class RlAttnOperand(ctypes.Structure):
     """include/fortattack_rollout.h RlAttnOperand."""
     _fields_ = [("ptr", ctypes.c_void_p), ("batch_stride", ctypes.c_int64), ("row_stride", ctypes.c_int64)]
@@ -119,6 +126,7 @@ def lib():
     L.rl_attn_mix_backward.argtypes = [P, P, P, vp, P, P, P, i32, i32, i32, i32, f32, vp]
     L.rl_relu_bwd_colsum_blocks.argtypes = [i64, i32]
     L.rl_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    L.rl_small_matmul.argtypes = [ctypes.POINTER(RlSmallMatmul), i32, vp]
     L.rl_colsum_blocks.argtypes = [i64, i32]
     L.rl_colsum.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     L.rl_relu_bwd_colsum_ld.argtypes = [vp, i32, vp, i32, vp, i32, vp, i64, i32, vp]

@@ -482,6 +482,49 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ x
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// ---- a handful of small fp32 products in one launch (the [d, d] folds of the attention projections and their backward) ----
+// C (+)= op(A) op(B), every dimension <= 256: 32 x 32 output tiles, one per block, K in steps of 32 through shared memory; plain
+// fp32 FMAs in a fixed order (bit-reproducible).  The folds are ~2 MFLOP each: what they cost before was their LAUNCHES (one
+// persistent tcgen05 launch + a weight pack + a partial-sum reduction per product).
+struct SmallMM { RlSmallMatmul it[RL_SMALL_MATMUL_MAX]; int tile0[RL_SMALL_MATMUL_MAX + 1]; int n; };
+
+__global__ void __launch_bounds__(256) small_matmul_kernel(const SmallMM p) {
+    __shared__ float As[32][33], Bs[32][33];
+    int k = 0;
+    while (k + 1 < p.n && (int)blockIdx.x >= p.tile0[k + 1]) ++k;
+    const RlSmallMatmul m = p.it[k];
+    const int t = (int)blockIdx.x - p.tile0[k], tn = (m.N + 31) / 32, i0 = (t / tn) * 32, j0 = (t % tn) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 8 rows of threads: thread (ty, tx) -> outputs (i0 + ty + 8 q, j0 + tx)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < m.K; k0 += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = ty + 8 * q;
+            // As[r][c] = op(A)[i0 + r][k0 + c],  Bs[r][c] = op(B)[k0 + r][j0 + c]
+            const int ai = i0 + r, ak = k0 + tx;
+            As[r][tx] = (ai < m.M && ak < m.K) ? (m.trans_a ? m.A[(size_t)ak * m.lda + ai] : m.A[(size_t)ai * m.lda + ak]) : 0.0f;
+            const int bk = k0 + r, bj = j0 + tx;
+            Bs[r][tx] = (bk < m.K && bj < m.N) ? (m.trans_b ? m.B[(size_t)bj * m.ldb + bk] : m.B[(size_t)bk * m.ldb + bj]) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float b = Bs[c][tx];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[ty + 8 * q][c], b, acc[q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = i0 + ty + 8 * q, j = j0 + tx;
+        if (i < m.M && j < m.N) {
+            float *c = m.C + (size_t)i * m.ldc + j;
+            *c = m.accumulate ? *c + acc[q] : acc[q];
+        }
+    }
+}
+
 }  // namespace rl
 
 static int attn_check(const char *who, int batch, int n, int m, int k, const RlAttnOperand *const *ops, int nops) {
@@ -617,6 +660,28 @@ extern "C" int rl_relu_bwd_colsum_ld(const float *d_dout, int ldd, const float *
         reinterpret_cast<float4 *>(d_partial), rows, cols / 4, ldd / 4, ldo / 4, ldp / 4);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "rl_relu_bwd_colsum: launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rl_small_matmul(const RlSmallMatmul *items, int n_items, void *stream) {
+    if (!items || n_items < 1 || n_items > RL_SMALL_MATMUL_MAX)
+        return fa_internal_fail(-1, "rl_small_matmul: 1 <= n_items <= %d", RL_SMALL_MATMUL_MAX);
+    rl::SmallMM p;
+    p.n = n_items;
+    int tiles = 0;
+    for (int k = 0; k < n_items; ++k) {
+        const RlSmallMatmul &m = items[k];
+        if (!m.A || !m.B || !m.C || m.M < 1 || m.N < 1 || m.K < 1 || m.M > 256 || m.N > 256 || m.K > 256 ||
+            m.lda < (m.trans_a ? m.M : m.K) || m.ldb < (m.trans_b ? m.K : m.N) || m.ldc < m.N)
+            return fa_internal_fail(-1, "rl_small_matmul: item %d: NULL pointer, a dimension outside 1..256 or a row stride below the row length", k);
+        p.it[k] = m;
+        p.tile0[k] = tiles;
+        tiles += ((m.M + 31) / 32) * ((m.N + 31) / 32);
+    }
+    p.tile0[n_items] = tiles;
+    rl::small_matmul_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fa_internal_fail(-2, "rl_small_matmul: launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

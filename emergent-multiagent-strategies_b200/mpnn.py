@@ -180,8 +180,8 @@ class MPNN(nn.Module):
             # Q/K/V/out projections folded into [d, d] products of the weights (rlcore/fused.py _MessageRound)
             # the [d, d] folds go through the same dense functions (own kernels, hand-written backward): W_query ... W_out
             # and update.0.weight receive their exact gradients through them
-            Mqk = fused.matmul_nt(ms.W_query[0], ms.W_key[0])                                  # W_query W_key^T
-            Wc = torch.cat((U1t, fused.matmul_nt(fused.matmul(ms.W_val[0], ms.W_out[0]), W[:, self.h_dim:])), dim=0)
+            Mqk, Wz = fused.fold_weights(ms.W_query[0], ms.W_key[0], ms.W_val[0], ms.W_out[0], W[:, self.h_dim:])
+            Wc = torch.cat((U1t, Wz), dim=0)                                                    # [U1^T ; W_val W_out U2^T]
             for _ in range(self.K):
                 h, attn = fused.message_round(h, Mqk, Wc, bias, n, ms.norm_factor)
             self._opp_attn = oattn

@@ -638,6 +638,60 @@ def heads(x, Wv0, bv0, Wp0, bp0, Wv2, bv2, Wd, bd):
     return _Heads.apply(x, Wv0, bv0, Wp0, bp0, Wv2, bv2, Wd, bd)
 
 
+# ---- the [d, d] folds of the attention projections: a handful of small products per launch ------------------------------------
+def small_matmul(items):
+    """items: list of (C, A, B, trans_a, trans_b) with C = op(A) op(B), all float32 CUDA matrices (unit column stride, every
+    dimension <= 256) that do not depend on each other: ONE launch (rl_small_matmul)."""
+    arr = (_capi.RlSmallMatmul * len(items))()
+    for k, (C, A, B, ta, tb) in enumerate(items):
+        for t in (C, A, B):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+                raise ValueError("small_matmul: float32 CUDA matrices with unit column stride expected")
+        M, N = C.shape
+        K = A.shape[0] if ta else A.shape[1]
+        if (A.shape[1] if ta else A.shape[0]) != M or (B.shape[1] if tb else B.shape[0]) != K or (B.shape[0] if tb else B.shape[1]) != N:
+            raise ValueError("small_matmul: shapes do not chain")
+        arr[k] = _capi.RlSmallMatmul(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, A.stride(0), B.stride(0), C.stride(0),
+                                     int(ta), int(tb), 0)
+    _capi.check(_lib().rl_small_matmul(arr, len(items), torch.cuda.current_stream(items[0][0].device).cuda_stream))
+
+
+class _FoldWeights(torch.autograd.Function):
+    """(Mqk, Wz) = (W_query W_key^T, W_val W_out U2^T): the projections of the message attention folded into two [d, d] weights
+    (see _MessageRound).  Forward is two launches of small products, backward two more -- before, each of the three products and
+    of their six backward products was a persistent tcgen05 launch with its own weight pack and partial-sum reduction."""
+
+    @staticmethod
+    def forward(ctx, Wq, Wk, Wv, Wout, U2):
+        Wq, Wk, Wv, Wout, U2 = (t.detach() for t in (Wq, Wk, Wv, Wout, U2))
+        d = Wq.shape[0]
+        new = lambda *sh: torch.empty(*sh, device=Wq.device)
+        Mqk, Wvo, Wz = new(d, Wk.shape[0]), new(Wv.shape[0], Wout.shape[1]), new(Wv.shape[0], U2.shape[0])
+        small_matmul([(Mqk, Wq, Wk, False, True), (Wvo, Wv, Wout, False, False)])
+        small_matmul([(Wz, Wvo, U2, False, True)])
+        ctx.save_for_backward(Wq, Wk, Wv, Wout, U2, Wvo)
+        return Mqk, Wz
+
+    @staticmethod
+    def backward(ctx, dMqk, dWz):
+        Wq, Wk, Wv, Wout, U2, Wvo = ctx.saved_tensors
+        dMqk, dWz = dMqk.contiguous(), dWz.contiguous()
+        like = torch.empty_like
+        dWq, dWk, dWv, dWout, dU2, dWvo = like(Wq), like(Wk), like(Wv), like(Wout), torch.empty(U2.shape, device=U2.device), like(Wvo)
+        small_matmul([(dWvo, dWz, U2, False, False), (dU2, dWz, Wvo, True, False), (dWq, dMqk, Wk, False, False),
+                      (dWk, dMqk, Wq, True, False)])
+        small_matmul([(dWv, dWvo, Wout, False, True), (dWout, Wv, dWvo, True, False)])
+        return dWq, dWk, dWv, dWout, dU2
+
+
+def fold_weights(Wq, Wk, Wv, Wout, U2):
+    """-> (W_query W_key^T, W_val W_out U2^T) with autograd; one small-product launch per dependency level on CUDA float32,
+    plain torch otherwise."""
+    if Wq.is_cuda and Wq.dtype == torch.float32 and max(Wq.shape + Wk.shape + Wv.shape + Wout.shape + U2.shape) <= 256:
+        return _FoldWeights.apply(Wq, Wk, Wv, Wout, U2)
+    return Wq @ Wk.t(), (Wv @ Wout) @ U2.t()
+
+
 # ---- one message-passing round with the projections folded into the weights --------------------------------------------
 def _col(t, col, batch):
     """Columns `col`... of a row-major [agents * batch, width] tensor as an attention operand (agent-major rows)."""

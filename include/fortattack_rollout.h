@@ -130,6 +130,21 @@ int rl_attn_mix_backward(const RlAttnOperand *dout, const RlAttnOperand *A, cons
 int rl_relu_bwd_colsum_blocks(long long rows, int cols);     /* number of partial rows, or -1 for unsupported sizes */
 int rl_relu_bwd_colsum(const float *d_dout, const float *d_out, float *d_dpre, float *d_partial, long long rows, int cols,
                        void *stream);
+/* Up to RL_SMALL_MATMUL_MAX small fp32 products in ONE launch:  C (+)= op(A) op(B),  op(X) = X or X^T, every dimension <= 256,
+ * row-major with row strides.  The folds of the attention projections into [d, d] weights (W_query W_key^T, W_val W_out U2^T:
+ * rlcore/fused.py fold_weights, mpnn.py:286-327 folded) and their backward are six products of ~2 MFLOP per optimizer step;
+ * the items of one call must not depend on each other.  Plain fp32 FMAs in a fixed order (bit-reproducible). */
+#define RL_SMALL_MATMUL_MAX 8
+typedef struct RlSmallMatmul {
+    const float *A, *B;
+    float *C;
+    int32_t M, N, K;                  /* C is M x N, the reduction runs over K */
+    int32_t lda, ldb, ldc;            /* row strides (floats) of A, B, C as stored */
+    int32_t trans_a, trans_b;         /* op(A) = A^T (A stored K x M) / op(B) = B^T (B stored N x K) */
+    int32_t accumulate;               /* C += instead of C = */
+} RlSmallMatmul;
+int rl_small_matmul(const RlSmallMatmul *items, int n_items, void *stream);
+
 /* out[c] = sum_r x[r][c] for a tall row-major matrix (cols a power of two <= 256, row stride ld): the bias gradients of the
  * dense layers (rows of dpre, or relu_bwd_colsum's per-block partials) in one launch, partial sums added in a fixed order
  * (bit-reproducible).  d_scratch: 4 + rl_colsum_blocks(rows, cols) * cols floats, first word zero before the first call. */

@@ -302,6 +302,27 @@ def test_colsum_matches_float64_and_is_reproducible(rows, cols, ld):
     assert torch.equal(got, fused.colsum(x))
 
 
+def test_fold_weights_matches_autograd():
+    """fused.fold_weights (rl_small_matmul: the [d, d] folds of the attention projections, forward and backward in two launches
+    each) == the torch expressions W_query W_key^T, (W_val W_out) U2^T and their autograd gradients; bit-reproducible."""
+    fused = import_module(PKG + ".rlcore.fused")
+    gen = torch.Generator().manual_seed(9)
+    for d, k, h in ((128, 128, 128), (64, 48, 72), (128, 37, 200)):
+        mk = lambda *sh: (torch.randn(*sh, generator=gen) / sh[-1] ** 0.5).cuda().requires_grad_()
+        Wq, Wk, Wv, Wout, W = mk(d, k), mk(d, k), mk(d, k), mk(k, d), mk(h, 2 * d)
+        U2 = W[:, d:]
+        g1, g2 = torch.randn(d, d, generator=gen).cuda(), torch.randn(d, h, generator=gen).cuda()
+        Mqk, Wz = fused.fold_weights(Wq, Wk, Wv, Wout, U2)
+        got = torch.autograd.grad((Mqk * g1).sum() + (Wz * g2).sum(), (Wq, Wk, Wv, Wout, W))
+        rq, rz = Wq.double() @ Wk.double().t(), (Wv.double() @ Wout.double()) @ U2.double().t()
+        ref = torch.autograd.grad((rq * g1.double()).sum() + (rz * g2.double()).sum(), (Wq, Wk, Wv, Wout, W))
+        assert float((Mqk.double() - rq).abs().max()) < 1e-5 and float((Wz.double() - rz).abs().max()) < 1e-5
+        for a, b in zip(got, ref):
+            assert float((a.double() - b.double()).abs().max()) < 1e-5 * (1.0 + float(b.abs().max())), (d, k, h)
+        M2, Z2 = fused.fold_weights(Wq, Wk, Wv, Wout, U2)
+        assert torch.equal(M2, Mqk) and torch.equal(Z2, Wz)
+
+
 def test_loss_from_logits_matches_categorical_and_torch_loss():
     """rl_ppo_loss_logits == FixedCategorical(logits).log_probs / .entropy (rlcore/distributions.py:9-17) fed to the torch
     expressions of ppo.py:150-187: statistics, the gradient with respect to values and LOGITS (torch autograd through
