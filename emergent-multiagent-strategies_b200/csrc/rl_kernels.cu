@@ -500,11 +500,22 @@ __global__ void __launch_bounds__(256) small_matmul_kernel(const SmallMM p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int r = ty + 8 * q;
-            // As[r][c] = op(A)[i0 + r][k0 + c],  Bs[r][c] = op(B)[k0 + r][j0 + c]
-            const int ai = i0 + r, ak = k0 + tx;
-            As[r][tx] = (ai < m.M && ak < m.K) ? (m.trans_a ? m.A[(size_t)ak * m.lda + ai] : m.A[(size_t)ai * m.lda + ak]) : 0.0f;
-            const int bk = k0 + r, bj = j0 + tx;
-            Bs[r][tx] = (bk < m.K && bj < m.N) ? (m.trans_b ? m.B[(size_t)bj * m.ldb + bk] : m.B[(size_t)bk * m.ldb + bj]) : 0.0f;
+            // As[r][c] = op(A)[i0 + r][k0 + c],  Bs[r][c] = op(B)[k0 + r][j0 + c]; tx always runs along the dimension that is
+            // contiguous in memory (full-line loads), transposed operands are turned through the padded tiles
+            if (m.trans_a) {
+                const int ak = k0 + r, ai = i0 + tx;
+                As[tx][r] = (ai < m.M && ak < m.K) ? m.A[(size_t)ak * m.lda + ai] : 0.0f;
+            } else {
+                const int ai = i0 + r, ak = k0 + tx;
+                As[r][tx] = (ai < m.M && ak < m.K) ? m.A[(size_t)ai * m.lda + ak] : 0.0f;
+            }
+            if (m.trans_b) {
+                const int bj = j0 + r, bk = k0 + tx;
+                Bs[tx][r] = (bk < m.K && bj < m.N) ? m.B[(size_t)bj * m.ldb + bk] : 0.0f;
+            } else {
+                const int bk = k0 + r, bj = j0 + tx;
+                Bs[r][tx] = (bk < m.K && bj < m.N) ? m.B[(size_t)bk * m.ldb + bj] : 0.0f;
+            }
         }
         __syncthreads();
 #pragma unroll
