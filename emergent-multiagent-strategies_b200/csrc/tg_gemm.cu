@@ -7,16 +7,19 @@
 //               straight from their row-major tiles through MN-major shared-memory descriptors
 //   tg_adam_step  gradient-norm clip + Adam for all parameter tensors in two launches
 //
-// tg_linear_kernel, persistent, one CTA per SM, 416 threads:
-//   warps 0-3   epilogue: thread = accumulator row (tensor-memory lane); scales by the row's and the weight's inverse
-//               power-of-two scale, transposes 32x32 blocks through shared memory so that global stores are full lines,
-//               adds bias / ReLU / the previous output (accumulate)
-//   warps 4-11  loaders: coalesced float4 reads of a 128-row x 128-column group of x, per-row amax -> power-of-two scale,
-//               hi = fp16(x s), lo = fp16(x s - hi), 16-byte stores into the canonical no-swizzle K-major layout
-//               (8-row core matrices contiguous: SBO = 128; k-chunk stride LBO = 2048 + 16: the pad makes the stores of
-//               a warp whose lanes run along k bank-conflict free)
-//   warp 12     MMA issuer (converged warp, one elected lane): per 64-column stage 4 k-steps x {hi.hi, hi.lo, lo.hi}
-//   ring of NST stages (full/empty mbarriers), two accumulator buffers in tensor memory (acc_full/acc_empty), weights
+// tg_linear_kernel<STAGED, TMA_OUT>, persistent, one CTA per SM, 544 threads (576 in the staged form):
+//   warps 0-7   epilogue: thread = accumulator row (tensor-memory lane; warps w and w + 4 share a lane window and split the
+//               16-column blocks).  TMA_OUT: scales, bias, ReLU in registers, the row's 16 values into the warp's swizzled
+//               32 x 16 tile, ONE cp.async.bulk.tensor store per block (an added term arrives by tensor-map loads of the same
+//               blocks).  Otherwise: 32 x 16 blocks transposed through shared memory and stored with STG.128.
+//   warps 8-15  loaders: a 128-row x 128-column group of x, per-row amax -> power-of-two scale, hi = fp16(x s),
+//               lo = fp16(x s - hi), 16-byte stores into the canonical no-swizzle K-major layout (8-row core matrices
+//               contiguous: SBO = 128; k-chunk stride LBO = 2048 + 16: the pad makes the stores of a warp whose lanes run along k
+//               bank-conflict free).  STAGED (K = 64 / 128): the rows come out of a shared-memory ring that the producer warp
+//               fills with one tensor-map load per 32-row chunk; otherwise coalesced float4 global loads.
+//   warp 16     MMA issuer (converged warp, one elected lane): per 64-column stage 4 k-steps x {hi.hi, hi.lo, lo.hi}
+//   warp 17     (staged form) producer of the raw ring
+//   ring of NST operand stages (full/empty mbarriers), two accumulator buffers in tensor memory (acc_full/acc_empty), weights
 //   (fp16 hi/lo planes, packed by tg_pack_weight) resident in shared memory for the whole launch.
 // K = 256 is handled as two 128-column groups with their own row scales and their own accumulators (summed in the
 // epilogue), so the per-row scale never has to wait for more than 128 columns.
@@ -550,7 +553,6 @@ template <int WR> struct WG {
     static constexpr int NB = WR == 64 ? 4 : 8, SMEM = NB * (int)BLOCK;
 };
 constexpr int MAX_NB = 8;
-__device__ uint32_t g_dbg_lbo = 0, g_dbg_sbo = 0;
 
 struct WgParams {
     const float *x, *y;
