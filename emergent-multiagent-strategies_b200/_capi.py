@@ -144,6 +144,7 @@ def lib():
     L.tg_debug_staged.argtypes = [i32]
     L.tg_debug_wgrad_rows.argtypes = [i32]
     L.tg_debug_tma_out.argtypes = [i32]
+    L.tg_debug_wgrad_staged.argtypes = [i32]
     L.mw_step.argtypes = [vp, vp, vp, vp, vp]
     L.mw_scenario_obs_dim.argtypes = [i32, i32, i32, i32]
     L.mw_scenario_callbacks.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp]

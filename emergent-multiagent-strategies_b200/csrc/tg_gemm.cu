@@ -548,11 +548,17 @@ __global__ void __launch_bounds__(256) tg_pack_kernel(const float *w, int N, int
 // Two block heights: 64 rows (ring of 4 blocks: two row steps of a one-block-per-operand product in flight) and 32 rows
 // (ring of 8) for products with a 256-wide operand, whose row step needs THREE blocks -- with 64-row blocks only one more
 // block fits beside a step, and the loaders idle while its twelve-MMA groups run.
-template <int WR> struct WG {
+template <int WR, bool STAGED = false> struct WG {
     static constexpr uint32_t LBO = WR * 16 + 16, PLANE = 16 * LBO, BLOCK = 3 * PLANE;      // 64: 1040, 16640, 49920; 32: 528, 8448, 25344
-    static constexpr int NB = WR == 64 ? 4 : 8, SMEM = NB * (int)BLOCK;
+    // staged form: the raw fp32 rows of an operand block (WR rows x <= 128 columns) arrive in a ring of 64 KB by tensor-map loads
+    // and the loader warps convert from there; the operand ring gives up a quarter of its blocks for it (conversion, not the
+    // MMAs, is what a row step waits for, so three / six blocks keep the tensor pipe fed)
+    static constexpr int NB = STAGED ? (WR == 64 ? 3 : 6) : (WR == 64 ? 4 : 8);
+    static constexpr uint32_t RAW_CHUNK = WR * 512u;
+    static constexpr int NRAW = STAGED ? 65536 / (int)RAW_CHUNK : 0;
+    static constexpr int SMEM = NB * (int)BLOCK + NRAW * (int)RAW_CHUNK;
 };
-constexpr int MAX_NB = 8;
+constexpr int MAX_NB = 8, MAX_WRAW = 4;
 
 struct WgParams {
     const float *x, *y;
@@ -591,16 +597,20 @@ __device__ __forceinline__ void split8_bf16(const float4 &a, const float4 &b, ui
     l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
 }
 
-template <int WROWS>
-__global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) {
-    constexpr uint32_t FB_LBO = WG<WROWS>::LBO, PLANE = WG<WROWS>::PLANE, BLOCK = WG<WROWS>::BLOCK;
-    constexpr int NB = WG<WROWS>::NB;
+template <int WROWS, bool STAGED>
+__global__ void __launch_bounds__(STAGED ? THREADS_STAGED : THREADS, 1)
+tg_wgrad_kernel(const WgParams p, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
+    typedef WG<WROWS, STAGED> L;
+    constexpr uint32_t FB_LBO = L::LBO, PLANE = L::PLANE, BLOCK = L::BLOCK;
+    constexpr int NB = L::NB;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[MAX_NB], bar_empty[MAX_NB], bar_done;
+    __shared__ __align__(8) uint64_t bar_full[MAX_NB], bar_empty[MAX_NB], bar_done, bar_raw_full[MAX_WRAW], bar_raw_empty[MAX_WRAW];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *raw = smem + (size_t)NB * BLOCK;                      // STAGED: [NRAW][WROWS][<= 128] fp32, dense rows
     if (tid == 0) {
         for (int s = 0; s < NB; ++s) { mbar_init(&bar_full[s], LOAD_THREADS); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < L::NRAW; ++s) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], LOAD_WARPS); }
         mbar_init(&bar_done, 1);
         mbar_fence_init();
     }
@@ -651,6 +661,67 @@ __global__ void __launch_bounds__(THREADS, 1) tg_wgrad_kernel(const WgParams p) 
         }
         if (elect_one()) umma_commit(&bar_done);
         __syncwarp();
+    } else if (STAGED && warp == PROD_WARP) {
+        // producer (staged form): one tensor-map load per operand block (WROWS rows x the block's columns, dense rows; rows past
+        // the matrix arrive as zeros) into the raw ring
+        if (lane == 0) {
+            uint32_t rc = 0;
+            for (int step = blockIdx.x; step < p.n_steps; step += gridDim.x) {
+                for (int k = 0; k < nblk; ++k, ++rc) {
+                    const uint32_t rs = rc % (uint32_t)L::NRAW, rph = (rc / (uint32_t)L::NRAW) & 1u;
+                    const bool isx = k < p.ab;
+                    const int width = isx ? p.a : p.b, f0 = (isx ? k : k - p.ab) * 128, bw = width < 128 ? width : 128;
+                    mbar_wait(&bar_raw_empty[rs], rph ^ 1u, p.status, 14);
+                    mbar_expect_tx(&bar_raw_full[rs], (uint32_t)(WROWS * bw * 4));
+                    tma_load_2d(isx ? &xmap : &ymap, smem_u32(raw + rs * L::RAW_CHUNK), f0, step * WROWS, &bar_raw_full[rs]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (STAGED && warp >= LOAD_WARP0) {
+        // converters (staged form): the same lane mapping and split as the register loaders below, rows read from the raw ring
+        const int lw = warp - LOAD_WARP0, sub = lane >> 3, kc = lane & 7;
+        constexpr int WQ = WROWS / LOAD_WARPS / 4;
+        uint32_t bc = 0;
+        for (int step = blockIdx.x; step < p.n_steps; step += gridDim.x) {
+            for (int k = 0; k < nblk; ++k, ++bc) {
+                const uint32_t rs = bc % (uint32_t)L::NRAW, rph = (bc / (uint32_t)L::NRAW) & 1u, s = bc % NB;
+                const bool isx = k < p.ab;
+                const int width = isx ? p.a : p.b, bw = width < 128 ? width : 128;
+                mbar_wait(&bar_raw_full[rs], rph, p.status, 15);
+                float4 v[WQ][2][2];
+#pragma unroll
+                for (int q = 0; q < WQ; ++q) {
+                    const int r = lw * (WQ * 4) + q * 4 + sub;
+                    const uint8_t *src = raw + rs * L::RAW_CHUNK + (uint32_t)r * (uint32_t)(bw * 4) + (uint32_t)kc * 32u;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        v[q][h][0] = v[q][h][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (h * 64 + kc * 8 < bw) {
+                            v[q][h][0] = *reinterpret_cast<const float4 *>(src + h * 256);
+                            v[q][h][1] = *reinterpret_cast<const float4 *>(src + h * 256 + 16);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_raw_empty[rs]);
+                mbar_wait(&bar_empty[s], ((bc / NB) & 1u) ^ 1u, p.status, 12);
+                uint8_t *blk = smem + (size_t)s * BLOCK;
+#pragma unroll
+                for (int q = 0; q < WQ; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 hh, mm, ll;
+                        split8_bf16(v[q][h][0], v[q][h][1], hh, mm, ll);
+                        uint8_t *d = blk + (uint32_t)(h * 8 + kc) * FB_LBO + (uint32_t)(lw * (WQ * 4) + q * 4 + sub) * 16u;
+                        *reinterpret_cast<uint4 *>(d) = hh;
+                        *reinterpret_cast<uint4 *>(d + PLANE) = mm;
+                        *reinterpret_cast<uint4 *>(d + 2 * PLANE) = ll;
+                    }
+                fence_async_smem();
+                mbar_arrive(&bar_full[s]);
+            }
+        }
     } else if (warp >= LOAD_WARP0) {
         // loaders: the global loads of operand block idx + 1 are in flight while block idx is split and stored (two register
         // buffers), so the load latency is paid once per CTA, not once per block
@@ -842,6 +913,7 @@ bool g_ready[MAX_DEVICES] = {};
 int g_sms[MAX_DEVICES] = {};
 uint32_t g_wg_lbo = 128, g_wg_sbo = 0;      // descriptor fields of tg_wgrad's MN-major operands (sbo 0 = the block's feature-chunk stride)
 int g_wg_rows = 0;             // tg_debug_wgrad_rows: force the block height of tg_wgrad (32 / 64; 0 = by shape)
+bool g_wg_staged = true;       // tg_debug_wgrad_staged(0): keep tg_wgrad on the register loaders
 int g_tma_out = 1;             // tg_debug_tma_out(0): keep tg_linear's epilogue on STG stores
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -869,8 +941,10 @@ int prepare(int *sms) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_linear_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<64>::SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<32>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<64, false>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<32, false>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<64, true>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tg::tg_wgrad_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::WG<32, true>::SMEM);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return fa_internal_fail(-2, "tg: device setup: %s", cudaGetErrorString(e));
         g_ready[dev] = true;
@@ -994,10 +1068,28 @@ extern "C" int tg_wgrad(const float *d_x, int ldx, int a, const float *d_y, int 
     p.n_steps = (int)((rows + wr - 1) / wr);
     p.vx = (ldx % 4 == 0) && (((uintptr_t)d_x & 15) == 0);
     p.vy = (ldy % 4 == 0) && (((uintptr_t)d_y & 15) == 0);
-    p.lbo = g_wg_lbo; p.sbo = g_wg_sbo ? g_wg_sbo : (wr == 64 ? tg::WG<64>::LBO : tg::WG<32>::LBO);
+    p.lbo = g_wg_lbo; p.sbo = g_wg_sbo ? g_wg_sbo : (wr == 64 ? tg::WG<64, false>::LBO : tg::WG<32, false>::LBO);
     const int grid = p.n_steps < sms ? p.n_steps : sms;
-    if (wr == 64) tg::tg_wgrad_kernel<64><<<grid, tg::THREADS, tg::WG<64>::SMEM, (cudaStream_t)stream>>>(p);
-    else tg::tg_wgrad_kernel<32><<<grid, tg::THREADS, tg::WG<32>::SMEM, (cudaStream_t)stream>>>(p);
+    // staged form: both operands in whole 8-column chunks with 16-byte aligned rows
+    CUtensorMap xmap, ymap;
+    memset(&xmap, 0, sizeof(xmap));
+    memset(&ymap, 0, sizeof(ymap));
+    bool staged = g_wg_staged && p.vx && p.vy && a % 8 == 0 && b % 8 == 0 && encode_tiled() != nullptr;
+    if (staged) {
+        const cuuint32_t estr[2] = {1, 1};
+        const cuuint64_t xdim[2] = {(cuuint64_t)a, (cuuint64_t)rows}, xstr[1] = {(cuuint64_t)ldx * 4};
+        const cuuint64_t ydim[2] = {(cuuint64_t)b, (cuuint64_t)rows}, ystr[1] = {(cuuint64_t)ldy * 4};
+        const cuuint32_t xbox[2] = {(cuuint32_t)(a < 128 ? a : 128), (cuuint32_t)wr}, ybox[2] = {(cuuint32_t)(b < 128 ? b : 128), (cuuint32_t)wr};
+        staged = encode_tiled()(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d_x), xdim, xstr, xbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                 encode_tiled()(&ymap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d_y), ydim, ystr, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    const cudaStream_t st = (cudaStream_t)stream;
+    if (wr == 64 && staged) tg::tg_wgrad_kernel<64, true><<<grid, tg::THREADS_STAGED, tg::WG<64, true>::SMEM, st>>>(p, xmap, ymap);
+    else if (wr == 64) tg::tg_wgrad_kernel<64, false><<<grid, tg::THREADS, tg::WG<64, false>::SMEM, st>>>(p, xmap, ymap);
+    else if (staged) tg::tg_wgrad_kernel<32, true><<<grid, tg::THREADS_STAGED, tg::WG<32, true>::SMEM, st>>>(p, xmap, ymap);
+    else tg::tg_wgrad_kernel<32, false><<<grid, tg::THREADS, tg::WG<32, false>::SMEM, st>>>(p, xmap, ymap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_wgrad: launch: %s", cudaGetErrorString(e));
     tg::tg_reduce_kernel<<<(a * b * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float *)d_scratch, grid, a, b, d_dw, lddw, accumulate);
@@ -1029,11 +1121,11 @@ extern "C" int tg_kernel_info(int which, int32_t *regs, int32_t *block, int32_t 
     if (int rc = prepare(nullptr)) return rc;
     cudaFuncAttributes at;
     const cudaError_t e = which == 0 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<false, true>)
-                        : (which == 2 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<true, true>) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel<64>));
+                        : (which == 2 ? cudaFuncGetAttributes(&at, tg::tg_linear_kernel<true, true>) : cudaFuncGetAttributes(&at, tg::tg_wgrad_kernel<64, true>));
     if (e != cudaSuccess) return fa_internal_fail(-2, "tg_kernel_info: %s", cudaGetErrorString(e));
     if (regs) *regs = at.numRegs;
     if (block) *block = which == 2 ? tg::THREADS_STAGED : tg::THREADS;
-    if (smem) *smem = (which == 1 ? tg::WG<64>::SMEM : tg::SMEM_LIMIT) + (int)at.sharedSizeBytes;
+    if (smem) *smem = (which == 1 ? tg::WG<64, true>::SMEM : tg::SMEM_LIMIT) + (int)at.sharedSizeBytes;
     return 0;
 }
 
@@ -1055,5 +1147,10 @@ extern "C" int tg_debug_staged(int on) {
 
 extern "C" int tg_debug_tma_out(int on) {
     g_tma_out = on != 0;
+    return 0;
+}
+
+extern "C" int tg_debug_wgrad_staged(int on) {
+    g_wg_staged = on != 0;
     return 0;
 }

@@ -97,6 +97,11 @@ int tg_debug_tma_out(int on);
 /* tg_wgrad stages its operands in blocks of 64 rows (ring of 4), or of 32 rows (ring of 8) when an operand is wider than 128
  * columns (three blocks per row step).  tg_debug_wgrad_rows(32 | 64) forces one height, 0 restores the choice by shape. */
 int tg_debug_wgrad_rows(int rows);
+/* tg_wgrad has the same two loader forms as tg_linear: STAGED (both operands in whole 8-column chunks with 16-byte aligned rows:
+ * a producer warp fetches the raw fp32 rows of every operand block with one tensor-map load, the loader warps convert from
+ * shared memory; operand ring of 3 / 6 blocks + a 64 KB raw ring) and the register form (operand ring of 4 / 8 blocks).  Same
+ * arithmetic and the same partition of the rows: bit-equal results (test).  tg_debug_wgrad_staged(0) keeps the register form. */
+int tg_debug_wgrad_staged(int on);
 
 /* tg_linear has two loader forms with identical arithmetic: the STAGED form (K = 64 or 128, 16-byte aligned rows: a producer
  * warp streams raw fp32 rows into a shared-memory ring with bulk copies and the loader warps convert from there) and the

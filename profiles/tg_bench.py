@@ -11,6 +11,8 @@ if os.environ.get("TG_BENCH_STAGED") == "0":       # A/B: keep tg_linear on the 
     import_module("emergent-multiagent-strategies_b200._capi").lib().tg_debug_staged(0)
 if os.environ.get("TG_BENCH_TMA_OUT") == "0":      # A/B: keep tg_linear's epilogue on STG stores
     import_module("emergent-multiagent-strategies_b200._capi").lib().tg_debug_tma_out(0)
+if os.environ.get("TG_BENCH_WGRAD_STAGED") == "0":   # A/B: keep tg_wgrad on the register loaders
+    import_module("emergent-multiagent-strategies_b200._capi").lib().tg_debug_wgrad_staged(0)
 if os.environ.get("TG_BENCH_WGRAD_ROWS"):          # A/B: force tg_wgrad's block height (32 / 64)
     import_module("emergent-multiagent-strategies_b200._capi").lib().tg_debug_wgrad_rows(int(os.environ["TG_BENCH_WGRAD_ROWS"]))
 

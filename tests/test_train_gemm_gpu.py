@@ -118,6 +118,28 @@ def test_wgrad_block_heights(rows, a, b):
         assert e_rel < 2e-6, (wr, e_rel, e_abs)
 
 
+@pytest.mark.parametrize("rows,a,b,lda,ldb", [(5000, 128, 128, 128, 128), (4099, 256, 128, 256, 128), (3001, 128, 256, 128, 256),
+                                               (1000, 64, 64, 128, 64), (33, 64, 8, 64, 8), (70000, 128, 64, 256, 192), (777, 8, 128, 8, 128)])
+def test_wgrad_staged_form_equals_register_form(rows, a, b, lda, ldb):
+    """The tensor-map staged loaders of tg_wgrad and the register loaders split the same values into the same operand blocks and
+    partition the rows the same way: results are bit-equal, for contiguous and strided operands and ragged row counts."""
+    L = _capi.lib()
+    gen = torch.Generator().manual_seed(rows + a + b)
+    x, y = _rows(gen, rows, lda, True).cuda()[:, lda - a:], _rows(gen, rows, ldb, False).cuda()[:, :b]
+    outs = []
+    for on in (1, 0):
+        L.tg_debug_wgrad_staged(on)
+        try:
+            outs.append(fused.tg_wgrad(x, y))
+        finally:
+            L.tg_debug_wgrad_staged(1)
+    fused.tg_check_status("cuda:0")
+    assert torch.equal(outs[0], outs[1])
+    ref = x.double().t() @ y.double()
+    bound = x.double().abs().t() @ y.double().abs()
+    assert float(((outs[0].double() - ref).abs() / (bound + 1e-30)).max()) < 2e-6
+
+
 def test_wgrad_descriptor_probe():
     """Prints the error of the built-in MN-major descriptor fields and of the swapped pair (diagnostic for the layout)."""
     gen = torch.Generator().manual_seed(0)
