@@ -727,6 +727,15 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     e0.record(); tr2.update(); e1.record()
     torch.cuda.synchronize(dev)
     update_graph_ms = e0.elapsed_time(e1)
+    # the same graph-replayed update with the two teams one after the other (overlap_teams=False; what earlier rounds measured)
+    tr2.overlap_teams = False
+    tr2.update()
+    torch.cuda.synchronize(dev)
+    e0, e1 = ev(), ev()
+    e0.record(); tr2.update(); e1.record()
+    torch.cuda.synchronize(dev)
+    update_graph_seq_ms = e0.elapsed_time(e1)
+    tr2.overlap_teams = True
     e0, e1 = ev(), ev()
     e0.record(); tr2.recompute_old(); e1.record()
     torch.cuda.synchronize(dev)
@@ -746,6 +755,7 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     return {"workload": "FortAttack 3v3 (BASELINE.json configs[2]), %d envs, T=%d rollout with the MPNN policy + one JointPPO update" % (E, T),
             "rollout_agent_steps_per_s": E * A * T / (collect_ms * 1e-3), "collect_ms": collect_ms,
             "us_per_rollout_step": collect_ms * 1e3 / T, "wrap_horizon_ms": wrap_ms, "ppo_update_ms": update_ms, "ppo_update_graph_ms": update_graph_ms,
+            "ppo_update_graph_sequential_teams_ms": update_graph_seq_ms,
             "ppo_update_cublas_fp32_ms": update_cublas_ms, "recompute_old_ms": recompute_ms,
             "policy_weights": "marlsave/tmp_1/ep2520.pt (baseline/_ref)" if models is not None else "random init (baseline/_ref absent)",
             "ppo_update": "4 epochs x 32 minibatches x 2 teams = 256 optimizer steps, fp32-grade arithmetic: every dense product on "

@@ -143,6 +143,22 @@ class JointPPO(object):
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
     def _update_fused(self, rollouts_list, index_batches=None):
+        return self._update_fused_end(self._update_fused_begin(rollouts_list, index_batches))
+
+    def update_begin(self, rollouts_list, opp_rollouts_list, shared):
+        """Enqueue a whole fused update on the CURRENT stream without waiting for it; update_end(handle) returns the three
+        averaged losses (the update's only host synchronisation).  BatchedTrainer.update uses the pair to run the two teams'
+        updates on two streams at once.  Returns None when this update cannot take the fused path (the caller then uses
+        update())."""
+        if not (shared is not None and self.use_clipped_value_loss and rollouts_list[0].rewards.is_cuda):
+            return None
+        self._shared = shared
+        return self._update_fused_begin(rollouts_list, None)
+
+    def update_end(self, handle):
+        return self._update_fused_end(handle)
+
+    def _update_fused_begin(self, rollouts_list, index_batches=None):
         try:
             from .. import fused
         except ImportError:
@@ -156,20 +172,28 @@ class JointPPO(object):
         totals = torch.zeros(3, device=dev)
         params = [p for p in self.actor_critic.parameters()]
         world = self._world()
-        n_updates = 0
+        self._adv_fresh = True               # the captured step copies the advantages into its own buffer once per update
+        perms = None
+        if index_batches is None:
+            # every epoch's permutation is drawn up front (same draws, same order as one per epoch) and goes to the device
+            # in one asynchronous copy from pinned memory: a copy from pageable memory makes the host wait for the stream,
+            # and the host has to stay ahead of the device for the whole update
+            perms = [self._perm(rollouts_list[0]) for _ in range(self.ppo_epoch)]
+            perms = [q if q.is_cuda else q.pin_memory().to(dev, non_blocking=True) for q in perms]
         for epoch in range(self.ppo_epoch):
             if index_batches is not None:
                 batches = index_batches[epoch]
             else:
-                perm = self._perm(rollouts_list[0])
+                perm = perms[epoch]
                 batches = [perm[i:i + mini_batch_size] for i in range(0, batch_size, mini_batch_size)]
             for idx in batches:
                 idx = idx.to(dev).contiguous()
                 if self._graphed_step(fused, R, (a0, n, o0, m), idx, advantages, totals, mini_batch_size, world):
-                    n_updates += 1
                     continue
                 self._minibatch_step(fused, R, (a0, n, o0, m), idx, advantages, totals, params, world)
-                n_updates += 1
+        return totals
+
+    def _update_fused_end(self, totals):
         # (several ranks: the per-step sums were made global inside _minibatch_step, nothing left to reduce)
         # the reference divides the summed losses by ppo_epoch * num_mini_batch whatever the number of minibatches the
         # sampler produced (ppo.py:198-202: a ragged tail adds one more term to the sums)
@@ -178,9 +202,11 @@ class JointPPO(object):
 
     def _minibatch_step(self, fused, R, team, idx, advantages, totals, params, world):
         fused.pack_cache(True)               # weights are constant from here to the optimizer kernel: packs are reused
+        prev_scope = fused.scratch_scope(id(self))      # this trainer's own partial-sum / counter / status storage
         try:
             self._minibatch_step_body(fused, R, team, idx, advantages, totals, params, world)
         finally:
+            fused.scratch_scope(prev_scope)
             fused.pack_cache(False)
 
     def _minibatch_step_body(self, fused, R, team, idx, advantages, totals, params, world):
@@ -286,7 +312,9 @@ class JointPPO(object):
             torch.cuda.current_stream(idx.device).wait_stream(side)
             g["graph"] = graph
         g["idx"].copy_(idx)
-        g["adv"].copy_(advantages)              # (same tensor for a whole update; 2 % of a step)
+        if getattr(self, "_adv_fresh", True):   # the advantages are one tensor for a whole update: copied at its first replay
+            g["adv"].copy_(advantages)
+            self._adv_fresh = False
         g["totals"].zero_()
         g["graph"].replay()
         totals += g["totals"]

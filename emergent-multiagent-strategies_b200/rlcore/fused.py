@@ -70,10 +70,28 @@ LOSS_ACTIONS = 8
 _LOSS_SCRATCH = {}
 
 
+_SCOPE = 0
+
+
+def scratch_scope(token):
+    """Scratch buffers (partial sums, counters, status words) are kept per (device, scope).  JointPPO brackets its optimizer
+    steps with scratch_scope(id(self)) / scratch_scope(0): the two teams' updates may run on different streams at the same time
+    (rollout.BatchedTrainer.update) and must not share that storage.  A scope, unlike the current stream, is the same for the
+    eager warm-up steps and the captured graph, so nothing is allocated (or zeroed) inside a capture."""
+    global _SCOPE
+    prev, _SCOPE = _SCOPE, token
+    return prev
+
+
+def _stream_key(dev):
+    return (torch.device(dev), _SCOPE)
+
+
 def _loss_scratch(dev):
-    s = _LOSS_SCRATCH.get(dev)
+    key = _stream_key(dev)
+    s = _LOSS_SCRATCH.get(key)
     if s is None:
-        s = _LOSS_SCRATCH[dev] = torch.zeros(int(_lib().rl_ppo_loss_logits_scratch_floats()), device=dev)
+        s = _LOSS_SCRATCH[key] = torch.zeros(int(_lib().rl_ppo_loss_logits_scratch_floats()), device=dev)
     return s
 
 
@@ -221,20 +239,22 @@ _TG = {}
 
 
 def _tg_state(dev):
-    st = _TG.get(dev)
+    key = _stream_key(dev)
+    st = _TG.get(key)
     if st is None:
-        st = _TG[dev] = {"status": torch.zeros(1, dtype=torch.int32, device=dev),
+        st = _TG[key] = {"status": torch.zeros(1, dtype=torch.int32, device=dev),
                          "scratch": torch.empty(_lib().tg_wgrad_scratch_bytes(256, 128), dtype=torch.uint8, device=dev)}
     return st
 
 
 def tg_check_status(dev):
     """Synchronising: raises if any dense kernel so far reported a pipeline timeout (a protocol bug, never expected)."""
-    st = _TG.get(torch.device(dev))
-    if st is not None:
-        code = int(st["status"].item())
-        if code:
-            raise _capi.FaError("tg_gemm pipeline timeout (wait site %d)" % code)
+    dev = torch.device(dev)
+    for (d, _scope), st in list(_TG.items()):
+        if d == dev or (d.type == dev.type and dev.index is None):
+            code = int(st["status"].item())
+            if code:
+                raise _capi.FaError("tg_gemm pipeline timeout (wait site %d)" % code)
 
 
 def _row_major(t):
@@ -343,9 +363,10 @@ def colsum(x):
     if ld < cols:
         return x.sum(0)
     need = 4 + 1024 * 256
-    sc = _COLSUM_SCRATCH.get(x.device)
+    key = _stream_key(x.device)
+    sc = _COLSUM_SCRATCH.get(key)
     if sc is None:
-        sc = _COLSUM_SCRATCH[x.device] = torch.zeros(need, device=x.device)
+        sc = _COLSUM_SCRATCH[key] = torch.zeros(need, device=x.device)
     out = torch.empty(cols, device=x.device)
     _capi.check(L.rl_colsum(x.data_ptr(), rows, cols, ld, out.data_ptr(), sc.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
     return out

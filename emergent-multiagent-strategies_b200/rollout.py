@@ -95,8 +95,10 @@ class BatchedTrainer(object):
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
                  use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False,
-                 graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=False, exact_old="auto"):
+                 graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=False, exact_old="auto",
+                 overlap_teams=True):
         self.device = torch.device(device)
+        self.overlap_teams = bool(overlap_teams)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
         self.gamma, self.tau = gamma, tau
@@ -331,16 +333,46 @@ class BatchedTrainer(object):
             train_guards_only = self.ensemble is not None
         vals = []
         trainers = self.trainers[:1] if train_guards_only else self.trainers
+        jobs = []
         for t, trainer in enumerate(trainers):
             own = [self.roll.agents[i] for i in self.teams[t]]
             opp = [self.roll.agents[i] for i in self.teams[1 - t]]
             lo, olo = self.teams[t][0], self.teams[1 - t][0]
             shared = (self.roll, lo, len(own), olo, len(opp)) if self.fused_update else None
-            vals.append(trainer.update(own, opp, shared=shared))
+            jobs.append((trainer, own, opp, shared))
+        if self._overlap_ok(jobs):
+            vals = self._update_overlapped(jobs)
+        else:
+            vals = [trainer.update(own, opp, shared=shared) for trainer, own, opp, shared in jobs]
         if self.fused is not None:                         # the optimizer moved the weights: re-pack the kernel's blob
             for f in self.fused:
                 f.refresh()
         return vals
+
+    def _overlap_ok(self, jobs):
+        """The two teams' updates share nothing but read-only rollout blocks (each team has its own network, optimizer and
+        scratch), so on one rank they are enqueued on two streams and run at the same time.  Several ranks keep them one after
+        the other: two captured collectives of one communicator must not be in flight together."""
+        return (self.overlap_teams and len(jobs) == 2 and self.device.type == "cuda" and self.process_group is None
+                and all(sh is not None and tr.use_clipped_value_loss for tr, _o, _p, sh in jobs))
+
+    def _update_overlapped(self, jobs):
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_team_streams", None) is None:
+            self._team_streams = [torch.cuda.Stream(self.device) for _ in jobs]
+        handles = []
+        for (trainer, own, opp, shared), st in zip(jobs, self._team_streams):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = bool(trainer.allow_tf32)
+                try:
+                    handles.append(trainer.update_begin(own, opp, shared))
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        for st in self._team_streams:
+            main.wait_stream(st)
+        return [trainer.update_end(h) for (trainer, _o, _p, _s), h in zip(jobs, handles)]
 
     def after_update(self):
         self.roll.after_update()

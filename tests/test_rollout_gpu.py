@@ -448,6 +448,33 @@ def test_graph_captured_update_tracks_eager_update():
     assert worst < 2e-3, worst
 
 
+@pytest.mark.parametrize("graph_update", [False, True])
+def test_overlapped_team_updates_equal_sequential(graph_update):
+    """BatchedTrainer.update enqueues the two teams' updates on two streams (overlap_teams, the default on one rank).  The
+    teams share nothing but read-only rollout blocks, every kernel has a fixed summation order and its own scratch scope,
+    so losses and weights must equal those of one update after the other BIT FOR BIT."""
+    ro = import_module(PKG + ".rollout")
+    out = []
+    for ov in (True, False):
+        torch.manual_seed(33)
+        tr = ro.BatchedTrainer(512, 3, 3, num_steps=16, max_episode_steps=9, seed=5, ppo_epoch=2, num_mini_batch=8,
+                               graph_update=graph_update, overlap_teams=ov)
+        vals = []
+        for it in range(3):
+            tr.collect(); tr.wrap_horizon()
+            torch.manual_seed(70 + it)
+            vals.append(tr.update())
+            tr.after_update()
+        torch.cuda.synchronize()
+        out.append((vals, [p.detach().clone() for pol in tr.policies for p in pol.parameters()]))
+        assert (getattr(tr, "_team_streams", None) is not None) == ov
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert torch.equal(a, b), float((a - b).abs().max())
+    fused = import_module(PKG + ".rlcore.fused")
+    fused.tg_check_status("cuda:0")
+
+
 def test_attacker_ensemble_play():
     """K frozen attacker checkpoints, one drawn per env at every episode start (learner.py:119-140,
     train_fortattack_v2.py:34-35,110-111): each env's attacker rows come from the checkpoint it is assigned to."""
