@@ -861,6 +861,9 @@ def train_config4_share(torch, dev, dist, world, rank, E=8192, T=128):
            "allreduce_share_of_update": (256 * ar_us * 1e-3 / upd) if ar_us else 0.0, "replica_weight_spread": spread,
            "update_path": "tcgen05 dense kernels + own attention / loss / Adam kernels, optimizer step replayed from a CUDA graph "
                           "(NCCL all-reduce captured in it)",
+           "teams_overlapped": world == 1,
+           "teams_note": "one rank: the two teams' updates (and recompute_old passes) run on two streams at the same time; several "
+                         "ranks: one team after the other (two captured collectives of one communicator are never in flight together)",
            "policy_weights": "marlsave/tmp_1/ep2520.pt" if models is not None else "random init",
            "losses": [[float(x) for x in v] for v in vals]}
     del tr

@@ -76,6 +76,29 @@ def pack_mpnn(m, device=None):
     return blob.contiguous()
 
 
+_OUT_DTYPES = {"value": torch.float32, "action": torch.int64, "action_i32": torch.int32, "logp": torch.float32,
+               "entropy": torch.float32, "logits": torch.float32}
+
+
+def _check_outputs(out, n, E, dev):
+    """The kernel writes through raw pointers: every output must have the element type, device and size it assumes."""
+    for key, t in out.items():
+        if key not in _OUT_DTYPES:
+            raise ValueError("unknown output %r (expected one of %s)" % (key, sorted(_OUT_DTYPES)))
+        if t.dtype != _OUT_DTYPES[key] or t.device != dev:
+            raise ValueError("output %r must be %s on %s, got %s on %s" % (key, _OUT_DTYPES[key], dev, t.dtype, t.device))
+        if not t.is_contiguous() or t.numel() != n * E * (ACTIONS if key == "logits" else 1):
+            raise ValueError("output %r must be contiguous with %d rows" % (key, n * E))
+
+
+def _check_env_lists(env_order, env_offsets, E, K, dev):
+    if (env_order.dtype != torch.int32 or env_offsets.dtype != torch.int32 or env_order.numel() != E
+            or (K is not None and env_offsets.numel() != K + 1) or env_offsets.numel() < 2
+            or not env_order.is_contiguous() or not env_offsets.is_contiguous()
+            or env_order.device != dev or env_offsets.device != dev):
+        raise ValueError("env_order (int32 [E]) and env_offsets (int32 [K+1]) must be contiguous tensors on %s" % (dev,))
+
+
 class FusedPolicy(object):
     """Rollout-time forward of one team's MPNN in a single kernel launch."""
 
@@ -120,8 +143,10 @@ class FusedPolicy(object):
             raise ValueError("own/opp must be [%d,E,6] / [%d,E,6], got %s / %s" % (n, m, tuple(own.shape), tuple(opp.shape)))
         if own.dtype != torch.float32 or opp.dtype != torch.float32 or not own.is_contiguous() or not opp.is_contiguous():
             raise ValueError("observations must be contiguous float32")
-        out = dict(out or {})
         dev = self.device
+        if own.device != dev or opp.device != dev:
+            raise ValueError("observations must live on %s (the kernel reads raw device pointers)" % (dev,))
+        out = dict(out or {})
         for key, dt, shape in (("value", torch.float32, (n, E)), ("action", torch.int64, (n, E)),
                                ("action_i32", torch.int32, (n, E)), ("logp", torch.float32, (n, E))):
             if key not in out:
@@ -130,13 +155,20 @@ class FusedPolicy(object):
             out["entropy"] = torch.empty((n, E), dtype=torch.float32, device=dev)
         if want_logits and "logits" not in out:
             out["logits"] = torch.empty((n, E, ACTIONS), dtype=torch.float32, device=dev)
-        for key, t in out.items():
-            if not t.is_contiguous() or t.numel() != n * E * (ACTIONS if key == "logits" else 1):
-                raise ValueError("output %r must be contiguous with %d rows" % (key, n * E))
+        _check_outputs(out, n, E, dev)
         if mode == MODE_EVAL:
+            if action_in is None or action_in.numel() != n * E:
+                raise ValueError("MODE_EVAL needs action_in with one action per (agent, env) row (%d)" % (n * E))
             action_in = action_in.to(device=dev, dtype=torch.int64).contiguous()
-        if env_sel is not None and (env_sel.dtype != torch.int32 or env_sel.numel() != E or not env_sel.is_contiguous()):
-            raise ValueError("env_sel must be a contiguous int32 tensor with one entry per environment")
+        if env_sel is not None and (env_sel.dtype != torch.int32 or env_sel.numel() != E or not env_sel.is_contiguous()
+                                    or env_sel.device != dev):
+            raise ValueError("env_sel must be a contiguous int32 tensor on %s with one entry per environment" % (dev,))
+        if (env_order is None) != (env_offsets is None):
+            raise ValueError("env_order and env_offsets come together")
+        if env_order is not None:
+            _check_env_lists(env_order, env_offsets, E, None, dev)
+            if not 0 <= int(sel_value) < env_offsets.numel() - 1:
+                raise ValueError("sel_value %d outside the %d groups of env_offsets" % (sel_value, env_offsets.numel() - 1))
         stream = torch.cuda.current_stream(dev).cuda_stream
         _capi.check(self._lib.mp_forward(self.blob.data_ptr(), own.data_ptr(), opp.data_ptr(), n, m, E, mode,
                                          self.seed, self.calls, self.counter.data_ptr(), self.env_id0, self._ptr(action_in),
@@ -180,14 +212,16 @@ def forward_ensemble(policies, own, opp, env_order, env_offsets, mode=MODE_SAMPL
     E = own.shape[1]
     if own.shape != (n, E, OBS_DIM) or opp.shape != (m, E, OBS_DIM) or not own.is_contiguous() or not opp.is_contiguous():
         raise ValueError("own/opp must be contiguous [%d,E,6] / [%d,E,6]" % (n, m))
-    if env_order.dtype != torch.int32 or env_offsets.dtype != torch.int32 or env_order.numel() != E or env_offsets.numel() != len(policies) + 1:
-        raise ValueError("env_order int32 [E] and env_offsets int32 [K+1] are required")
+    if own.device != dev or opp.device != dev or own.dtype != torch.float32 or opp.dtype != torch.float32:
+        raise ValueError("observations must be float32 on %s" % (dev,))
+    if any(f.n != n or f.m != m or f.device != dev for f in policies):
+        raise ValueError("every checkpoint of an ensemble must have the team shape and device of the first")
+    _check_env_lists(env_order, env_offsets, E, len(policies), dev)
     out = dict(out or {})
     for key, dt in (("value", torch.float32), ("action", torch.int64), ("action_i32", torch.int32), ("logp", torch.float32)):
         if key not in out:
             out[key] = torch.empty((n, E), dtype=dt, device=dev)
-        if not out[key].is_contiguous() or out[key].numel() != n * E:
-            raise ValueError("output %r must be contiguous with %d rows" % (key, n * E))
+    _check_outputs(out, n, E, dev)
     blobs = (ctypes.c_void_p * len(policies))(*[f.blob.data_ptr() for f in policies])
     _capi.check(lead._lib.mp_forward_ensemble(blobs, len(policies), own.data_ptr(), opp.data_ptr(), n, m, E, mode, lead.seed,
                                               lead.calls, lead.counter.data_ptr(), lead.env_id0, out["value"].data_ptr(),

@@ -278,24 +278,41 @@ class BatchedTrainer(object):
         rlcore/fused.py), so that ratio = exp(new - old) is 1 at the first minibatch of the update (ppo.py:163).
         Rows are agent-major per chunk of time steps, exactly the minibatch layout (ppo.py:222-234)."""
         R, T, E = self.roll, self.T, self.E
+        two = self.overlap_teams and self.device.type == "cuda" and self.ensemble is None
+        main = torch.cuda.current_stream(self.device) if two else None
+        if two and getattr(self, "_team_streams", None) is None:
+            self._team_streams = [torch.cuda.Stream(self.device) for _ in self.policies]
         for t, policy in enumerate(self.policies):
             if t == 1 and self.ensemble is not None:       # frozen attackers are not trained
                 continue
-            team, opp = self.teams[t], self.teams[1 - t]
-            lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
-            n = hi - lo
-            steps = max(1, chunk_rows // (max(n, ohi - olo) * E))
-            policy.fused_no_grad = True
-            try:
-                for s0 in range(0, T, steps):
-                    s1 = min(T, s0 + steps)
-                    rows = lambda x, a, b: x[s0:s1, a:b].transpose(0, 1).reshape(-1, x.shape[-1])
-                    v, lp, _, _ = policy.evaluate_actions(rows(R.obs, lo, hi), None, rows(R.obs, olo, ohi), None,
-                                                          rows(R.actions, lo, hi))
-                    R.value_preds[s0:s1, lo:hi] = v.view(n, s1 - s0, E, 1).transpose(0, 1)
-                    R.action_log_probs[s0:s1, lo:hi] = lp.view(n, s1 - s0, E, 1).transpose(0, 1)
-            finally:
-                policy.fused_no_grad = False
+            if two:                                        # the teams write disjoint slices: one stream each
+                self._team_streams[t].wait_stream(main)
+            if two:
+                with torch.cuda.stream(self._team_streams[t]):
+                    self._recompute_team(t, policy, chunk_rows)
+            else:
+                self._recompute_team(t, policy, chunk_rows)
+        if two:
+            for st in self._team_streams:
+                main.wait_stream(st)
+
+    def _recompute_team(self, t, policy, chunk_rows):
+        R, T, E = self.roll, self.T, self.E
+        team, opp = self.teams[t], self.teams[1 - t]
+        lo, hi, olo, ohi = team[0], team[-1] + 1, opp[0], opp[-1] + 1
+        n = hi - lo
+        steps = max(1, chunk_rows // (max(n, ohi - olo) * E))
+        policy.fused_no_grad = True
+        try:
+            for s0 in range(0, T, steps):
+                s1 = min(T, s0 + steps)
+                rows = lambda x, a, b: x[s0:s1, a:b].transpose(0, 1).reshape(-1, x.shape[-1])
+                v, lp, _, _ = policy.evaluate_actions(rows(R.obs, lo, hi), None, rows(R.obs, olo, ohi), None,
+                                                      rows(R.actions, lo, hi))
+                R.value_preds[s0:s1, lo:hi] = v.view(n, s1 - s0, E, 1).transpose(0, 1)
+                R.action_log_probs[s0:s1, lo:hi] = lp.view(n, s1 - s0, E, 1).transpose(0, 1)
+        finally:
+            policy.fused_no_grad = False
 
     # -- Learner.wrap_horizon (learner.py:191-211) ---------------------------------------------------
     @torch.no_grad()

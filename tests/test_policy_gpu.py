@@ -185,3 +185,33 @@ def test_act_surface_matches_module_statistics():
     assert (value - v_ref).abs().max() < 3e-2 * max(1.0, float(v_ref.abs().max()))
     assert (action == a_ref).float().mean() > 0.97          # arg-max flips only where two logits nearly tie
     assert (fp.get_value(own.view(-1, 6), None, opp.view(-1, 6), None) - value).abs().max() == 0
+
+
+def test_forward_rejects_buffers_the_kernel_would_misread():
+    """mp_forward takes raw pointers: wrong element types, sizes or devices must be refused before the launch."""
+    n, m, E = 3, 3, 64
+    net = make(n, m, seed=5).cuda()
+    fp = pk.FusedPolicy(net, seed=1)
+    gen = torch.Generator().manual_seed(9)
+    own, opp = pu.random_obs(n, E, gen, "cuda"), pu.random_obs(m, E, gen, "cuda")
+    order = torch.arange(E, dtype=torch.int32, device="cuda")
+    offsets = torch.tensor([0, E], dtype=torch.int32, device="cuda")
+    bad = [dict(own=own.cpu()), dict(out={"value": torch.empty(n, E, dtype=torch.float64, device="cuda")}),
+           dict(out={"action": torch.empty(n, E, dtype=torch.int32, device="cuda")}),
+           dict(out={"logp": torch.empty(n, E)}), dict(out={"values": torch.empty(n, E, device="cuda")}),
+           dict(mode=pk.MODE_EVAL), dict(mode=pk.MODE_EVAL, action_in=torch.zeros(n * E - 1, dtype=torch.int64)),
+           dict(env_order=order), dict(env_order=order.long(), env_offsets=offsets),
+           dict(env_order=order[:-1].contiguous(), env_offsets=offsets), dict(env_order=order, env_offsets=offsets, sel_value=1),
+           dict(env_sel=torch.zeros(E, dtype=torch.int32))]
+    for kw in bad:
+        args = dict(own=own, opp=opp)
+        args.update(kw)
+        with pytest.raises(ValueError):
+            fp.forward(**args)
+    with pytest.raises(ValueError):
+        pk.forward_ensemble([fp], own, opp, order, offsets[:1].contiguous())
+    with pytest.raises(ValueError):
+        pk.forward_ensemble([fp], own, opp, order.cpu(), offsets)
+    ok = fp.forward(own, opp, pk.MODE_ARGMAX, env_order=order, env_offsets=offsets, sel_value=0)
+    assert torch.isfinite(ok["value"]).all()
+    fp.check_status()
