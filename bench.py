@@ -828,7 +828,8 @@ def train_config4_share(torch, dev, dist, world, rank, E=8192, T=128):
     ar_us, spread, nbytes = None, 0.0, 0
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        flat = torch.zeros(sum(p.numel() for p in tr.policies[0].parameters()) + 5, device=dev)
+        # the joint two-team step all-reduces ONE buffer holding both teams' gradients (+ 5 loss / normaliser terms each)
+        flat = torch.zeros(sum(sum(p.numel() for p in pol.parameters()) + 5 for pol in tr.policies), device=dev)
         nbytes = flat.numel() * 4
         for _ in range(5):
             dist.all_reduce(flat)
@@ -857,13 +858,15 @@ def train_config4_share(torch, dev, dist, world, rank, E=8192, T=128):
                        "iteration = rollout + recompute_old + GAE + JointPPO update (4 epochs x 32 minibatches x 2 teams)" % (E, world, T),
            "rollout_ms": col, "recompute_old_and_gae_ms": wrap, "update_ms": upd, "iteration_ms": tot,
            "agent_steps_per_s_trained": world * E * 10 * T / (tot * 1e-3), "optimizer_steps": 256,
-           "collectives_per_optimizer_step": 1 if world > 1 else 0, "allreduce_us": ar_us, "allreduce_bytes": nbytes,
-           "allreduce_share_of_update": (256 * ar_us * 1e-3 / upd) if ar_us else 0.0, "replica_weight_spread": spread,
-           "update_path": "tcgen05 dense kernels + own attention / loss / Adam kernels, optimizer step replayed from a CUDA graph "
+           "collectives_per_optimizer_step": 0.5 if world > 1 else 0, "allreduce_us": ar_us, "allreduce_bytes": nbytes,
+           "allreduce_share_of_update": (128 * ar_us * 1e-3 / upd) if ar_us else 0.0, "replica_weight_spread": spread,
+           "update_path": "tcgen05 dense kernels + own attention / loss / Adam kernels, optimizer steps replayed from a CUDA graph "
                           "(NCCL all-reduce captured in it)",
-           "teams_overlapped": world == 1,
+           "teams_overlapped": True,
            "teams_note": "one rank: the two teams' updates (and recompute_old passes) run on two streams at the same time; several "
-                         "ranks: one team after the other (two captured collectives of one communicator are never in flight together)",
+                         "ranks: the two teams' optimizer steps are the two branches of ONE captured graph around ONE all-reduce "
+                         "of a flat buffer with both teams' gradients (128 collectives per update instead of 256; never two "
+                         "collectives of the communicator in flight)",
            "policy_weights": "marlsave/tmp_1/ep2520.pt" if models is not None else "random init",
            "losses": [[float(x) for x in v] for v in vals]}
     del tr

@@ -158,7 +158,9 @@ class JointPPO(object):
     def update_end(self, handle):
         return self._update_fused_end(handle)
 
-    def _update_fused_begin(self, rollouts_list, index_batches=None):
+    def _prepare_fused(self, rollouts_list, index_batches=None):
+        """Everything a fused update needs before its first optimizer step: normalised advantages [n, T, E], the minibatch index
+        tensors of all epochs in order (on the device), the loss accumulator."""
         try:
             from .. import fused
         except ImportError:
@@ -169,10 +171,6 @@ class JointPPO(object):
         dev = advantages.device
         batch_size = T * P
         mini_batch_size = int(batch_size / self.num_mini_batch)
-        totals = torch.zeros(3, device=dev)
-        params = [p for p in self.actor_critic.parameters()]
-        world = self._world()
-        self._adv_fresh = True               # the captured step copies the advantages into its own buffer once per update
         perms = None
         if index_batches is None:
             # every epoch's permutation is drawn up front (same draws, same order as one per epoch) and goes to the device
@@ -180,17 +178,25 @@ class JointPPO(object):
             # and the host has to stay ahead of the device for the whole update
             perms = [self._perm(rollouts_list[0]) for _ in range(self.ppo_epoch)]
             perms = [q if q.is_cuda else q.pin_memory().to(dev, non_blocking=True) for q in perms]
+        batches = []
         for epoch in range(self.ppo_epoch):
             if index_batches is not None:
-                batches = index_batches[epoch]
+                batches += [idx.to(dev).contiguous() for idx in index_batches[epoch]]
             else:
                 perm = perms[epoch]
-                batches = [perm[i:i + mini_batch_size] for i in range(0, batch_size, mini_batch_size)]
-            for idx in batches:
-                idx = idx.to(dev).contiguous()
-                if self._graphed_step(fused, R, (a0, n, o0, m), idx, advantages, totals, mini_batch_size, world):
-                    continue
-                self._minibatch_step(fused, R, (a0, n, o0, m), idx, advantages, totals, params, world)
+                batches += [perm[i:i + mini_batch_size].contiguous() for i in range(0, batch_size, mini_batch_size)]
+        self._adv_fresh = True               # the captured step copies the advantages into its own buffer once per update
+        return {"fused": fused, "R": R, "team": (a0, n, o0, m), "advantages": advantages, "batches": batches,
+                "mini_batch_size": mini_batch_size, "totals": torch.zeros(3, device=dev),
+                "params": [p for p in self.actor_critic.parameters()], "world": self._world()}
+
+    def _update_fused_begin(self, rollouts_list, index_batches=None):
+        st = self._prepare_fused(rollouts_list, index_batches)
+        fused, R, team, advantages, totals = st["fused"], st["R"], st["team"], st["advantages"], st["totals"]
+        for idx in st["batches"]:
+            if self._graphed_step(fused, R, team, idx, advantages, totals, st["mini_batch_size"], st["world"]):
+                continue
+            self._minibatch_step(fused, R, team, idx, advantages, totals, st["params"], st["world"])
         return totals
 
     def _update_fused_end(self, totals):
@@ -200,16 +206,19 @@ class JointPPO(object):
         v, a, e = (totals / (self.ppo_epoch * self.num_mini_batch)).tolist()
         return v, a, e
 
-    def _minibatch_step(self, fused, R, team, idx, advantages, totals, params, world):
+    def _minibatch_step(self, fused, R, team, idx, advantages, totals, params, world, fill_only=False):
+        """fill_only: stop after the flat buffer holds this rank's gradients and loss sums (the several-ranks form of the
+        step, whatever the world size); the caller runs the collective and _ranks_apply_flat itself (BatchedTrainer's joint
+        step: both teams' halves around ONE all-reduce)."""
         fused.pack_cache(True)               # weights are constant from here to the optimizer kernel: packs are reused
         prev_scope = fused.scratch_scope(id(self))      # this trainer's own partial-sum / counter / status storage
         try:
-            self._minibatch_step_body(fused, R, team, idx, advantages, totals, params, world)
+            self._minibatch_step_body(fused, R, team, idx, advantages, totals, params, world, fill_only)
         finally:
             fused.scratch_scope(prev_scope)
             fused.pack_cache(False)
 
-    def _minibatch_step_body(self, fused, R, team, idx, advantages, totals, params, world):
+    def _minibatch_step_body(self, fused, R, team, idx, advantages, totals, params, world, fill_only=False):
         a0, n, o0, m = team
         (obs_batch, mask, obs_opp_batch, actions_batch, value_preds_batch, return_batch, masks_batch,
          old_log_probs_batch, adv_targ, alive_sum) = fused.gather_minibatch(R, idx, a0, n, o0, m, advantages)
@@ -231,6 +240,9 @@ class JointPPO(object):
                 return fused.ppo_loss(values, action_log_probs, dist_entropy, value_preds_batch, return_batch, old_log_probs_batch,
                                       adv_targ, mask, norm_, self.clip_param, self.value_loss_coef, self.entropy_coef)
         count = mask.new_full((1,), float(mask.numel()))
+        if fill_only:
+            self._ranks_fill_flat(loss_of, mask, alive_sum, count, params)
+            return
         if world == 1:
             norm = torch.where(alive_sum != 0, alive_sum, count)          # mask.mean() != 0 else 1 (ppo.py:150-187)
             loss, stats = loss_of(norm)
@@ -243,16 +255,26 @@ class JointPPO(object):
         # (ppo.py:150-187 with global sums), so each rank differentiates its UN-normalised local sums (norm = 1), the
         # gradients travel together with the two normaliser terms and the three loss sums in one persistent flat buffer,
         # and the division by the global normaliser happens after the all-reduce (inside the optimizer kernel).
+        self._ranks_fill_flat(loss_of, mask, alive_sum, count, params)
+        self._allreduce(self._flat_grads(params)[0])
+        self._ranks_apply_flat(totals, params)
+
+    def _ranks_fill_flat(self, loss_of, mask, alive_sum, count, params):
+        """Backward of the un-normalised local loss sums; gradients + [alive sum, count, three loss sums] into the flat buffer."""
         if getattr(self, "_one", None) is None or self._one.device != mask.device:
             self._one = torch.ones(1, device=mask.device)
         loss, stats = loss_of(self._one)
         self.optimizer.zero_grad()
         loss.backward()
-        flat, views = self._flat_grads(params)
+        flat, _views = self._flat_grads(params)
         total = flat.numel() - 5
         torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params], out=flat[:total])
         torch.cat([alive_sum, count, stats[:3]], out=flat[total:])
-        self._allreduce(flat)
+
+    def _ranks_apply_flat(self, totals, params):
+        """After the all-reduce of the flat buffer: divide by the global normaliser, clip, Adam, loss sums."""
+        flat, views = self._flat_grads(params)
+        total = flat.numel() - 5
         inv = 1.0 / torch.where(flat[total:total + 1] != 0, flat[total:total + 1], flat[total + 1:total + 2])
         if self._tg_adam:
             self.optimizer.step(self.max_grad_norm, grad_scale=inv, grads=views)
@@ -261,6 +283,19 @@ class JointPPO(object):
                 p.grad = v * inv
             self._clip_and_step()
         totals += flat[total + 2:] * inv
+
+    def use_flat_buffer(self, flat, params=None):
+        """Install a caller-owned flat gradient buffer ([sum(numel) + 5] floats, e.g. one segment of a buffer that several
+        trainers share so that ONE collective serves all of them: BatchedTrainer's joint step)."""
+        params = [p for p in self.actor_critic.parameters()] if params is None else params
+        total = sum(p.numel() for p in params)
+        if flat.numel() != total + 5 or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise ValueError("flat buffer must be contiguous float32 with %d elements" % (total + 5))
+        views, off = [], 0
+        for p in params:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self._fg = (tuple(id(p) for p in params), flat, views)
 
     def _flat_grads(self, params):
         """Persistent flat buffer [sum(numel) + 5] and its per-parameter views (allocated once per parameter set)."""
@@ -280,6 +315,7 @@ class JointPPO(object):
         """Drop the captured optimizer-step graph (it holds this process group's NCCL kernels): call before
         dist.destroy_process_group(), or teardown waits on the graph's communicator references."""
         self._g = None
+        self._joint = None                   # (BatchedTrainer keeps its joint two-team step graph on the first trainer)
 
     def _graphed_step(self, fused, R, team, idx, advantages, totals, mini_batch_size, world):
         """Replay (or, on its fourth call, capture) the optimizer step as one CUDA graph.  Returns False when the step

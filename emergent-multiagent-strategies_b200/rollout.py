@@ -98,7 +98,7 @@ class BatchedTrainer(object):
                  graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=False, exact_old="auto",
                  overlap_teams=True):
         self.device = torch.device(device)
-        self.overlap_teams = bool(overlap_teams)
+        self.overlap_teams = overlap_teams if overlap_teams == "joint" else bool(overlap_teams)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
         self.gamma, self.tau = gamma, tau
@@ -357,7 +357,9 @@ class BatchedTrainer(object):
             lo, olo = self.teams[t][0], self.teams[1 - t][0]
             shared = (self.roll, lo, len(own), olo, len(opp)) if self.fused_update else None
             jobs.append((trainer, own, opp, shared))
-        if self._overlap_ok(jobs):
+        if self._joint_ok(jobs):
+            vals = self._update_joint(jobs)
+        elif self._overlap_ok(jobs):
             vals = self._update_overlapped(jobs)
         else:
             vals = [trainer.update(own, opp, shared=shared) for trainer, own, opp, shared in jobs]
@@ -390,6 +392,94 @@ class BatchedTrainer(object):
         for st in self._team_streams:
             main.wait_stream(st)
         return [trainer.update_end(h) for (trainer, _o, _p, _s), h in zip(jobs, handles)]
+
+    def _joint_ok(self, jobs):
+        """Several ranks (or overlap_teams="joint"): the two teams' optimizer steps run as the two branches of ONE captured
+        graph around ONE all-reduce of a flat buffer that holds both teams' gradients -- the teams overlap as on one rank, and
+        there is never more than one collective of the communicator in flight."""
+        want = self.overlap_teams == "joint" or (self.overlap_teams and self.process_group is not None)
+        return (want and len(jobs) == 2 and self.device.type == "cuda"
+                and all(sh is not None and tr.use_clipped_value_loss and tr.graph_update and tr._tg_adam for tr, _o, _p, sh in jobs))
+
+    def _update_joint(self, jobs):
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        trs = [j[0] for j in jobs]
+        if getattr(self, "_team_streams", None) is None:
+            self._team_streams = [torch.cuda.Stream(dev) for _ in jobs]
+        sizes = [sum(p.numel() for p in tr.actor_critic.parameters()) + 5 for tr in trs]
+        J = getattr(trs[0], "_joint", None)
+        if J is None or J["flat"].numel() != sum(sizes):
+            J = trs[0]._joint = {"flat": torch.zeros(sum(sizes), device=dev), "key": None}
+        off = 0
+        for tr, sz in zip(trs, sizes):                   # each trainer's flat gradient buffer is its segment of the shared one
+            tr.use_flat_buffer(J["flat"][off:off + sz])
+            off += sz
+        sts = []
+        for tr, own, _opp, shared in jobs:
+            tr._shared = shared
+            prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = bool(tr.allow_tf32)
+            try:
+                sts.append(tr._prepare_fused(own))
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        nb, mbs = len(sts[0]["batches"]), sts[0]["mini_batch_size"]
+        assert len(sts[1]["batches"]) == nb and sts[1]["mini_batch_size"] == mbs
+        key = (id(self.roll), tuple(st["team"] for st in sts), mbs, tuple(tuple(st["advantages"].shape) for st in sts))
+        if J["key"] != key:
+            J.update(key=key, eager=0, graph=None, idx=[torch.empty_like(st["batches"][0]) for st in sts],
+                     adv=[torch.empty_like(st["advantages"]) for st in sts], totals=[torch.zeros_like(st["totals"]) for st in sts])
+        adv_fresh = True
+        for k in range(nb):
+            idxs = [st["batches"][k] for st in sts]
+            full = all(i.numel() == mbs for i in idxs)
+            if not full or (J["graph"] is None and J["eager"] < 3):
+                # a ragged last minibatch, or the warm-up steps a capture needs: one team after the other, each with its own
+                # all-reduce (of its segment of the shared buffer)
+                J["eager"] += int(full)
+                for tr, st, idx in zip(trs, sts, idxs):
+                    tr._minibatch_step(st["fused"], st["R"], st["team"], idx, st["advantages"], st["totals"], st["params"], st["world"])
+                continue
+            if J["graph"] is None:
+                self._capture_joint(J, trs, sts, idxs, main)
+            for t, st in enumerate(sts):
+                J["idx"][t].copy_(idxs[t])
+                if adv_fresh:
+                    J["adv"][t].copy_(st["advantages"])
+                J["totals"][t].zero_()
+            adv_fresh = False
+            J["graph"].replay()
+            for t, st in enumerate(sts):
+                st["totals"] += J["totals"][t]
+        return [tr.update_end(st["totals"]) for tr, st in zip(trs, sts)]
+
+    def _capture_joint(self, J, trs, sts, idxs, main):
+        dev = self.device
+        for t, st in enumerate(sts):
+            J["idx"][t].copy_(idxs[t])
+            J["adv"][t].copy_(st["advantages"])
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(main)
+        for tr in trs:
+            tr.optimizer.zero_grad(set_to_none=True)
+        # (a process group's watchdog thread polls its events while we capture -> thread-local mode, as in JointPPO._graphed_step)
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local" if self.process_group is not None else "global"):
+            for t, (tr, st) in enumerate(zip(trs, sts)):
+                ts = self._team_streams[t]
+                ts.wait_stream(side)                     # fork: each team's forward / backward on its own branch
+                with torch.cuda.stream(ts):
+                    tr._minibatch_step(st["fused"], st["R"], st["team"], J["idx"][t], J["adv"][t], J["totals"][t], st["params"],
+                                       st["world"], fill_only=True)
+            for ts in self._team_streams:
+                side.wait_stream(ts)                     # join
+            trs[0]._allreduce(J["flat"])                 # ONE collective: both teams' gradients, normalisers and loss sums
+            for t, (tr, st) in enumerate(zip(trs, sts)):
+                tr._ranks_apply_flat(J["totals"][t], st["params"])
+        main.wait_stream(side)
+        J["graph"] = graph
 
     def after_update(self):
         self.roll.after_update()

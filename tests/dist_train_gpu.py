@@ -50,6 +50,35 @@ def main():
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     spread = float((hi - lo).abs().max())
     ok &= spread == 0.0 and all(torch.isfinite(torch.tensor(v)).all() for v in vals)
+    # -- 3. graph-replayed optimizer steps: the joint two-team step (both teams' branches of one graph around ONE all-reduce,
+    #       the default with a process group) against one team after the other (one captured all-reduce per team step) --------
+    res = []
+    for ov in (True, False):
+        torch.manual_seed(0)
+        tg = ro.BatchedTrainer(E, 3, 3, num_steps=T, max_episode_steps=12, device=dev, seed=7, env_id0=rank * E, ppo_epoch=2,
+                               num_mini_batch=4, process_group=dist.group.WORLD, graph_update=True, overlap_teams=ov)
+        tg.load_models(tr.state()["models"])
+        gv = []
+        for it in range(2):
+            tg.collect(); tg.recompute_old(); tg.wrap_horizon()
+            torch.manual_seed(100 + it)
+            gv.append(tg.update())
+            tg.after_update()
+        w = torch.cat([p.detach().reshape(-1) for pol in tg.policies for p in pol.parameters()])
+        lo, hi = w.clone(), w.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        captured = getattr(tg.trainers[0], "_joint", None) is not None if ov else tg.trainers[0]._g is not None
+        res.append((w, gv, float((hi - lo).abs().max()), captured))
+        for trn in tg.trainers:
+            trn.release_graphs()
+        del tg
+    joint_diff = float((res[0][0] - res[1][0]).abs().max())
+    loss_diff = max(abs(a - b) for va, vb in zip(res[0][1], res[1][1]) for ta, tb in zip(va, vb) for a, b in zip(ta, tb))
+    ok &= res[0][2] == 0.0 and res[1][2] == 0.0 and res[0][3] and res[1][3] and joint_diff < 2e-5 and loss_diff < 1e-4
+    if rank == 0:
+        print("dist_train_gpu: joint two-team step vs sequential: max weight difference %.2e, loss difference %.2e, replica "
+              "spreads %.1e / %.1e, graphs captured %s / %s" % (joint_diff, loss_diff, res[0][2], res[1][2], res[0][3], res[1][3]), flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

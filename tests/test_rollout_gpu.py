@@ -475,6 +475,33 @@ def test_overlapped_team_updates_equal_sequential(graph_update):
     fused.tg_check_status("cuda:0")
 
 
+def test_joint_two_team_step_tracks_sequential_updates():
+    """overlap_teams="joint" (the default form with a process group, forced here on one rank): both teams' forward / backward
+    as the two branches of ONE captured graph, the several-ranks form of the step (un-normalised sums, one flat buffer for
+    both teams, division by the normaliser inside the optimizer kernel).  Losses and weights follow one team after the other."""
+    ro = import_module(PKG + ".rollout")
+    out = []
+    for ov in ("joint", False):
+        torch.manual_seed(33)
+        tr = ro.BatchedTrainer(512, 3, 3, num_steps=16, max_episode_steps=9, seed=5, ppo_epoch=2, num_mini_batch=8,
+                               graph_update=True, overlap_teams=ov)
+        vals = []
+        for it in range(2):
+            tr.collect(); tr.wrap_horizon()
+            torch.manual_seed(70 + it)
+            vals.append(tr.update())
+            tr.after_update()
+        torch.cuda.synchronize()
+        out.append((vals, [p.detach().clone() for pol in tr.policies for p in pol.parameters()], tr))
+    J = out[0][2].trainers[0]._joint
+    assert J is not None and J["graph"] is not None and out[1][2].trainers[0]._g["graph"] is not None
+    for va, vb in zip(out[0][0], out[1][0]):
+        assert np.allclose(va, vb, rtol=5e-3, atol=5e-4), (va, vb)
+    worst = max(float((a - b).abs().max()) for a, b in zip(out[0][1], out[1][1]))
+    assert worst < 2e-3, worst
+    import_module(PKG + ".rlcore.fused").tg_check_status("cuda:0")
+
+
 def test_attacker_ensemble_play():
     """K frozen attacker checkpoints, one drawn per env at every episode start (learner.py:119-140,
     train_fortattack_v2.py:34-35,110-111): each env's attacker rows come from the checkpoint it is assigned to."""
