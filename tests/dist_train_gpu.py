@@ -75,7 +75,11 @@ def main():
         del tg
     joint_diff = float((res[0][0] - res[1][0]).abs().max())
     loss_diff = max(abs(a - b) for va, vb in zip(res[0][1], res[1][1]) for ta, tb in zip(va, vb) for a, b in zip(ta, tb))
-    ok &= res[0][2] == 0.0 and res[1][2] == 0.0 and res[0][3] and res[1][3] and joint_diff < 2e-5 and loss_diff < 1e-4
+    # two ranks: a + b == b + a, so one collective over the shared buffer and one per team give the same bits; more ranks: the
+    # collective's summation order may depend on the buffer layout, and Adam turns a last-bit gradient difference of a
+    # cancelling component into a fraction of lr per step
+    tol_w, tol_l = (0.0, 0.0) if world == 2 else (2e-3, 5e-3)
+    ok &= res[0][2] == 0.0 and res[1][2] == 0.0 and res[0][3] and res[1][3] and joint_diff <= tol_w and loss_diff <= tol_l
     if rank == 0:
         print("dist_train_gpu: joint two-team step vs sequential: max weight difference %.2e, loss difference %.2e, replica "
               "spreads %.1e / %.1e, graphs captured %s / %s" % (joint_diff, loss_diff, res[0][2], res[1][2], res[0][3], res[1][3]), flush=True)
