@@ -666,7 +666,7 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
     ro = importlib.import_module("emergent-multiagent-strategies_b200.rollout")
     pk = importlib.import_module("emergent-multiagent-strategies_b200.policy_kernel")
     torch.manual_seed(0)
-    tr = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0)
+    tr = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, graph_update=False)   # (eager update timed below)
     models = shipped_models(torch)                                          # weights of marlsave/tmp_1/ep2520.pt
     if models is not None:
         tr.load_models(models)
@@ -716,7 +716,7 @@ def rollout_config3(fab, torch, dev, E=16384, T=128):
         update_cublas_ms = e0.elapsed_time(e1)
     finally:
         fused.DENSE = "tcgen05"
-    # ... and with the optimizer step replayed from a CUDA graph (opt-in JointPPO(graph_update=True))
+    # ... and with the optimizer steps replayed from CUDA graphs (BatchedTrainer's default on CUDA) and the teams overlapped
     tr2 = ro.BatchedTrainer(E, NG, NA, num_steps=T, max_episode_steps=CAP, device=dev, seed=0, graph_update=True)
     if models is not None:
         tr2.load_models(models)

@@ -95,9 +95,13 @@ class BatchedTrainer(object):
                  seed=0, env_id0=0, hidden_dim=128, gamma=0.99, tau=0.95, clip_param=0.2, ppo_epoch=4,
                  num_mini_batch=32, value_loss_coef=0.5, entropy_coef=0.01, lr=1e-4, max_grad_norm=0.5,
                  use_clipped_value_loss=True, process_group=None, fused_policy="auto", allow_tf32=False,
-                 graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=False, exact_old="auto",
+                 graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=None, exact_old="auto",
                  overlap_teams=True):
         self.device = torch.device(device)
+        # graph_update: replay the optimizer steps from CUDA graphs (JointPPO(graph_update=True)); default on for CUDA devices --
+        # an eager step is bound by the host's ~140 launches, and the joint two-team step of several ranks needs the graph
+        if graph_update is None:
+            graph_update = self.device.type == "cuda" and bool(fused_update)
         self.overlap_teams = overlap_teams if overlap_teams == "joint" else bool(overlap_teams)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
