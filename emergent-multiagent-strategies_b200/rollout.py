@@ -98,10 +98,13 @@ class BatchedTrainer(object):
                  graph_rollouts=True, attacker_ensemble=None, fused_update=True, graph_update=None, exact_old="auto",
                  overlap_teams=True):
         self.device = torch.device(device)
-        # graph_update: replay the optimizer steps from CUDA graphs (JointPPO(graph_update=True)); default on for CUDA devices --
-        # an eager step is bound by the host's ~140 launches, and the joint two-team step of several ranks needs the graph
+        # graph_update: replay the optimizer steps from CUDA graphs (JointPPO(graph_update=True)); an eager step is bound by the
+        # host's ~140 launches.  Default: on for a single-rank CUDA trainer.  With a process group it stays opt-in, because a
+        # captured step then holds the group's NCCL kernels and dist.destroy_process_group() waits for ever unless
+        # release_graphs() ran first (seen as a teardown hang, profiles/r4g_dist_train_2gpu.log) -- a caller who asks for it
+        # (as bench.py does) also gets the joint two-team step, and owes the trainer a release_graphs() before teardown.
         if graph_update is None:
-            graph_update = self.device.type == "cuda" and bool(fused_update)
+            graph_update = self.device.type == "cuda" and bool(fused_update) and process_group is None
         self.overlap_teams = overlap_teams if overlap_teams == "joint" else bool(overlap_teams)
         self.E, self.ng, self.na, self.T = n_envs, n_guards, n_attackers, num_steps
         self.A = n_guards + n_attackers
@@ -484,6 +487,13 @@ class BatchedTrainer(object):
                 tr._ranks_apply_flat(J["totals"][t], st["params"])
         main.wait_stream(side)
         J["graph"] = graph
+
+    def release_graphs(self):
+        """Drop every captured graph (rollout collection, optimizer steps, the joint two-team step).  Required before
+        dist.destroy_process_group() when the trainer has a process group and graph_update=True."""
+        for trn in self.trainers:
+            trn.release_graphs()
+        self._graph = None
 
     def after_update(self):
         self.roll.after_update()

@@ -88,6 +88,11 @@ def main():
     if rank == 0:
         print("dist_train_gpu: world %d shard-invariant rollouts %s, replica weight spread after update %.1e, losses %s -> %s"
               % (world, ok, spread, vals, "OK" if flag.item() == 1.0 else "FAILED"), flush=True)
+    # captured optimizer steps hold the group's NCCL kernels: drop them before the group goes away (a trainer that was given
+    # graph_update=True and is still alive here makes destroy_process_group wait for ever)
+    tr.release_graphs()
+    ref.release_graphs()
+    torch.cuda.synchronize(dev)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 
