@@ -489,8 +489,10 @@ class BatchedTrainer(object):
         J["graph"] = graph
 
     def release_graphs(self):
-        """Drop every captured graph (rollout collection, optimizer steps, the joint two-team step).  Required before
-        dist.destroy_process_group() when the trainer has a process group and graph_update=True."""
+        """Drop every captured graph (rollout collection, optimizer steps, the joint two-team step); the next collect() /
+        update() captures again.  Required before dist.destroy_process_group() when the trainer has a process group and
+        graph_update=True, and after changing anything a captured step bakes in as a kernel argument (learning rate, clip,
+        loss coefficients, max_grad_norm, the episode cap) -- the reference's scripts keep all of these constant."""
         for trn in self.trainers:
             trn.release_graphs()
         self._graph = None
