@@ -225,3 +225,33 @@ def test_tcgen05_wiring_of_the_whole_network(n, m, monkeypatch):
     assert set(g0) == set(g1)
     for k in g0:
         assert torch.allclose(g0[k], g1[k], rtol=1e-8, atol=1e-9), (k, float((g0[k] - g1[k]).abs().max()))
+
+
+def test_scratch_scope_and_flat_buffer_host_logic():
+    """Host logic of the overlapped team updates that needs no GPU: scratch storage is keyed by (device, scope) and scopes
+    nest; JointPPO.use_flat_buffer hands out views of a caller-owned segment and refuses a wrong size."""
+    assert fused.scratch_scope(0) == 0
+    k0 = fused._stream_key("cpu")
+    prev = fused.scratch_scope(1234)
+    assert prev == 0 and fused._stream_key("cpu") == (torch.device("cpu"), 1234) and fused._stream_key("cpu") != k0
+    inner = fused.scratch_scope(99)
+    assert inner == 1234 and fused._stream_key("cpu")[1] == 99
+    fused.scratch_scope(inner)
+    fused.scratch_scope(prev)
+    assert fused._stream_key("cpu") == k0
+    ppo = import_module(PKG + ".rlcore.algo.ppo")
+    net = mp.MPNN(action_space=Shape(8), num_agents=2, num_opp_agents=2, num_entities=0, input_size=6, hidden_dim=32, pos_index=2)
+    tr = ppo.JointPPO(net, 0.2, 1, 1, 0.5, 0.01, lr=1e-4, max_grad_norm=0.5)
+    params = [p for p in net.parameters()]
+    total = sum(p.numel() for p in params)
+    shared = torch.zeros(2 * (total + 5))
+    tr.use_flat_buffer(shared[total + 5:])
+    flat, views = tr._flat_grads(params)
+    assert flat.data_ptr() == shared[total + 5:].data_ptr() and flat.numel() == total + 5
+    assert [tuple(v.shape) for v in views] == [tuple(p.shape) for p in params]
+    views[0].fill_(1.0)
+    assert float(shared[total + 5:total + 5 + params[0].numel()].sum()) == params[0].numel() and float(shared[:total + 5].sum()) == 0.0
+    with pytest.raises(ValueError):
+        tr.use_flat_buffer(shared[:total])
+    tr.release_graphs()
+    assert tr._g is None and tr._joint is None
