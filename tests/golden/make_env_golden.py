@@ -2,7 +2,7 @@
 
     python tests/golden/make_env_golden.py
 
-Writes tests/golden/env_3v3.npz, env_5v5.npz, env_2v1.npz and copies the reference's own
+Writes tests/golden/env_{3v3,5v5,2v1,1v1,4v2,1v5,5v1}.npz and copies the reference's own
 recorded trajectory out_files/1.npy (written by test_fortattack.py:129-133) to
 tests/golden/ref_traj_5v5.npy.
 
@@ -128,7 +128,12 @@ def run(n_guards, n_attackers, n_trans, caps, seed):
 def main():
     specs = [("env_3v3.npz", 3, 3, 1500, [100, 25, 60], 11),
              ("env_5v5.npz", 5, 5, 500, [100, 30], 12),
-             ("env_2v1.npz", 2, 1, 200, [40, 15], 13)]
+             ("env_2v1.npz", 2, 1, 200, [40, 15], 13),
+             # the smallest and the most lopsided team shapes the kernels are instantiated for (oracle pinning on the CPU)
+             ("env_1v1.npz", 1, 1, 300, [30, 12], 14),
+             ("env_4v2.npz", 4, 2, 300, [50, 20], 15),
+             ("env_1v5.npz", 1, 5, 300, [60, 25], 16),
+             ("env_5v1.npz", 5, 1, 300, [40, 25], 17)]
     for name, g, a, n, caps, seed in specs:
         out = run(g, a, n, caps, seed)
         path = os.path.join(HERE, name)

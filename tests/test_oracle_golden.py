@@ -6,7 +6,7 @@ import fa_oracle
 import golden_util
 
 
-@pytest.mark.parametrize("name", ["env_3v3.npz", "env_5v5.npz", "env_2v1.npz"])
+@pytest.mark.parametrize("name", ["env_3v3.npz", "env_5v5.npz", "env_2v1.npz", "env_1v1.npz", "env_4v2.npz", "env_1v5.npz", "env_5v1.npz"])
 def test_oracle_matches_reference_transitions(name):
     g = golden_util.load(name)
     N, A = g["act"].shape
