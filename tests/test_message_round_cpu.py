@@ -255,3 +255,62 @@ def test_scratch_scope_and_flat_buffer_host_logic():
         tr.use_flat_buffer(shared[:total])
     tr.release_graphs()
     assert tr._g is None and tr._joint is None
+
+
+def test_flat_buffer_halves_of_the_several_ranks_step():
+    """JointPPO._ranks_fill_flat / _ranks_apply_flat around a SIMULATED all-reduce (the sum of two ranks' flat buffers), with two
+    trainers sharing one buffer as in BatchedTrainer's joint step: every parameter ends where one process holding both ranks'
+    data and the reference's normalisation (sums / global alive count, ppo.py:150-187) puts it."""
+    ppo = import_module(PKG + ".rlcore.algo.ppo")
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return mp.MPNN(action_space=Shape(8), num_agents=2, num_opp_agents=2, num_entities=0, input_size=6, hidden_dim=32, pos_index=2)
+
+    def local_sums(net, x, mask):
+        """un-normalised local sums of a toy loss that touches every parameter the same way on all ranks"""
+        s = sum((p * p).sum() for p in net.parameters())
+        per_row = (x * mask).sum(1)
+        return per_row, s
+
+    gen = torch.Generator().manual_seed(5)
+    data = [(torch.randn(7, 3, generator=gen), (torch.rand(7, 1, generator=gen) > 0.4).float()) for _ in range(2)]    # two ranks
+    teams = []
+    for seed in (1, 2):                                   # two teams = two trainers on ONE shared flat buffer
+        nets = [make(seed) for _ in range(3)]             # rank 0, rank 1, the single-process reference
+        trs = [ppo.JointPPO(n, 0.2, 1, 1, 0.5, 0.01, lr=1e-3, max_grad_norm=0.5) for n in nets]
+        teams.append((nets, trs))
+    sizes = [sum(p.numel() for p in teams[t][0][0].parameters()) + 5 for t in range(2)]
+    shared = [torch.zeros(sum(sizes)) for _ in range(2)]  # one buffer per simulated rank
+    for t, (nets, trs) in enumerate(teams):
+        off = sum(sizes[:t])
+        for r in range(2):
+            trs[r].use_flat_buffer(shared[r][off:off + sizes[t]])
+    for t, (nets, trs) in enumerate(teams):
+        for r in range(2):
+            x, mask = data[r]
+            net, params = nets[r], [p for p in nets[r].parameters()]
+
+            def loss_of(norm, net=net, x=x, mask=mask):
+                per_row, s = local_sums(net, x, mask)
+                total = (per_row.sum() * s) / norm.reshape(())
+                return total, torch.stack([total.detach(), total.detach() * 2, total.detach() * 3, total.detach()])
+            trs[r]._ranks_fill_flat(loss_of, mask, mask.sum().view(1), mask.new_full((1,), float(mask.numel())), params)
+    reduced = shared[0] + shared[1]                       # the ONE all-reduce of the joint step
+    for r in range(2):
+        shared[r].copy_(reduced)
+    for t, (nets, trs) in enumerate(teams):
+        totals = [torch.zeros(3) for _ in range(2)]
+        for r in range(2):
+            trs[r]._ranks_apply_flat(totals[r], [p for p in nets[r].parameters()])
+        # the single-process reference: both ranks' rows, divided by the global alive count, clip + Adam
+        ref, rtr = nets[2], trs[2]
+        alive = sum(float(m.sum()) for _x, m in data)
+        loss = sum(local_sums(ref, x, m)[0].sum() * local_sums(ref, x, m)[1] for x, m in data) / alive
+        rtr.optimizer.zero_grad()
+        loss.backward()
+        rtr._clip_and_step()
+        for pa, pb, pr in zip(nets[0].parameters(), nets[1].parameters(), ref.parameters()):
+            assert torch.equal(pa, pb)                                        # replicas identical
+            assert torch.allclose(pa, pr, rtol=1e-5, atol=1e-7), float((pa - pr).abs().max())
+        assert torch.allclose(totals[0], torch.stack([loss.detach(), loss.detach() * 2, loss.detach() * 3]), rtol=1e-5)
